@@ -1,0 +1,501 @@
+// sph_api.cu -- the C ABI of include/sph_b200.h: context, buffers, step orchestration.
+//
+// One step = the reference's FluidSimulation::Update (engine/physics/physicsWorld.cc:39-111):
+//   predict+key -> radix sort -> table -> reorder -> density -> pressure -> viscosity -> integrate
+// all enqueued on the context's stream; six CUDA-event timers mirror getElapsedTime* (:184-212).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "sph_context.h"
+
+using namespace sphb200;
+
+namespace {
+std::string g_create_error;
+std::mutex g_create_mutex;
+constexpr float kPi = (float)3.14159265358979323846264338327950288;   // glm::pi<float>()
+}
+
+namespace sphb200 {
+
+int fail(SphContext* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    else { std::lock_guard<std::mutex> l(g_create_mutex); g_create_error = msg; }
+    return code;
+}
+int cuda_fail(SphContext* c, cudaError_t e, const char* what)
+{
+    return fail(c, SPH_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static int ceil_log2(uint64_t v)
+{
+    int b = 0;
+    while ((1ull << b) < v && b < 63) b++;
+    return b;
+}
+
+int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
+{
+    const SphParams& p = c->params;
+    memset(P, 0, sizeof(*P));
+    P->n = n; P->n_owned = n; P->mode = c->mode; P->gravity = p.gravity ? 1 : 0;
+    P->r = p.interaction_radius; P->sqr_r = p.sqr_radius; P->rho0 = p.target_density;
+    P->k = p.pressure_multiplier; P->kn = p.near_pressure_multiplier; P->mu = p.viscosity_strength;
+    P->g = p.gravity_scale;
+    for (int a = 0; a < 3; a++) P->half[a] = p.bound[a] * 0.5f;                  // physicsWorld.cc:88
+    const float r = p.interaction_radius;
+    // the reference recomputes these per call in fp32 (kernels.h:29,41,53,65,77); same expressions, once
+    P->vol2 = 15 / (2 * kPi * powf(r, 5));
+    P->vol3 = 15.0f / (kPi * powf(r, 6));
+    P->s2 = 15.0f / (powf(r, 5) * kPi);
+    P->s3 = 45 / (powf(r, 6) * kPi);
+    P->sv = 315 / (64 * kPi * powf(fabsf(r), 9));
+    P->rr = r * r;
+    for (int a = 0; a < 3; a++) { P->gmin[a] = c->gmin[a]; P->gdim[a] = c->gdim[a]; }
+    P->ncell = c->ncell;
+    P->modM = n ? (UINT64_MAX / n + 1) : 0;
+    return SPH_OK;
+}
+
+// GRID geometry: cover the box plus two cells of margin per side for predicted positions that
+// overshoot the walls; anything further out clamps into the border cells (still a superset walk).
+static int update_grid_geometry(SphContext* c)
+{
+    const SphParams& p = c->params;
+    if (!(p.interaction_radius > 0.0f)) return fail(c, SPH_ERR_INVALID, "interaction_radius must be > 0");
+    uint64_t cells = 1;
+    for (int a = 0; a < 3; a++) {
+        const float half = p.bound[a] * 0.5f;
+        if (!(half >= 0.0f) || !std::isfinite(half)) return fail(c, SPH_ERR_INVALID, "bound must be finite and >= 0");
+        const double q = std::floor((double)half / (double)p.interaction_radius);
+        if (q > 1e8) return fail(c, SPH_ERR_INVALID, "bound / interaction_radius too large for the grid table");
+        const int hi = (int)q + 2, lo = -(int)q - 3;
+        c->gmin[a] = lo;
+        c->gdim[a] = hi - lo + 1;
+        cells *= (uint64_t)c->gdim[a];
+    }
+    if (cells > (1ull << 31))
+        return fail(c, SPH_ERR_INVALID, "grid table would exceed 2^31 cells; use SPH_TABLE_REFERENCE_HASH");
+    c->ncell = (uint32_t)cells;
+    return SPH_OK;
+}
+
+int ensure_tables(SphContext* c, const DevParams& P)
+{
+    const size_t need = (P.mode == SPH_TABLE_GRID) ? (size_t)P.ncell + 2 : (size_t)c->cap + 1;
+    if (need > c->table_cap) {
+        SPH_CUDA(c, cudaStreamSynchronize(c->st));
+        if (c->tstart) cudaFree(c->tstart);
+        c->tstart = nullptr; c->table_cap = 0;
+        SPH_CUDA(c, cudaMalloc(&c->tstart, need * sizeof(uint32_t)));
+        c->table_cap = need;
+    }
+    if (P.mode == SPH_TABLE_GRID) {
+        const size_t gneed = 1 + 3 * ((size_t)P.ncell / 2048 + 4);
+        if (gneed > c->gap_cap) {
+            SPH_CUDA(c, cudaStreamSynchronize(c->st));
+            if (c->gap_list) cudaFree(c->gap_list);
+            c->gap_list = nullptr; c->gap_cap = 0;
+            SPH_CUDA(c, cudaMalloc(&c->gap_list, gneed * sizeof(uint32_t)));
+            c->gap_cap = gneed;
+        }
+    } else if (!c->tend) {
+        SPH_CUDA(c, cudaMalloc(&c->tend, ((size_t)c->cap + 1) * sizeof(uint32_t)));
+    }
+    return SPH_OK;
+}
+
+}  // namespace sphb200
+
+static void free_all(SphContext* c)
+{
+    void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
+                    c->perm_a, c->perm_b, c->ncount, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+}
+
+extern "C" {
+
+int sph_abi_version(void) { return SPH_B200_ABI_VERSION; }
+
+void sph_default_params(SphParams* p)
+{   // physicsWorld.h:96-106,145
+    p->interaction_radius = 0.35f;
+    p->sqr_radius = 0.35f * 0.35f;
+    p->target_density = 99.7f;
+    p->pressure_multiplier = 300.0f;
+    p->near_pressure_multiplier = 20.0f;
+    p->viscosity_strength = 0.5f;
+    p->gravity_scale = 10.0f;
+    p->gravity = 0;
+    p->bound[0] = p->bound[1] = p->bound[2] = 20.0f;
+}
+
+const char* sph_last_error(const SphContext* ctx)
+{
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> l(g_create_mutex);
+    return g_create_error.c_str();
+}
+
+int sph_create(SphContext** out, int device, uint32_t capacity)
+{
+    if (!out) return fail(nullptr, SPH_ERR_INVALID, "sph_create: out is NULL");
+    *out = nullptr;
+    if (capacity == 0) return fail(nullptr, SPH_ERR_INVALID, "sph_create: capacity must be > 0");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SPH_ERR_CUDA, std::string("sph_create: no CUDA device (there is no CPU fallback): ") +
+                                               cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SPH_ERR_INVALID, "sph_create: bad device ordinal");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+
+    SphContext* c = new SphContext();
+    c->device = device;
+    c->cap = capacity;
+    sph_default_params(&c->params);
+    const size_t cap = capacity;
+#define ALLOC(ptr, bytes)                                                        \
+    do {                                                                         \
+        e = cudaMalloc((void**)&(ptr), (bytes));                                 \
+        if (e != cudaSuccess) { free_all(c); delete c; return cuda_fail(nullptr, e, "cudaMalloc " #ptr); } \
+    } while (0)
+    e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    ALLOC(c->A_pos, cap * 16); ALLOC(c->A_vel, cap * 16);
+    ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
+    ALLOC(c->pred, cap * 16);  ALLOC(c->velp, cap * 16);
+    ALLOC(c->dens, cap * 8);
+    ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
+    ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
+    ALLOC(c->ncount, cap * 4);
+    ALLOC(c->stage, cap * 32);
+    c->counts_cap = radix_sort_temp_entries(capacity);
+    ALLOC(c->counts, c->counts_cap * 4);
+#undef ALLOC
+    for (auto& ev : c->ev) {
+        e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) { free_all(c); delete c; return cuda_fail(nullptr, e, "cudaEventCreate"); }
+    }
+    int rc = update_grid_geometry(c);
+    if (rc != SPH_OK) { std::string m = c->err; free_all(c); delete c; return fail(nullptr, rc, m); }
+    *out = c;
+    return SPH_OK;
+}
+
+int sph_destroy(SphContext* c)
+{
+    if (!c) return SPH_OK;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    multi_teardown(c);
+    free_all(c);
+    delete c;
+    return SPH_OK;
+}
+
+int sph_set_params(SphContext* c, const SphParams* p)
+{
+    if (!c || !p) return SPH_ERR_INVALID;
+    const SphParams old = c->params;
+    c->params = *p;
+    int rc = update_grid_geometry(c);
+    if (rc != SPH_OK) { c->params = old; update_grid_geometry(c); return rc; }
+    return SPH_OK;
+}
+
+int sph_get_params(const SphContext* c, SphParams* p)
+{
+    if (!c || !p) return SPH_ERR_INVALID;
+    *p = c->params;
+    return SPH_OK;
+}
+
+int sph_set_table_mode(SphContext* c, int mode)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (mode != SPH_TABLE_GRID && mode != SPH_TABLE_REFERENCE_HASH) return fail(c, SPH_ERR_INVALID, "unknown table mode");
+    if (mode == SPH_TABLE_REFERENCE_HASH && c->nranks > 1)
+        return fail(c, SPH_ERR_UNSUPPORTED, "slab mode uses the grid table (the reference table is global)");
+    c->mode = mode;
+    return SPH_OK;
+}
+int sph_get_table_mode(const SphContext* c) { return c ? c->mode : -1; }
+int sph_set_stage_timing(SphContext* c, int enabled) { if (!c) return SPH_ERR_INVALID; c->timing = enabled != 0; return SPH_OK; }
+int sph_set_neighbour_count_tap(SphContext* c, int enabled) { if (!c) return SPH_ERR_INVALID; c->nc_tap = enabled != 0; return SPH_OK; }
+uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
+uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
+
+int sph_get_grid(const SphContext* c, int32_t* dims3, int32_t* origin3)
+{
+    if (!c) return SPH_ERR_INVALID;
+    for (int a = 0; a < 3; a++) { if (dims3) dims3[a] = c->gdim[a]; if (origin3) origin3[a] = c->gmin[a]; }
+    return SPH_OK;
+}
+
+int sph_upload_state(SphContext* c, uint32_t n, const float* pos3, const float* vel3)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_INVALID, "slab mode: use sph_upload_owned");
+    if (n > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_upload_state: n exceeds capacity");
+    if (n && !pos3) return fail(c, SPH_ERR_INVALID, "sph_upload_state: pos3 is NULL");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    float* dpos = (float*)c->stage;
+    float* dvel = (float*)(c->stage + (size_t)c->cap * 12);
+    if (n) {
+        SPH_CUDA(c, cudaMemcpyAsync(dpos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st));
+        if (vel3) SPH_CUDA(c, cudaMemcpyAsync(dvel, vel3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st));
+        launch_pack_state(c->st, dpos, vel3 ? dvel : nullptr, nullptr, c->A_pos, c->A_vel, n, &c->launches);
+        SPH_CUDA(c, cudaGetLastError());
+    }
+    c->n = n;
+    c->step_valid = false;
+    c->ncount_valid = false;
+    return SPH_OK;
+}
+
+// the whole step; dt == 0 with `advance == false` is InitializeData's tail (lookup + densities only)
+static int run_step(SphContext* c, float dt, bool advance)
+{
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    DevParams P;
+    int rc = make_dev_params(c, c->n, &P);
+    if (rc != SPH_OK) return rc;
+    if (c->n == 0) return SPH_OK;
+    rc = ensure_tables(c, P);
+    if (rc != SPH_OK) return rc;
+    const bool timing = c->timing && advance;
+    cudaStream_t st = c->st;
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
+    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P, dt, &c->launches);
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+    const int bits = ceil_log2(P.mode == SPH_TABLE_GRID ? (uint64_t)P.ncell : (uint64_t)P.n);
+    c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, P.n, bits, c->counts,
+                                       &c->launches);
+    const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
+    const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
+    launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
+    launch_reorder(st, perm, c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
+    launch_density(st, c->pred, c->tstart, c->tend, c->dens, c->nc_tap ? c->ncount : nullptr, P, &c->launches);
+    c->ncount_valid = c->nc_tap;
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
+    if (advance) {
+        launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, P, dt, &c->launches);
+        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
+        // v'' goes into S_vel: dead after the pressure pass read it, and never read by the viscosity pass
+        launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, P, dt, &c->launches);
+        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
+        launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
+        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[6], st));
+        c->ev_recorded = timing;
+    } else {
+        // keep "every per-particle array shares the device order": adopt the sorted order
+        SPH_CUDA(c, cudaMemcpyAsync(c->A_pos, c->S_pos, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
+        SPH_CUDA(c, cudaMemcpyAsync(c->A_vel, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
+        SPH_CUDA(c, cudaMemcpyAsync(c->velp, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
+    }
+    SPH_CUDA(c, cudaGetLastError());
+    c->step_valid = true;
+    return SPH_OK;
+}
+
+int sph_step(SphContext* c, float dt)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return multi_step(c, dt);
+    return run_step(c, dt, true);
+}
+
+int sph_step_n(SphContext* c, float dt, uint32_t nsteps)
+{
+    for (uint32_t i = 0; i < nsteps; i++) {
+        int rc = sph_step(c, dt);
+        if (rc != SPH_OK) return rc;
+    }
+    return SPH_OK;
+}
+
+int sph_refresh_densities(SphContext* c)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_refresh_densities: single-GPU contexts only");
+    return run_step(c, 0.0f, false);
+}
+
+int sph_synchronize(SphContext* c)
+{
+    if (!c) return SPH_ERR_INVALID;
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    return SPH_OK;
+}
+
+int sph_spawn_grid(SphContext* c, uint32_t n)
+{   // InitializeData (:112-147) + GridArrangement (:518-557); host-side lattice, same fp32 expressions
+    if (!c) return SPH_ERR_INVALID;
+    if (n > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_spawn_grid: n exceeds capacity");
+    std::vector<float> pos((size_t)n * 3, 0.0f);
+    const int per_axis = (int)ceil(powf((float)(int)n, (1.0f / 3.0f)));
+    const float gap = 0.215f;
+    const float total = per_axis * gap;
+    uint32_t i = 0;
+    for (int ly = 0; ly < per_axis && i < n; ly++)
+        for (int lx = 0; lx < per_axis && i < n; lx++)
+            for (int lz = 0; lz < per_axis && i < n; lz++) {
+                const float xo = lx * gap, yo = ly * gap, zo = lz * gap;
+                const float wx = (0 - ((total - gap) / 2.0f));
+                const float wy = (0 + (total - gap) / 2.0f);
+                const float wz = (0 - (total - gap) / 2.0f);
+                pos[3 * (size_t)i] = wx + xo; pos[3 * (size_t)i + 1] = wy - yo; pos[3 * (size_t)i + 2] = wz + zo;
+                i++;
+            }
+    int rc = sph_upload_state(c, n, pos.data(), nullptr);
+    if (rc != SPH_OK) return rc;
+    rc = sph_refresh_densities(c);                       // :144-145
+    if (rc != SPH_OK) return rc;
+    return sph_synchronize(c);                           // pos is a local: the H2D copy must finish first
+}
+
+static size_t field_bytes(int field, size_t n)
+{
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED:
+    case SPH_FIELD_VEL_AFTER_PRESSURE: case SPH_FIELD_VEL_AFTER_VISCOSITY: return n * 12;
+    case SPH_FIELD_OUT_POSITIONS: case SPH_FIELD_COLORS: return n * 16;
+    case SPH_FIELD_DENSITIES: return n * 8;
+    case SPH_FIELD_HASH: case SPH_FIELD_KEY: case SPH_FIELD_NEIGHBOUR_COUNT: case SPH_FIELD_SPEED_NORMALIZED: return n * 4;
+    default: return 0;
+    }
+}
+
+}  // extern "C"
+
+int sphb200::export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n)
+{
+    const void* src = nullptr;
+    bool needs_step = true;
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_OUT_POSITIONS: src = c->A_pos; needs_step = false; break;
+    case SPH_FIELD_VELOCITIES: case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: src = c->A_vel; needs_step = false; break;
+    case SPH_FIELD_DENSITIES: src = c->dens; break;
+    case SPH_FIELD_PREDICTED: case SPH_FIELD_HASH: case SPH_FIELD_KEY: src = c->pred; break;
+    case SPH_FIELD_VEL_AFTER_PRESSURE: src = c->velp; break;
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: src = c->S_vel; break;
+    case SPH_FIELD_NEIGHBOUR_COUNT:
+        if (!c->ncount_valid) return fail(c, SPH_ERR_INVALID, "neighbour counts not recorded: enable the tap before the step");
+        src = c->ncount; break;
+    default: return fail(c, SPH_ERR_INVALID, "unknown field");
+    }
+    if (needs_step && !c->step_valid) return fail(c, SPH_ERR_INVALID, "field needs a step (or spawn/refresh) first");
+    DevParams P;
+    make_dev_params(c, c->n, &P);
+    launch_export(c->st, field, c->A_pos, src, nullptr, dev_out, n, P, by_id, &c->launches);
+    SPH_CUDA(c, cudaGetLastError());
+    return SPH_OK;
+}
+
+extern "C" {
+
+int sph_download(SphContext* c, int field, void* host, size_t host_bytes)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_INVALID, "slab mode: use sph_download_owned");
+    const size_t need = field_bytes(field, c->n);
+    if (need == 0 && c->n) return fail(c, SPH_ERR_INVALID, "unknown field");
+    if (host_bytes < need) return fail(c, SPH_ERR_INVALID, "sph_download: host buffer too small");
+    if (c->n == 0) return SPH_OK;
+    if (!host) return fail(c, SPH_ERR_INVALID, "sph_download: host is NULL");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    int rc = export_field(c, field, c->stage, true, c->n);
+    if (rc != SPH_OK) return rc;
+    SPH_CUDA(c, cudaMemcpyAsync(host, c->stage, need, cudaMemcpyDeviceToHost, c->st));
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    return SPH_OK;
+}
+
+int sph_download_table(SphContext* c, int table, void* host, size_t host_bytes, size_t* out_len)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (!c->step_valid) return fail(c, SPH_ERR_INVALID, "tables need a step (or spawn/refresh) first");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const void* src = nullptr;
+    size_t len = c->n;
+    switch (table) {
+    case SPH_TABLE_SORTED_INDEX:
+        launch_export_ids(c->st, c->A_pos, (uint32_t*)c->stage, c->n, &c->launches);
+        src = c->stage; break;
+    case SPH_TABLE_SORTED_KEY: src = c->sorted_where ? c->key_b : c->key_a; break;
+    case SPH_TABLE_SORTED_HASH: {
+        int rc = export_field(c, SPH_FIELD_HASH, c->stage, false, c->n);
+        if (rc != SPH_OK) return rc;
+        src = c->stage; } break;
+    case SPH_TABLE_START_INDICES:
+        src = c->tstart;
+        len = (c->mode == SPH_TABLE_GRID) ? (size_t)c->ncell + 1 : (size_t)c->n;
+        break;
+    default: return fail(c, SPH_ERR_INVALID, "unknown table");
+    }
+    if (out_len) *out_len = len;
+    if (!host) return SPH_OK;                                  // length query
+    if (host_bytes < len * 4) return fail(c, SPH_ERR_INVALID, "sph_download_table: host buffer too small");
+    if (len) SPH_CUDA(c, cudaMemcpyAsync(host, src, len * 4, cudaMemcpyDeviceToHost, c->st));
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    return SPH_OK;
+}
+
+int sph_get_particle(SphContext* c, uint32_t index, float* out10)
+{
+    if (!c || !out10) return SPH_ERR_INVALID;
+    for (int i = 0; i < 10; i++) out10[i] = 0.0f;
+    if (index >= c->n || c->nranks > 1) return SPH_OK;       // bounds check returns zeros (:151,157,163,168,174,180)
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    float* d = (float*)c->stage;
+    SPH_CUDA(c, cudaMemsetAsync(d, 0, 10 * sizeof(float), c->st));
+    launch_find_particle(c->st, c->A_pos, c->A_vel, c->step_valid ? c->dens : nullptr, c->n, index, d, &c->launches);
+    SPH_CUDA(c, cudaMemcpyAsync(out10, d, 10 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    return SPH_OK;
+}
+
+int sph_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return SPH_ERR_INVALID;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SPH_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return SPH_OK;
+}
+
+int sph_host_unregister(void* ptr)
+{
+    if (!ptr) return SPH_ERR_INVALID;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SPH_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    return SPH_OK;
+}
+
+int sph_get_timings(SphContext* c, double* out6)
+{
+    if (!c || !out6) return SPH_ERR_INVALID;
+    if (c->ev_recorded) {
+        SPH_CUDA(c, cudaSetDevice(c->device));
+        SPH_CUDA(c, cudaEventSynchronize(c->ev[6]));
+        for (int i = 0; i < 6; i++) {
+            float ms = 0;
+            SPH_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+            c->timings[i] = ms;
+        }
+    }
+    for (int i = 0; i < 6; i++) out6[i] = c->timings[i];
+    return SPH_OK;
+}
+
+}  // extern "C"

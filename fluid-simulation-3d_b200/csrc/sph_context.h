@@ -1,0 +1,74 @@
+// sph_context.h -- the object behind the opaque SphContext handle.
+#pragma once
+#include <string>
+#include <vector>
+#include "sph_internal.h"
+
+struct ncclComm;
+
+struct SphContext {
+    int device = 0;
+    uint32_t cap = 0;            // row capacity of every per-particle array
+    uint32_t n = 0;              // rows in use (single GPU: particles; slab mode: owned particles)
+    SphParams params;
+    int mode = SPH_TABLE_GRID;
+    bool timing = true;
+    bool nc_tap = false;
+    cudaStream_t st = nullptr;
+
+    // persistent state, device order
+    float4 *A_pos = nullptr, *A_vel = nullptr;
+    // per-step arrays, sorted order of the step
+    float4 *S_pos = nullptr, *S_vel = nullptr, *pred = nullptr, *velp = nullptr;
+    float2* dens = nullptr;
+    uint32_t *key_a = nullptr, *key_b = nullptr, *perm_a = nullptr, *perm_b = nullptr;
+    uint32_t* ncount = nullptr;
+    uint32_t *tstart = nullptr, *tend = nullptr;
+    size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
+    uint32_t* gap_list = nullptr;
+    size_t gap_cap = 0;
+    uint32_t* counts = nullptr;  // radix sort digit matrix
+    size_t counts_cap = 0;
+    unsigned char* stage = nullptr;   // device staging for upload / export (cap * 32 B)
+    int sorted_where = 0;        // 0: sorted keys in key_a, 1: key_b
+    bool step_valid = false;     // per-step arrays describe the current device order
+    bool ncount_valid = false;
+
+    cudaEvent_t ev[7] = {};
+    bool ev_recorded = false;
+    double timings[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t launches = 0;
+    std::string err;
+
+    // geometry of the GRID table, derived from params
+    int gmin[3] = {0, 0, 0};
+    int gdim[3] = {1, 1, 1};
+    uint32_t ncell = 1;
+
+    // slab-decomposed multi-GPU (sph_multi.cu)
+    ncclComm* comm = nullptr;
+    int rank = 0, nranks = 1;
+    std::vector<float> planes;   // nranks + 1 z planes
+    struct SlabState* slab = nullptr;
+};
+
+namespace sphb200 {
+
+int fail(SphContext* c, int code, const std::string& msg);
+int cuda_fail(SphContext* c, cudaError_t e, const char* what);
+#define SPH_CUDA(c, call)                                                      \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return sphb200::cuda_fail((c), e__, #call);    \
+    } while (0)
+
+// derive kernel parameters (constants with the reference's fp32 expressions, grid geometry)
+int make_dev_params(SphContext* c, uint32_t n, DevParams* P);
+int ensure_tables(SphContext* c, const DevParams& P);
+int export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n);
+
+// sph_multi.cu
+int multi_step(SphContext* c, float dt);
+void multi_teardown(SphContext* c);
+
+}  // namespace sphb200

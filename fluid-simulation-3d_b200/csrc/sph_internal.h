@@ -1,0 +1,70 @@
+// sph_internal.h -- shared declarations of the B200 SPH step (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sph_b200.h"
+
+namespace sphb200 {
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+// Normalisation constants are computed on the HOST with the reference's own fp32
+// expressions (kernels.h:29,41,53,65,77; SURVEY App.A Q17).
+struct DevParams {
+    uint32_t n;             // particles on this device (owned + ghosts in slab mode)
+    uint32_t n_owned;       // slab mode: owned particles are rows [0, n_owned) BEFORE sorting; == n otherwise
+    int      mode;          // SphTableMode
+    int      gravity;
+    float    r, sqr_r, rho0, k, kn, mu, g;
+    float    half[3];       // BoundScale * 0.5f (physicsWorld.cc:88)
+    float    vol2, vol3;    // SmoothingPow2 / Pow3 volumes
+    float    s2, s3;        // SmoothingDerivativePow2 / Pow3 scales
+    float    sv;            // SmoothingViscoPoly6 scale
+    float    rr;            // r*r
+    // GRID table: cell g = clamp(floor(pred/r) - gmin, 0, gdim-1); key = (gz*gdim.y + gy)*gdim.x + gx
+    int      gmin[3];
+    int      gdim[3];
+    uint32_t ncell;
+    // REFERENCE_HASH table: key = hash % n via Lemire fastmod, M = 2^64 / n + 1
+    uint64_t modM;
+};
+
+struct SortTemp {
+    uint32_t* counts;       // [256][nblocks] digit counts -> exclusive offsets
+    size_t    counts_len;
+};
+
+// ---- sph_sort.cu ----------------------------------------------------------
+// Stable LSD radix sort of (key, value) pairs on `bits` low key bits.  vals_in == nullptr
+// means "value = row index".  Returns 0 if the result is in (keys_a, vals_a), 1 if in (keys_b, vals_b).
+size_t radix_sort_temp_entries(uint32_t n);
+int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                     bool vals_identity, uint32_t n, int bits, uint32_t* counts, uint64_t* launches);
+
+// ---- sph_kernels.cu -------------------------------------------------------
+void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint32_t* hash_out,
+                        const DevParams& P, float dt, uint64_t* launches);
+void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* table_start, uint32_t* table_end,
+                        uint32_t* gap_list, const DevParams& P, uint64_t* launches);
+void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
+                    float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P, float dt, uint64_t* launches);
+void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
+                    float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches);
+void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const DevParams& P, float dt,
+                     uint64_t* launches);
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p,
+                      const uint32_t* tstart, const uint32_t* tend, float4* vel_v, const DevParams& P, float dt,
+                      uint64_t* launches);
+void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
+                      const DevParams& P, float dt, uint64_t* launches);
+
+// upload / export helpers (original particle index order <-> device order)
+void launch_pack_state(cudaStream_t st, const float* pos3, const float* vel3, const uint32_t* ids,
+                       float4* pos, float4* vel, uint32_t n, uint64_t* launches);
+void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void* src2, void* out,
+                   uint32_t n, const DevParams& P, bool by_id, uint64_t* launches);
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float2* dens, uint32_t n,
+                          uint32_t id, float* out10, uint64_t* launches);
+void launch_export_ids(cudaStream_t st, const float4* id_src, uint32_t* out, uint32_t n, uint64_t* launches);
+
+}  // namespace sphb200

@@ -1,0 +1,569 @@
+// sph_kernels.cu -- sm_100a kernels of the per-timestep SPH update.
+//
+// Stage map (reference: engine/physics/physicsWorld.cc, kernels: engine/physics/kernels.h):
+//   k_predict_key   S1 :42-48 (+CalculateExternalFoce :313-323) and the key half of S2 :473-482
+//   k_build_table*  S2 :486-496 (start table) -- GRID mode builds a gap-free prefix table instead
+//   k_reorder       "particle reordering for locality": gathers the state into sorted order
+//   k_density       S3 :304-311, 325-365         k_pressure  S4 :367-422
+//   k_viscosity     S5 :424-464 (snapshot/Jacobi) k_integrate S6 :81-108
+//
+// Data layout: SoA of float4 rows in DEVICE ORDER (= sorted order of the latest step):
+//   pos4  = (x, y, z, bits(global particle id))      vel4 = (vx, vy, vz, 0)
+//   pred4 = (px, py, pz, float(hash))                dens = float2 (rho, near rho)
+//
+// Exactness rules (SURVEY App.A Q5/Q6/Q8): everything that feeds an integer result (cell, hash, key,
+// the d^2 <= sqrRadius predicate) is computed with explicit round-to-nearest, non-fused
+// __fmul_rn/__fadd_rn/__fdiv_rn in the reference's operation order.  Float-only results may use FMA
+// and approximate sqrt/rcp (tolerance 1e-5 of the stage scale, tests/test_parity_gpu.py).
+#include "sph_internal.h"
+
+namespace sphb200 {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// PositionToCellCoord (:499-503): floor(pos / r) with true IEEE division, C-cast to int.
+__device__ __forceinline__ int3 cell_of(float x, float y, float z, float r)
+{
+    int3 c;
+    c.x = __float2int_rz(floorf(__fdiv_rn(x, r)));
+    c.y = __float2int_rz(floorf(__fdiv_rn(y, r)));
+    c.z = __float2int_rz(floorf(__fdiv_rn(z, r)));
+    return c;
+}
+// HashCell (:505-511): (uint32_t)float on the reference's platform = two's-complement wrap (Q5).
+__device__ __forceinline__ uint32_t hash_cell(int cx, int cy, int cz)
+{
+    return (uint32_t)cx * 15823u + (uint32_t)cy * 9737333u + (uint32_t)cz * 440817757u;
+}
+// GetKeyFromHash (:513-516): hash % n, exact for every 32-bit operand pair (Lemire fastmod).
+__device__ __forceinline__ uint32_t key_of_hash(uint32_t h, const DevParams& P)
+{
+    const uint64_t low = P.modM * (uint64_t)h;
+    return (uint32_t)__umul64hi(low, (uint64_t)P.n);
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ int3 grid_cell(int3 c, const DevParams& P)
+{
+    int3 g;
+    g.x = clampi(c.x - P.gmin[0], 0, P.gdim[0] - 1);
+    g.y = clampi(c.y - P.gmin[1], 0, P.gdim[1] - 1);
+    g.z = clampi(c.z - P.gmin[2], 0, P.gdim[2] - 1);
+    return g;
+}
+__device__ __forceinline__ uint32_t grid_key(int3 g, const DevParams& P)
+{
+    return ((uint32_t)g.z * (uint32_t)P.gdim[1] + (uint32_t)g.y) * (uint32_t)P.gdim[0] + (uint32_t)g.x;
+}
+
+// S1: velocity += externalForce * dt ; predicted = position + velocity * (1/120)   (:45-47, Q1)
+__device__ __forceinline__ void predict(const float4 p, float4& v, float3& pred, const DevParams& P, float dt)
+{
+    const float gy = P.gravity ? -P.g : 0.0f;
+    v.x = __fadd_rn(v.x, __fmul_rn(0.0f, dt));
+    v.y = __fadd_rn(v.y, __fmul_rn(gy, dt));
+    v.z = __fadd_rn(v.z, __fmul_rn(0.0f, dt));
+    const float look = 1.0f / 120.0f;
+    pred.x = __fadd_rn(p.x, __fmul_rn(v.x, look));
+    pred.y = __fadd_rn(p.y, __fmul_rn(v.y, look));
+    pred.z = __fadd_rn(p.z, __fmul_rn(v.z, look));
+}
+
+__global__ void __launch_bounds__(256)
+k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
+              uint32_t* __restrict__ hash_out, const DevParams P, const float dt)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    const float4 p = pos[s];
+    float4 v = vel[s];
+    float3 pr;
+    predict(p, v, pr, P, dt);
+    const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
+    if (P.mode == SPH_TABLE_REFERENCE_HASH) {
+        const uint32_t h = hash_cell(c.x, c.y, c.z);
+        key[s] = key_of_hash(h, P);
+        if (hash_out) hash_out[s] = h;
+    } else {
+        key[s] = grid_key(grid_cell(c, P), P);
+        if (hash_out) hash_out[s] = hash_cell(c.x, c.y, c.z);
+    }
+}
+
+// ---- S2 tables -------------------------------------------------------------
+// REFERENCE_HASH: startIndices[key] = first sorted row of the bucket (:486-496); we also keep the
+// bucket end so the walk needs no per-row key compare (:343).
+__global__ void __launch_bounds__(256)
+k_fill_u32(uint32_t* __restrict__ p, const uint32_t v, const uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_build_table_hash(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict__ tstart,
+                   uint32_t* __restrict__ tend, const uint32_t n)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t k = key_sorted[s];
+    if (s == 0 || key_sorted[s - 1] != k) tstart[k] = s;
+    if (s == n - 1 || key_sorted[s + 1] != k) tend[k] = s + 1;
+}
+
+// GRID: prefix table t[c] = number of rows with key < c, for c in [0, ncell]; rows of cell c are
+// [t[c], t[c+1]).  Built straight from the sorted keys: the row s at which the key steps from a to b
+// owns the entries (a, b]; a warp fills its gaps cooperatively so the table is written exactly once,
+// coalesced, with no memset and no scan.  Gaps wider than kBigGap go to a worklist for k_fill_gaps.
+constexpr uint32_t kBigGap = 2048;
+
+__global__ void __launch_bounds__(256)
+k_build_table_grid(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict__ table,
+                   uint32_t* __restrict__ gap_list, const uint32_t n, const uint32_t ncell)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;   // s in [0, n]: s == n closes the table
+    const int lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = 0;                                     // this row owns table[lo..hi)
+    if (s <= n) {
+        const uint32_t b = (s < n) ? key_sorted[s] : ncell;      // virtual key ncell after the last row
+        const uint32_t a1 = (s == 0) ? 0u : key_sorted[s - 1] + 1u;
+        lo = a1; hi = b + 1u;
+        if (s == n) hi = ncell + 1u;
+        if (s < n && s > 0 && key_sorted[s - 1] == b) hi = lo;   // same cell as the previous row: nothing
+    }
+    uint32_t len = hi > lo ? hi - lo : 0u;
+    if (len > kBigGap) {
+        const uint32_t slot = atomicAdd(&gap_list[0], 1u);
+        gap_list[1 + 3 * slot] = lo; gap_list[2 + 3 * slot] = hi; gap_list[3 + 3 * slot] = s;
+        len = 0;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, len > 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t glo = __shfl_sync(0xffffffffu, lo, src);
+        const uint32_t glen = __shfl_sync(0xffffffffu, len, src);
+        const uint32_t gs = __shfl_sync(0xffffffffu, s, src);
+        for (uint32_t i = lane; i < glen; i += 32) table[glo + i] = gs;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
+{
+    const uint32_t ngaps = gap_list[0];
+    for (uint32_t g = 0; g < ngaps; g++) {
+        const uint32_t lo = gap_list[1 + 3 * g], hi = gap_list[2 + 3 * g], s = gap_list[3 + 3 * g];
+        for (uint64_t i = (uint64_t)lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+             i += (uint64_t)gridDim.x * blockDim.x)
+            table[i] = s;
+    }
+}
+
+// ---- reorder ----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_reorder(const uint32_t* __restrict__ perm, const float4* __restrict__ pos, const float4* __restrict__ vel,
+          float4* __restrict__ pos_s, float4* __restrict__ vel_s, float4* __restrict__ pred_s,
+          const DevParams P, const float dt)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    const uint32_t src = perm[s];
+    const float4 p = pos[src];
+    float4 v = vel[src];
+    float3 pr;
+    predict(p, v, pr, P, dt);          // bit-identical to k_predict_key: same inputs, same operations
+    const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
+    const uint32_t h = hash_cell(c.x, c.y, c.z);
+    pos_s[s] = p;
+    vel_s[s] = v;
+    pred_s[s] = make_float4(pr.x, pr.y, pr.z, __uint2float_rn(h));   // spatialLookup[].y is float(hash) (:480)
+}
+
+// ---- neighbour walk ---------------------------------------------------------
+// Calls f(j, pred_j) for every candidate row the reference's walk would reach for a particle at pi.
+template <int MODE, class F>
+__device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pred_s,
+                                                   const uint32_t* __restrict__ tstart,
+                                                   const uint32_t* __restrict__ tend,
+                                                   const float4 pi, const DevParams& P, F&& f)
+{
+    const int3 c = cell_of(pi.x, pi.y, pi.z, P.r);
+    if (MODE == SPH_TABLE_REFERENCE_HASH) {
+        #pragma unroll 1
+        for (int i = 0; i < 27; i++) {               // offsets[27]: x outer, y, z inner (physicsWorld.h:131-143)
+            const int dx = i / 9 - 1, dy = (i / 3) % 3 - 1, dz = i % 3 - 1;
+            const uint32_t h = hash_cell(c.x + dx, c.y + dy, c.z + dz);
+            const uint32_t key = key_of_hash(h, P);
+            const uint32_t b = __ldg(&tstart[key]);
+            if (b >= P.n) continue;                  // 0x7FFFFFFF: empty bucket (:339)
+            const uint32_t e = __ldg(&tend[key]);
+            const float hf = __uint2float_rn(h);
+            for (uint32_t j = b; j < e; j++) {
+                const float4 q = __ldg(&pred_s[j]);
+                if (q.w != hf) continue;             // `index.y != hash`, compared in float (:346)
+                f(j, q);
+            }
+        }
+    } else {
+        const int3 g = grid_cell(c, P);
+        const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
+        #pragma unroll 1
+        for (int dz = -1; dz <= 1; dz++) {
+            const int z = g.z + dz;
+            if (z < 0 || z >= P.gdim[2]) continue;
+            #pragma unroll 1
+            for (int dy = -1; dy <= 1; dy++) {
+                const int y = g.y + dy;
+                if (y < 0 || y >= P.gdim[1]) continue;
+                const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
+                const uint32_t b = __ldg(&tstart[row + x0]);
+                const uint32_t e = __ldg(&tstart[row + x1 + 1]);
+                for (uint32_t j = b; j < e; j++) f(j, __ldg(&pred_s[j]));
+            }
+        }
+    }
+}
+
+// glm::dot on the offset, no FMA: (x*x + y*y) + z*z   (Q8)
+__device__ __forceinline__ float sqr_dist(const float4 q, const float4 pi, float& ox, float& oy, float& oz)
+{
+    ox = __fsub_rn(q.x, pi.x); oy = __fsub_rn(q.y, pi.y); oz = __fsub_rn(q.z, pi.z);
+    return __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_density(const float4* __restrict__ pred_s, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend,
+          float2* __restrict__ dens, uint32_t* __restrict__ ncount, const DevParams P)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const float4 pi = pred_s[i];
+    float rho = 0.0f, rhon = 0.0f;
+    uint32_t cnt = 0;
+    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t, const float4 q) {
+        float ox, oy, oz;
+        const float d2 = sqr_dist(q, pi, ox, oy, oz);
+        if (d2 > P.sqr_r) return;                    // :357
+        cnt++;
+        const float d = sqrt_approx(d2);
+        if (d < P.r) {                               // kernels.h:27,39
+            const float v = P.r - d;
+            rho += v * v * P.vol2;
+            rhon += v * v * v * P.vol3;
+        }
+    });
+    dens[i] = make_float2(rho, rhon);
+    if (ncount) ncount[i] = cnt;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_pressure(const float4* __restrict__ pred_s, const float2* __restrict__ dens, const float4* __restrict__ vel_s,
+           const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_p,
+           const DevParams P, const float dt)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const float4 pi = pred_s[i];
+    const float2 di = dens[i];
+    const float pressure = (di.x - P.rho0) * P.k;    // :371
+    const float npressure = di.y * P.kn;             // :372
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t j, const float4 q) {
+        if (j == i) return;                          // :396
+        float ox, oy, oz;
+        const float d2 = sqr_dist(q, pi, ox, oy, oz);
+        if (d2 > P.sqr_r) return;                    // :402
+        const float2 dj = __ldg(&dens[j]);
+        const float pj = (dj.x - P.rho0) * P.k;
+        const float npj = dj.y * P.kn;
+        const float shared = (pressure + pj) * 0.5f;
+        const float nshared = (npressure + npj) * 0.5f;
+        const float d = sqrt_approx(d2);
+        float dirx = 0.0f, diry = 1.0f, dirz = 0.0f; // :414
+        if (d > 0.0f) { const float inv = rcp_approx(d); dirx = ox * inv; diry = oy * inv; dirz = oz * inv; }
+        float coef = 0.0f;
+        if (d <= P.r) {                              // kernels.h:51,63
+            const float v = P.r - d;
+            coef = (-v * P.s2) * shared * rcp_approx(dj.x) + (-v * v * P.s3) * nshared * rcp_approx(dj.y);
+        }
+        fx += dirx * coef; fy += diry * coef; fz += dirz * coef;
+    });
+    const float4 v = vel_s[i];
+    const float s = dt / di.x;                       // :421  (F / rho) * dt
+    vel_p[i] = make_float4(v.x + fx * s, v.y + fy * s, v.z + fz * s, 0.0f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_viscosity(const float4* __restrict__ pred_s, const float4* __restrict__ vel_p,
+            const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_v,
+            const DevParams P, const float dt)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const float4 pi = pred_s[i];
+    const float4 vi = vel_p[i];
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t j, const float4 q) {
+        if (j == i) return;                          // :450
+        float ox, oy, oz;
+        const float d2 = sqr_dist(q, pi, ox, oy, oz);
+        if (d2 > P.sqr_r) return;                    // :456
+        const float v = P.rr - d2;                   // kernels.h:78  r*r - dist*dist
+        if (v > 0.0f) {                              // dist < radius
+            const float w = v * v * v * P.sv;
+            const float4 vj = __ldg(&vel_p[j]);      // snapshot: every particle reads post-pressure velocities
+            fx += (vj.x - vi.x) * w; fy += (vj.y - vi.y) * w; fz += (vj.z - vi.z) * w;
+        }
+    });
+    const float s = P.mu * dt;                       // :463
+    vel_v[i] = make_float4(vi.x + fx * s, vi.y + fy * s, vi.z + fz * s, 0.0f);
+}
+
+// S6 (:84-107)
+__global__ void __launch_bounds__(256)
+k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
+            float4* __restrict__ vel_out, const DevParams P, const float dt)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    float4 p = pos_s[s];
+    float4 v = vel_v[s];
+    p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+    p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+    p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    const float damp = -0.95f;                       // -1 * dampFactor
+    #define SPH_COLLIDE(c, h)                                                             \
+        if (__fsub_rn(h, fabsf(p.c)) <= 0.0f) {                                           \
+            const float sg = (p.c > 0.0f) ? 1.0f : ((p.c < 0.0f) ? -1.0f : 0.0f);         \
+            p.c = __fmul_rn(h, sg);                                                       \
+            v.c = __fmul_rn(v.c, damp);                                                   \
+        }
+    SPH_COLLIDE(x, P.half[0])
+    SPH_COLLIDE(y, P.half[1])
+    SPH_COLLIDE(z, P.half[2])
+    #undef SPH_COLLIDE
+    v.w = 0.0f;
+    pos_out[s] = p;      // .w still carries the particle id
+    vel_out[s] = v;
+}
+
+// ---- upload / export --------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_state(const float* __restrict__ pos3, const float* __restrict__ vel3, const uint32_t* __restrict__ ids,
+             float4* __restrict__ pos, float4* __restrict__ vel, const uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = ids ? ids[i] : i;
+    pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], __uint_as_float(id));
+    vel[i] = vel3 ? make_float4(vel3[3 * i], vel3[3 * i + 1], vel3[3 * i + 2], 0.0f) : make_float4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ float4 speed_color(float t)
+{   // FluidSimCPU::updateColors (fluidSimCPU.cc:100-125)
+    const float4 c1 = make_float4(0.0f, 0.75f, 1.0f, 1.0f), c2 = make_float4(0.0f, 1.0f, 0.0f, 1.0f);
+    const float4 c3 = make_float4(1.0f, 1.0f, 0.0f, 1.0f), c4 = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
+    const float b1 = 0.33f, b2 = 0.66f;
+    float a; float4 lo, hi;
+    if (t <= b1) { a = t / b1; lo = c1; hi = c2; }
+    else if (t <= b2) { a = (t - b1) / (b2 - b1); lo = c2; hi = c3; }
+    else { a = (t - b2) / (1.0f - b2); lo = c3; hi = c4; }
+    const float ia = 1.0f - a;
+    return make_float4(ia * lo.x + a * hi.x, ia * lo.y + a * hi.y, ia * lo.z + a * hi.z, ia * lo.w + a * hi.w);
+}
+
+// out[dst] = field of device row s, dst = particle id (by_id) or s.
+__global__ void __launch_bounds__(256)
+k_export(const int field, const float4* __restrict__ id_src, const void* __restrict__ src,
+         void* __restrict__ out, const uint32_t n, const bool by_id, const DevParams P)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t dst = by_id ? __float_as_uint(id_src[s].w) : s;
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED:
+    case SPH_FIELD_VEL_AFTER_PRESSURE: case SPH_FIELD_VEL_AFTER_VISCOSITY: {
+        const float4 a = ((const float4*)src)[s];
+        float* o = (float*)out + 3 * (size_t)dst;
+        o[0] = a.x; o[1] = a.y; o[2] = a.z;
+    } break;
+    case SPH_FIELD_OUT_POSITIONS: {
+        const float4 a = ((const float4*)src)[s];
+        ((float4*)out)[dst] = make_float4(a.x, a.y, a.z, 0.34f);          // :107
+    } break;
+    case SPH_FIELD_DENSITIES:
+        ((float2*)out)[dst] = ((const float2*)src)[s];
+        break;
+    case SPH_FIELD_HASH: case SPH_FIELD_KEY: {       // pure functions of the predicted position (:477-479)
+        const float4 a = ((const float4*)src)[s];
+        const int3 c = cell_of(a.x, a.y, a.z, P.r);
+        const uint32_t h = hash_cell(c.x, c.y, c.z);
+        ((uint32_t*)out)[dst] = (field == SPH_FIELD_HASH) ? h : key_of_hash(h, P);
+    } break;
+    case SPH_FIELD_NEIGHBOUR_COUNT:
+        ((uint32_t*)out)[dst] = ((const uint32_t*)src)[s];
+        break;
+    case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: {
+        const float4 a = ((const float4*)src)[s];
+        const float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+        const float t = fminf(fmaxf(len, 0.0f), 1.5f) / 1.5f;              // :181
+        if (field == SPH_FIELD_SPEED_NORMALIZED) ((float*)out)[dst] = t;
+        else ((float4*)out)[dst] = speed_color(t);
+    } break;
+    default: break;
+    }
+}
+
+// getPosition/getVelocity/getDensity/getNearDensity/getSpeed/getSpeedNormalzied (:149-182) for one id
+__global__ void __launch_bounds__(256)
+k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const float2* __restrict__ dens,
+                const uint32_t n, const uint32_t id, float* __restrict__ out10)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = pos[s];
+    if (__float_as_uint(p.w) != id) return;
+    const float4 v = vel[s];
+    const float len = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    out10[0] = p.x; out10[1] = p.y; out10[2] = p.z; out10[3] = v.x; out10[4] = v.y; out10[5] = v.z;
+    if (dens) { const float2 d = dens[s]; out10[6] = d.x; out10[7] = d.y; }
+    out10[8] = len;
+    out10[9] = fminf(fmaxf(len, 0.0f), 1.5f) / 1.5f;
+}
+
+__global__ void __launch_bounds__(256)
+k_export_ids(const float4* __restrict__ id_src, uint32_t* __restrict__ out, const uint32_t n)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) out[s] = __float_as_uint(id_src[s].w);
+}
+
+inline uint32_t blocks_for(uint32_t n, int threads) { return (n + threads - 1) / threads; }
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------
+void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint32_t* hash_out,
+                        const DevParams& P, float dt, uint64_t* launches)
+{
+    if (P.n == 0) return;
+    k_predict_key<<<blocks_for(P.n, 256), 256, 0, st>>>(pos, vel, key, hash_out, P, dt);
+    ++*launches;
+}
+
+void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* tstart, uint32_t* tend,
+                        uint32_t* gap_list, const DevParams& P, uint64_t* launches)
+{
+    if (P.mode == SPH_TABLE_REFERENCE_HASH) {
+        if (P.n) { k_fill_u32<<<blocks_for(P.n, 256), 256, 0, st>>>(tstart, 0x7FFFFFFFu, P.n); ++*launches; }   // INT_MAX = empty (:481)
+        if (P.n) { k_build_table_hash<<<blocks_for(P.n, 256), 256, 0, st>>>(key_sorted, tstart, tend, P.n); ++*launches; }
+    } else {
+        cudaMemsetAsync(gap_list, 0, sizeof(uint32_t), st);
+        k_build_table_grid<<<blocks_for(P.n + 1, 256), 256, 0, st>>>(key_sorted, tstart, gap_list, P.n, P.ncell);
+        k_fill_gaps<<<148, 256, 0, st>>>(tstart, gap_list);
+        *launches += 2;
+    }
+}
+
+void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
+                    float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P, float dt, uint64_t* launches)
+{
+    if (P.n == 0) return;
+    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, pos, vel, pos_s, vel_s, pred_s, P, dt);
+    ++*launches;
+}
+
+void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
+                    float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches)
+{
+    if (P.n == 0) return;
+    if (P.mode == SPH_TABLE_REFERENCE_HASH)
+        k_density<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
+    else
+        k_density<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
+    ++*launches;
+}
+
+void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const DevParams& P, float dt,
+                     uint64_t* launches)
+{
+    if (P.n == 0) return;
+    if (P.mode == SPH_TABLE_REFERENCE_HASH)
+        k_pressure<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
+    else
+        k_pressure<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
+    ++*launches;
+}
+
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p,
+                      const uint32_t* tstart, const uint32_t* tend, float4* vel_v, const DevParams& P, float dt,
+                      uint64_t* launches)
+{
+    if (P.n == 0) return;
+    if (P.mode == SPH_TABLE_REFERENCE_HASH)
+        k_viscosity<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
+    else
+        k_viscosity<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
+    ++*launches;
+}
+
+void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
+                      const DevParams& P, float dt, uint64_t* launches)
+{
+    if (P.n == 0) return;
+    k_integrate<<<blocks_for(P.n, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    ++*launches;
+}
+
+void launch_pack_state(cudaStream_t st, const float* pos3, const float* vel3, const uint32_t* ids,
+                       float4* pos, float4* vel, uint32_t n, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_pack_state<<<blocks_for(n, 256), 256, 0, st>>>(pos3, vel3, ids, pos, vel, n);
+    ++*launches;
+}
+
+void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void*, void* out,
+                   uint32_t n, const DevParams& P, bool by_id, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_export<<<blocks_for(n, 256), 256, 0, st>>>(field, id_src, src, out, n, by_id, P);
+    ++*launches;
+}
+
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float2* dens, uint32_t n,
+                          uint32_t id, float* out10, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_find_particle<<<blocks_for(n, 256), 256, 0, st>>>(pos, vel, dens, n, id, out10);
+    ++*launches;
+}
+
+void launch_export_ids(cudaStream_t st, const float4* id_src, uint32_t* out, uint32_t n, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_export_ids<<<blocks_for(n, 256), 256, 0, st>>>(id_src, out, n);
+    ++*launches;
+}
+
+}  // namespace sphb200

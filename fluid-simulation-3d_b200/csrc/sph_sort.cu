@@ -1,0 +1,182 @@
+// sph_sort.cu -- device radix sort of (cell key, row) pairs for the per-step neighbour table.
+//
+// Replaces the reference's serial std::sort over float rows (physicsWorld.cc:484) with a STABLE
+// least-significant-digit radix sort, 8-bit digits, only as many passes as the key range needs
+// (3 passes for up to 16 M cells / buckets).  Stable => equal keys keep their incoming order, which
+// is the canonical tie order the parity tests compare against (SURVEY App.A Q14).
+//
+// Per pass: (1) per-block digit histogram, (2) one-block exclusive scan of the [digit][block]
+// matrix, (3) scatter with a warp-synchronous stable rank (match.any + per-warp digit counters in
+// shared memory).  Blocks own a contiguous span of tiles so the scanned matrix stays small
+// (<= 256 x 1184 entries) at any N.  HBM traffic per pass: keys read twice, pairs written once
+// = 20 B/pair (algorithmic 16 B/pair).
+#include "sph_internal.h"
+
+namespace sphb200 {
+
+namespace {
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItems = 8;                          // keys per thread per tile
+constexpr int kTile = kSortThreads * kItems;       // 2048 keys
+constexpr uint32_t kMaxSortBlocks = 148 * 8;
+
+struct SortGeom { uint32_t nblocks, tiles_per_block; };
+
+inline SortGeom sort_geom(uint32_t n)
+{
+    uint32_t tiles = (n + kTile - 1) / kTile;
+    if (tiles == 0) tiles = 1;
+    SortGeom g;
+    g.tiles_per_block = (tiles + kMaxSortBlocks - 1) / kMaxSortBlocks;
+    g.nblocks = (tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+    return g;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ counts, uint32_t n, int shift,
+             uint32_t tiles_per_block, uint32_t nblocks)
+{
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t span = (uint64_t)tiles_per_block * kTile;
+    const uint64_t begin = (uint64_t)blockIdx.x * span;
+    uint64_t end = begin + span;
+    if (end > n) end = n;
+    for (uint64_t i = begin + threadIdx.x; i < end; i += kSortThreads) {
+        uint32_t d = (keys[i] >> shift) & 0xFFu;
+        atomicAdd(&hist[d], 1u);
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// exclusive scan of `total` counters by ONE block of 1024 threads
+__global__ void __launch_bounds__(1024)
+k_radix_scan(uint32_t* __restrict__ counts, uint32_t total)
+{
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t chunk = (total + 1023u) / 1024u;
+    const uint32_t b = threadIdx.x * chunk;
+    const uint32_t e = min(b + chunk, total);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += counts[i];
+    // block exclusive scan of `sum`
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+        uint32_t winc = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_sums[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + inc - sum;
+    for (uint32_t i = b; i < e; i++) { uint32_t c = counts[i]; counts[i] = run; run += c; }
+}
+
+template <bool kIdentity>
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                const uint32_t* __restrict__ offsets, uint32_t n, int shift,
+                uint32_t tiles_per_block, uint32_t nblocks)
+{
+    __shared__ uint32_t cnt[kSortWarps][256];
+    __shared__ uint32_t base[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    base[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+
+    for (uint32_t t = 0; t < tiles_per_block; t++) {
+        const uint64_t tile_base = ((uint64_t)blockIdx.x * tiles_per_block + t) * kTile;
+        if (tile_base >= n) break;
+        #pragma unroll
+        for (int w = 0; w < kSortWarps; w++) cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+
+        uint32_t key[kItems], rank[kItems];
+        #pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const uint64_t idx = tile_base + (uint64_t)warp * (32 * kItems) + r * 32 + lane;
+            const bool valid = idx < n;
+            key[r] = valid ? keys_in[idx] : 0u;
+            const uint32_t d = (key[r] >> shift) & 0xFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader && valid) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = old + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // per digit: exclusive scan across the warps of this tile, then advance the block's running base
+            const int d = threadIdx.x;
+            uint32_t run = 0;
+            #pragma unroll
+            for (int w = 0; w < kSortWarps; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run + base[d]; run += c; }
+            base[d] += run;   // only thread d touches base[d] / cnt[*][d] here
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int r = 0; r < kItems; r++) {
+            const uint64_t idx = tile_base + (uint64_t)warp * (32 * kItems) + r * 32 + lane;
+            if (idx < n) {
+                const uint32_t d = (key[r] >> shift) & 0xFFu;
+                const uint32_t dst = cnt[warp][d] + rank[r];
+                keys_out[dst] = key[r];
+                vals_out[dst] = kIdentity ? (uint32_t)idx : vals_in[idx];
+            }
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+size_t radix_sort_temp_entries(uint32_t n)
+{
+    SortGeom g = sort_geom(n);
+    return (size_t)256 * g.nblocks;
+}
+
+int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                     bool vals_identity, uint32_t n, int bits, uint32_t* counts, uint64_t* launches)
+{
+    if (n == 0) return 0;
+    const SortGeom g = sort_geom(n);
+    int passes = (bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    uint32_t *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
+    int where = 0;
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        k_radix_hist<<<g.nblocks, kSortThreads, 0, st>>>(kin, counts, n, shift, g.tiles_per_block, g.nblocks);
+        k_radix_scan<<<1, 1024, 0, st>>>(counts, 256u * g.nblocks);
+        if (p == 0 && vals_identity)
+            k_radix_scatter<true><<<g.nblocks, kSortThreads, 0, st>>>(kin, nullptr, kout, vout, counts, n, shift,
+                                                                       g.tiles_per_block, g.nblocks);
+        else
+            k_radix_scatter<false><<<g.nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, counts, n, shift,
+                                                                        g.tiles_per_block, g.nblocks);
+        if (launches) *launches += 3;
+        uint32_t* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        where ^= 1;
+    }
+    return where;
+}
+
+}  // namespace sphb200

@@ -1,0 +1,126 @@
+// host/FluidSimulation.h -- the reference's solver class, re-hosted on the B200 C ABI.
+//
+// Same namespace, class name, public member functions and public data members as
+// Physics::Fluid::FluidSimulation in the reference (engine/physics/physicsWorld.h:29-153), so the
+// application code that drives the CPU solver (fluidSimCPU.cc:13,29,38,45,58,106; gameApp.cc:306-410)
+// compiles against it unchanged.  All arithmetic happens in libsph_b200.so (include/sph_b200.h);
+// this class only owns the host mirrors the renderer reads (`positions`, `OutPositions`).
+//
+// Build inside the reference tree with -DSPH_B200_USE_GLM (after config.h, which pulls in glm), or
+// stand-alone (this repo's tests) where vec3/vec4 are layout-compatible PODs.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "sph_b200.h"
+
+#ifdef SPH_B200_USE_GLM
+namespace sphb200 { using vec3 = glm::vec3; using vec4 = glm::vec4; }
+#else
+namespace sphb200 {
+struct vec3 { float x, y, z; vec3() : x(0), y(0), z(0) {} vec3(float X, float Y, float Z) : x(X), y(Y), z(Z) {} };
+struct vec4 { float x, y, z, w; vec4() : x(0), y(0), z(0), w(0) {} vec4(float X, float Y, float Z, float W) : x(X), y(Y), z(Z), w(W) {} };
+}
+#endif
+#ifndef SPH_B200_HAVE_UINT32
+typedef uint32_t uint32;     // engine/config.h:19-39
+#endif
+
+namespace Physics
+{
+	namespace Fluid
+	{
+		class FluidSimulation
+		{
+		public:
+			using vec3 = sphb200::vec3;
+			using vec4 = sphb200::vec4;
+
+			static FluidSimulation& getInstance();                              // physicsWorld.cc:32-37
+
+			void Update(float deltatime);                                        // :39-111
+			void InitializeData(int particleAmmount, vec3 Centre = vec3(0, 0, 0)); // :112-147
+
+			vec3 getPosition(uint32 particleIndex);                              // :149-153
+			vec3 getVelocity(uint32 particleIndex);                              // :155-159
+			float getDensity(uint32 particleIndex);                              // :161-165
+			float getNearDensity(uint32 particleIndex);                          // :166-170
+			float getSpeed(uint32 particleIndex);                                // :172-176
+			float getSpeedNormalzied(uint32 particleIndex);                      // :178-182
+
+			double getElapsedTimeGravity();                                      // :184-212
+			double getElapsedTimeSpatial();
+			double getElapsedTimeDensity();
+			double getElapsedTimePressure();
+			double getElapsedTimeViscosity();
+			double getElapsedTimePosNColl();
+
+			void setSimulationTime(float time);                                  // :214-302
+			float getSimulationTime();
+			void setGravity(bool status);
+			bool getGravityStatus();
+			void setInteractionRadius(float value);
+			float getInteractionRadius();
+			void setDensityTarget(float value);
+			float getDensityTarget();
+			void setPressureMultiplier(float value);
+			float getPressureMultiplier();
+			void setNearPressureMultiplier(float value);
+			float getNearPressureMultiplier();
+			void setViscosityStrength(float value);
+			float getViscosityStrength();
+			void setGravityScale(float value);
+			float getGravityScale();
+			void setBound(const vec3& value);
+			vec3 getBounds();
+
+			std::vector<vec3> positions;                                         // physicsWorld.h:79
+			std::vector<vec4> OutPositions;                                      // physicsWorld.h:80
+
+			// ---- B200 additions (no counterpart in the reference) ----
+			void setDevice(int cudaDevice);            // before InitializeData; default 0
+			void setTableMode(int sphTableMode);       // SPH_TABLE_GRID (default) / SPH_TABLE_REFERENCE_HASH
+			// Which host mirrors Update() refreshes: OutPositions (what the renderer uploads,
+			// fluidSimCPU.cc:58) is on by default; `positions` costs a second copy and is off by default.
+			void setHostMirrors(bool outPositions, bool positionsToo);
+			// Push host-side edits of `positions` (and optionally velocities, n*3 floats) to the device.
+			void uploadState(const float* velocities3 = nullptr);
+			void downloadVelocities(std::vector<vec3>& out);
+			void downloadDensities(std::vector<float>& rhoNearRhoPairs);
+			void downloadColors(std::vector<vec4>& out);   // FluidSimCPU::updateColors on the device
+			SphContext* context() { return ctx; }
+			const std::string& lastError() const { return error; }
+
+		private:
+			FluidSimulation() {}
+			FluidSimulation(const FluidSimulation& cpy) = delete;
+			~FluidSimulation();
+
+			void ensureContext(uint32_t capacity);
+			void pushParams();
+			void check(int rc, const char* what);
+			void refreshTimings();
+			void readParticle(uint32 index);
+
+			SphContext* ctx = nullptr;
+			SphParams params = defaultParams();
+			static SphParams defaultParams() { SphParams p; sph_default_params(&p); return p; }
+			uint32 numParticles = 0;
+			uint32_t capacity = 0;
+			int device = 0;
+			int tableMode = SPH_TABLE_GRID;
+			bool mirrorOut = true, mirrorPos = false;
+			float simTime = 0.0f;
+			double timings[6] = {0, 0, 0, 0, 0, 0};
+			bool timingsFresh = true;
+			float cached[10] = {0};
+			uint32 cachedIndex = 0xFFFFFFFFu;
+			bool cacheValid = false;
+			void* pinnedOut = nullptr; size_t pinnedOutBytes = 0;
+			void* pinnedPos = nullptr; size_t pinnedPosBytes = 0;
+			std::string error;
+		};
+	}
+}

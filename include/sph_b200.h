@@ -1,0 +1,171 @@
+/* include/sph_b200.h -- C ABI of the B200-native SPH step (libsph_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of Allkams/Fluid-Simulation-3D: the
+ * per-timestep update Physics::Fluid::FluidSimulation::Update(dt)
+ * (engine/physics/physicsWorld.cc:39-111) and the neighbour structure it builds
+ * (UpdateSpatialLookup, :466-498).  The reference has no FFI layer; its seam is
+ * the C++ class in engine/physics/physicsWorld.h:32-80.  Every entry point below
+ * names the reference member it replaces.  The C++ class of the same shape that
+ * sits on top of this ABI is fluid-simulation-3d_b200/host/FluidSimulation.h;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain C, opaque handle, int status (0 = SPH_OK); the message of
+ * the last failure is sph_last_error(ctx).  Host buffers are caller-owned,
+ * tightly packed fp32 in the reference's AoS layouts (vec3 = 3 floats, vec4 = 4,
+ * vec2 = 2) and always in ORIGINAL PARTICLE INDEX order, whatever order the
+ * device keeps internally.  One host thread per context.  All device work of a
+ * context is ordered on one CUDA stream; calls that fill host memory return
+ * after the data is there.  There is no CPU fallback: without a CUDA device
+ * sph_create fails with SPH_ERR_CUDA.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_B200_ABI_VERSION 1
+
+enum SphStatus {
+    SPH_OK = 0,
+    SPH_ERR_INVALID = 1,   /* bad argument / bad state */
+    SPH_ERR_CUDA = 2,      /* CUDA runtime failure (message holds cudaGetErrorString) */
+    SPH_ERR_NCCL = 3,      /* NCCL failure */
+    SPH_ERR_CAPACITY = 4,  /* particle count exceeds the context's capacity */
+    SPH_ERR_UNSUPPORTED = 5
+};
+
+/* Solver parameters = the private data members of the reference class with their
+ * in-class defaults (physicsWorld.h:96-106,145), set through its setters
+ * (physicsWorld.cc:214-302). */
+typedef struct SphParams {
+    float   interaction_radius;        /* interactionRadius  0.35 : cell size and kernel support */
+    float   sqr_radius;                /* sqrRadius          0.35f*0.35f : the d^2 cull. A separate
+                                          constant in the reference (const member, never derived
+                                          from the radius) -- kept separate here on purpose. */
+    float   target_density;            /* TargetDensity      99.7 */
+    float   pressure_multiplier;       /* pressureMultiplier 300  */
+    float   near_pressure_multiplier;  /* nearPressureMultiplier 20 */
+    float   viscosity_strength;        /* viscosityStrength  0.5  */
+    float   gravity_scale;             /* gravityScale       10   */
+    int32_t gravity;                   /* gravity            false */
+    float   bound[3];                  /* BoundScale         (20,20,20): full box extents, centred on 0 */
+} SphParams;
+
+/* Which neighbour table the step builds and walks.
+ *  SPH_TABLE_GRID            B200 layout (default): cell key = linear index of the reference's
+ *                            integer cell floor(pred/r) inside the bounding box, x fastest, so the
+ *                            3 x-adjacent cells of each of the 9 (y,z) rows are ONE contiguous run
+ *                            of the sorted arrays and neighbouring particles sit in neighbouring
+ *                            memory.  Same neighbour sets as the reference.
+ *  SPH_TABLE_REFERENCE_HASH  the reference's own structure on the device: key = HashCell % N
+ *                            (physicsWorld.cc:505-516), table length N, bucket walk with the
+ *                            float-rounded hash filter (:343-346).  Bit-exact keys / sorted order /
+ *                            start table; scatters neighbouring cells across memory. */
+enum SphTableMode { SPH_TABLE_GRID = 0, SPH_TABLE_REFERENCE_HASH = 1 };
+
+/* Arrays sph_download can return (original particle index order). */
+enum SphField {
+    SPH_FIELD_POSITIONS = 0,      /* float[N][3]  FluidSimulation::positions      (physicsWorld.h:79) */
+    SPH_FIELD_OUT_POSITIONS = 1,  /* float[N][4]  FluidSimulation::OutPositions, w = 0.34 (:80, .cc:107) */
+    SPH_FIELD_VELOCITIES = 2,     /* float[N][3]  velocity            (getVelocity, .cc:155-159) */
+    SPH_FIELD_DENSITIES = 3,      /* float[N][2]  densities (rho, near rho) (getDensity/getNearDensity, .cc:161-170) */
+    SPH_FIELD_PREDICTED = 4,      /* float[N][3]  predictedPositions of the last step (.cc:47) */
+    SPH_FIELD_VEL_AFTER_PRESSURE = 5,   /* float[N][3] velocity after CalculatePressureForce (.cc:421) */
+    SPH_FIELD_VEL_AFTER_VISCOSITY = 6,  /* float[N][3] velocity after CalculateViscosityForce (.cc:463), before collision */
+    SPH_FIELD_HASH = 7,           /* uint32[N]    HashCell(PositionToCellCoord(pred))  (.cc:477-478) */
+    SPH_FIELD_KEY = 8,            /* uint32[N]    hash % N                              (.cc:479) */
+    SPH_FIELD_NEIGHBOUR_COUNT = 9,/* uint32[N]    candidates surviving every filter of CalculateDensity (.cc:339-357), incl. self */
+    SPH_FIELD_SPEED_NORMALIZED = 10, /* float[N]  getSpeedNormalzied (.cc:178-182) */
+    SPH_FIELD_COLORS = 11         /* float[N][4]  speed gradient of FluidSimCPU::updateColors (fluidSimCPU.cc:100-125) */
+};
+
+/* Tables sph_download_table can return (sorted sequence / table order, not particle order). */
+enum SphTable {
+    SPH_TABLE_SORTED_INDEX = 0,   /* uint32[N]  particle index of each sorted row  (spatialLookup[].x, .cc:480-484) */
+    SPH_TABLE_SORTED_KEY = 1,     /* uint32[N]  key of each sorted row             (spatialLookup[].z) */
+    SPH_TABLE_START_INDICES = 2,  /* uint32[len] REFERENCE_HASH: startIndices, len N, 0x7FFFFFFF = empty (.cc:481,486-496)
+                                                 GRID: prefix table, len cells+1: rows of cell c are [t[c], t[c+1]) */
+    SPH_TABLE_SORTED_HASH = 3     /* uint32[N]  exact u32 hash of each sorted row  (spatialLookup[].y before float rounding) */
+};
+
+typedef struct SphContext SphContext;
+
+/* -- lifetime ------------------------------------------------------------- */
+/* getInstance() (.cc:32-37): one context owns every device buffer for up to `capacity` particles. */
+int  sph_create(SphContext** out, int device, uint32_t capacity);
+int  sph_destroy(SphContext* ctx);
+const char* sph_last_error(const SphContext* ctx);   /* ctx may be NULL: error of the last failed sph_create */
+int  sph_abi_version(void);
+
+/* -- parameters (setters/getters .cc:214-302) ------------------------------ */
+void sph_default_params(SphParams* p);
+int  sph_set_params(SphContext* ctx, const SphParams* p);
+int  sph_get_params(const SphContext* ctx, SphParams* p);
+int  sph_set_table_mode(SphContext* ctx, int mode);
+int  sph_get_table_mode(const SphContext* ctx);
+/* 1 (default): record the six stage timers with CUDA events each step (getElapsedTime*, .cc:184-212) */
+int  sph_set_stage_timing(SphContext* ctx, int enabled);
+/* 1: also keep neighbour counts during the density pass (debug tap, off by default) */
+int  sph_set_neighbour_count_tap(SphContext* ctx, int enabled);
+
+/* -- state ---------------------------------------------------------------- */
+/* InitializeData(n) (.cc:112-147): cube lattice spawn (GridArrangement :518-557), velocities zero,
+ * then the initial lookup + densities.  */
+int  sph_spawn_grid(SphContext* ctx, uint32_t n);
+/* Replace the particle state: positions[N][3], velocity[N][3] (NULL = zeros). */
+int  sph_upload_state(SphContext* ctx, uint32_t n, const float* pos3, const float* vel3);
+uint32_t sph_num_particles(const SphContext* ctx);
+
+/* -- the hot path ---------------------------------------------------------- */
+/* Update(deltatime) (.cc:39-111): S1 predict, S2 lookup, S3 density, S4 pressure, S5 viscosity
+ * (snapshot semantics), S6 integrate + box collision.  Asynchronous: returns when
+ * the work is enqueued; sph_download / sph_synchronize wait for it. */
+int  sph_step(SphContext* ctx, float dt);
+int  sph_step_n(SphContext* ctx, float dt, uint32_t nsteps);
+int  sph_synchronize(SphContext* ctx);
+/* rebuild lookup + densities for the current positions without advancing (InitializeData's tail, .cc:144-145) */
+int  sph_refresh_densities(SphContext* ctx);
+
+/* -- read-back ------------------------------------------------------------- */
+int  sph_download(SphContext* ctx, int field, void* host, size_t host_bytes);
+int  sph_download_table(SphContext* ctx, int table, void* host, size_t host_bytes, size_t* out_len);
+/* getPosition/getVelocity/getDensity/getNearDensity/getSpeed/getSpeedNormalzied (.cc:149-182):
+ * out10 = pos xyz, vel xyz, rho, near rho, speed, speed normalised; all zero when index >= N. */
+int  sph_get_particle(SphContext* ctx, uint32_t index, float* out10);
+/* ms: gravity(predict), spatial, density, pressure, viscosity, position+collision (.cc:184-212) */
+int  sph_get_timings(SphContext* ctx, double* out6);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t sph_launch_count(const SphContext* ctx);
+/* grid-table geometry: dims[3], origin cell[3] (for tests) */
+int  sph_get_grid(const SphContext* ctx, int32_t* dims3, int32_t* origin3);
+
+/* -- host memory helpers ---------------------------------------------------- */
+/* Page-lock / unlock a caller-owned host range in place (cudaHostRegister) so uploads and downloads
+ * through it run at full PCIe rate; optional, purely a performance hint. */
+int  sph_host_register(void* ptr, size_t bytes);
+int  sph_host_unregister(void* ptr);
+
+/* -- slab-decomposed multi-GPU (one context per rank / GPU) ---------------- */
+/* Size of the opaque rendezvous blob (an ncclUniqueId). Rank 0 fills it, the host runtime
+ * broadcasts it (torch.distributed / MPI / file), every rank passes it to sph_comm_init. */
+size_t sph_comm_id_bytes(void);
+int  sph_comm_get_id(void* id_out, size_t id_bytes);
+int  sph_comm_init(SphContext* ctx, int rank, int nranks, const void* id, size_t id_bytes);
+/* Slab planes along z: rank k owns z in [planes[k], planes[k+1]); planes has nranks+1 entries. */
+int  sph_comm_set_planes(SphContext* ctx, const float* planes);
+/* Upload this rank's OWNED particles with their global ids. */
+int  sph_upload_owned(SphContext* ctx, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3);
+/* Download this rank's owned particles (device order): ids + requested field. */
+int  sph_download_owned(SphContext* ctx, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n);
+/* counters of the last step: owned, ghosts received (lo, hi), migrated out (lo, hi) */
+int  sph_comm_stats(const SphContext* ctx, uint32_t* out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

@@ -358,7 +358,12 @@ static void pressure_of(const Oracle* o, uint32_t particleIndex, float deltatime
                 float t2 = dir[a] * d3 * sharedNearPressure / neighborNearDensity;
                 F[a] += t2;
             }
-            sc += fabsf(d2 * sharedPressure / neighborDensity) + fabsf(d3 * sharedNearPressure / neighborNearDensity);
+            /* tolerance scale: same terms with cancellation-free magnitudes (|rho| + rho0 instead of rho - rho0) */
+            {
+                float magP = ((fabsf(density) + fabsf(o->p.target_density)) + (fabsf(neighborDensity) + fabsf(o->p.target_density)))
+                             * fabsf(o->p.pressure_multiplier) * 0.5f;
+                sc += fabsf(d2 * magP / neighborDensity) + fabsf(d3 * sharedNearPressure / neighborNearDensity);
+            }
         }
     }
     if (vout) for (int a = 0; a < 3; a++) vout[a] = o->vel[3 * particleIndex + a] + (F[a] / density) * deltatime;

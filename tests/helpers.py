@@ -1,0 +1,114 @@
+"""Shared parity machinery: run one step on the GPU (through the C ABI) and on the oracle, compare.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8(a)): integer outputs bit-exact; fp32 outputs
+|gpu - ref| <= 1e-5 * max(|ref|, S) with S the stage's cancellation-free term scale, single step.
+"""
+import numpy as np
+
+import __graft_entry__ as g
+
+REL = 1e-5
+
+
+def oracle_pair(n, params):
+    """(value oracle, scale oracle).  Values come from the UNMODIFIED reference when oracle/_ref is
+    built, else from the C restatement; the term scales always come from the restatement."""
+    ob = g.load_oracle()
+    port = ob.PortOracle(n, **params)
+    ref = ob.RefOracle(n, **params) if ob.have_ref() else port
+    return ref, port
+
+
+def oracle_step(scene, dt, jacobi=True):
+    ref, port = oracle_pair(scene["n"], scene["params"])
+    for o in ({id(ref): ref, id(port): port}).values():
+        o.set_state(scene["pos"], scene["vel"])
+        o.step(dt, jacobi=jacobi)
+    ps, vs = port.force_scales(dt)
+    return ref, ps, vs
+
+
+def canonical_order(sorted_idx, sorted_key):
+    """Sort each equal-key run by ascending particle index (SURVEY App.A Q14)."""
+    order = np.lexsort((sorted_idx, sorted_key))
+    return sorted_idx[order]
+
+
+def grid_keys(cells, dims, origin):
+    gc = np.clip(cells.astype(np.int64) - origin.astype(np.int64), 0, dims.astype(np.int64) - 1)
+    return ((gc[:, 2] * dims[1] + gc[:, 1]) * dims[0] + gc[:, 0]).astype(np.uint32)
+
+
+def assert_close(name, got, ref, scale, rel=REL):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    tol = rel * np.maximum(np.abs(ref), np.asarray(scale, np.float64))
+    err = np.abs(got - ref)
+    bad = err > tol
+    assert np.all(np.isfinite(got)), name + ": non-finite values"
+    if bad.any():
+        i = int(np.argmax(err / np.maximum(tol, 1e-300)))
+        raise AssertionError("%s: %d/%d outside %g tolerance; worst got=%r ref=%r tol=%g" %
+                             (name, int(bad.sum()), bad.size, rel, got.flat[i], ref.flat[i], tol.flat[i]))
+    return float((err / np.maximum(tol, 1e-300)).max()) * rel
+
+
+def check_step(pkg, scene, mode, dt, report=None):
+    """One GPU step vs one oracle step on the same state.  Returns a dict of worst relative errors."""
+    n = scene["n"]
+    sim = pkg.FluidSimulation(n, device=0, table_mode=mode, **scene["params"])
+    try:
+        sim.set_neighbour_count_tap(True)
+        sim.upload_state(scene["pos"], scene["vel"])
+        sim.step(dt)
+        ref, ps, vs = oracle_step(scene, dt)
+        out = {}
+        # ---- integers: bit-exact
+        pred = sim.download("predicted")
+        assert np.array_equal(pred.view(np.uint32), ref.predicted().view(np.uint32)), "predicted positions not bit-exact"
+        h, k, cells = ref.hash_key()
+        assert np.array_equal(sim.download("hash"), h), "hash"
+        assert np.array_equal(sim.download("key"), k), "key"
+        nc = sim.download("neighbour_count")
+        nc_ref = ref.neighbour_counts()
+        assert np.array_equal(nc, nc_ref), "neighbour counts: %d differ" % int((nc != nc_ref).sum())
+        out["mean_neighbours"] = float(nc.mean())
+        s_idx = sim.download_table("sorted_index")
+        s_key = sim.download_table("sorted_key")
+        assert np.array_equal(np.sort(s_idx), np.arange(n, dtype=np.uint32)), "sorted index is not a permutation"
+        assert np.all(s_key[1:] >= s_key[:-1]), "sorted keys not sorted"
+        table = sim.download_table("start_indices")
+        if mode == pkg.TABLE_REFERENCE_HASH:
+            r_idx, r_hash, r_key = ref.sorted_lookup()
+            assert np.array_equal(s_key, r_key), "sorted key sequence"
+            assert np.array_equal(table, ref.start_indices()), "start table"
+            assert np.array_equal(canonical_order(s_idx, s_key), canonical_order(r_idx, r_key)), "sorted order (canonical ties)"
+            assert np.array_equal(s_key, k[s_idx]), "sorted key vs per-particle key"
+        else:
+            dims, origin = sim.grid()
+            gk = grid_keys(cells, dims, origin)
+            assert np.array_equal(s_key, gk[s_idx]), "grid key of sorted rows"
+            ncell = int(dims[0]) * int(dims[1]) * int(dims[2])
+            assert table.size == ncell + 1 and table[0] == 0 and table[-1] == n
+            assert np.array_equal(table, np.searchsorted(s_key, np.arange(ncell + 1, dtype=np.uint64)).astype(np.uint32)), "prefix table"
+        # ---- floats
+        dref = ref.densities()
+        out["density"] = assert_close("density", sim.download("densities"), dref, 0.0)
+        vp_ref = ref.vel_after_pressure()
+        out["vel_after_pressure"] = assert_close("vel_after_pressure", sim.download("vel_after_pressure"), vp_ref, ps[:, None])
+        vv_ref = ref.vel_after_viscosity()
+        out["vel_after_viscosity"] = assert_close("vel_after_viscosity", sim.download("vel_after_viscosity"), vv_ref,
+                                                  (ps + vs)[:, None])
+        pos_ref, vel_ref = ref.positions(), ref.velocities()
+        speed = np.abs(vv_ref).max(axis=1, keepdims=True)
+        out["positions"] = assert_close("positions", sim.download("positions"), pos_ref, speed * dt + (ps + vs)[:, None] * dt)
+        # a wall hit flips the velocity sign; both sides must agree on who hit
+        out["velocities"] = assert_close("velocities", sim.download("velocities"), vel_ref, (ps + vs)[:, None])
+        o4 = sim.download("out_positions")
+        assert np.array_equal(o4[:, :3].view(np.uint32), sim.download("positions").view(np.uint32))
+        assert np.all(o4[:, 3] == np.float32(0.34))
+        if report is not None:
+            report.update(out)
+        return out
+    finally:
+        sim.close()

@@ -1,0 +1,55 @@
+"""-m gpu: the CUDA step (through the C ABI) against the oracle on identical input states."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from helpers import check_step
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scenes(pkg):
+    from fluid_simulation_3d_b200 import scenes as sc
+    return sc
+
+
+MODES = ["grid", "reference_hash"]
+
+
+def _mode(pkg, name):
+    return pkg.TABLE_GRID if name == "grid" else pkg.TABLE_REFERENCE_HASH
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("side", [8, 16, 24])
+def test_dam_break_step(pkg, scenes, mode, side):
+    out = check_step(pkg, scenes.small_dam_break(side), _mode(pkg, mode), scenes.DT)
+    assert 5 < out["mean_neighbours"] < 40
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_dense_column_step(pkg, scenes, mode):
+    out = check_step(pkg, scenes.small_column(14, 40, 14), _mode(pkg, mode), scenes.DT)
+    assert out["mean_neighbours"] > 50
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_moving_state_negative_coords(pkg, scenes, mode):
+    """Random velocities, block centred on the origin (all eight sign octants: Q5), some particles
+    beyond the walls so the collision branch and the clamped border cells are exercised."""
+    rng = np.random.default_rng(3)
+    n = 6000
+    bound = (6.0, 5.0, 4.0)
+    pos = (rng.random((n, 3), dtype=np.float32) - 0.5) * np.array(bound, np.float32) * 1.02
+    vel = (rng.random((n, 3), dtype=np.float32) - 0.5) * 8.0
+    sc = dict(pos=pos.astype(np.float32), vel=vel.astype(np.float32), n=n,
+              params=dict(gravity=1, viscosity_strength=0.7, bound=bound))
+    check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_gravity_off_defaults(pkg, scenes, mode):
+    sc = scenes.small_dam_break(12)
+    sc["params"] = dict(bound=sc["bound"])          # reference defaults: gravity off (physicsWorld.h:105)
+    check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
