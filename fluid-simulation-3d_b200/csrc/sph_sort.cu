@@ -5,8 +5,8 @@
 // (3 passes for up to 16 M cells / buckets).  Stable => equal keys keep their incoming order, which
 // is the canonical tie order the parity tests compare against (SURVEY App.A Q14).
 //
-// Per pass: (1) per-block digit histogram, (2) one-block exclusive scan of the [digit][block]
-// matrix, (3) scatter with a warp-synchronous stable rank (match.any + per-warp digit counters in
+// Per pass: (1) per-block digit histogram, (2) per-digit row scan of the [digit][block]
+// matrix (256 blocks), (3) scatter with a warp-synchronous stable rank (match.any + per-warp digit counters in
 // shared memory).  Blocks own a contiguous span of tiles so the scanned matrix stays small
 // (<= 256 x 1184 entries) at any N.  HBM traffic per pass: keys read twice, pairs written once
 // = 20 B/pair (algorithmic 16 B/pair).
@@ -52,53 +52,68 @@ k_radix_hist(const uint32_t* __restrict__ keys, uint32_t* __restrict__ counts, u
     counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
-// exclusive scan of `total` counters by ONE block of 1024 threads
-__global__ void __launch_bounds__(1024)
-k_radix_scan(uint32_t* __restrict__ counts, uint32_t total)
+// Row scan: block d turns row d of the [digit][block] count matrix into its exclusive prefix (in
+// place, coalesced, carry across 256-wide chunks) and writes the row total to totals[d].  The
+// scatter kernel adds the exclusive scan of the 256 totals itself.
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_rowscan(uint32_t* __restrict__ counts, uint32_t* __restrict__ totals, uint32_t nblocks)
 {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t chunk = (total + 1023u) / 1024u;
-    const uint32_t b = threadIdx.x * chunk;
-    const uint32_t e = min(b + chunk, total);
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; i++) sum += counts[i];
-    // block exclusive scan of `sum`
+    __shared__ uint32_t warp_sums[kSortWarps];
+    __shared__ uint32_t carry_s;
+    uint32_t* row = counts + (size_t)blockIdx.x * nblocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sums[warp] = inc;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sums[lane];
-        uint32_t winc = w;
+    for (uint32_t base = 0; base < nblocks; base += kSortThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? row[i] : 0u;
+        uint32_t inc = v;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        warp_sums[lane] = winc - w;
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        #pragma unroll
+        for (int w = 0; w < kSortWarps; w++) if (w < warp) wbase += warp_sums[w];
+        const uint32_t carry = carry_s;
+        if (i < nblocks) row[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == kSortThreads - 1) carry_s = carry + wbase + inc;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = warp_sums[warp] + inc - sum;
-    for (uint32_t i = b; i < e; i++) { uint32_t c = counts[i]; counts[i] = run; run += c; }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
 template <bool kIdentity>
 __global__ void __launch_bounds__(kSortThreads)
 k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                const uint32_t* __restrict__ offsets, uint32_t n, int shift,
+                const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals, uint32_t n, int shift,
                 uint32_t tiles_per_block, uint32_t nblocks)
 {
     __shared__ uint32_t cnt[kSortWarps][256];
     __shared__ uint32_t base[256];
+    __shared__ uint32_t wsum[kSortWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    base[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    {   // digit base = exclusive scan of the 256 digit totals (thread d owns digit d)
+        const uint32_t v = totals[threadIdx.x];
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        #pragma unroll
+        for (int w = 0; w < kSortWarps; w++) if (w < warp) wbase += wsum[w];
+        base[threadIdx.x] = wbase + inc - v + offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    }
 
     for (uint32_t t = 0; t < tiles_per_block; t++) {
         const uint64_t tile_base = ((uint64_t)blockIdx.x * tiles_per_block + t) * kTile;
@@ -148,8 +163,8 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
 
 size_t radix_sort_temp_entries(uint32_t n)
 {
-    SortGeom g = sort_geom(n);
-    return (size_t)256 * g.nblocks;
+    (void)n;                                   // nblocks is not monotonic in n: size for the maximum
+    return (size_t)256 * kMaxSortBlocks + 256; // count matrix + digit totals
 }
 
 int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
@@ -157,6 +172,7 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
 {
     if (n == 0) return 0;
     const SortGeom g = sort_geom(n);
+    uint32_t* totals = counts + (size_t)256 * g.nblocks;
     int passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
     uint32_t *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
@@ -164,12 +180,12 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
         k_radix_hist<<<g.nblocks, kSortThreads, 0, st>>>(kin, counts, n, shift, g.tiles_per_block, g.nblocks);
-        k_radix_scan<<<1, 1024, 0, st>>>(counts, 256u * g.nblocks);
+        k_radix_rowscan<<<256, kSortThreads, 0, st>>>(counts, totals, g.nblocks);
         if (p == 0 && vals_identity)
-            k_radix_scatter<true><<<g.nblocks, kSortThreads, 0, st>>>(kin, nullptr, kout, vout, counts, n, shift,
+            k_radix_scatter<true><<<g.nblocks, kSortThreads, 0, st>>>(kin, nullptr, kout, vout, counts, totals, n, shift,
                                                                        g.tiles_per_block, g.nblocks);
         else
-            k_radix_scatter<false><<<g.nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, counts, n, shift,
+            k_radix_scatter<false><<<g.nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, counts, totals, n, shift,
                                                                         g.tiles_per_block, g.nblocks);
         if (launches) *launches += 3;
         uint32_t* t = kin; kin = kout; kout = t;
