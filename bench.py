@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- M particle-updates/s of the per-timestep SPH update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME]
+
+N = 1 : config C2 (1 M-particle box-fill dam break, BASELINE.json configs[1]) on one B200.
+N > 1 : config C4 (64 M-particle dam break, configs[3]) slab-decomposed along z over N ranks
+        (launched by torch.distributed.run, one rank per GPU); total work fixed => "strong".
+A "step" is one FluidSimulation::Update(dt) (engine/physics/physicsWorld.cc:39-111) over all particles.
+
+One JSON line on rank 0:
+  value     whole-job M particle-updates/s, state resident in HBM, CUDA events on the solver's stream,
+            L2 flushed between timed steps (the flush is outside the event pairs)
+  e2e       the same metric through the host-facing call sequence with HOST (pinned) buffers:
+            sph_upload_state (H2D positions+velocities) -> sph_step -> sph_download(OutPositions) (D2H)
+  roofline  dominant kernel: algorithmic bytes / its CUDA-event duration / measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host, bounded sample
+--impl reference times the reference CPU implementation alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "M particle-updates/s"
+# algorithmic (compulsory) bytes per particle-update, SURVEY.md 8(d) / DESIGN.md
+A_BYTES = dict(predict_key=72, sort=52, table=12, reorder=68, density=32, pressure=64, viscosity=56,
+               integrate=84, step=440)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(scene_name, steps, warmup, budget_s=25.0):
+    """Time the reference CPU Update() on a bounded sample of the workload.  Returns a dict."""
+    ob = graft.load_oracle()
+    pkg = graft.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    kind = "reference" if ob.have_ref() else "port"
+    # per-particle cost is flat in N (0.13-0.16 M updates/s from 10 k to 1 M), so a sub-block
+    # of the same lattice / rule is a faithful sample; size it so (steps + warmup) fit the budget
+    rate_guess = 0.14e6
+    total = max(1, steps + warmup)
+    side = int(round((budget_s * rate_guess / total) ** (1.0 / 3.0)))
+    full = scenes.CONFIGS[scene_name][0] if scene_name in scenes.CONFIGS else 100
+    side = max(16, min(side, full))
+    sc = scenes.small_dam_break(side, seed=scenes.CONFIGS.get(scene_name, (0, 0, 0, 7))[3])
+    orc = (ob.RefOracle if kind == "reference" else ob.PortOracle)(sc["n"], **sc["params"])
+    orc.set_state(sc["pos"], sc["vel"])
+    step = (lambda: orc.update(scenes.DT)) if kind == "reference" else (lambda: orc.step(scenes.DT, jacobi=True))
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=sc["n"] * steps / dt / 1e6, unit=METRIC, cores=1, kind=kind, ms_per_step=dt / steps * 1e3,
+                sample="%d^3 = %d-particle corner block of the %s lattice (same spacing, jitter, bounds rule, dt), "
+                       "%d steps after %d warm-up, %s" % (side, sc["n"], scene_name, steps, warmup,
+                                                          "unmodified reference Update() (serial PSTL: TBB absent)"
+                                                          if kind == "reference" else "C restatement, 1 thread"),
+                n=sc["n"])
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    name = "C2_dambreak_1M" if args.gpus == 1 else "C4_dambreak_64M"
+    if args.config:
+        name = args.config
+    r = cpu_reference_run(name, args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "M updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "sample_particles": r["n"]},
+            "cpu_baseline": {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"], "host_cores": os.cpu_count()},
+            "e2e": {"value": r["value"], "unit": "M updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--table", default="grid", choices=["grid", "refhash"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        if rank == 0:
+            sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE\n" % (args.gpus, world))
+    pkg = graft.load_package()
+    from fluid_simulation_3d_b200 import scenes
+
+    if world == 1:
+        result = bench_single(args, pkg, scenes, torch, local_rank)
+    else:
+        from fluid_simulation_3d_b200 import slab_driver
+        result = slab_driver.bench_multi(args, pkg, scenes, torch, dist, rank, world, local_rank, METRIC, A_BYTES,
+                                         measured_peaks, ClockSampler)
+    if rank == 0 and result is not None:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_single(args, pkg, scenes, torch, dev):
+    name = args.config or "C2_dambreak_1M"
+    sc = scenes.config(name)
+    n = sc["n"]
+    mode = pkg.TABLE_GRID if args.table == "grid" else pkg.TABLE_REFERENCE_HASH
+    sim = pkg.FluidSimulation(n, device=dev, table_mode=mode, **sc["params"])
+    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=dev)
+    dt = scenes.DT
+    # pinned host buffers of the reference's own layouts: positions vec3, velocity vec3, OutPositions vec4
+    h_pos = torch.from_numpy(sc["pos"]).pin_memory()
+    h_vel = torch.from_numpy(sc["vel"]).pin_memory()
+    h_out = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    sim.upload_state_ptr(n, h_pos.data_ptr(), h_vel.data_ptr())
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)
+
+    def l2_flush():
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+
+    for _ in range(args.warmup):
+        sim.step(dt)
+    sim.synchronize()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: one CUDA-event pair per step on the solver's stream, L2 flushed between
+    clocks = ClockSampler(dev)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = np.zeros(6)
+    l0 = sim.launch_count()
+    for a, b in ev:
+        l2_flush()
+        a.record(stream)
+        sim.step(dt)
+        b.record(stream)
+        stage += sim.timings()          # waits for the step's last stage event
+    sim.synchronize()
+    torch.cuda.synchronize()
+    launches = sim.launch_count() - l0
+    clk = clocks.stop()
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(ms.sum())
+    value = n * args.steps / (total_ms * 1e-3) / 1e6
+    stage /= args.steps
+
+    # ---- steady state: K steps back to back, no flush (what a simulation loop sees)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sim.set_stage_timing(False)
+    a.record(stream)
+    for _ in range(args.steps):
+        sim.step(dt)
+    b.record(stream)
+    sim.synchronize()
+    steady_ms = a.elapsed_time(b) / args.steps
+    sim.set_stage_timing(True)
+
+    # ---- end to end through host buffers: H2D state, step, D2H OutPositions, every step
+    for _ in range(2):
+        sim.upload_state_ptr(n, h_pos.data_ptr(), h_vel.data_ptr())
+        sim.step(dt)
+        sim.download_ptr("out_positions", h_out.data_ptr(), n * 16)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.upload_state_ptr(n, h_pos.data_ptr(), h_vel.data_ptr())
+        sim.step(dt)
+        sim.download_ptr("out_positions", h_out.data_ptr(), n * 16)   # returns when the host buffer is filled
+    e2e_s = time.perf_counter() - t0
+    e2e = n * args.steps / e2e_s / 1e6
+
+    peak, peak_src = measured_peaks()
+    names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
+    gather = {"density": stage[2], "pressure": stage[3], "viscosity": stage[4]}
+    dom = max(gather, key=gather.get)
+    dom_ms = gather[dom]
+    achieved = A_BYTES[dom] * n / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(name, {}).get(dom)
+        except Exception:
+            traffic = None
+    result = {
+        "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
+                               "r=0.35, gravity on, mu=%.2f, dt=0.016667" % (name, n, tuple(round(x, 3) for x in sc["bound"]),
+                                                                          sc["params"]["viscosity_strength"]),
+                   "particles": n, "table": args.table,
+                   "l2": "flushed between timed steps (256 MiB fill outside the event pairs)" if flush is not None
+                         else "not flushed"},
+        "steady_state": {"value": n / (steady_ms * 1e-3) / 1e6, "ms_per_step": steady_ms,
+                         "note": "K steps back to back, no L2 flush, stage timers off"},
+        "stage_ms": {k: float(v) for k, v in zip(names, stage)},
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),
+                     "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
+                              "algorithmic_bytes_per_particle": A_BYTES["step"]}},
+        "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "path": "sph_upload_state(pinned pos3+vel3) -> sph_step -> sph_download(OUT_POSITIONS, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+    sim.close()
+    if not args.no_cpu_baseline:
+        r = cpu_reference_run(name if name in scenes.CONFIGS else "C2_dambreak_1M", steps=2, warmup=1, budget_s=20.0)
+        result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
+                                  "sample": r["sample"], "host_cores": os.cpu_count()}
+    return result
+
+
+if __name__ == "__main__":
+    main()

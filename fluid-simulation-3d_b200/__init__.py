@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_spawn_grid", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
-    "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count",
+    "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
     "sph_upload_owned", "sph_download_owned", "sph_comm_stats",
 ]
@@ -90,6 +90,8 @@ def load_library():
     L.sph_get_timings.argtypes = [vp, vp]
     L.sph_launch_count.argtypes = [vp]
     L.sph_launch_count.restype = C.c_uint64
+    L.sph_stream.argtypes = [vp]
+    L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
     L.sph_host_register.argtypes = [vp, C.c_size_t]
     L.sph_host_unregister.argtypes = [vp]
@@ -254,6 +256,9 @@ class FluidSimulation:
 
     def launch_count(self):
         return int(self.L.sph_launch_count(self.h))
+
+    def stream_ptr(self):
+        return int(self.L.sph_stream(self.h) or 0)
 
     def grid(self):
         d = np.zeros(3, np.int32)

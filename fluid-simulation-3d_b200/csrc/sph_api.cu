@@ -233,6 +233,7 @@ int sph_set_stage_timing(SphContext* c, int enabled) { if (!c) return SPH_ERR_IN
 int sph_set_neighbour_count_tap(SphContext* c, int enabled) { if (!c) return SPH_ERR_INVALID; c->nc_tap = enabled != 0; return SPH_OK; }
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
+void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
 
 int sph_get_grid(const SphContext* c, int32_t* dims3, int32_t* origin3)
 {

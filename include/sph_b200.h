@@ -141,6 +141,8 @@ int  sph_get_particle(SphContext* ctx, uint32_t index, float* out10);
 int  sph_get_timings(SphContext* ctx, double* out6);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t sph_launch_count(const SphContext* ctx);
+/* the context's cudaStream_t (as void*), so a caller can order its own events / copies against the step */
+void* sph_stream(const SphContext* ctx);
 /* grid-table geometry: dims[3], origin cell[3] (for tests) */
 int  sph_get_grid(const SphContext* ctx, int32_t* dims3, int32_t* origin3);
 

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sph_b200.h declares; struct layout;
+the host C++ class library links against it.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import __graft_entry__ as g
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sph_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sph_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_the_binding_lists(pkg):
+    assert header_functions() == sorted(pkg.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert lib.sph_abi_version() == 1
+
+
+def test_exports_are_plain_c(pkg):
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for name in header_functions():
+        assert name in exported, name + " is not an unmangled export"
+
+
+def test_params_struct_layout_and_defaults(pkg):
+    assert C.sizeof(pkg.SphParams) == 44
+    p = pkg.default_params()
+    assert abs(p.interaction_radius - 0.35) < 1e-7 and abs(p.sqr_radius - 0.1225) < 1e-7
+    assert abs(p.target_density - 99.7) < 1e-5 and p.pressure_multiplier == 300 and p.near_pressure_multiplier == 20
+    assert p.viscosity_strength == 0.5 and p.gravity_scale == 10 and p.gravity == 0       # gravity off by default
+    assert list(p.bound) == [20, 20, 20]
+
+
+def test_create_without_gpu_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.SphError) as e:
+        pkg.FluidSimulation(16)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_library_does_not_link_the_oracle(pkg):
+    out = subprocess.run(["ldd", pkg.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "sph_oracle" not in out and "sph_ref" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "fluid-simulation-3d_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cc", ".h", ".cuh", ".py")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle/" not in txt.replace("oracle/_ref", "").replace("oracle/", "oracle/") or f == "__init__.py" or \
+                    "load_oracle" not in txt, f
+
+
+def test_host_class_library_links(pkg):
+    host = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "libfluidsim_b200_host.so")
+    assert os.path.exists(host), "run __graft_entry__.build()"
+    out = subprocess.run(["nm", "-DC", "--defined-only", host], stdout=subprocess.PIPE, text=True).stdout
+    for sym in ("Physics::Fluid::FluidSimulation::Update(float)", "Physics::Fluid::FluidSimulation::getInstance()",
+                "Physics::Fluid::FluidSimulation::InitializeData(int,", "Physics::Fluid::FluidSimulation::getSpeedNormalzied(",
+                "Physics::Fluid::FluidSimulation::setBound("):
+        assert sym in out, sym

@@ -1,0 +1,208 @@
+"""CPU: pin the C restatement (oracle/sph_oracle.c) against the golden vectors generated from the
+UNMODIFIED reference, and -- where oracle/_ref is built -- against the reference itself, live."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def params_of(gold):
+    p = gold["params"]
+    return dict(interaction_radius=p[0], target_density=p[1], pressure_multiplier=p[2], near_pressure_multiplier=p[3],
+                viscosity_strength=p[4], gravity_scale=p[5], gravity=int(p[6]), bound=tuple(p[7:10]))
+
+
+def test_golden_files_present():
+    assert len(GOLDEN) >= 4
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_port_matches_golden_bit_for_bit(ob, path):
+    """Given the reference's own sorted tie order, every intermediate of the restated step is
+    bit-identical to the unmodified reference's."""
+    gold = np.load(path)
+    n = gold["pos0"].shape[0]
+    dt = float(gold["dt"])
+    o = ob.PortOracle(n, **params_of(gold))
+    o.set_state(gold["pos0"], gold["vel0"])
+    o.stage_predict(dt)
+    assert np.array_equal(bits(o.predicted()), bits(gold["pred"]))
+    o.stage_spatial(forced_order=gold["sorted_idx"])
+    h, k, cells = o.hash_key()
+    assert np.array_equal(h, gold["hash"]) and np.array_equal(k, gold["key"]) and np.array_equal(cells, gold["cells"])
+    si, sh, sk = o.sorted_lookup()
+    assert np.array_equal(sk, gold["sorted_key"]) and np.array_equal(sh, gold["sorted_hash"])
+    assert np.array_equal(o.start_indices(), gold["start"])
+    o.stage_density()
+    assert np.array_equal(bits(o.densities()), bits(gold["dens"]))
+    assert np.array_equal(o.neighbour_counts(), gold["ncount"])
+    o.stage_pressure(dt)
+    assert np.array_equal(bits(o.vel_after_pressure()), bits(gold["vel_press"]))
+    o.stage_viscosity(dt, jacobi=True)
+    assert np.array_equal(bits(o.vel_after_viscosity()), bits(gold["vel_visc"]))
+    o.stage_integrate(dt)
+    assert np.array_equal(bits(o.positions()), bits(gold["pos1"]))
+    assert np.array_equal(bits(o.velocities()), bits(gold["vel1"]))
+    assert np.array_equal(bits(o.out_positions()), bits(gold["out1"]))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_port_own_sort_is_canonical_and_close(ob, path):
+    """With its own (stable, index-ordered) sort the port's key sequence and start table are still
+    bit-exact; floats differ from the reference only by summation order."""
+    gold = np.load(path)
+    n = gold["pos0"].shape[0]
+    dt = float(gold["dt"])
+    o = ob.PortOracle(n, **params_of(gold))
+    o.set_state(gold["pos0"], gold["vel0"])
+    o.step(dt, jacobi=True)
+    si, sh, sk = o.sorted_lookup()
+    assert np.array_equal(sk, gold["sorted_key"])
+    assert np.array_equal(o.start_indices(), gold["start"])
+    canon = gold["sorted_idx"][np.lexsort((gold["sorted_idx"], gold["sorted_key"]))]
+    assert np.array_equal(si, canon)
+    assert np.array_equal(o.neighbour_counts(), gold["ncount"])
+    assert np.allclose(o.densities(), gold["dens"], rtol=2e-6, atol=0)
+    assert np.allclose(o.positions(), gold["pos1"], rtol=0, atol=2e-5)
+
+
+def test_port_in_place_viscosity_matches_verbatim_update(ob):
+    """Gauss-Seidel (index-order, in-place) viscosity of the port == the reference's verbatim Update()."""
+    gold = np.load(os.path.join(HERE, "golden", "dambreak_12.npz"))
+    n = gold["pos0"].shape[0]
+    dt = float(gold["dt"])
+    o = ob.PortOracle(n, **params_of(gold))
+    o.set_state(gold["pos0"], gold["vel0"])
+    o.stage_predict(dt)
+    o.stage_spatial(forced_order=gold["sorted_idx"])
+    o.stage_density(); o.stage_pressure(dt); o.stage_viscosity(dt, jacobi=False); o.stage_integrate(dt)
+    assert np.array_equal(bits(o.positions()), bits(gold["upd_pos"]))
+    assert np.array_equal(bits(o.velocities()), bits(gold["upd_vel"]))
+    assert np.array_equal(bits(o.densities()), bits(gold["upd_dens"]))
+    # and the two viscosity semantics really differ (SURVEY App.A Q11)
+    assert not np.array_equal(bits(gold["upd_vel"]), bits(gold["vel1"]))
+
+
+def test_spawn_matches_reference_initialize_data(ob):
+    gold = np.load(os.path.join(HERE, "golden", "spawn_1000.npz"))
+    o = ob.PortOracle(1000, gravity=1)
+    o.spawn_grid()
+    assert np.array_equal(bits(o.positions()), bits(gold["pos0"]))
+    assert np.allclose(o.densities(), gold["spawn_dens"], rtol=2e-6)
+
+
+def test_smoothing_kernels_known_answers(ob):
+    """kernels.h:25-82 closed forms, incl. the float abs() of Q3 (an int abs() would give inf)."""
+    r = 0.35
+    k = ob.PortOracle.kernels(0.1, r)
+    pi = np.pi
+    want = [(r - 0.1) ** 2 * 15 / (2 * pi * r ** 5), (r - 0.1) ** 3 * 15 / (pi * r ** 6), -(r - 0.1) * 15 / (pi * r ** 5),
+            -(r - 0.1) ** 2 * 45 / (pi * r ** 6), (r * r - 0.01) ** 3 * 315 / (64 * pi * r ** 9)]
+    assert np.allclose(k, want, rtol=2e-6)
+    assert abs(k[4] - 28.3026) < 1e-3                       # SURVEY 8(c) probe value
+    edge = ob.PortOracle.kernels(np.float32(r), np.float32(r))
+    assert edge[0] == 0 and edge[1] == 0 and edge[4] == 0   # dist < radius is strict
+    assert np.all(ob.PortOracle.kernels(0.5, r) == 0)
+
+
+def test_negative_cell_hash_wraps(ob):
+    """Q5: (uint32_t) of a negative cell wraps two's-complement; Q6: floor of true division."""
+    o = ob.PortOracle(4, bound=(100, 100, 100))
+    pos = np.array([[-0.1, -0.36, 0.34], [0.0, 0.35, -0.35], [-7.0, 3.3, -12.2], [0.7, -0.7, 0.0]], np.float32)
+    o.set_state(pos, np.zeros_like(pos))
+    o.stage_predict(0.0)
+    h, k, c = o.hash_key()
+    r = np.float32(0.35)
+    want_c = np.floor(pos / r).astype(np.int64)
+    assert np.array_equal(c, want_c)
+    want_h = (want_c[:, 0] * 15823 + want_c[:, 1] * 9737333 + want_c[:, 2] * 440817757) % (1 << 32)
+    assert np.array_equal(h.astype(np.int64), want_h)
+    assert np.array_equal(k, (want_h % 4).astype(np.uint32))
+
+
+def test_empty_and_single_particle(ob):
+    o = ob.PortOracle(1)
+    o.set_state(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32))
+    o.step(0.016667)
+    d = o.densities()
+    assert d[0, 0] > 0 and o.neighbour_counts()[0] == 1          # density includes self (Q7)
+    assert np.all(o.velocities() == 0)
+
+
+needs_ref = pytest.mark.skipif(not g.load_oracle().have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@needs_ref
+def test_live_reference_staged_equals_update_without_viscosity(ob):
+    """The harness' restated S1/S6 lambdas are bit-identical to the reference's Update() (mu = 0)."""
+    g.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(10)
+    p = dict(sc["params"], viscosity_strength=0.0)
+    r = ob.RefOracle(sc["n"], **p)
+    r.set_state(sc["pos"], sc["vel"])
+    r.update(scenes.DT)
+    a = (r.positions(), r.velocities(), r.densities(), r.out_positions())
+    r.set_state(sc["pos"], sc["vel"])
+    r.step(scenes.DT, jacobi=True)
+    b = (r.positions(), r.velocities(), r.densities(), r.out_positions())
+    for x, y in zip(a, b):
+        assert np.array_equal(bits(x), bits(y))
+    r.set_state(sc["pos"], sc["vel"])
+    r.set_params(viscosity_strength=0.5)
+    r.update(scenes.DT)
+    c = r.velocities()
+    r.set_state(sc["pos"], sc["vel"])
+    r.step(scenes.DT, jacobi=False)
+    assert np.array_equal(bits(c), bits(r.velocities()))
+
+
+@needs_ref
+def test_live_reference_vs_port_default_scene(ob):
+    """Default scene (InitializeData(10000), the reference's own spawn), 3 steps, in-place viscosity."""
+    dt = float(np.float32(0.016667))
+    r = ob.RefOracle(10000, spawn=True, gravity=1)
+    p = ob.PortOracle(10000, gravity=1)
+    p.spawn_grid()
+    assert np.array_equal(bits(p.positions()), bits(r.positions()))
+    for _ in range(3):
+        r.update(dt)
+        idx, _, _ = r.sorted_lookup()
+        p.stage_predict(dt); p.stage_spatial(forced_order=idx); p.stage_density(); p.stage_pressure(dt)
+        p.stage_viscosity(dt, jacobi=False); p.stage_integrate(dt)
+        assert np.array_equal(bits(p.positions()), bits(r.positions()))
+        assert np.array_equal(bits(p.velocities()), bits(r.velocities()))
+        assert np.array_equal(bits(p.densities()), bits(r.densities()))
+
+
+@needs_ref
+def test_live_reference_getters_bounds(ob):
+    r = ob.RefOracle(64, spawn=True)
+    assert np.all(r.getter_probe(64) == 0) and np.all(r.getter_probe(2 ** 31) == 0)      # OOB -> zeros
+    assert r.getter_probe(0)[6] > 0
+    assert np.allclose(ob.RefOracle.kernels(0.1, 0.35), ob.PortOracle.kernels(0.1, 0.35), rtol=0, atol=0)
+
+
+def test_openmp_port_is_thread_count_invariant(ob):
+    g.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(10)
+    res = []
+    for t in (1, 4):
+        o = ob.PortOracle(sc["n"], threads=t, **sc["params"])
+        o.set_state(sc["pos"], sc["vel"])
+        o.step(scenes.DT, jacobi=True)
+        res.append((o.positions(), o.velocities(), o.densities()))
+    ob.PortOracle.lib().oracle_set_threads(1)
+    for x, y in zip(*res):
+        assert np.array_equal(bits(x), bits(y))
