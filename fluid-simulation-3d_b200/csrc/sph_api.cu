@@ -58,6 +58,8 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     for (int a = 0; a < 3; a++) { P->gmin[a] = c->gmin[a]; P->gdim[a] = c->gdim[a]; }
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
+    P->row0 = 0; P->row1 = n; P->n_a = n;
+    P->slab = 0; P->zlo = 0; P->gz_global = c->gdim[2]; P->own_lo = 0; P->own_hi = c->gdim[2];
     return SPH_OK;
 }
 
@@ -276,7 +278,7 @@ static int run_step(SphContext* c, float dt, bool advance)
     const bool timing = c->timing && advance;
     cudaStream_t st = c->st;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
-    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P, dt, &c->launches);
+    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
     const int bits = ceil_log2(P.mode == SPH_TABLE_GRID ? (uint64_t)P.ncell : (uint64_t)P.n);
     c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, P.n, bits, c->counts,
@@ -284,7 +286,7 @@ static int run_step(SphContext* c, float dt, bool advance)
     const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
     const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
     launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
-    launch_reorder(st, perm, c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    launch_reorder(st, perm, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
     launch_density(st, c->pred, c->tstart, c->tend, c->dens, c->nc_tap ? c->ncount : nullptr, P, &c->launches);
     c->ncount_valid = c->nc_tap;

@@ -26,7 +26,18 @@ struct DevParams {
     uint32_t ncell;
     // REFERENCE_HASH table: key = hash % n via Lemire fastmod, M = 2^64 / n + 1
     uint64_t modM;
+    // rows the gather / integrate kernels process: [row0, row1)  (single GPU: [0, n))
+    uint32_t row0, row1;
+    // slab mode (multi-GPU): the local table holds global z layers [zlo, zlo + gdim[2]); this rank
+    // owns global layers [own_lo, own_hi).  Single GPU: slab = 0, zlo = 0, gz_global = gdim[2].
+    int      slab;
+    int      zlo, gz_global, own_lo, own_hi;
+    int      has_lo, has_hi;   // a neighbour rank exists below / above
+    uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
 };
+
+// slab mode: classification of an owned row by the z layer of its predicted position
+enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8 };
 
 struct SortTemp {
     uint32_t* counts;       // [256][nblocks] digit counts -> exclusive offsets
@@ -41,12 +52,15 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
                      bool vals_identity, uint32_t n, int bits, uint32_t* counts, uint64_t* launches);
 
 // ---- sph_kernels.cu -------------------------------------------------------
-void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint32_t* hash_out,
-                        const DevParams& P, float dt, uint64_t* launches);
+void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
+                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint64_t* launches);
+void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
+                      uint64_t* launches);
 void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* table_start, uint32_t* table_end,
                         uint32_t* gap_list, const DevParams& P, uint64_t* launches);
 void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
-                    float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P, float dt, uint64_t* launches);
+                    const float4* ghost_pred, float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P,
+                    float dt, uint64_t* launches);
 void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
                     float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches);
 void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, const float4* vel_s,

@@ -63,7 +63,7 @@ __device__ __forceinline__ int3 grid_cell(int3 c, const DevParams& P)
     int3 g;
     g.x = clampi(c.x - P.gmin[0], 0, P.gdim[0] - 1);
     g.y = clampi(c.y - P.gmin[1], 0, P.gdim[1] - 1);
-    g.z = clampi(c.z - P.gmin[2], 0, P.gdim[2] - 1);
+    g.z = clampi(clampi(c.z - P.gmin[2], 0, P.gz_global - 1) - P.zlo, 0, P.gdim[2] - 1);
     return g;
 }
 __device__ __forceinline__ uint32_t grid_key(int3 g, const DevParams& P)
@@ -86,23 +86,50 @@ __device__ __forceinline__ void predict(const float4 p, float4& v, float3& pred,
 
 __global__ void __launch_bounds__(256)
 k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
-              uint32_t* __restrict__ hash_out, const DevParams P, const float dt)
+              uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
+    if (s >= rows) return;
     const float4 p = pos[s];
     float4 v = vel[s];
     float3 pr;
     predict(p, v, pr, P, dt);
     const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
     if (P.mode == SPH_TABLE_REFERENCE_HASH) {
-        const uint32_t h = hash_cell(c.x, c.y, c.z);
-        key[s] = key_of_hash(h, P);
-        if (hash_out) hash_out[s] = h;
-    } else {
-        key[s] = grid_key(grid_cell(c, P), P);
-        if (hash_out) hash_out[s] = hash_cell(c.x, c.y, c.z);
+        key[s] = key_of_hash(hash_cell(c.x, c.y, c.z), P);
+        return;
     }
+    if (P.slab) {
+        // slab mode: ownership follows the z layer of the PREDICTED position, so every owned row finds
+        // all its 27 cells in the local table (own layers + one ghost layer per side)
+        const int gz = clampi(c.z - P.gmin[2], 0, P.gz_global - 1);
+        uint8_t k = CLS_STAY;
+        if (may_migrate) {
+            if (gz < P.own_lo && P.has_lo) k = CLS_MIG_LO;
+            else if (gz >= P.own_hi && P.has_hi) k = CLS_MIG_HI;
+            else {
+                if (gz == P.own_lo && P.has_lo) k |= CLS_GHOST_LO;
+                if (gz == P.own_hi - 1 && P.has_hi) k |= CLS_GHOST_HI;
+            }
+            cls[s] = k;
+        }
+        if (k & (CLS_MIG_LO | CLS_MIG_HI)) { key[s] = P.ncell; return; }      // leaves this rank: sorts past the table
+        int3 g = grid_cell(c, P);
+        g.z = clampi(gz, P.own_lo, P.own_hi - 1) - P.zlo;                     // (a row that cannot migrate is kept in range)
+        key[s] = grid_key(g, P);
+        return;
+    }
+    key[s] = grid_key(grid_cell(c, P), P);
+}
+
+// slab mode: keys of the ghost rows (predicted positions received from / kept for the neighbour ranks)
+__global__ void __launch_bounds__(256)
+k_ghost_key(const float4* __restrict__ ghost_pred, uint32_t* __restrict__ key, const uint32_t rows, const DevParams P)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= rows) return;
+    const float4 q = ghost_pred[s];
+    key[s] = grid_key(grid_cell(cell_of(q.x, q.y, q.z, P.r), P), P);
 }
 
 // ---- S2 tables -------------------------------------------------------------
@@ -178,12 +205,20 @@ k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
 // ---- reorder ----------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ perm, const float4* __restrict__ pos, const float4* __restrict__ vel,
-          float4* __restrict__ pos_s, float4* __restrict__ vel_s, float4* __restrict__ pred_s,
-          const DevParams P, const float dt)
+          const float4* __restrict__ ghost_pred, float4* __restrict__ pos_s, float4* __restrict__ vel_s,
+          float4* __restrict__ pred_s, const DevParams P, const float dt)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n) return;
     const uint32_t src = perm[s];
+    if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
+        const float4 q = ghost_pred[src - P.n_a];
+        const int3 c = cell_of(q.x, q.y, q.z, P.r);
+        pred_s[s] = make_float4(q.x, q.y, q.z, __uint2float_rn(hash_cell(c.x, c.y, c.z)));
+        pos_s[s] = make_float4(q.x, q.y, q.z, __uint_as_float(0xFFFFFFFFu));
+        vel_s[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
     const float4 p = pos[src];
     float4 v = vel[src];
     float3 pr;
@@ -252,8 +287,8 @@ __global__ void __launch_bounds__(kThreads)
 k_density(const float4* __restrict__ pred_s, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend,
           float2* __restrict__ dens, uint32_t* __restrict__ ncount, const DevParams P)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
     const float4 pi = pred_s[i];
     float rho = 0.0f, rhon = 0.0f;
     uint32_t cnt = 0;
@@ -279,8 +314,8 @@ k_pressure(const float4* __restrict__ pred_s, const float2* __restrict__ dens, c
            const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_p,
            const DevParams P, const float dt)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
     const float4 pi = pred_s[i];
     const float2 di = dens[i];
     const float pressure = (di.x - P.rho0) * P.k;    // :371
@@ -317,8 +352,8 @@ k_viscosity(const float4* __restrict__ pred_s, const float4* __restrict__ vel_p,
             const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_v,
             const DevParams P, const float dt)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
     const float4 pi = pred_s[i];
     const float4 vi = vel_p[i];
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;
@@ -343,8 +378,8 @@ __global__ void __launch_bounds__(256)
 k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
             float4* __restrict__ vel_out, const DevParams P, const float dt)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
+    const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.row1) return;
     float4 p = pos_s[s];
     float4 v = vel_v[s];
     p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
@@ -362,8 +397,8 @@ k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, 
     SPH_COLLIDE(z, P.half[2])
     #undef SPH_COLLIDE
     v.w = 0.0f;
-    pos_out[s] = p;      // .w still carries the particle id
-    vel_out[s] = v;
+    pos_out[s - P.row0] = p;      // .w still carries the particle id; owned rows compact to [0, row1-row0)
+    vel_out[s - P.row0] = v;
 }
 
 // ---- upload / export --------------------------------------------------------
@@ -462,11 +497,19 @@ inline uint32_t blocks_for(uint32_t n, int threads) { return (n + threads - 1) /
 }  // namespace
 
 // ---- launchers ---------------------------------------------------------------
-void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint32_t* hash_out,
-                        const DevParams& P, float dt, uint64_t* launches)
+void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
+                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint64_t* launches)
 {
-    if (P.n == 0) return;
-    k_predict_key<<<blocks_for(P.n, 256), 256, 0, st>>>(pos, vel, key, hash_out, P, dt);
+    if (rows == 0) return;
+    k_predict_key<<<blocks_for(rows, 256), 256, 0, st>>>(pos, vel, key, cls, rows, may_migrate, P, dt);
+    ++*launches;
+}
+
+void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
+                      uint64_t* launches)
+{
+    if (rows == 0) return;
+    k_ghost_key<<<blocks_for(rows, 256), 256, 0, st>>>(ghost_pred, key, rows, P);
     ++*launches;
 }
 
@@ -485,21 +528,22 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
 }
 
 void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
-                    float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P, float dt, uint64_t* launches)
+                    const float4* ghost_pred, float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P,
+                    float dt, uint64_t* launches)
 {
     if (P.n == 0) return;
-    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, pos, vel, pos_s, vel_s, pred_s, P, dt);
+    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, pos, vel, ghost_pred, pos_s, vel_s, pred_s, P, dt);
     ++*launches;
 }
 
 void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
                     float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches)
 {
-    if (P.n == 0) return;
+    if (P.row1 <= P.row0) return;
     if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_density<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
+        k_density<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
     else
-        k_density<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
+        k_density<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
     ++*launches;
 }
 
@@ -507,11 +551,11 @@ void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, 
                      const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const DevParams& P, float dt,
                      uint64_t* launches)
 {
-    if (P.n == 0) return;
+    if (P.row1 <= P.row0) return;
     if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_pressure<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
+        k_pressure<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
     else
-        k_pressure<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
+        k_pressure<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
     ++*launches;
 }
 
@@ -519,19 +563,19 @@ void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p
                       const uint32_t* tstart, const uint32_t* tend, float4* vel_v, const DevParams& P, float dt,
                       uint64_t* launches)
 {
-    if (P.n == 0) return;
+    if (P.row1 <= P.row0) return;
     if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_viscosity<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
+        k_viscosity<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
     else
-        k_viscosity<SPH_TABLE_GRID><<<blocks_for(P.n, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
+        k_viscosity<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
     ++*launches;
 }
 
 void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
                       const DevParams& P, float dt, uint64_t* launches)
 {
-    if (P.n == 0) return;
-    k_integrate<<<blocks_for(P.n, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    if (P.row1 <= P.row0) return;
+    k_integrate<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
     ++*launches;
 }
 

@@ -1,18 +1,543 @@
-// sph_multi.cu -- slab-decomposed multi-GPU step (placeholder until the single-GPU path is proven).
+// sph_multi.cu -- slab-decomposed multi-GPU step: one context (= one process, one GPU) per z-slab.
+//
+// The reference is single-process; this is the north-star's new capability.  Design:
+//  * The global GRID table geometry (cell = floor(pred/r) inside the box) is identical on all ranks.
+//    Rank k OWNS the particles whose PREDICTED position falls in global z layers [L_k, L_k+1); its
+//    local table spans those layers plus ONE ghost layer per side, so every owned particle finds all
+//    27 cells locally and the neighbour sets equal the single-GPU ones exactly.
+//  * Per step: (1) predict + classify every owned row (stay / migrate lo|hi / also-a-ghost-for lo|hi),
+//    (2) order-preserving pack of migrants (raw state) and ghosts (predicted positions), (3) ONE
+//    exchange round with both neighbours carrying migrants + ghosts (counts first), (4) one sort of
+//    owned + ghost rows; z is the slowest key digit so the sorted array is
+//    [ghost-lo layer | owned rows | ghost-hi layer | departed rows] and every later halo is a
+//    CONTIGUOUS row range, (5) density on owned rows -> halo of densities -> pressure -> halo of v'
+//    -> viscosity -> integrate, which writes the owned rows back compacted.
+//  * Halos 2 and 3 are plain ncclSend/ncclRecv of contiguous ranges of the sorted arrays straight
+//    into the neighbour's ghost rows: both sides hold the same particles in the same order because
+//    the sort is stable and both build the layer from (the owner's resident rows in owner order,
+//    then the rows that migrated in this step in sender order).  The range lengths are cross-checked
+//    every step; a mismatch is an error, never a hang.
+#include <nccl.h>
+
+#include <cstring>
+#include <string>
+
 #include "sph_context.h"
 
-namespace sphb200 {
-int multi_step(SphContext* c, float) { return fail(c, SPH_ERR_UNSUPPORTED, "slab mode not built yet"); }
-void multi_teardown(SphContext*) {}
+using namespace sphb200;
+
+struct SlabState {
+    uint32_t xcap = 0;          // rows per exchange buffer
+    uint32_t gcap = 0;          // rows of the ghost buffer
+    uint8_t* cls = nullptr;     // [cap] classification of owned rows
+    float4* mig_send[2] = {nullptr, nullptr};     // [2*xcap] pos rows then vel rows, lo / hi
+    float4* ghost_send[2] = {nullptr, nullptr};   // [xcap] predicted positions, lo / hi
+    float4* keep[2] = {nullptr, nullptr};         // [xcap] migrants that stay visible as ghosts, lo / hi
+    float4* ghost_pred = nullptr;                 // [gcap] recv_lo | keep_lo | recv_hi | keep_hi
+    uint32_t* block_counts = nullptr;             // [6][nblocks]
+    uint32_t* dev_small = nullptr;                // 64 u32: totals[6], recv counts[4], picks[8], peer counts[4]
+    uint32_t* host_small = nullptr;               // pinned mirror
+    uint32_t nblocks_cap = 0;
+    std::vector<int> layers;                      // nranks + 1 global layer indices
+    uint32_t o0 = 0, o1 = 0;                      // owned rows of the sorted arrays in the last step
+    uint32_t stats[5] = {0, 0, 0, 0, 0};
+    bool have_planes = false;
+};
+
+namespace {
+
+enum { L_MIG_LO = 0, L_GHOST_LO = 1, L_MIG_HI = 2, L_GHOST_HI = 3, L_KEEP_LO = 4, L_KEEP_HI = 5, NLISTS = 6 };
+constexpr int kPackThreads = 256;
+
+#define SPH_NCCL(c, call)                                                                   \
+    do {                                                                                    \
+        ncclResult_t r__ = (call);                                                          \
+        if (r__ != ncclSuccess)                                                             \
+            return fail((c), SPH_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+
+__device__ __forceinline__ bool in_list(uint8_t k, int list, bool keep)
+{
+    switch (list) {
+    case L_MIG_LO: return k & CLS_MIG_LO;
+    case L_MIG_HI: return k & CLS_MIG_HI;
+    case L_GHOST_LO: return k & CLS_GHOST_LO;
+    case L_GHOST_HI: return k & CLS_GHOST_HI;
+    case L_KEEP_LO: return (k & CLS_MIG_LO) && keep;
+    default: return (k & CLS_MIG_HI) && keep;
+    }
 }
 
-using namespace sphb200;
-extern "C" {
-size_t sph_comm_id_bytes(void) { return 128; }
-int sph_comm_get_id(void*, size_t) { return SPH_ERR_UNSUPPORTED; }
-int sph_comm_init(SphContext* c, int, int, const void*, size_t) { return fail(c, SPH_ERR_UNSUPPORTED, "slab mode not built yet"); }
-int sph_comm_set_planes(SphContext* c, const float*) { return fail(c, SPH_ERR_UNSUPPORTED, "slab mode not built yet"); }
-int sph_upload_owned(SphContext* c, uint32_t, const uint32_t*, const float*, const float*) { return fail(c, SPH_ERR_UNSUPPORTED, "slab mode not built yet"); }
-int sph_download_owned(SphContext* c, int, uint32_t*, void*, size_t, uint32_t*) { return fail(c, SPH_ERR_UNSUPPORTED, "slab mode not built yet"); }
-int sph_comm_stats(const SphContext*, uint32_t*) { return SPH_ERR_UNSUPPORTED; }
+// a migrant stays visible as a ghost when it lands in the layer right across the plane
+__device__ __forceinline__ bool lands_adjacent(const float4 p, const float4 v0, const DevParams& P, float dt, float4* pred_out)
+{
+    float4 v = v0;
+    const float gy = P.gravity ? -P.g : 0.0f;
+    v.x = __fadd_rn(v.x, __fmul_rn(0.0f, dt));
+    v.y = __fadd_rn(v.y, __fmul_rn(gy, dt));
+    v.z = __fadd_rn(v.z, __fmul_rn(0.0f, dt));
+    const float look = 1.0f / 120.0f;
+    const float px = __fadd_rn(p.x, __fmul_rn(v.x, look));
+    const float py = __fadd_rn(p.y, __fmul_rn(v.y, look));
+    const float pz = __fadd_rn(p.z, __fmul_rn(v.z, look));
+    *pred_out = make_float4(px, py, pz, 0.0f);
+    int gz = __float2int_rz(floorf(__fdiv_rn(pz, P.r))) - P.gmin[2];
+    gz = gz < 0 ? 0 : (gz > P.gz_global - 1 ? P.gz_global - 1 : gz);
+    return gz == P.own_lo - 1 || gz == P.own_hi;
 }
+
+__global__ void __launch_bounds__(kPackThreads)
+k_slab_count(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
+             uint32_t* __restrict__ block_counts, const uint32_t rows, const uint32_t nblocks, const DevParams P,
+             const float dt)
+{
+    __shared__ uint32_t cnt[NLISTS];
+    if (threadIdx.x < NLISTS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t k = 0;
+    bool keep = false;
+    if (s < rows) {
+        k = cls[s];
+        if (k & (CLS_MIG_LO | CLS_MIG_HI)) { float4 pr; keep = lands_adjacent(pos[s], vel[s], P, dt, &pr); }
+    }
+    #pragma unroll
+    for (int l = 0; l < NLISTS; l++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, in_list(k, l, keep));
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt[l], __popc(b));
+    }
+    __syncthreads();
+    if (threadIdx.x < NLISTS) block_counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// one block per list: exclusive scan of its row of block counts, total to totals[list]
+__global__ void __launch_bounds__(kPackThreads)
+k_slab_scan(uint32_t* __restrict__ block_counts, uint32_t* __restrict__ totals, const uint32_t nblocks)
+{
+    __shared__ uint32_t wsum[kPackThreads / 32];
+    __shared__ uint32_t carry_s;
+    uint32_t* row = block_counts + (size_t)blockIdx.x * nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += kPackThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? row[i] : 0u;
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += wsum[w];
+        const uint32_t carry = carry_s;
+        if (i < nblocks) row[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == kPackThreads - 1) carry_s = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+}
+
+// order-preserving pack: list l, entry rank = (#members in earlier blocks) + (#members before me in this block)
+__global__ void __launch_bounds__(kPackThreads)
+k_slab_pack(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
+            const uint32_t* __restrict__ block_offsets, float4* __restrict__ mig_lo, float4* __restrict__ mig_hi,
+            float4* __restrict__ ghost_lo, float4* __restrict__ ghost_hi, float4* __restrict__ keep_lo,
+            float4* __restrict__ keep_hi, const uint32_t rows, const uint32_t nblocks, const uint32_t xcap,
+            const DevParams P, const float dt)
+{
+    __shared__ uint32_t wcnt[NLISTS][kPackThreads / 32];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t k = 0;
+    bool keep = false;
+    float4 p = make_float4(0, 0, 0, 0), v = p, pr = p;
+    if (s < rows) {
+        k = cls[s];
+        if (k) { p = pos[s]; v = vel[s]; keep = lands_adjacent(p, v, P, dt, &pr); }
+    }
+    uint32_t ball[NLISTS];
+    #pragma unroll
+    for (int l = 0; l < NLISTS; l++) {
+        ball[l] = __ballot_sync(0xffffffffu, in_list(k, l, keep));
+        if (lane == 0) wcnt[l][warp] = __popc(ball[l]);
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int l = 0; l < NLISTS; l++) {
+        if (!in_list(k, l, keep)) continue;
+        uint32_t off = block_offsets[(size_t)l * nblocks + blockIdx.x];
+        for (int w = 0; w < warp; w++) off += wcnt[l][w];
+        off += __popc(ball[l] & ((1u << lane) - 1u));
+        if (off >= xcap) continue;                       // overflow is detected on the host from the totals
+        switch (l) {
+        case L_MIG_LO: mig_lo[off] = p; mig_lo[xcap + off] = v; break;
+        case L_MIG_HI: mig_hi[off] = p; mig_hi[xcap + off] = v; break;
+        case L_GHOST_LO: ghost_lo[off] = pr; break;
+        case L_GHOST_HI: ghost_hi[off] = pr; break;
+        case L_KEEP_LO: keep_lo[off] = pr; break;
+        default: keep_hi[off] = pr; break;
+        }
+    }
+}
+
+__global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __restrict__ out, uint32_t i0, uint32_t i1,
+                            uint32_t i2, uint32_t i3, uint32_t i4)
+{
+    if (threadIdx.x == 0) {
+        out[0] = table[i0]; out[1] = table[i1]; out[2] = table[i2]; out[3] = table[i3]; out[4] = table[i4];
+        // boundary-layer lengths this rank will SEND in the later halos: lo, hi
+        out[5] = table[i1] - table[i0];
+        out[6] = table[i3] - table[i2];
+    }
+}
+
+int ceil_log2_u64(uint64_t v) { int b = 0; while ((1ull << b) < v && b < 63) b++; return b; }
+
+}  // namespace
+
+namespace sphb200 {
+
+void multi_teardown(SphContext* c)
+{
+    if (c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
+    SlabState* s = c->slab;
+    if (!s) return;
+    void* ptrs[] = {s->cls, s->mig_send[0], s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0], s->keep[1],
+                    s->ghost_pred, s->block_counts, s->dev_small};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->host_small) cudaFreeHost(s->host_small);
+    delete s;
+    c->slab = nullptr;
+}
+
+static int slab_params(SphContext* c, DevParams* P, uint32_t n_rows)
+{
+    SlabState* s = c->slab;
+    make_dev_params(c, n_rows, P);
+    const int GZ = c->gdim[2];
+    const int own_lo = s->layers[c->rank], own_hi = s->layers[c->rank + 1];
+    const int has_lo = c->rank > 0, has_hi = c->rank < c->nranks - 1;
+    const int zlo = own_lo - (has_lo ? 1 : 0), zhi = own_hi + (has_hi ? 1 : 0);
+    P->slab = 1; P->zlo = zlo; P->gz_global = GZ; P->own_lo = own_lo; P->own_hi = own_hi;
+    P->has_lo = has_lo; P->has_hi = has_hi;
+    P->gdim[2] = zhi - zlo;
+    P->ncell = (uint32_t)((uint64_t)P->gdim[0] * P->gdim[1] * P->gdim[2]);
+    P->mode = SPH_TABLE_GRID;
+    return SPH_OK;
+}
+
+int multi_step(SphContext* c, float dt)
+{
+    SlabState* s = c->slab;
+    if (!s || !c->comm) return fail(c, SPH_ERR_INVALID, "slab mode: call sph_comm_init first");
+    if (!s->have_planes) return fail(c, SPH_ERR_INVALID, "slab mode: call sph_comm_set_planes first");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    cudaStream_t st = c->st;
+    const uint32_t n_old = c->n;
+    const int lo = c->rank - 1, hi = c->rank + 1;
+    const bool has_lo = c->rank > 0, has_hi = c->rank < c->nranks - 1;
+    DevParams P;
+    slab_params(c, &P, n_old);
+    int rc = ensure_tables(c, P);
+    if (rc != SPH_OK) return rc;
+    const bool timing = c->timing;
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
+
+    // (1) predict + classify + key of the resident rows
+    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, &c->launches);
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+
+    // (2) order-preserving pack of the six lists
+    const uint32_t nblocks = n_old ? (n_old + kPackThreads - 1) / kPackThreads : 1;
+    uint32_t* totals = s->dev_small;            // [6]
+    uint32_t* rcounts = s->dev_small + 8;       // [4] from lo: (mig, ghost), from hi: (mig, ghost)
+    uint32_t* picks = s->dev_small + 16;        // [8]
+    uint32_t* peer = s->dev_small + 24;         // [2] boundary lengths of the neighbours' layers
+    SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
+    if (n_old) {
+        k_slab_count<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, n_old, nblocks, P, dt);
+        k_slab_scan<<<NLISTS, kPackThreads, 0, st>>>(s->block_counts, totals, nblocks);
+        k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->mig_send[0],
+                                                      s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0],
+                                                      s->keep[1], n_old, nblocks, s->xcap, P, dt);
+        c->launches += 3;
+    }
+    // (3a) counts to / from the neighbours
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) { SPH_NCCL(c, ncclSend(totals + 0, 2, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 0, 2, ncclUint32, lo, comm, st)); }
+    if (has_hi) { SPH_NCCL(c, ncclSend(totals + 2, 2, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 2, 2, ncclUint32, hi, comm, st)); }
+    SPH_NCCL(c, ncclGroupEnd());
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(c, cudaStreamSynchronize(st));
+    const uint32_t* T = s->host_small;
+    const uint32_t* R = s->host_small + 8;
+    for (int l = 0; l < NLISTS; l++)
+        if (T[l] > s->xcap) return fail(c, SPH_ERR_CAPACITY, "slab mode: exchange buffer too small (raise capacity)");
+    const uint32_t mig_in_lo = R[0], ghost_in_lo = R[1], mig_in_hi = R[2], ghost_in_hi = R[3];
+    const uint32_t n_a = n_old + mig_in_lo + mig_in_hi;                 // resident + arrived (departed rows still inside)
+    const uint32_t n_ghost = ghost_in_lo + T[L_KEEP_LO] + ghost_in_hi + T[L_KEEP_HI];
+    if ((uint64_t)n_a + n_ghost > c->cap || n_ghost > s->gcap)
+        return fail(c, SPH_ERR_CAPACITY, "slab mode: capacity too small for arrivals + ghosts");
+    // (3b) payloads: migrants land straight behind the resident rows, ghosts in the ghost buffer
+    float4* g_recv_lo = s->ghost_pred;
+    float4* g_keep_lo = g_recv_lo + ghost_in_lo;
+    float4* g_recv_hi = g_keep_lo + T[L_KEEP_LO];
+    float4* g_keep_hi = g_recv_hi + ghost_in_hi;
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) {
+        if (T[L_MIG_LO]) {
+            SPH_NCCL(c, ncclSend(s->mig_send[0], (size_t)T[L_MIG_LO] * 4, ncclFloat, lo, comm, st));
+            SPH_NCCL(c, ncclSend(s->mig_send[0] + s->xcap, (size_t)T[L_MIG_LO] * 4, ncclFloat, lo, comm, st));
+        }
+        if (T[L_GHOST_LO]) SPH_NCCL(c, ncclSend(s->ghost_send[0], (size_t)T[L_GHOST_LO] * 4, ncclFloat, lo, comm, st));
+        if (mig_in_lo) {
+            SPH_NCCL(c, ncclRecv(c->A_pos + n_old, (size_t)mig_in_lo * 4, ncclFloat, lo, comm, st));
+            SPH_NCCL(c, ncclRecv(c->A_vel + n_old, (size_t)mig_in_lo * 4, ncclFloat, lo, comm, st));
+        }
+        if (ghost_in_lo) SPH_NCCL(c, ncclRecv(g_recv_lo, (size_t)ghost_in_lo * 4, ncclFloat, lo, comm, st));
+    }
+    if (has_hi) {
+        if (T[L_MIG_HI]) {
+            SPH_NCCL(c, ncclSend(s->mig_send[1], (size_t)T[L_MIG_HI] * 4, ncclFloat, hi, comm, st));
+            SPH_NCCL(c, ncclSend(s->mig_send[1] + s->xcap, (size_t)T[L_MIG_HI] * 4, ncclFloat, hi, comm, st));
+        }
+        if (T[L_GHOST_HI]) SPH_NCCL(c, ncclSend(s->ghost_send[1], (size_t)T[L_GHOST_HI] * 4, ncclFloat, hi, comm, st));
+        if (mig_in_hi) {
+            SPH_NCCL(c, ncclRecv(c->A_pos + n_old + mig_in_lo, (size_t)mig_in_hi * 4, ncclFloat, hi, comm, st));
+            SPH_NCCL(c, ncclRecv(c->A_vel + n_old + mig_in_lo, (size_t)mig_in_hi * 4, ncclFloat, hi, comm, st));
+        }
+        if (ghost_in_hi) SPH_NCCL(c, ncclRecv(g_recv_hi, (size_t)ghost_in_hi * 4, ncclFloat, hi, comm, st));
+    }
+    SPH_NCCL(c, ncclGroupEnd());
+    if (T[L_KEEP_LO]) SPH_CUDA(c, cudaMemcpyAsync(g_keep_lo, s->keep[0], (size_t)T[L_KEEP_LO] * 16, cudaMemcpyDeviceToDevice, st));
+    if (T[L_KEEP_HI]) SPH_CUDA(c, cudaMemcpyAsync(g_keep_hi, s->keep[1], (size_t)T[L_KEEP_HI] * 16, cudaMemcpyDeviceToDevice, st));
+
+    // (4) keys of the arrivals (they may not migrate again this step) and of the ghosts; one sort of everything
+    const uint32_t n_all = n_a + n_ghost;
+    slab_params(c, &P, n_all);
+    P.n_a = n_a;
+    launch_predict_key(st, c->A_pos + n_old, c->A_vel + n_old, c->key_a + n_old, nullptr, n_a - n_old, false, P, dt, &c->launches);
+    launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, &c->launches);
+    const int bits = ceil_log2_u64((uint64_t)P.ncell + 1);
+    c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, n_all, bits, c->counts, &c->launches);
+    const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
+    const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
+    // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
+    DevParams PT = P;
+    PT.ncell = P.ncell + 1;
+    launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
+    launch_reorder(st, perm, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    // owned rows and boundary layers of the sorted arrays
+    const uint32_t plane = (uint32_t)P.gdim[0] * (uint32_t)P.gdim[1];
+    const uint32_t l_own_lo = (uint32_t)(P.own_lo - P.zlo), l_own_hi = (uint32_t)(P.own_hi - P.zlo);
+    k_slab_pick<<<1, 32, 0, st>>>(c->tstart, picks, l_own_lo * plane, (l_own_lo + 1) * plane, (l_own_hi - 1) * plane,
+                                  l_own_hi * plane, P.ncell);
+    ++c->launches;
+    // cross-check: the neighbour's boundary layer must be exactly as long as my ghost layer
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) { SPH_NCCL(c, ncclSend(picks + 5, 1, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(peer + 0, 1, ncclUint32, lo, comm, st)); }
+    if (has_hi) { SPH_NCCL(c, ncclSend(picks + 6, 1, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(peer + 1, 1, ncclUint32, hi, comm, st)); }
+    SPH_NCCL(c, ncclGroupEnd());
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(c, cudaStreamSynchronize(st));
+    const uint32_t* K = s->host_small + 16;
+    const uint32_t o0 = K[0], b_lo_end = K[1], b_hi_begin = K[2], o1 = K[3], live_end = K[4];
+    const uint32_t peer_lo = s->host_small[24], peer_hi = s->host_small[25];
+    if ((has_lo && peer_lo != o0) || (has_hi && peer_hi != live_end - o1))
+        return fail(c, SPH_ERR_INVALID, "slab mode: ghost layer and neighbour boundary layer disagree (" +
+                                            std::to_string(o0) + " vs " + std::to_string(peer_lo) + ", " +
+                                            std::to_string(live_end - o1) + " vs " + std::to_string(peer_hi) + ")");
+    s->o0 = o0; s->o1 = o1;
+    P.row0 = o0; P.row1 = o1;
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
+
+    // (5) density on owned rows, halo of densities
+    launch_density(st, c->pred, c->tstart, c->tend, c->dens, c->nc_tap ? c->ncount : nullptr, P, &c->launches);
+    c->ncount_valid = c->nc_tap;
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) {
+        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 2, ncclFloat, lo, comm, st));
+        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 2, ncclFloat, lo, comm, st));
+    }
+    if (has_hi) {
+        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 2, ncclFloat, hi, comm, st));
+        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 2, ncclFloat, hi, comm, st));
+    }
+    SPH_NCCL(c, ncclGroupEnd());
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
+
+    // pressure, halo of post-pressure velocities
+    launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, P, dt, &c->launches);
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) {
+        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->velp + o0, (size_t)(b_lo_end - o0) * 4, ncclFloat, lo, comm, st));
+        if (o0) SPH_NCCL(c, ncclRecv(c->velp, (size_t)o0 * 4, ncclFloat, lo, comm, st));
+    }
+    if (has_hi) {
+        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->velp + b_hi_begin, (size_t)(o1 - b_hi_begin) * 4, ncclFloat, hi, comm, st));
+        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->velp + o1, (size_t)(live_end - o1) * 4, ncclFloat, hi, comm, st));
+    }
+    SPH_NCCL(c, ncclGroupEnd());
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
+
+    launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, P, dt, &c->launches);
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
+    launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
+    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[6], st));
+    c->ev_recorded = timing;
+    SPH_CUDA(c, cudaGetLastError());
+    c->n = o1 - o0;
+    c->step_valid = true;
+    s->stats[0] = c->n; s->stats[1] = o0; s->stats[2] = live_end - o1; s->stats[3] = T[L_MIG_LO]; s->stats[4] = T[L_MIG_HI];
+    return SPH_OK;
+}
+
+}  // namespace sphb200
+
+extern "C" {
+
+size_t sph_comm_id_bytes(void) { return sizeof(ncclUniqueId); }
+
+int sph_comm_get_id(void* id_out, size_t id_bytes)
+{
+    if (!id_out || id_bytes < sizeof(ncclUniqueId)) return SPH_ERR_INVALID;
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, SPH_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+    memcpy(id_out, &id, sizeof(id));
+    return SPH_OK;
+}
+
+int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id_bytes)
+{
+    if (!c || !id || id_bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks) return SPH_ERR_INVALID;
+    if (c->comm) return fail(c, SPH_ERR_INVALID, "sph_comm_init: already initialised");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm;
+    SPH_NCCL(c, ncclCommInitRank(&comm, nranks, uid, rank));
+    c->comm = (ncclComm*)comm;
+    c->rank = rank; c->nranks = nranks; c->mode = SPH_TABLE_GRID;
+    SlabState* s = new SlabState();
+    c->slab = s;
+    s->xcap = c->cap / 8 > 65536 ? c->cap / 8 : (c->cap < 65536 ? c->cap : 65536);
+    s->gcap = 4 * s->xcap;
+    s->nblocks_cap = (c->cap + kPackThreads - 1) / kPackThreads;
+    SPH_CUDA(c, cudaMalloc(&s->cls, c->cap));
+    for (int d = 0; d < 2; d++) {
+        SPH_CUDA(c, cudaMalloc(&s->mig_send[d], (size_t)s->xcap * 32));
+        SPH_CUDA(c, cudaMalloc(&s->ghost_send[d], (size_t)s->xcap * 16));
+        SPH_CUDA(c, cudaMalloc(&s->keep[d], (size_t)s->xcap * 16));
+    }
+    SPH_CUDA(c, cudaMalloc(&s->ghost_pred, (size_t)s->gcap * 16));
+    SPH_CUDA(c, cudaMalloc(&s->block_counts, (size_t)NLISTS * s->nblocks_cap * 4));
+    SPH_CUDA(c, cudaMalloc(&s->dev_small, 64 * sizeof(uint32_t)));
+    SPH_CUDA(c, cudaMallocHost(&s->host_small, 64 * sizeof(uint32_t)));
+    return SPH_OK;
+}
+
+int sph_comm_set_planes(SphContext* c, const float* planes)
+{
+    if (!c || !planes) return SPH_ERR_INVALID;
+    SlabState* s = c->slab;
+    if (!s) return fail(c, SPH_ERR_INVALID, "sph_comm_set_planes: call sph_comm_init first");
+    const int GZ = c->gdim[2];
+    std::vector<int> L(c->nranks + 1);
+    for (int k = 0; k <= c->nranks; k++) {
+        int l = (int)floorf(planes[k] / c->params.interaction_radius) - c->gmin[2];
+        L[k] = l < 0 ? 0 : (l > GZ ? GZ : l);
+    }
+    L[0] = 0; L[c->nranks] = GZ;
+    for (int k = 0; k < c->nranks; k++)
+        if (L[k + 1] - L[k] < 2) return fail(c, SPH_ERR_INVALID, "sph_comm_set_planes: every slab needs at least two cell layers");
+    s->layers = L;
+    s->have_planes = true;
+    c->planes.assign(planes, planes + c->nranks + 1);
+    return SPH_OK;
+}
+
+int sph_upload_owned(SphContext* c, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (n > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_upload_owned: n exceeds capacity");
+    if (n && (!pos3 || !global_id)) return fail(c, SPH_ERR_INVALID, "sph_upload_owned: NULL input");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    float* dpos = (float*)c->stage;
+    float* dvel = (float*)(c->stage + (size_t)c->cap * 12);
+    uint32_t* dids = (uint32_t*)(c->stage + (size_t)c->cap * 24);
+    if (n) {
+        SPH_CUDA(c, cudaMemcpyAsync(dpos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st));
+        if (vel3) SPH_CUDA(c, cudaMemcpyAsync(dvel, vel3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st));
+        SPH_CUDA(c, cudaMemcpyAsync(dids, global_id, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+        launch_pack_state(c->st, dpos, vel3 ? dvel : nullptr, dids, c->A_pos, c->A_vel, n, &c->launches);
+        SPH_CUDA(c, cudaGetLastError());
+    }
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    c->n = n;
+    c->step_valid = false;
+    c->ncount_valid = false;
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; }
+    return SPH_OK;
+}
+
+int sph_download_owned(SphContext* c, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n)
+{
+    if (!c) return SPH_ERR_INVALID;
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n = c->n;
+    if (out_n) *out_n = n;
+    if (!n) return SPH_OK;
+    size_t per = 0;
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED: case SPH_FIELD_VEL_AFTER_PRESSURE:
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: per = 12; break;
+    case SPH_FIELD_OUT_POSITIONS: case SPH_FIELD_COLORS: per = 16; break;
+    case SPH_FIELD_DENSITIES: per = 8; break;
+    case SPH_FIELD_HASH: case SPH_FIELD_KEY: case SPH_FIELD_NEIGHBOUR_COUNT: case SPH_FIELD_SPEED_NORMALIZED: per = 4; break;
+    default: return fail(c, SPH_ERR_INVALID, "unknown field");
+    }
+    if (host && host_bytes < per * n) return fail(c, SPH_ERR_INVALID, "sph_download_owned: host buffer too small");
+    if (global_id) {
+        launch_export_ids(c->st, c->A_pos, (uint32_t*)c->stage, n, &c->launches);
+        SPH_CUDA(c, cudaMemcpyAsync(global_id, c->stage, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+        SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    }
+    if (host) {
+        // per-step arrays live at sorted rows [o0, o1); the state arrays were compacted to [0, n)
+        const uint32_t off = c->slab ? c->slab->o0 : 0;
+        const void* src = nullptr;
+        bool needs_step = true;
+        switch (field) {
+        case SPH_FIELD_POSITIONS: case SPH_FIELD_OUT_POSITIONS: src = c->A_pos; needs_step = false; break;
+        case SPH_FIELD_VELOCITIES: case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: src = c->A_vel; needs_step = false; break;
+        case SPH_FIELD_DENSITIES: src = c->dens + off; break;
+        case SPH_FIELD_PREDICTED: case SPH_FIELD_HASH: case SPH_FIELD_KEY: src = c->pred + off; break;
+        case SPH_FIELD_VEL_AFTER_PRESSURE: src = c->velp + off; break;
+        case SPH_FIELD_VEL_AFTER_VISCOSITY: src = c->S_vel + off; break;
+        case SPH_FIELD_NEIGHBOUR_COUNT:
+            if (!c->ncount_valid) return fail(c, SPH_ERR_INVALID, "neighbour counts not recorded");
+            src = c->ncount + off; break;
+        }
+        if (needs_step && !c->step_valid) return fail(c, SPH_ERR_INVALID, "field needs a step first");
+        DevParams P;
+        make_dev_params(c, n, &P);
+        launch_export(c->st, field, c->A_pos, src, nullptr, c->stage, n, P, false, &c->launches);
+        SPH_CUDA(c, cudaGetLastError());
+        SPH_CUDA(c, cudaMemcpyAsync(host, c->stage, per * n, cudaMemcpyDeviceToHost, c->st));
+        SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    }
+    return SPH_OK;
+}
+
+int sph_comm_stats(const SphContext* c, uint32_t* out5)
+{
+    if (!c || !out5 || !c->slab) return SPH_ERR_INVALID;
+    for (int i = 0; i < 5; i++) out5[i] = c->slab->stats[i];
+    return SPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+"""Host-side driver of the slab-decomposed multi-GPU step (one process per GPU, torch.distributed for
+the rendezvous only; every data-path byte moves inside libsph_b200.so over NCCL).
+
+  planes / layers : the box is cut along z at CELL-LAYER granularity; rank k owns the particles whose
+                    predicted position lies in global grid layers [L_k, L_k+1)
+  SlabSimulation  : per-rank wrapper -- comm init (ncclUniqueId broadcast through torch.distributed),
+                    upload of the rank's particles with their global ids, step, gather for parity
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+def layer_of(z, r, gmin_z, gz):
+    """Global z layer of a coordinate, with the device's arithmetic: floor(float32(z) / float32(r))."""
+    q = np.floor(np.asarray(z, np.float32) / np.float32(r)).astype(np.int64) - int(gmin_z)
+    return np.clip(q, 0, int(gz) - 1)
+
+
+def choose_layers(z_sample, nranks, r, gmin_z, gz):
+    """Cut layers [0, gz) into nranks contiguous groups with ~equal particle counts (>= 2 layers each)."""
+    lay = layer_of(z_sample, r, gmin_z, gz)
+    hist = np.bincount(lay, minlength=int(gz)).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    total = cum[-1]
+    L = [0]
+    for k in range(1, nranks):
+        target = total * k / nranks
+        cut = int(np.searchsorted(cum, target, side="left"))
+        if cut > 0 and abs(cum[cut - 1] - target) <= abs(cum[min(cut, gz)] - target):
+            cut -= 1
+        cut = max(cut, L[-1] + 2)
+        cut = min(cut, int(gz) - 2 * (nranks - k))
+        L.append(cut)
+    L.append(int(gz))
+    for k in range(nranks):
+        if L[k + 1] - L[k] < 2:
+            raise ValueError("cannot give every rank two cell layers: %r" % (L,))
+    return L
+
+
+def planes_from_layers(L, r, gmin_z):
+    """z value inside the first layer of each slab: the library floors it back to the same layer."""
+    return np.array([(l + gmin_z + 0.5) * r for l in L], dtype=np.float32)
+
+
+def owner_of(z, L, r, gmin_z, gz):
+    lay = layer_of(z, r, gmin_z, gz)
+    return np.searchsorted(np.asarray(L[1:-1]), lay, side="right")
+
+
+class SlabSimulation:
+    """One rank of the slab-decomposed solver."""
+
+    def __init__(self, pkg, capacity, rank, nranks, device, id_bytes, **params):
+        self.pkg, self.rank, self.nranks = pkg, rank, nranks
+        self.sim = pkg.FluidSimulation(capacity, device=device, table_mode=pkg.TABLE_GRID, **params)
+        L = self.sim.L
+        buf = (C.c_ubyte * len(id_bytes)).from_buffer_copy(id_bytes)
+        self.sim._check(L.sph_comm_init(self.sim.h, rank, nranks, buf, len(id_bytes)))
+        self.dims, self.origin = self.sim.grid()
+        self.r = float(self.sim.get_params().interaction_radius)
+
+    @staticmethod
+    def make_id(pkg):
+        L = pkg.load_library()
+        nb = int(L.sph_comm_id_bytes())
+        buf = (C.c_ubyte * nb)()
+        rc = L.sph_comm_get_id(buf, nb)
+        if rc != 0:
+            raise pkg.SphError("sph_comm_get_id failed: %d" % rc)
+        return bytes(buf)
+
+    def set_layers(self, layers):
+        self.layers = list(layers)
+        planes = planes_from_layers(self.layers, self.r, int(self.origin[2]))
+        self.sim._check(self.sim.L.sph_comm_set_planes(self.sim.h, C.c_void_p(planes.ctypes.data)))
+
+    def upload_owned(self, ids, pos, vel=None):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        vp = None
+        if vel is not None:
+            vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
+            vp = C.c_void_p(vel.ctypes.data)
+        self.sim._check(self.sim.L.sph_upload_owned(self.sim.h, ids.size, C.c_void_p(ids.ctypes.data),
+                                                    C.c_void_p(pos.ctypes.data), vp))
+
+    def step(self, dt):
+        self.sim.step(dt)
+
+    def download_owned(self, field):
+        fid = self.pkg.FIELDS[field]
+        comps, dt = self.pkg._FIELD_SHAPE[fid]
+        n = self.sim.n
+        ids = np.empty(n, np.uint32)
+        out = np.empty((n, comps) if comps else (n,), dt)
+        cnt = C.c_uint32(0)
+        self.sim._check(self.sim.L.sph_download_owned(self.sim.h, fid, C.c_void_p(ids.ctypes.data),
+                                                      C.c_void_p(out.ctypes.data), out.nbytes, C.byref(cnt)))
+        assert cnt.value == n
+        return ids, out
+
+    def stats(self):
+        out = np.zeros(5, np.uint32)
+        self.sim._check(self.sim.L.sph_comm_stats(self.sim.h, C.c_void_p(out.ctypes.data)))
+        return dict(owned=int(out[0]), ghosts_lo=int(out[1]), ghosts_hi=int(out[2]), migrated_lo=int(out[3]),
+                    migrated_hi=int(out[4]))
+
+    def close(self):
+        self.sim.close()
+
+
+def broadcast_id(pkg, dist, torch, rank, device):
+    """ncclUniqueId from rank 0 to everyone through torch.distributed (rendezvous plumbing only)."""
+    nb = int(pkg.load_library().sph_comm_id_bytes())
+    if dist.get_backend() == "nccl":
+        t = torch.zeros(nb, dtype=torch.uint8, device="cuda:%d" % device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(SlabSimulation.make_id(pkg)), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+    obj = [SlabSimulation.make_id(pkg) if rank == 0 else None]
+    dist.broadcast_object_list(obj, 0)
+    return obj[0]
+
+
+def lattice_ids_for_rank(nx, ny, nz, iz_lo, iz_hi):
+    """Global ids of the lattice sites with iz in [iz_lo, iz_hi): id = (iy*nx + ix)*nz + iz."""
+    iz = np.arange(max(iz_lo, 0), min(iz_hi, nz), dtype=np.uint64)
+    base = (np.arange(nx * ny, dtype=np.uint64) * np.uint64(nz))[:, None]
+    return (base + iz[None, :]).reshape(-1)
+
+
+def generate_rank_particles(scenes, name, layers, rank, r, gmin_z, gz):
+    """This rank's share of a lattice config without materialising the whole set: generate the z range of
+    sites that can fall into the rank's layers (+1 site of slack for the jitter), keep the exact ones."""
+    nx, ny, nz, seed = scenes.CONFIGS[name]
+    bound = (3 * nx * scenes.GAP0, 1.5 * ny * scenes.GAP0, nz * scenes.GAP0 + scenes.GAP0)
+    z0 = -bound[2] / 2 + scenes.GAP0 / 2
+    zlo = (layers[rank] + gmin_z) * r
+    zhi = (layers[rank + 1] + gmin_z) * r
+    iz_lo = int(np.floor((zlo - z0) / scenes.GAP0)) - 1
+    iz_hi = int(np.ceil((zhi - z0) / scenes.GAP0)) + 2
+    ids = lattice_ids_for_rank(nx, ny, nz, iz_lo, iz_hi)
+    pos, vel, _ = scenes.dam_break(nx, ny, nz, seed, ids=ids)
+    own = owner_of(pos[:, 2], layers, r, gmin_z, gz) == rank
+    return ids[own].astype(np.uint32), pos[own], vel[own], bound
+
+
+def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler):
+    name = args.config or "C4_dambreak_64M"
+    nx, ny, nz, seed = scenes.CONFIGS[name]
+    n_total = nx * ny * nz
+    bound = (3 * nx * scenes.GAP0, 1.5 * ny * scenes.GAP0, nz * scenes.GAP0 + scenes.GAP0)
+    params = dict(gravity=1, viscosity_strength=0.5, bound=bound)
+    cap = int(n_total / world * 1.25) + (1 << 20)
+    idb = broadcast_id(pkg, dist, torch, rank, dev)
+    slab = SlabSimulation(pkg, cap, rank, world, dev, idb, **params)
+    gmin_z, gz = int(slab.origin[2]), int(slab.dims[2])
+    # lattice: equal z extents hold equal counts; sample one (x,y) column to place the cuts
+    col = np.arange(nz, dtype=np.uint64)
+    zs, _, _ = scenes.dam_break(nx, ny, nz, seed, ids=col)
+    layers = choose_layers(zs[:, 2], world, slab.r, gmin_z, gz)
+    slab.set_layers(layers)
+    ids, pos, vel, _ = generate_rank_particles(scenes, name, layers, rank, slab.r, gmin_z, gz)
+    slab.upload_owned(ids, pos, vel)
+    del pos, vel, ids
+    dt = scenes.DT
+    stream = torch.cuda.ExternalStream(slab.sim.stream_ptr(), device=dev)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)
+    for _ in range(args.warmup):
+        slab.step(dt)
+    slab.sim.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = ClockSampler(dev)
+    clocks.start()
+    l0 = slab.sim.launch_count()
+    stage = np.zeros(6)
+    total_ms = 0.0
+    for _ in range(args.steps):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+        slab.sim.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        slab.step(dt)
+        b.record(stream)
+        slab.sim.synchronize()
+        stage += slab.sim.timings()
+        total_ms += a.elapsed_time(b)
+    launches = slab.sim.launch_count() - l0
+    clk = clocks.stop()
+    # max over ranks of the device time of the timed region
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda:%d" % dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    st = torch.tensor(stage / args.steps, dtype=torch.float64, device="cuda:%d" % dev)
+    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    stage = st.cpu().numpy()
+    owned = torch.tensor([slab.sim.n], dtype=torch.int64, device="cuda:%d" % dev)
+    dist.all_reduce(owned)
+    lt = torch.tensor([launches], dtype=torch.int64, device="cuda:%d" % dev)
+    dist.all_reduce(lt)
+    value = n_total * args.steps / (total_ms * 1e-3) / 1e6
+
+    # end to end: every step each rank re-uploads its owned state from pinned host memory and reads its
+    # OutPositions back (ids included), through the slab ABI
+    ids_h, pos_h = slab.download_owned("positions")
+    _, vel_h = slab.download_owned("velocities")
+    n_own = ids_h.size
+    tp = torch.from_numpy(pos_h).pin_memory(); tv = torch.from_numpy(vel_h).pin_memory(); ti = torch.from_numpy(ids_h.astype(np.int32)).pin_memory()
+    out_h = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+    L = slab.sim.L
+    e2e_steps = max(2, min(args.steps, 5))
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        slab.sim._check(L.sph_upload_owned(slab.sim.h, n_own, C.c_void_p(ti.data_ptr()), C.c_void_p(tp.data_ptr()), C.c_void_p(tv.data_ptr())))
+        slab.step(dt)
+        cnt = C.c_uint32(0)
+        slab.sim._check(L.sph_download_owned(slab.sim.h, pkg.FIELDS["out_positions"], None, C.c_void_p(out_h.data_ptr()),
+                                             cap * 16, C.byref(cnt)))
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda:%d" % dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = n_total * e2e_steps / e2e_s / 1e6
+    stats = slab.stats()
+    slab.close()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    gather = {"density": stage[2], "pressure": stage[3], "viscosity": stage[4]}
+    dom = max(gather, key=gather.get)
+    achieved = A_BYTES[dom] * (n_total / world) / (gather[dom] * 1e-3) / 1e9
+    names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
+    return {
+        "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d particles, slab-decomposed along z over %d ranks (layers %s), ghost halo x3 + "
+                               "migration per step over NCCL" % (name, n_total, world, layers),
+                   "particles": n_total, "table": "grid", "owned_total_after": int(owned.item()),
+                   "l2": "flushed between timed steps" if flush is not None else "not flushed",
+                   "rank0_last_step": stats},
+        "stage_ms": {k: float(v) for k, v in zip(names, stage)},
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per": "rank (max over ranks)",
+                     "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(gather[dom]),
+                     "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9 / world,
+                              "frac": A_BYTES["step"] * value * 1e6 / 1e9 / world / peak}},
+        "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": int(n_total) * 28, "d2h_bytes_per_step": int(n_total) * 16,
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                "path": "per rank: sph_upload_owned(pinned ids+pos3+vel3) -> sph_step -> sph_download_owned(OUT_POSITIONS, pinned)"},
+        "gpu_launches": int(lt.item()),
+        "clocks": clk,
+    }
