@@ -54,6 +54,29 @@ class SphError(RuntimeError):
 _lib = None
 
 
+def _preload_torch_nccl():
+    """PyTorch bundles its own libnccl.so.2; a process must hold exactly one NCCL, and libsph_b200.so
+    adopts whichever is already loaded, so make sure it is the one torch will want."""
+    import importlib.util
+    import sys
+    if "torch" in sys.modules:
+        return
+    for mod in ("nvidia.nccl",):
+        try:
+            spec = importlib.util.find_spec(mod)
+        except (ImportError, ValueError):
+            spec = None
+        if spec and spec.submodule_search_locations:
+            for d in spec.submodule_search_locations:
+                path = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(path):
+                    try:
+                        C.CDLL(path, mode=C.RTLD_GLOBAL)
+                    except OSError:
+                        pass
+                    return
+
+
 def load_library():
     """Load libsph_b200.so; raises loudly if it has not been built (no fallback of any kind)."""
     global _lib
@@ -62,6 +85,7 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise SphError("libsph_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(make -C fluid-simulation-3d_b200). There is no CPU fallback.")
+    _preload_torch_nccl()
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
     L.sph_create.argtypes = [C.POINTER(vp), C.c_int, u32]

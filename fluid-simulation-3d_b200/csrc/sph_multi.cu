@@ -18,13 +18,65 @@
 //    then the rows that migrated in this step in sender order).  The range lengths are cross-checked
 //    every step; a mismatch is an error, never a hang.
 #include <nccl.h>
+#include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "sph_context.h"
 
 using namespace sphb200;
+
+// NCCL is bound at run time, not link time: a host process that already carries an NCCL (PyTorch
+// bundles its own libnccl.so.2) must keep exactly one copy, so we adopt the loaded one if there is
+// one, else $SPH_NCCL_LIB, else the system libnccl.so.2.  Only the long-stable point-to-point API is used.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void load_nccl()
+{
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) { const char* p = getenv("SPH_NCCL_LIB"); if (p && *p) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_nccl.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+#define SPH_SYM(field, name)                                                                  \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));                  \
+    if (!g_nccl.field) { g_nccl.error = std::string("libnccl.so.2 lacks ") + name; return; }
+    SPH_SYM(GetUniqueId, "ncclGetUniqueId") SPH_SYM(CommInitRank, "ncclCommInitRank") SPH_SYM(CommDestroy, "ncclCommDestroy")
+    SPH_SYM(Send, "ncclSend") SPH_SYM(Recv, "ncclRecv") SPH_SYM(GroupStart, "ncclGroupStart") SPH_SYM(GroupEnd, "ncclGroupEnd")
+    SPH_SYM(GetErrorString, "ncclGetErrorString")
+#undef SPH_SYM
+    g_nccl.ok = true;
+}
+const NcclApi& nccl()
+{
+    std::call_once(g_nccl_once, load_nccl);
+    return g_nccl;
+}
+}  // namespace
+#define ncclGetUniqueId nccl().GetUniqueId
+#define ncclCommInitRank nccl().CommInitRank
+#define ncclCommDestroy nccl().CommDestroy
+#define ncclSend nccl().Send
+#define ncclRecv nccl().Recv
+#define ncclGroupStart nccl().GroupStart
+#define ncclGroupEnd nccl().GroupEnd
+#define ncclGetErrorString nccl().GetErrorString
 
 struct SlabState {
     uint32_t xcap = 0;          // rows per exchange buffer
@@ -404,6 +456,7 @@ size_t sph_comm_id_bytes(void) { return sizeof(ncclUniqueId); }
 int sph_comm_get_id(void* id_out, size_t id_bytes)
 {
     if (!id_out || id_bytes < sizeof(ncclUniqueId)) return SPH_ERR_INVALID;
+    if (!nccl().ok) return fail(nullptr, SPH_ERR_NCCL, nccl().error);
     ncclUniqueId id;
     ncclResult_t r = ncclGetUniqueId(&id);
     if (r != ncclSuccess) return fail(nullptr, SPH_ERR_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
@@ -415,6 +468,7 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
 {
     if (!c || !id || id_bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks) return SPH_ERR_INVALID;
     if (c->comm) return fail(c, SPH_ERR_INVALID, "sph_comm_init: already initialised");
+    if (!nccl().ok) return fail(c, SPH_ERR_NCCL, nccl().error);
     SPH_CUDA(c, cudaSetDevice(c->device));
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
