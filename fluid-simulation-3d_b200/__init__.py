@@ -31,7 +31,7 @@ TABLES = dict(sorted_index=0, sorted_key=1, start_indices=2, sorted_hash=3)
 ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
-    "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_spawn_grid", "sph_upload_state",
+    "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
@@ -100,6 +100,7 @@ def load_library():
     L.sph_get_table_mode.argtypes = [vp]
     L.sph_set_stage_timing.argtypes = [vp, C.c_int]
     L.sph_set_neighbour_count_tap.argtypes = [vp, C.c_int]
+    L.sph_set_neighbour_list_capacity.argtypes = [vp, u32]
     L.sph_spawn_grid.argtypes = [vp, u32]
     L.sph_upload_state.argtypes = [vp, u32, vp, vp]
     L.sph_num_particles.argtypes = [vp]
@@ -211,6 +212,9 @@ class FluidSimulation:
 
     def set_neighbour_count_tap(self, on):
         self._check(self.L.sph_set_neighbour_count_tap(self.h, int(on)))
+
+    def set_neighbour_list_capacity(self, k):
+        self._check(self.L.sph_set_neighbour_list_capacity(self.h, int(k)))
 
     # -- state
     @property

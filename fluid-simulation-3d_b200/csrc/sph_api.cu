@@ -55,6 +55,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->s3 = 45 / (powf(r, 6) * kPi);
     P->sv = 315 / (64 * kPi * powf(fabsf(r), 9));
     P->rr = r * r;
+    P->cull_hi = nextafterf((float)((double)p.sqr_radius * (1.0 + 5e-7)), INFINITY);
     for (int a = 0; a < 3; a++) { P->gmin[a] = c->gmin[a]; P->gdim[a] = c->gdim[a]; }
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
@@ -111,12 +112,29 @@ int ensure_tables(SphContext* c, const DevParams& P)
     return SPH_OK;
 }
 
+int ensure_list(SphContext* c, NbrList* L)
+{
+    if (c->list_k && c->list_k_alloc < c->list_k) {
+        SPH_CUDA(c, cudaStreamSynchronize(c->st));
+        if (c->nlist) cudaFree(c->nlist);
+        c->nlist = nullptr; c->list_k_alloc = 0;
+        cudaError_t e = cudaMalloc(&c->nlist, (size_t)c->list_k * c->cap * sizeof(uint32_t));
+        if (e != cudaSuccess) { cudaGetLastError(); c->list_k = 0; }        // no room: fall back to walking every pass
+        else c->list_k_alloc = c->list_k;
+    }
+    L->idx = c->list_k ? c->nlist : nullptr;
+    L->cnt = c->ncount;
+    L->k = c->list_k;
+    L->stride = c->cap;
+    return SPH_OK;
+}
+
 }  // namespace sphb200
 
 static void free_all(SphContext* c)
 {
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
-                    c->perm_a, c->perm_b, c->ncount, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+                    c->perm_a, c->perm_b, c->ncount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
@@ -175,7 +193,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     ALLOC(c->A_pos, cap * 16); ALLOC(c->A_vel, cap * 16);
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
     ALLOC(c->pred, cap * 16);  ALLOC(c->velp, cap * 16);
-    ALLOC(c->dens, cap * 8);
+    ALLOC(c->dens, cap * 16);
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
     ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
     ALLOC(c->ncount, cap * 4);
@@ -233,6 +251,13 @@ int sph_set_table_mode(SphContext* c, int mode)
 int sph_get_table_mode(const SphContext* c) { return c ? c->mode : -1; }
 int sph_set_stage_timing(SphContext* c, int enabled) { if (!c) return SPH_ERR_INVALID; c->timing = enabled != 0; return SPH_OK; }
 int sph_set_neighbour_count_tap(SphContext* c, int enabled) { if (!c) return SPH_ERR_INVALID; c->nc_tap = enabled != 0; return SPH_OK; }
+int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (entries > 4096) return fail(c, SPH_ERR_INVALID, "neighbour list capacity above 4096 entries per particle");
+    c->list_k = entries;
+    return SPH_OK;
+}
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
 void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
@@ -288,14 +313,17 @@ static int run_step(SphContext* c, float dt, bool advance)
     launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
     launch_reorder(st, perm, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
-    launch_density(st, c->pred, c->tstart, c->tend, c->dens, c->nc_tap ? c->ncount : nullptr, P, &c->launches);
-    c->ncount_valid = c->nc_tap;
+    NbrList L;
+    rc = ensure_list(c, &L);
+    if (rc != SPH_OK) return rc;
+    launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (advance) {
-        launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, P, dt, &c->launches);
+        launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
         if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
         // v'' goes into S_vel: dead after the pressure pass read it, and never read by the viscosity pass
-        launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, P, dt, &c->launches);
+        launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, L, P, dt, &c->launches);
         if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
         launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
         if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[6], st));

@@ -20,9 +20,12 @@ struct SphContext {
     float4 *A_pos = nullptr, *A_vel = nullptr;
     // per-step arrays, sorted order of the step
     float4 *S_pos = nullptr, *S_vel = nullptr, *pred = nullptr, *velp = nullptr;
-    float2* dens = nullptr;
+    float4* dens = nullptr;      // (rho, near rho, 1/rho, 1/near rho)
     uint32_t *key_a = nullptr, *key_b = nullptr, *perm_a = nullptr, *perm_b = nullptr;
-    uint32_t* ncount = nullptr;
+    uint32_t* ncount = nullptr;  // neighbour count incl. self of every row (density pass); also the list lengths
+    uint32_t* nlist = nullptr;   // neighbour list, k-major: entry k of row i at nlist[k * cap + i]
+    uint32_t list_k = 64;        // entries per row (0: lists off)
+    uint32_t list_k_alloc = 0;
     uint32_t *tstart = nullptr, *tend = nullptr;
     size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
     uint32_t* gap_list = nullptr;
@@ -66,6 +69,7 @@ int cuda_fail(SphContext* c, cudaError_t e, const char* what);
 int make_dev_params(SphContext* c, uint32_t n, DevParams* P);
 int ensure_tables(SphContext* c, const DevParams& P);
 int export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n);
+int ensure_list(SphContext* c, NbrList* L);
 
 // sph_multi.cu
 int multi_step(SphContext* c, float dt);

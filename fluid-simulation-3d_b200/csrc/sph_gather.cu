@@ -1,0 +1,305 @@
+// sph_gather.cu -- the three neighbour-gather passes for the GRID table, second generation.
+//
+//   density   S3  physicsWorld.cc:304-311, 325-365      pressure  S4  :367-422
+//   viscosity S5  :424-464 (snapshot semantics)          kernels   engine/physics/kernels.h:25-82
+//
+// ncu on the first version (thread per particle, scalar math; profiles/r01_gather_v1_C2.txt) showed the
+// passes are INSTRUCTION-ISSUE bound (76-87 % issue-active, L1 61 %), not HBM bound, so this version
+// minimises instructions per (particle, candidate) test:
+//
+//  * TWO particles per thread, tested against each candidate with sm_100a packed fp32x2 math
+//    (FADD2 / FMUL2 / FFMA2: one instruction per pair of lanes' worth of work) -- 6 packed instructions
+//    + 1 shared 16-byte load per candidate for both particles.
+//  * TWO PHASES.  Phase A culls with the FMA-fused d^2 against a conservatively widened radius
+//    (cull_hi) and pushes survivors on a per-particle shared-memory stack; phase B pops them and
+//    applies the reference's EXACT predicate  d^2 = (ox*ox + oy*oy) + oz*oz (no FMA), !(d^2 > sqrRadius)
+//    before evaluating the smoothing kernels, so neighbour sets stay bit-exact while the 84 % of
+//    candidates that fail never reach the expensive code and the evaluation runs without divergence.
+//  * All loops are made warp-uniform (redux.sync max of the row lengths), so stack flushes are
+//    collective and the warp stays converged.
+//  * The two particles of a thread are consecutive sorted rows and share the 9 row windows (x window =
+//    union of both).  The rare thread whose two rows lie in different (y,z) rows hands its second
+//    particle to a warp-cooperative pass (32 lanes stride the candidates, shuffle reduction).
+#include <cstdlib>
+
+#include "sph_gather.cuh"
+
+namespace sphb200 {
+
+namespace {
+
+constexpr int GT = 128;    // threads per block (2 particles each)
+constexpr int GK = 16;     // stack entries per particle (a small stack keeps shared memory from eating the L1)
+constexpr int GCH = 4;     // candidates per chunk = loads in flight per thread between two overflow checks
+// evaluate one candidate; the density pass also records it in the neighbour list
+template <int PASS>
+__device__ __forceinline__ void accept(const GatherArgs& A, const DevParams& P, const Self& s, const uint32_t j,
+                                       const Fetched& f, Acc& acc)
+{
+    const uint32_t before = acc.cnt;
+    const bool ok = eval<PASS>(P, s, j, f, acc);
+    if (PASS == PASS_DENSITY && ok && A.list_idx && before < A.list_k)
+        A.list_idx[(size_t)before * A.list_stride + s.i] = j;
+}
+
+// ---- generation 1: one thread per particle walks the table (both table modes) -------------------
+// Also the fallback of the list kernels for a particle whose list overflowed.
+template <int MODE, int PASS>
+__device__ __forceinline__ void walk_particle(const GatherArgs& A, const DevParams& P, const Self& s, Acc& acc)
+{
+    for_each_candidate<MODE>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) {
+        Fetched f;
+        f.q = q;
+        f.aux = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (PASS != PASS_DENSITY) {
+            float ox, oy, oz;
+            if (sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r) return;      // do not fetch the aux row of a non-neighbour
+            f.aux = (PASS == PASS_PRESSURE) ? __ldg(&A.dens[j]) : __ldg(&A.velp[j]);
+        }
+        accept<PASS>(A, P, s, j, f, acc);
+    });
+}
+
+constexpr int kWalkThreads = 128;
+
+template <int MODE, int PASS>
+__global__ void __launch_bounds__(kWalkThreads)
+k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
+{
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
+    const Self s = load_self<PASS>(A, P, i);
+    Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+    walk_particle<MODE, PASS>(A, P, s, acc);
+    finish<PASS>(A, P, s, acc, dt);
+}
+
+// ---- neighbour-list passes: pressure and viscosity replay the exact neighbour set recorded by the
+// density pass (same predicted positions, same predicate => same set), 4 entries in flight per thread.
+template <int MODE, int PASS>
+__global__ void __launch_bounds__(kWalkThreads)
+k_gather_list(const GatherArgs A, const DevParams P, const float dt)
+{
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
+    const Self s = load_self<PASS>(A, P, i);
+    Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+    const uint32_t cnt = A.list_cnt[i];
+    if (cnt > A.list_k) {                                  // overflowed list: walk the table like generation 1
+        walk_particle<MODE, PASS>(A, P, s, acc);
+    } else {
+        const uint32_t* __restrict__ col = A.list_idx + i;
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+            uint32_t j[4];
+            Fetched f[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) j[u] = (k0 + u < cnt) ? __ldg(&col[(size_t)(k0 + u) * A.list_stride]) : s.i;
+            #pragma unroll
+            for (int u = 0; u < 4; u++) f[u] = fetch<PASS>(A, j[u]);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) (void)eval<PASS>(P, s, j[u], f[u], acc);   // padding entries are the particle itself: skipped
+        }
+    }
+    finish<PASS>(A, P, s, acc, dt);
+}
+
+// 9 row windows of a cell: rows (dy, dz), x window [xa, xb]
+__device__ __forceinline__ void row_range(const uint32_t* __restrict__ table, const DevParams& P, const int3 g,
+                                          const int xa, const int xb, const int r9, uint32_t& b, uint32_t& e)
+{
+    const int dz = r9 / 3 - 1, dy = r9 % 3 - 1;
+    const int z = g.z + dz, y = g.y + dy;
+    b = e = 0;
+    if (r9 >= 9 || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
+    const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
+    b = __ldg(&table[row + xa]);
+    e = __ldg(&table[row + xb + 1]);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(GT)
+k_gather2(const GatherArgs A, const DevParams P, const float dt)
+{
+    __shared__ uint32_t stk[2][GK][GT];
+    const int tid = threadIdx.x;
+    const uint32_t last = P.row1 - 1;
+    const uint32_t i0r = P.row0 + 2u * (blockIdx.x * GT + tid), i1r = i0r + 1u;
+    const bool valid0 = i0r <= last, valid1 = i1r <= last;
+    const Self s0 = load_self<PASS>(A, P, valid0 ? i0r : last);
+    Self s1 = load_self<PASS>(A, P, valid1 ? i1r : last);
+    const int3 g0 = grid_cell(cell_of(s0.p.x, s0.p.y, s0.p.z, P.r), P);
+    const int3 g1 = grid_cell(cell_of(s1.p.x, s1.p.y, s1.p.z, P.r), P);
+    const bool straddle = valid1 && (g0.y != g1.y || g0.z != g1.z);
+    const bool pair = valid1 && !straddle;
+    // a particle that is not processed in the packed loop is parked far away: it never passes the cull
+    const float far = 1.0e18f;
+    const uint64_t px = pk(s0.p.x, pair ? s1.p.x : far), py = pk(s0.p.y, pair ? s1.p.y : far), pz = pk(s0.p.z, pair ? s1.p.z : far);
+    const int xa = max((pair ? min(g0.x, g1.x) : g0.x) - 1, 0);
+    const int xb = min((pair ? max(g0.x, g1.x) : g0.x) + 1, P.gdim[0] - 1);
+    Acc a0 = {0.0f, 0.0f, 0.0f, 0u}, a1 = {0.0f, 0.0f, 0.0f, 0u};
+    uint32_t n0 = 0, n1 = 0;
+    const uint32_t nlast = P.n - 1;
+    const float cull_hi = P.cull_hi;
+
+    // phase B: pop both stacks in lockstep; the fetches of entry k+1 are issued before entry k is evaluated
+    auto flush = [&]() {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, max(n0, n1));
+        uint32_t j0 = n0 ? stk[0][0][tid] : s0.i, j1 = n1 ? stk[1][0][tid] : s1.i;
+        Fetched f0 = fetch<PASS>(A, j0), f1 = fetch<PASS>(A, j1);
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t nj0 = (k + 1 < n0) ? stk[0][k + 1][tid] : s0.i, nj1 = (k + 1 < n1) ? stk[1][k + 1][tid] : s1.i;
+            const Fetched nf0 = fetch<PASS>(A, nj0), nf1 = fetch<PASS>(A, nj1);
+            if (k < n0) accept<PASS>(A, P, s0, j0, f0, a0);
+            if (k < n1) accept<PASS>(A, P, s1, j1, f1, a1);
+            j0 = nj0; j1 = nj1; f0 = nf0; f1 = nf1;
+        }
+        n0 = n1 = 0;
+    };
+
+    // phase A: every thread walks its own 9 row windows as ONE flat candidate sequence, GCH candidates per
+    // iteration; the warp iterates until its slowest thread is done (trip = max of the TOTAL candidate
+    // counts, not the sum of per-row maxima).  The next row's range is fetched one row ahead.
+    int r = 0;
+    uint32_t j, e, bn, en;
+    row_range(A.table, P, g0, xa, xb, 0, j, e);
+    row_range(A.table, P, g0, xa, xb, 1, bn, en);
+    auto advance = [&]() {
+        do {
+            r++; j = bn; e = en;
+            row_range(A.table, P, g0, xa, xb, r + 1, bn, en);
+        } while (r < 9 && j >= e);
+    };
+    if (j >= e) advance();
+    while (__any_sync(0xffffffffu, r < 9)) {
+        const bool act = r < 9;
+        const uint32_t jb = act ? j : 0u, ee = act ? e : 0u;
+        float4 q[GCH];
+        #pragma unroll
+        for (int u = 0; u < GCH; u++) q[u] = __ldg(&A.pred[min(jb + u, nlast)]);
+        #pragma unroll
+        for (int u = 0; u < GCH; u++) {
+            const uint32_t jj = jb + u;
+            const uint64_t ox = sub2(pk(q[u].x, q[u].x), px), oy = sub2(pk(q[u].y, q[u].y), py), oz = sub2(pk(q[u].z, q[u].z), pz);
+            const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
+            float d0, d1;
+            upk(d2, d0, d1);
+            const bool in = jj < ee;
+            if (in && !(d0 > cull_hi)) { stk[0][n0][tid] = jj; n0++; }
+            if (in && !(d1 > cull_hi)) { stk[1][n1][tid] = jj; n1++; }
+        }
+        if (act) { j += GCH; if (j >= e) advance(); }
+        if (__any_sync(0xffffffffu, max(n0, n1) > GK - GCH)) flush();
+    }
+    flush();
+    if (valid0) finish<PASS>(A, P, s0, a0, dt);
+    if (pair) finish<PASS>(A, P, s1, a1, dt);
+
+    // second particles whose row differs from the first's: one at a time, whole warp on the candidates
+    uint32_t todo = __ballot_sync(0xffffffffu, straddle);
+    const int lane = tid & 31;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t ic = __shfl_sync(0xffffffffu, s1.i, src);
+        const Self sc = load_self<PASS>(A, P, ic);
+        const int3 gc = grid_cell(cell_of(sc.p.x, sc.p.y, sc.p.z, P.r), P);
+        const int ca = max(gc.x - 1, 0), cb = min(gc.x + 1, P.gdim[0] - 1);
+        Acc ac = {0.0f, 0.0f, 0.0f, 0u};
+        #pragma unroll 1
+        for (int r9 = 0; r9 < 9; r9++) {
+            uint32_t b, e;
+            row_range(A.table, P, gc, ca, cb, r9, b, e);
+            for (uint32_t j = b + lane; j < e; j += 32) term<PASS>(A, P, sc, j, ac);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ac.a += __shfl_xor_sync(0xffffffffu, ac.a, o);
+            ac.b += __shfl_xor_sync(0xffffffffu, ac.b, o);
+            ac.c += __shfl_xor_sync(0xffffffffu, ac.c, o);
+            ac.cnt += __shfl_xor_sync(0xffffffffu, ac.cnt, o);
+        }
+        if (lane == src) finish<PASS>(A, P, sc, ac, dt);
+    }
+}
+
+template <int PASS>
+void launch(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
+{
+    if (P.row1 <= P.row0) return;
+    const uint32_t rows = P.row1 - P.row0;
+    const uint32_t threads = (rows + 1) / 2;
+    k_gather2<PASS><<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P, dt);
+    ++*launches;
+}
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------------------------
+// SPH_GATHER selects the enumeration: "list" (default: density walks and records the neighbour list,
+// pressure + viscosity replay it), "v1" (every pass walks the table), "v2" (GRID table only: packed
+// two-phase cull in every pass).
+static int gather_variant()
+{
+    static const int v = [] {
+        const char* e = getenv("SPH_GATHER");
+        if (e && e[0] == 'v' && e[1] == '1') return 1;
+        if (e && e[0] == 'v' && e[1] == '2') return 2;
+        return 0;
+    }();
+    return v;
+}
+
+template <int PASS>
+static void launch_walk_or_list(cudaStream_t st, GatherArgs A, const DevParams& P, float dt, bool use_list, uint64_t* launches)
+{
+    if (P.row1 <= P.row0) return;
+    const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
+    if (!use_list || PASS == PASS_DENSITY) {
+        if (P.mode == SPH_TABLE_REFERENCE_HASH) k_gather_walk<SPH_TABLE_REFERENCE_HASH, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
+        else k_gather_walk<SPH_TABLE_GRID, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
+    } else {
+        if (P.mode == SPH_TABLE_REFERENCE_HASH) k_gather_list<SPH_TABLE_REFERENCE_HASH, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
+        else k_gather_list<SPH_TABLE_GRID, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
+    }
+    ++*launches;
+}
+
+static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const uint32_t* tend, const NbrList& L)
+{
+    GatherArgs A = {};
+    A.pred = pred_s; A.table = tstart; A.tend = tend;
+    if (gather_variant() == 0 && L.idx && L.k) { A.list_idx = L.idx; A.list_k = L.k; A.list_stride = L.stride; }
+    A.list_cnt = L.cnt;
+    return A;
+}
+
+void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
+                    float4* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
+{
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.dens_out = dens; A.ncount = L.cnt;
+    if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
+    else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);
+}
+
+void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+                     float dt, uint64_t* launches)
+{
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.dens = dens; A.vel_s = vel_s; A.velp_out = vel_p;
+    if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_PRESSURE>(st, A, P, dt, launches);
+    else launch_walk_or_list<PASS_PRESSURE>(st, A, P, dt, A.list_idx != nullptr, launches);
+}
+
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+                      const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
+                      uint64_t* launches)
+{
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.velp = vel_p; A.velv_out = vel_v;
+    if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_VISCOSITY>(st, A, P, dt, launches);
+    else launch_walk_or_list<PASS_VISCOSITY>(st, A, P, dt, A.list_idx != nullptr, launches);
+}
+
+}  // namespace sphb200

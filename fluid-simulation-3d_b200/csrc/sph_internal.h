@@ -20,6 +20,7 @@ struct DevParams {
     float    s2, s3;        // SmoothingDerivativePow2 / Pow3 scales
     float    sv;            // SmoothingViscoPoly6 scale
     float    rr;            // r*r
+    float    cull_hi;       // sqr_r * (1 + 5e-7) rounded up: conservative prefilter for the FMA-fused d^2 (sph_gather.cu)
     // GRID table: cell g = clamp(floor(pred/r) - gmin, 0, gdim-1); key = (gz*gdim.y + gy)*gdim.x + gx
     int      gmin[3];
     int      gdim[3];
@@ -61,13 +62,20 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
 void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
                     const float4* ghost_pred, float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P,
                     float dt, uint64_t* launches);
+// neighbour list recorded by the density pass (k-major: entry k of row i at idx[k*stride + i])
+struct NbrList {
+    uint32_t* idx;      // nullptr: no list, every pass walks the table
+    uint32_t* cnt;      // [rows] neighbour count incl. self (always written by the density pass)
+    uint32_t  k;        // entries per row before a row counts as overflowed
+    uint32_t  stride;
+};
 void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
-                    float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches);
-void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const DevParams& P, float dt,
-                     uint64_t* launches);
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p,
-                      const uint32_t* tstart, const uint32_t* tend, float4* vel_v, const DevParams& P, float dt,
+                    float4* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
+void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+                     float dt, uint64_t* launches);
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+                      const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
                       uint64_t* launches);
 void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
                       const DevParams& P, float dt, uint64_t* launches);
@@ -77,7 +85,7 @@ void launch_pack_state(cudaStream_t st, const float* pos3, const float* vel3, co
                        float4* pos, float4* vel, uint32_t n, uint64_t* launches);
 void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void* src2, void* out,
                    uint32_t n, const DevParams& P, bool by_id, uint64_t* launches);
-void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float2* dens, uint32_t n,
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float4* dens, uint32_t n,
                           uint32_t id, float* out10, uint64_t* launches);
 void launch_export_ids(cudaStream_t st, const float4* id_src, uint32_t* out, uint32_t n, uint64_t* launches);
 

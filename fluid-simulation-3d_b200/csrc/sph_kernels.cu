@@ -15,74 +15,15 @@
 // the d^2 <= sqrRadius predicate) is computed with explicit round-to-nearest, non-fused
 // __fmul_rn/__fadd_rn/__fdiv_rn in the reference's operation order.  Float-only results may use FMA
 // and approximate sqrt/rcp (tolerance 1e-5 of the stage scale, tests/test_parity_gpu.py).
+#include <cstdlib>
+
 #include "sph_internal.h"
+#include "sph_device.cuh"
 
 namespace sphb200 {
 
 namespace {
 
-constexpr int kThreads = 128;
-
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float y;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// PositionToCellCoord (:499-503): floor(pos / r) with true IEEE division, C-cast to int.
-__device__ __forceinline__ int3 cell_of(float x, float y, float z, float r)
-{
-    int3 c;
-    c.x = __float2int_rz(floorf(__fdiv_rn(x, r)));
-    c.y = __float2int_rz(floorf(__fdiv_rn(y, r)));
-    c.z = __float2int_rz(floorf(__fdiv_rn(z, r)));
-    return c;
-}
-// HashCell (:505-511): (uint32_t)float on the reference's platform = two's-complement wrap (Q5).
-__device__ __forceinline__ uint32_t hash_cell(int cx, int cy, int cz)
-{
-    return (uint32_t)cx * 15823u + (uint32_t)cy * 9737333u + (uint32_t)cz * 440817757u;
-}
-// GetKeyFromHash (:513-516): hash % n, exact for every 32-bit operand pair (Lemire fastmod).
-__device__ __forceinline__ uint32_t key_of_hash(uint32_t h, const DevParams& P)
-{
-    const uint64_t low = P.modM * (uint64_t)h;
-    return (uint32_t)__umul64hi(low, (uint64_t)P.n);
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-__device__ __forceinline__ int3 grid_cell(int3 c, const DevParams& P)
-{
-    int3 g;
-    g.x = clampi(c.x - P.gmin[0], 0, P.gdim[0] - 1);
-    g.y = clampi(c.y - P.gmin[1], 0, P.gdim[1] - 1);
-    g.z = clampi(clampi(c.z - P.gmin[2], 0, P.gz_global - 1) - P.zlo, 0, P.gdim[2] - 1);
-    return g;
-}
-__device__ __forceinline__ uint32_t grid_key(int3 g, const DevParams& P)
-{
-    return ((uint32_t)g.z * (uint32_t)P.gdim[1] + (uint32_t)g.y) * (uint32_t)P.gdim[0] + (uint32_t)g.x;
-}
-
-// S1: velocity += externalForce * dt ; predicted = position + velocity * (1/120)   (:45-47, Q1)
-__device__ __forceinline__ void predict(const float4 p, float4& v, float3& pred, const DevParams& P, float dt)
-{
-    const float gy = P.gravity ? -P.g : 0.0f;
-    v.x = __fadd_rn(v.x, __fmul_rn(0.0f, dt));
-    v.y = __fadd_rn(v.y, __fmul_rn(gy, dt));
-    v.z = __fadd_rn(v.z, __fmul_rn(0.0f, dt));
-    const float look = 1.0f / 120.0f;
-    pred.x = __fadd_rn(p.x, __fmul_rn(v.x, look));
-    pred.y = __fadd_rn(p.y, __fmul_rn(v.y, look));
-    pred.z = __fadd_rn(p.z, __fmul_rn(v.z, look));
-}
 
 __global__ void __launch_bounds__(256)
 k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
@@ -230,149 +171,6 @@ k_reorder(const uint32_t* __restrict__ perm, const float4* __restrict__ pos, con
     pred_s[s] = make_float4(pr.x, pr.y, pr.z, __uint2float_rn(h));   // spatialLookup[].y is float(hash) (:480)
 }
 
-// ---- neighbour walk ---------------------------------------------------------
-// Calls f(j, pred_j) for every candidate row the reference's walk would reach for a particle at pi.
-template <int MODE, class F>
-__device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pred_s,
-                                                   const uint32_t* __restrict__ tstart,
-                                                   const uint32_t* __restrict__ tend,
-                                                   const float4 pi, const DevParams& P, F&& f)
-{
-    const int3 c = cell_of(pi.x, pi.y, pi.z, P.r);
-    if (MODE == SPH_TABLE_REFERENCE_HASH) {
-        #pragma unroll 1
-        for (int i = 0; i < 27; i++) {               // offsets[27]: x outer, y, z inner (physicsWorld.h:131-143)
-            const int dx = i / 9 - 1, dy = (i / 3) % 3 - 1, dz = i % 3 - 1;
-            const uint32_t h = hash_cell(c.x + dx, c.y + dy, c.z + dz);
-            const uint32_t key = key_of_hash(h, P);
-            const uint32_t b = __ldg(&tstart[key]);
-            if (b >= P.n) continue;                  // 0x7FFFFFFF: empty bucket (:339)
-            const uint32_t e = __ldg(&tend[key]);
-            const float hf = __uint2float_rn(h);
-            for (uint32_t j = b; j < e; j++) {
-                const float4 q = __ldg(&pred_s[j]);
-                if (q.w != hf) continue;             // `index.y != hash`, compared in float (:346)
-                f(j, q);
-            }
-        }
-    } else {
-        const int3 g = grid_cell(c, P);
-        const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
-        #pragma unroll 1
-        for (int dz = -1; dz <= 1; dz++) {
-            const int z = g.z + dz;
-            if (z < 0 || z >= P.gdim[2]) continue;
-            #pragma unroll 1
-            for (int dy = -1; dy <= 1; dy++) {
-                const int y = g.y + dy;
-                if (y < 0 || y >= P.gdim[1]) continue;
-                const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
-                const uint32_t b = __ldg(&tstart[row + x0]);
-                const uint32_t e = __ldg(&tstart[row + x1 + 1]);
-                for (uint32_t j = b; j < e; j++) f(j, __ldg(&pred_s[j]));
-            }
-        }
-    }
-}
-
-// glm::dot on the offset, no FMA: (x*x + y*y) + z*z   (Q8)
-__device__ __forceinline__ float sqr_dist(const float4 q, const float4 pi, float& ox, float& oy, float& oz)
-{
-    ox = __fsub_rn(q.x, pi.x); oy = __fsub_rn(q.y, pi.y); oz = __fsub_rn(q.z, pi.z);
-    return __fadd_rn(__fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy)), __fmul_rn(oz, oz));
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-k_density(const float4* __restrict__ pred_s, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend,
-          float2* __restrict__ dens, uint32_t* __restrict__ ncount, const DevParams P)
-{
-    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.row1) return;
-    const float4 pi = pred_s[i];
-    float rho = 0.0f, rhon = 0.0f;
-    uint32_t cnt = 0;
-    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t, const float4 q) {
-        float ox, oy, oz;
-        const float d2 = sqr_dist(q, pi, ox, oy, oz);
-        if (d2 > P.sqr_r) return;                    // :357
-        cnt++;
-        const float d = sqrt_approx(d2);
-        if (d < P.r) {                               // kernels.h:27,39
-            const float v = P.r - d;
-            rho += v * v * P.vol2;
-            rhon += v * v * v * P.vol3;
-        }
-    });
-    dens[i] = make_float2(rho, rhon);
-    if (ncount) ncount[i] = cnt;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-k_pressure(const float4* __restrict__ pred_s, const float2* __restrict__ dens, const float4* __restrict__ vel_s,
-           const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_p,
-           const DevParams P, const float dt)
-{
-    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.row1) return;
-    const float4 pi = pred_s[i];
-    const float2 di = dens[i];
-    const float pressure = (di.x - P.rho0) * P.k;    // :371
-    const float npressure = di.y * P.kn;             // :372
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t j, const float4 q) {
-        if (j == i) return;                          // :396
-        float ox, oy, oz;
-        const float d2 = sqr_dist(q, pi, ox, oy, oz);
-        if (d2 > P.sqr_r) return;                    // :402
-        const float2 dj = __ldg(&dens[j]);
-        const float pj = (dj.x - P.rho0) * P.k;
-        const float npj = dj.y * P.kn;
-        const float shared = (pressure + pj) * 0.5f;
-        const float nshared = (npressure + npj) * 0.5f;
-        const float d = sqrt_approx(d2);
-        float dirx = 0.0f, diry = 1.0f, dirz = 0.0f; // :414
-        if (d > 0.0f) { const float inv = rcp_approx(d); dirx = ox * inv; diry = oy * inv; dirz = oz * inv; }
-        float coef = 0.0f;
-        if (d <= P.r) {                              // kernels.h:51,63
-            const float v = P.r - d;
-            coef = (-v * P.s2) * shared * rcp_approx(dj.x) + (-v * v * P.s3) * nshared * rcp_approx(dj.y);
-        }
-        fx += dirx * coef; fy += diry * coef; fz += dirz * coef;
-    });
-    const float4 v = vel_s[i];
-    const float s = dt / di.x;                       // :421  (F / rho) * dt
-    vel_p[i] = make_float4(v.x + fx * s, v.y + fy * s, v.z + fz * s, 0.0f);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-k_viscosity(const float4* __restrict__ pred_s, const float4* __restrict__ vel_p,
-            const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ tend, float4* __restrict__ vel_v,
-            const DevParams P, const float dt)
-{
-    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.row1) return;
-    const float4 pi = pred_s[i];
-    const float4 vi = vel_p[i];
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    for_each_candidate<MODE>(pred_s, tstart, tend, pi, P, [&](uint32_t j, const float4 q) {
-        if (j == i) return;                          // :450
-        float ox, oy, oz;
-        const float d2 = sqr_dist(q, pi, ox, oy, oz);
-        if (d2 > P.sqr_r) return;                    // :456
-        const float v = P.rr - d2;                   // kernels.h:78  r*r - dist*dist
-        if (v > 0.0f) {                              // dist < radius
-            const float w = v * v * v * P.sv;
-            const float4 vj = __ldg(&vel_p[j]);      // snapshot: every particle reads post-pressure velocities
-            fx += (vj.x - vi.x) * w; fy += (vj.y - vi.y) * w; fz += (vj.z - vi.z) * w;
-        }
-    });
-    const float s = P.mu * dt;                       // :463
-    vel_v[i] = make_float4(vi.x + fx * s, vi.y + fy * s, vi.z + fz * s, 0.0f);
-}
-
 // S6 (:84-107)
 __global__ void __launch_bounds__(256)
 k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
@@ -446,7 +244,7 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
         ((float4*)out)[dst] = make_float4(a.x, a.y, a.z, 0.34f);          // :107
     } break;
     case SPH_FIELD_DENSITIES:
-        ((float2*)out)[dst] = ((const float2*)src)[s];
+        { const float4 d = ((const float4*)src)[s]; ((float2*)out)[dst] = make_float2(d.x, d.y); }
         break;
     case SPH_FIELD_HASH: case SPH_FIELD_KEY: {       // pure functions of the predicted position (:477-479)
         const float4 a = ((const float4*)src)[s];
@@ -470,7 +268,7 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
 
 // getPosition/getVelocity/getDensity/getNearDensity/getSpeed/getSpeedNormalzied (:149-182) for one id
 __global__ void __launch_bounds__(256)
-k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const float2* __restrict__ dens,
+k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ dens,
                 const uint32_t n, const uint32_t id, float* __restrict__ out10)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,7 +278,7 @@ k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, 
     const float4 v = vel[s];
     const float len = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
     out10[0] = p.x; out10[1] = p.y; out10[2] = p.z; out10[3] = v.x; out10[4] = v.y; out10[5] = v.z;
-    if (dens) { const float2 d = dens[s]; out10[6] = d.x; out10[7] = d.y; }
+    if (dens) { const float4 d = dens[s]; out10[6] = d.x; out10[7] = d.y; }
     out10[8] = len;
     out10[9] = fminf(fmaxf(len, 0.0f), 1.5f) / 1.5f;
 }
@@ -536,41 +334,6 @@ void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, co
     ++*launches;
 }
 
-void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
-                    float2* dens, uint32_t* ncount, const DevParams& P, uint64_t* launches)
-{
-    if (P.row1 <= P.row0) return;
-    if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_density<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
-    else
-        k_density<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, tstart, tend, dens, ncount, P);
-    ++*launches;
-}
-
-void launch_pressure(cudaStream_t st, const float4* pred_s, const float2* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const DevParams& P, float dt,
-                     uint64_t* launches)
-{
-    if (P.row1 <= P.row0) return;
-    if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_pressure<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
-    else
-        k_pressure<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, dens, vel_s, tstart, tend, vel_p, P, dt);
-    ++*launches;
-}
-
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p,
-                      const uint32_t* tstart, const uint32_t* tend, float4* vel_v, const DevParams& P, float dt,
-                      uint64_t* launches)
-{
-    if (P.row1 <= P.row0) return;
-    if (P.mode == SPH_TABLE_REFERENCE_HASH)
-        k_viscosity<SPH_TABLE_REFERENCE_HASH><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
-    else
-        k_viscosity<SPH_TABLE_GRID><<<blocks_for(P.row1 - P.row0, kThreads), kThreads, 0, st>>>(pred_s, vel_p, tstart, tend, vel_v, P, dt);
-    ++*launches;
-}
-
 void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
                       const DevParams& P, float dt, uint64_t* launches)
 {
@@ -595,7 +358,7 @@ void launch_export(cudaStream_t st, int field, const float4* id_src, const void*
     ++*launches;
 }
 
-void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float2* dens, uint32_t n,
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float4* dens, uint32_t n,
                           uint32_t id, float* out10, uint64_t* launches)
 {
     if (n == 0) return;

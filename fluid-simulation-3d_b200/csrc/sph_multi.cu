@@ -407,22 +407,25 @@ int multi_step(SphContext* c, float dt)
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
 
     // (5) density on owned rows, halo of densities
-    launch_density(st, c->pred, c->tstart, c->tend, c->dens, c->nc_tap ? c->ncount : nullptr, P, &c->launches);
-    c->ncount_valid = c->nc_tap;
+    NbrList L;
+    rc = ensure_list(c, &L);
+    if (rc != SPH_OK) return rc;
+    launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    c->ncount_valid = true;
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) {
-        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 2, ncclFloat, lo, comm, st));
-        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 2, ncclFloat, lo, comm, st));
+        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 4, ncclFloat, lo, comm, st));
+        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 4, ncclFloat, lo, comm, st));
     }
     if (has_hi) {
-        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 2, ncclFloat, hi, comm, st));
-        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 2, ncclFloat, hi, comm, st));
+        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 4, ncclFloat, hi, comm, st));
+        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 4, ncclFloat, hi, comm, st));
     }
     SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
 
     // pressure, halo of post-pressure velocities
-    launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, P, dt, &c->launches);
+    launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) {
         if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->velp + o0, (size_t)(b_lo_end - o0) * 4, ncclFloat, lo, comm, st));
@@ -435,7 +438,7 @@ int multi_step(SphContext* c, float dt)
     SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
 
-    launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, P, dt, &c->launches);
+    launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, L, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
     launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[6], st));

@@ -112,6 +112,10 @@ int  sph_get_table_mode(const SphContext* ctx);
 int  sph_set_stage_timing(SphContext* ctx, int enabled);
 /* 1: also keep neighbour counts during the density pass (debug tap, off by default) */
 int  sph_set_neighbour_count_tap(SphContext* ctx, int enabled);
+/* Entries per particle of the neighbour list the density pass records for the pressure and viscosity
+ * passes (default 64; 0 = no list, every pass walks the table).  A particle with more neighbours than
+ * this is still exact: the later passes walk the table for it. */
+int  sph_set_neighbour_list_capacity(SphContext* ctx, uint32_t entries);
 
 /* -- state ---------------------------------------------------------------- */
 /* InitializeData(n) (.cc:112-147): cube lattice spawn (GridArrangement :518-557), velocities zero,
