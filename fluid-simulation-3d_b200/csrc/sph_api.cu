@@ -123,7 +123,8 @@ int ensure_list(SphContext* c, NbrList* L)
         else c->list_k_alloc = c->list_k;
     }
     L->idx = c->list_k ? c->nlist : nullptr;
-    L->cnt = c->ncount;
+    L->cnt = c->lcount;
+    L->ncount = c->ncount;
     L->k = c->list_k;
     L->stride = c->cap;
     return SPH_OK;
@@ -134,7 +135,7 @@ int ensure_list(SphContext* c, NbrList* L)
 static void free_all(SphContext* c)
 {
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
-                    c->perm_a, c->perm_b, c->ncount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
@@ -197,6 +198,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
     ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
     ALLOC(c->ncount, cap * 4);
+    ALLOC(c->lcount, cap * 4);
     ALLOC(c->stage, cap * 32);
     c->counts_cap = radix_sort_temp_entries(capacity);
     ALLOC(c->counts, c->counts_cap * 4);

@@ -23,6 +23,7 @@ struct SphContext {
     float4* dens = nullptr;      // (rho, near rho, 1/rho, 1/near rho)
     uint32_t *key_a = nullptr, *key_b = nullptr, *perm_a = nullptr, *perm_b = nullptr;
     uint32_t* ncount = nullptr;  // neighbour count incl. self of every row (density pass); also the list lengths
+    uint32_t* lcount = nullptr;  // list lengths
     uint32_t* nlist = nullptr;   // neighbour list, k-major: entry k of row i at nlist[k * cap + i]
     uint32_t list_k = 64;        // entries per row (0: lists off)
     uint32_t list_k_alloc = 0;

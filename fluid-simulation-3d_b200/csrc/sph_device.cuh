@@ -7,7 +7,7 @@ namespace sphb200 {
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ float rcp_approx(float x)

@@ -72,6 +72,7 @@ k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
     Acc acc = {0.0f, 0.0f, 0.0f, 0u};
     walk_particle<MODE, PASS>(A, P, s, acc);
     finish<PASS>(A, P, s, acc, dt);
+    if (PASS == PASS_DENSITY && A.list_cnt) A.list_cnt[i] = acc.cnt;
 }
 
 // ---- neighbour-list passes: pressure and viscosity replay the exact neighbour set recorded by the
@@ -222,6 +223,128 @@ k_gather2(const GatherArgs A, const DevParams P, const float dt)
     }
 }
 
+// ---- density pass, generation 3 (GRID table, neighbour list on) ------------------------------------
+// Phase A: two particles per thread cull every candidate of their shared 9 row windows with packed
+// fp32x2 math (FMA-fused d^2 against the conservatively widened cull_hi) and append the survivors to
+// the particles' NEIGHBOUR LIST COLUMNS in global memory -- pure predication, no divergent branch.
+// Phase B: each particle replays its own column, applies the reference's exact predicate and sums the
+// smoothing kernels.  The list therefore doubles as the compaction buffer of this pass and as the
+// input of the pressure and viscosity passes (which re-apply the exact predicate themselves, so the
+// <= 1e-6 fraction of borderline extras in the list is harmless).
+__global__ void __launch_bounds__(GT)
+k_density_pair(const GatherArgs A, const DevParams P)
+{
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t last = P.row1 - 1;
+    const uint32_t i0r = P.row0 + 2u * (blockIdx.x * GT + tid), i1r = i0r + 1u;
+    const bool valid0 = i0r <= last, valid1 = i1r <= last;
+    const Self s0 = load_self<PASS_DENSITY>(A, P, valid0 ? i0r : last);
+    const Self s1 = load_self<PASS_DENSITY>(A, P, valid1 ? i1r : last);
+    const int3 g0 = grid_cell(cell_of(s0.p.x, s0.p.y, s0.p.z, P.r), P);
+    const int3 g1 = grid_cell(cell_of(s1.p.x, s1.p.y, s1.p.z, P.r), P);
+    const bool straddle = valid1 && (g0.y != g1.y || g0.z != g1.z);
+    const bool pair = valid1 && !straddle;
+    const float far = 1.0e18f;       // a particle that is not processed here never passes the cull
+    const uint64_t px = pk(s0.p.x, pair ? s1.p.x : far), py = pk(s0.p.y, pair ? s1.p.y : far), pz = pk(s0.p.z, pair ? s1.p.z : far);
+    const int xa = max((pair ? min(g0.x, g1.x) : g0.x) - 1, 0);
+    const int xb = min((pair ? max(g0.x, g1.x) : g0.x) + 1, P.gdim[0] - 1);
+    const uint32_t K = A.list_k;
+    const size_t stride = A.list_stride;
+    uint32_t* col0 = A.list_idx + s0.i;
+    uint32_t* col1 = A.list_idx + s1.i;
+    uint32_t n0 = 0, n1 = 0;
+    const uint32_t nlast = P.n - 1;
+    const float cull_hi = P.cull_hi;
+
+    #pragma unroll 1
+    for (int r9 = 0; r9 < 9; r9++) {
+        uint32_t b, e;
+        row_range(A.table, P, g0, xa, xb, r9, b, e);
+        const uint32_t chunks = (__reduce_max_sync(0xffffffffu, e - b) + GCH - 1) / GCH;
+        #pragma unroll 1
+        for (uint32_t c = 0; c < chunks; c++) {
+            const uint32_t jb = b + c * GCH;
+            float4 q[GCH];
+            #pragma unroll
+            for (int u = 0; u < GCH; u++) q[u] = __ldg(&A.pred[min(jb + u, nlast)]);
+            #pragma unroll
+            for (int u = 0; u < GCH; u++) {
+                const uint32_t jj = jb + u;
+                const uint64_t ox = sub2(pk(q[u].x, q[u].x), px), oy = sub2(pk(q[u].y, q[u].y), py), oz = sub2(pk(q[u].z, q[u].z), pz);
+                const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
+                float d0, d1;
+                upk(d2, d0, d1);
+                const bool in = jj < e;
+                if (in && !(d0 > cull_hi)) { if (n0 < K) col0[(size_t)n0 * stride] = jj; n0++; }
+                if (in && !(d1 > cull_hi)) { if (n1 < K) col1[(size_t)n1 * stride] = jj; n1++; }
+            }
+        }
+    }
+
+    // phase B: replay both columns in lockstep, 4 entries in flight per particle
+    Acc a0 = {0.0f, 0.0f, 0.0f, 0u}, a1 = {0.0f, 0.0f, 0.0f, 0u};
+    const uint32_t m0 = min(n0, K), m1 = pair ? min(n1, K) : 0u;
+    const uint32_t m = __reduce_max_sync(0xffffffffu, max(m0, m1));
+    for (uint32_t k0 = 0; k0 < m; k0 += 4) {
+        uint32_t j0[4], j1[4];
+        Fetched f0[4], f1[4];
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            j0[u] = (k0 + u < m0) ? col0[(size_t)(k0 + u) * stride] : s0.i;   // plain loads: written by this thread above
+            j1[u] = (k0 + u < m1) ? col1[(size_t)(k0 + u) * stride] : s1.i;
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; u++) { f0[u] = fetch<PASS_DENSITY>(A, j0[u]); f1[u] = fetch<PASS_DENSITY>(A, j1[u]); }
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (k0 + u < m0) (void)eval<PASS_DENSITY>(P, s0, j0[u], f0[u], a0);
+            if (k0 + u < m1) (void)eval<PASS_DENSITY>(P, s1, j1[u], f1[u], a1);
+        }
+    }
+    GatherArgs W = A;            // the fallback walk must not record a second time
+    W.list_idx = nullptr;
+    if (n0 > K) { a0 = {0.0f, 0.0f, 0.0f, 0u}; walk_particle<SPH_TABLE_GRID, PASS_DENSITY>(W, P, s0, a0); }
+    if (pair && n1 > K) { a1 = {0.0f, 0.0f, 0.0f, 0u}; walk_particle<SPH_TABLE_GRID, PASS_DENSITY>(W, P, s1, a1); }
+    if (valid0) { finish<PASS_DENSITY>(A, P, s0, a0, 0.0f); A.list_cnt[s0.i] = n0; }
+    if (pair) { finish<PASS_DENSITY>(A, P, s1, a1, 0.0f); A.list_cnt[s1.i] = n1; }
+
+    // second particles that live in another (y,z) row than their partner: whole warp on one particle
+    uint32_t todo = __ballot_sync(0xffffffffu, straddle);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t ic = __shfl_sync(0xffffffffu, s1.i, src);
+        const Self sc = load_self<PASS_DENSITY>(A, P, ic);
+        const int3 gc = grid_cell(cell_of(sc.p.x, sc.p.y, sc.p.z, P.r), P);
+        const int ca = max(gc.x - 1, 0), cb = min(gc.x + 1, P.gdim[0] - 1);
+        uint32_t* colc = A.list_idx + ic;
+        Acc ac = {0.0f, 0.0f, 0.0f, 0u};
+        uint32_t nc = 0;
+        #pragma unroll 1
+        for (int r9 = 0; r9 < 9; r9++) {
+            uint32_t b, e;
+            row_range(A.table, P, gc, ca, cb, r9, b, e);
+            for (uint32_t jb = b; jb < e; jb += 32) {
+                const uint32_t j = jb + lane;
+                bool ok = false;
+                if (j < e) { const Fetched f = fetch<PASS_DENSITY>(A, j); ok = eval<PASS_DENSITY>(P, sc, j, f, ac); }
+                const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+                const uint32_t pos = nc + __popc(mask & ((1u << lane) - 1u));
+                if (ok && pos < K) colc[(size_t)pos * stride] = j;
+                nc += __popc(mask);
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ac.a += __shfl_xor_sync(0xffffffffu, ac.a, o);
+            ac.b += __shfl_xor_sync(0xffffffffu, ac.b, o);
+            ac.cnt += __shfl_xor_sync(0xffffffffu, ac.cnt, o);
+        }
+        if (lane == src) { finish<PASS_DENSITY>(A, P, sc, ac, 0.0f); A.list_cnt[ic] = nc; }
+    }
+}
+
 template <int PASS>
 void launch(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
 {
@@ -277,9 +400,14 @@ void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstar
                     float4* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
-    A.dens_out = dens; A.ncount = L.cnt;
+    A.dens_out = dens; A.ncount = L.ncount;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
-    else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);
+    else if (A.list_idx && P.mode == SPH_TABLE_GRID && !getenv("SPH_DENSITY_WALK")) {
+        if (P.row1 <= P.row0) return;
+        const uint32_t threads = (P.row1 - P.row0 + 1) / 2;
+        k_density_pair<<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P);
+        ++*launches;
+    } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);
 }
 
 void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,

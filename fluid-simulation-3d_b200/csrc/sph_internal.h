@@ -65,7 +65,8 @@ void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, co
 // neighbour list recorded by the density pass (k-major: entry k of row i at idx[k*stride + i])
 struct NbrList {
     uint32_t* idx;      // nullptr: no list, every pass walks the table
-    uint32_t* cnt;      // [rows] neighbour count incl. self (always written by the density pass)
+    uint32_t* cnt;      // [rows] list length (may exceed k: overflowed; may include <= 1e-6 borderline extras)
+    uint32_t* ncount;   // [rows] exact neighbour count incl. self (always written by the density pass)
     uint32_t  k;        // entries per row before a row counts as overflowed
     uint32_t  stride;
 };
