@@ -83,6 +83,8 @@ class PortOracle:
             L.oracle_set_wide_lookup.argtypes = [C.c_void_p, C.c_int]
             L.oracle_set_threads.argtypes = [C.c_int]
             L.oracle_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.oracle_set_predicted.argtypes = [C.c_void_p, C.c_void_p]
+            L.oracle_set_densities.argtypes = [C.c_void_p, C.c_void_p]
             L.oracle_stage_predict.argtypes = [C.c_void_p, C.c_float]
             L.oracle_stage_spatial.argtypes = [C.c_void_p, C.c_void_p]
             L.oracle_stage_pressure.argtypes = [C.c_void_p, C.c_float]
@@ -138,6 +140,14 @@ class PortOracle:
         pos = None if pos is None else _f32(pos).reshape(self.n, 3)
         vel = None if vel is None else _f32(vel).reshape(self.n, 3)
         self.L.oracle_set_state(self.h, None if pos is None else _p(pos), None if vel is None else _p(vel))
+
+    def set_predicted(self, pred):
+        pred = _f32(pred).reshape(self.n, 3)
+        self.L.oracle_set_predicted(self.h, _p(pred))
+
+    def set_densities(self, dens):
+        dens = _f32(dens).reshape(self.n, 2)
+        self.L.oracle_set_densities(self.h, _p(dens))
 
     def stage_predict(self, dt): self.L.oracle_stage_predict(self.h, dt)
 

@@ -98,6 +98,11 @@ void oracle_set_state(Oracle* o, const float* pos3, const float* vel3)
     if (vel3) memcpy(o->vel, vel3, (size_t)o->n * 12);
 }
 
+/* injection points for the slab-decomposition model (tests/slab_model.py): ghost rows get their predicted
+ * position, density and post-pressure velocity from the owning rank instead of computing them */
+void oracle_set_predicted(Oracle* o, const float* pred3) { memcpy(o->pred, pred3, (size_t)o->n * 12); }
+void oracle_set_densities(Oracle* o, const float* dens2) { memcpy(o->dens, dens2, (size_t)o->n * 8); }
+
 /* ---- smoothing kernels: kernels.h:25-82, constants recomputed per call (Q17) ---- */
 static inline float SmoothingPow2(float dist, float radius)
 {   /* kernels.h:25-34 */

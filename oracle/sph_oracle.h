@@ -40,6 +40,9 @@ void    oracle_set_wide_lookup(Oracle* o, int wide);/* 1: keep (index,hash,key) 
 void    oracle_spawn_grid(Oracle* o);               /* InitializeData :112-147 incl. initial lookup + densities */
 void    oracle_set_state(Oracle* o, const float* pos3, const float* vel3);
 
+void    oracle_set_predicted(Oracle* o, const float* pred3);   /* slab model: inject ghost rows */
+void    oracle_set_densities(Oracle* o, const float* dens2);
+
 /* stages */
 void    oracle_stage_predict(Oracle* o, float dt);                    /* :42-48  */
 void    oracle_stage_spatial(Oracle* o, const uint32_t* forced_order);/* :466-498; forced_order (particle ids in sorted sequence) replaces the sort's tie order */

@@ -1,0 +1,128 @@
+"""-m gpu: every candidate-enumeration variant and the neighbour-list overflow path give the same answers."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as g
+from helpers import check_step
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import __graft_entry__ as g
+from helpers import check_step
+pkg = g.load_package()
+from fluid_simulation_3d_b200 import scenes
+for mode in (pkg.TABLE_GRID, pkg.TABLE_REFERENCE_HASH):
+    check_step(pkg, scenes.small_dam_break(14), mode, scenes.DT)
+    check_step(pkg, scenes.small_column(10, 24, 10), mode, scenes.DT)
+print("VARIANT_OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY_WALK": "1"}],
+                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density"])
+def test_enumeration_variants_match_oracle(env):
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, os.path.join(ROOT, "tests"))], env=e, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "VARIANT_OK" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("cap", [0, 4, 16])
+def test_neighbour_list_overflow_and_disabled(pkg, cap):
+    """cap = 0: no list; cap = 4 / 16: most / some particles overflow and fall back to walking the table."""
+    from fluid_simulation_3d_b200 import scenes
+    import helpers
+    orig = pkg.FluidSimulation.__init__
+
+    def patched(self, *a, **k):
+        orig(self, *a, **k)
+        self.set_neighbour_list_capacity(cap)
+    pkg.FluidSimulation.__init__ = patched
+    try:
+        for mode in (pkg.TABLE_GRID, pkg.TABLE_REFERENCE_HASH):
+            helpers.check_step(pkg, scenes.small_dam_break(12), mode, scenes.DT)
+    finally:
+        pkg.FluidSimulation.__init__ = orig
+
+
+def test_multi_step_tracks_oracle(pkg, ob):
+    """20 consecutive steps: integer outputs stay exact as long as the float state agrees to the last bit
+    of the predicate; we assert the trajectory stays within a drift budget and never goes non-finite."""
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(12)
+    sim = pkg.FluidSimulation(sc["n"], **sc["params"])
+    sim.upload_state(sc["pos"], sc["vel"])
+    o = ob.PortOracle(sc["n"], threads=4, **sc["params"])
+    o.set_state(sc["pos"], sc["vel"])
+    for s in range(20):
+        sim.step(scenes.DT)
+        o.step(scenes.DT, jacobi=True)
+    ob.PortOracle.lib().oracle_set_threads(1)
+    p, q = sim.download("positions"), o.positions()
+    assert np.all(np.isfinite(p))
+    assert np.abs(p - q).max() < 5e-3, np.abs(p - q).max()
+    sim.close()
+
+
+def test_getters_timers_and_colors(pkg, ob):
+    from fluid_simulation_3d_b200 import scenes
+    sim = pkg.FluidSimulation(5000, gravity=1)
+    sim.spawn_grid(5000)                                    # InitializeData
+    o = ob.PortOracle(5000, gravity=1)
+    o.spawn_grid()
+    assert np.array_equal(sim.download("positions").view(np.uint32), o.positions().view(np.uint32))
+    assert np.allclose(sim.download("densities"), o.densities(), rtol=1e-5)
+    o4 = sim.download("out_positions")
+    assert np.all(o4[:, 3] == np.float32(0.34))
+    sim.step(scenes.DT)
+    o.step(scenes.DT)
+    t = sim.timings()
+    assert np.all(t > 0) and t.sum() < 1e3
+    one = sim.get_particle(17)
+    assert np.allclose(one[:3], sim.download("positions")[17]) and np.allclose(one[3:6], sim.download("velocities")[17])
+    assert np.allclose(one[6:8], sim.download("densities")[17])
+    assert np.all(sim.get_particle(5000) == 0) and np.all(sim.get_particle(2 ** 31) == 0)   # OOB -> zeros
+    v = sim.download("velocities")
+    spd = np.clip(np.linalg.norm(v, axis=1), 0, 1.5) / 1.5
+    assert np.allclose(sim.download("speed_normalized"), spd, atol=1e-6)
+    col = sim.download("colors")
+    assert col.shape == (5000, 4) and np.all(col[:, 3] == 1.0) and np.all((col >= 0) & (col <= 1.0 + 1e-6))
+    sim.close()
+
+
+def test_empty_and_tiny_inputs(pkg):
+    sim = pkg.FluidSimulation(8)
+    sim.upload_state(np.zeros((0, 3), np.float32))
+    sim.step(0.016667)                                      # zero particles: a no-op, not an error
+    assert sim.n == 0
+    sim.upload_state(np.array([[0.1, 0.2, 0.3]], np.float32))
+    sim.set_neighbour_count_tap(True)
+    sim.step(0.016667)
+    assert sim.download("neighbour_count")[0] == 1 and sim.download("densities")[0, 0] > 0
+    with pytest.raises(pkg.SphError):
+        sim.upload_state(np.zeros((9, 3), np.float32))      # above capacity
+    sim.close()
+
+
+def test_host_class_matches_c_abi(pkg):
+    demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
+    r = subprocess.run([demo, "4096", "3", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("n=4096")][0]
+    fnv = dict(kv.split("=") for kv in line.split())
+    ob = g.load_oracle()
+    sim = pkg.FluidSimulation(4096, gravity=1)
+    sim.spawn_grid(4096)
+    for _ in range(3):
+        sim.step(float(np.float32(0.016667)))
+    assert ob.fnv1a64(sim.download("positions")) == fnv["pos_fnv"]
+    assert ob.fnv1a64(sim.download("out_positions")) == fnv["out_fnv"]
+    sim.close()
