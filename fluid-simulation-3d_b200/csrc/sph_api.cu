@@ -98,7 +98,7 @@ int ensure_tables(SphContext* c, const DevParams& P)
         c->table_cap = need;
     }
     if (P.mode == SPH_TABLE_GRID) {
-        const size_t gneed = 1 + 3 * ((size_t)P.ncell / 2048 + 4);
+        const size_t gneed = 1 + 3 * ((size_t)P.ncell / 1024 + (size_t)P.ncell / 16384 + 8);   // worst case of k_build_table_grid's worklist
         if (gneed > c->gap_cap) {
             SPH_CUDA(c, cudaStreamSynchronize(c->st));
             if (c->gap_list) cudaFree(c->gap_list);

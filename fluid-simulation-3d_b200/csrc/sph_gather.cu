@@ -75,6 +75,79 @@ k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
     if (PASS == PASS_DENSITY && A.list_cnt) A.list_cnt[i] = acc.cnt;
 }
 
+// ---- density pass, two-phase, one thread per particle (default) ------------------------------------
+// Phase A walks the table and applies ONLY the reference's exact predicate; survivors are appended to the
+// particle's neighbour-list column with a predicated store (no divergent branch: ~16 instructions per
+// candidate, 4 loads in flight).  Phase B replays the column and evaluates the smoothing kernels, so
+// the expensive code runs for the ~16 % of candidates that are neighbours, converged.  The list is both
+// the compaction buffer of this pass and the input of the pressure / viscosity passes.
+__device__ __forceinline__ void st_if(uint32_t* p, const uint32_t v, const bool c)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.global.b32 [%0], %1; }" ::"l"(p), "r"(v), "r"((int)c));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads)
+k_density_list(const GatherArgs A, const DevParams P)
+{
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
+    const Self s = load_self<PASS_DENSITY>(A, P, i);
+    const uint32_t K = A.list_k;
+    const size_t stride = A.list_stride;
+    uint32_t* col = A.list_idx + i;
+    uint32_t n = 0;
+    auto test = [&](const uint32_t j, const float4 q, const bool in) {
+        float ox, oy, oz;
+        const bool ok = in && !(sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r);      // :357, exact (Q8)
+        st_if(col + (size_t)n * stride, j, ok && n < K);
+        n += ok;
+    };
+    if (MODE == SPH_TABLE_GRID) {
+        const int3 g = grid_cell(cell_of(s.p.x, s.p.y, s.p.z, P.r), P);
+        const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
+        const uint32_t nlast = P.n - 1;
+        #pragma unroll 1
+        for (int r9 = 0; r9 < 9; r9++) {
+            const int z = g.z + r9 / 3 - 1, y = g.y + r9 % 3 - 1;
+            if (z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) continue;
+            const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
+            const uint32_t b = __ldg(&A.table[row + x0]), e = __ldg(&A.table[row + x1 + 1]);
+            #pragma unroll 1
+            for (uint32_t jb = b; jb < e; jb += 4) {
+                float4 q[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = __ldg(&A.pred[min(jb + u, nlast)]);
+                #pragma unroll
+                for (int u = 0; u < 4; u++) test(jb + u, q[u], jb + u < e);
+            }
+        }
+    } else {
+        for_each_candidate<MODE>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) { test(j, q, true); });
+    }
+    asm volatile("" ::: "memory");                         // phase B reads what phase A stored
+    Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+    if (n > K) {                                           // overflowed column: evaluate by walking (nothing recorded twice)
+        GatherArgs W = A;
+        W.list_idx = nullptr;
+        walk_particle<MODE, PASS_DENSITY>(W, P, s, acc);
+    } else {
+        for (uint32_t k0 = 0; k0 < n; k0 += 4) {
+            uint32_t j[4];
+            Fetched f[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) j[u] = (k0 + u < n) ? col[(size_t)(k0 + u) * stride] : i;
+            #pragma unroll
+            for (int u = 0; u < 4; u++) f[u] = fetch<PASS_DENSITY>(A, j[u]);
+            #pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k0 + u < n) (void)eval<PASS_DENSITY>(P, s, j[u], f[u], acc);
+        }
+    }
+    finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
+    A.list_cnt[i] = n;
+}
+
 // ---- neighbour-list passes: pressure and viscosity replay the exact neighbour set recorded by the
 // density pass (same predicted positions, same predicate => same set), 4 entries in flight per thread.
 template <int MODE, int PASS>
@@ -372,6 +445,19 @@ static int gather_variant()
     return v;
 }
 
+// SPH_DENSITY selects the density kernel when the neighbour list is on: default two-phase list kernel,
+// "pair" = packed two-particles-per-thread cull (GRID only), "walk" = single-phase walk.
+static int density_variant()
+{
+    static const int v = [] {
+        const char* e = getenv("SPH_DENSITY");
+        if (e && e[0] == 'p') return 1;
+        if (e && e[0] == 'w') return 2;
+        return 0;
+    }();
+    return v;
+}
+
 template <int PASS>
 static void launch_walk_or_list(cudaStream_t st, GatherArgs A, const DevParams& P, float dt, bool use_list, uint64_t* launches)
 {
@@ -402,12 +488,18 @@ void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstar
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.dens_out = dens; A.ncount = L.ncount;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
-    else if (A.list_idx && P.mode == SPH_TABLE_GRID && !getenv("SPH_DENSITY_WALK")) {
+    else if (A.list_idx && density_variant() == 1 && P.mode == SPH_TABLE_GRID) {       // SPH_DENSITY=pair
         if (P.row1 <= P.row0) return;
         const uint32_t threads = (P.row1 - P.row0 + 1) / 2;
         k_density_pair<<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P);
         ++*launches;
-    } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);
+    } else if (A.list_idx && density_variant() == 0) {                                  // default: two-phase list density
+        if (P.row1 <= P.row0) return;
+        const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
+        if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
+        else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);
+        ++*launches;
+    } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);           // SPH_DENSITY=walk / no list
 }
 
 void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,

@@ -98,7 +98,8 @@ k_build_table_hash(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict
 // [t[c], t[c+1]).  Built straight from the sorted keys: the row s at which the key steps from a to b
 // owns the entries (a, b]; a warp fills its gaps cooperatively so the table is written exactly once,
 // coalesced, with no memset and no scan.  Gaps wider than kBigGap go to a worklist for k_fill_gaps.
-constexpr uint32_t kBigGap = 2048;
+constexpr uint32_t kBigGap = 1024;
+constexpr uint32_t kGapSegment = 16384;
 
 __global__ void __launch_bounds__(256)
 k_build_table_grid(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict__ table,
@@ -116,8 +117,16 @@ k_build_table_grid(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict
     }
     uint32_t len = hi > lo ? hi - lo : 0u;
     if (len > kBigGap) {
-        const uint32_t slot = atomicAdd(&gap_list[0], 1u);
-        gap_list[1 + 3 * slot] = lo; gap_list[2 + 3 * slot] = hi; gap_list[3 + 3 * slot] = s;
+        // wide gaps (air above the fluid, empty slabs) go to a worklist in kGapSegment pieces, one block each
+        for (uint32_t o = lo; o < hi; o += kGapSegment) {
+            const uint32_t slot = atomicAdd(&gap_list[0], 1u);
+            gap_list[1 + 3 * slot] = o; gap_list[2 + 3 * slot] = min(o + kGapSegment, hi); gap_list[3 + 3 * slot] = s;
+        }
+        len = 0;
+    } else if (len <= 2) {
+        // the common case inside the fluid (next occupied cell is adjacent): write it here
+        if (len >= 1) table[lo] = s;
+        if (len == 2) table[lo + 1] = s;
         len = 0;
     }
     uint32_t todo = __ballot_sync(0xffffffffu, len > 0);
@@ -135,11 +144,9 @@ __global__ void __launch_bounds__(256)
 k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
 {
     const uint32_t ngaps = gap_list[0];
-    for (uint32_t g = 0; g < ngaps; g++) {
+    for (uint32_t g = blockIdx.x; g < ngaps; g += gridDim.x) {       // one block per worklist entry
         const uint32_t lo = gap_list[1 + 3 * g], hi = gap_list[2 + 3 * g], s = gap_list[3 + 3 * g];
-        for (uint64_t i = (uint64_t)lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi;
-             i += (uint64_t)gridDim.x * blockDim.x)
-            table[i] = s;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) table[i] = s;
     }
 }
 
@@ -320,7 +327,7 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
     } else {
         cudaMemsetAsync(gap_list, 0, sizeof(uint32_t), st);
         k_build_table_grid<<<blocks_for(P.n + 1, 256), 256, 0, st>>>(key_sorted, tstart, gap_list, P.n, P.ncell);
-        k_fill_gaps<<<148, 256, 0, st>>>(tstart, gap_list);
+        k_fill_gaps<<<148 * 4, 256, 0, st>>>(tstart, gap_list);
         *launches += 2;
     }
 }

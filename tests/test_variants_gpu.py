@@ -26,8 +26,8 @@ print("VARIANT_OK")
 """
 
 
-@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY_WALK": "1"}],
-                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density"])
+@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}],
+                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density"])
 def test_enumeration_variants_match_oracle(env):
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, os.path.join(ROOT, "tests"))], env=e, cwd=ROOT,
