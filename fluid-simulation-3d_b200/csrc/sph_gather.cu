@@ -76,76 +76,111 @@ k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
 }
 
 // ---- density pass, two-phase, one thread per particle (default) ------------------------------------
-// Phase A walks the table and applies ONLY the reference's exact predicate; survivors are appended to the
-// particle's neighbour-list column with a predicated store (no divergent branch: ~16 instructions per
-// candidate, 4 loads in flight).  Phase B replays the column and evaluates the smoothing kernels, so
-// the expensive code runs for the ~16 % of candidates that are neighbours, converged.  The list is both
-// the compaction buffer of this pass and the input of the pressure / viscosity passes.
-__device__ __forceinline__ void st_if(uint32_t* p, const uint32_t v, const bool c)
+// Phase A walks the table and applies ONLY the reference's exact predicate; survivors are pushed on a
+// small per-thread shared-memory stack with a predicated store (no divergent branch, 4 candidate loads
+// in flight).  Phase B (flush) pops the stack, evaluates the smoothing kernels -- the expensive code runs
+// for the ~16 % of candidates that are neighbours, converged -- and writes the neighbour-list column the
+// pressure / viscosity passes replay.  Rows and segments are warp-uniform loop levels (redux.sync), so the
+// flush is collective and happens at most once per SEG candidates whatever the density.
+constexpr int KS = 48;     // stack entries per thread
+constexpr int SEG = 16;    // candidates between two flush checks
+
+template <int MODE>
+__device__ __forceinline__ void row_bounds(const GatherArgs& A, const DevParams& P, const int3 c, const int3 g,
+                                           const int x0, const int x1, const int r, uint32_t& b, uint32_t& e, float& hf)
 {
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.global.b32 [%0], %1; }" ::"l"(p), "r"(v), "r"((int)c));
+    b = e = 0;
+    hf = 0.0f;
+    if (MODE == SPH_TABLE_GRID) {                          // 9 rows (dy, dz) x one contiguous x window
+        const int z = g.z + r / 3 - 1, y = g.y + r % 3 - 1;
+        if (z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
+        const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
+        b = __ldg(&A.table[row + x0]);
+        e = __ldg(&A.table[row + x1 + 1]);
+    } else {                                               // 27 buckets, offsets[27] order (physicsWorld.h:131-143)
+        const uint32_t h = hash_cell(c.x + r / 9 - 1, c.y + (r / 3) % 3 - 1, c.z + r % 3 - 1);
+        const uint32_t key = key_of_hash(h, P);
+        const uint32_t s0 = __ldg(&A.table[key]);
+        if (s0 >= P.n) return;                             // 0x7FFFFFFF: empty bucket (:339)
+        b = s0;
+        e = __ldg(&A.tend[key]);
+        hf = __uint2float_rn(h);                           // `index.y != hash` is compared in float (:346)
+    }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kWalkThreads)
 k_density_list(const GatherArgs A, const DevParams P)
 {
-    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.row1) return;
+    __shared__ uint32_t stk[KS][kWalkThreads];
+    const int tid = threadIdx.x;
+    const uint32_t iraw = P.row0 + blockIdx.x * blockDim.x + tid;
+    const bool valid = iraw < P.row1;
+    const uint32_t i = valid ? iraw : P.row1 - 1;          // idle tail threads shadow the last row (they join the collectives)
     const Self s = load_self<PASS_DENSITY>(A, P, i);
-    const uint32_t K = A.list_k;
+    const uint32_t K = A.list_idx ? A.list_k : 0u;
     const size_t stride = A.list_stride;
     uint32_t* col = A.list_idx + i;
-    uint32_t n = 0;
-    auto test = [&](const uint32_t j, const float4 q, const bool in) {
-        float ox, oy, oz;
-        const bool ok = in && !(sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r);      // :357, exact (Q8)
-        st_if(col + (size_t)n * stride, j, ok && n < K);
-        n += ok;
-    };
-    if (MODE == SPH_TABLE_GRID) {
-        const int3 g = grid_cell(cell_of(s.p.x, s.p.y, s.p.z, P.r), P);
-        const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
-        const uint32_t nlast = P.n - 1;
-        #pragma unroll 1
-        for (int r9 = 0; r9 < 9; r9++) {
-            const int z = g.z + r9 / 3 - 1, y = g.y + r9 % 3 - 1;
-            if (z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) continue;
-            const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
-            const uint32_t b = __ldg(&A.table[row + x0]), e = __ldg(&A.table[row + x1 + 1]);
-            #pragma unroll 1
-            for (uint32_t jb = b; jb < e; jb += 4) {
-                float4 q[4];
-                #pragma unroll
-                for (int u = 0; u < 4; u++) q[u] = __ldg(&A.pred[min(jb + u, nlast)]);
-                #pragma unroll
-                for (int u = 0; u < 4; u++) test(jb + u, q[u], jb + u < e);
-            }
-        }
-    } else {
-        for_each_candidate<MODE>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) { test(j, q, true); });
-    }
-    asm volatile("" ::: "memory");                         // phase B reads what phase A stored
+    uint32_t n = 0, ns = 0;
     Acc acc = {0.0f, 0.0f, 0.0f, 0u};
-    if (n > K) {                                           // overflowed column: evaluate by walking (nothing recorded twice)
-        GatherArgs W = A;
-        W.list_idx = nullptr;
-        walk_particle<MODE, PASS_DENSITY>(W, P, s, acc);
-    } else {
-        for (uint32_t k0 = 0; k0 < n; k0 += 4) {
+
+    auto flush = [&]() {
+        for (uint32_t k0 = 0; k0 < ns; k0 += 4) {
             uint32_t j[4];
             Fetched f[4];
             #pragma unroll
-            for (int u = 0; u < 4; u++) j[u] = (k0 + u < n) ? col[(size_t)(k0 + u) * stride] : i;
+            for (int u = 0; u < 4; u++) j[u] = (k0 + u < ns) ? stk[k0 + u][tid] : i;
             #pragma unroll
             for (int u = 0; u < 4; u++) f[u] = fetch<PASS_DENSITY>(A, j[u]);
             #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (k0 + u < n) (void)eval<PASS_DENSITY>(P, s, j[u], f[u], acc);
+            for (int u = 0; u < 4; u++) {
+                if (k0 + u < ns) {
+                    (void)eval<PASS_DENSITY>(P, s, j[u], f[u], acc);
+                    if (valid && n + k0 + u < K) col[(size_t)(n + k0 + u) * stride] = j[u];
+                }
+            }
+        }
+        n += ns;
+        ns = 0;
+    };
+
+    const int3 c = cell_of(s.p.x, s.p.y, s.p.z, P.r);
+    const int3 g = grid_cell(c, P);
+    const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
+    constexpr int ROWS = (MODE == SPH_TABLE_GRID) ? 9 : 27;
+    #pragma unroll 1
+    for (int r = 0; r < ROWS; r++) {
+        uint32_t b, e;
+        float hf;
+        row_bounds<MODE>(A, P, c, g, x0, x1, r, b, e, hf);
+        const uint32_t segs = (__reduce_max_sync(0xffffffffu, e - b) + SEG - 1) / SEG;
+        #pragma unroll 1
+        for (uint32_t sg = 0; sg < segs; sg++) {
+            if (__any_sync(0xffffffffu, ns > KS - SEG)) flush();
+            const uint32_t j0 = b + sg * SEG;
+            const uint32_t je = min(j0 + SEG, e);
+            #pragma unroll 1
+            for (uint32_t jb = j0; jb < je; jb += 4) {
+                const float4* qp = A.pred + jb;            // the array is padded: reading up to 3 rows past `e` is safe
+                float4 q[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = __ldg(qp + u);
+                #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float ox, oy, oz;
+                    bool ok = (jb + u < je) && !(sqr_dist(q[u], s.p, ox, oy, oz) > P.sqr_r);   // :357, exact (Q8)
+                    if (MODE == SPH_TABLE_REFERENCE_HASH) ok = ok && (q[u].w == hf);
+                    if (ok) stk[ns][tid] = jb + u;
+                    ns += ok;
+                }
+            }
         }
     }
-    finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
-    A.list_cnt[i] = n;
+    flush();
+    if (valid) {
+        finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
+        if (A.list_cnt) A.list_cnt[i] = n;
+    }
 }
 
 // ---- neighbour-list passes: pressure and viscosity replay the exact neighbour set recorded by the
