@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
-    "sph_get_grid", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
+    "sph_get_grid", "sph_grid_x_subdivision", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
     "sph_upload_owned", "sph_download_owned", "sph_comm_stats",
 ]
 
@@ -118,6 +118,7 @@ def load_library():
     L.sph_stream.argtypes = [vp]
     L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
+    L.sph_grid_x_subdivision.argtypes = [vp]
     L.sph_host_register.argtypes = [vp, C.c_size_t]
     L.sph_host_unregister.argtypes = [vp]
     L.sph_comm_id_bytes.restype = C.c_size_t
@@ -287,6 +288,9 @@ class FluidSimulation:
 
     def stream_ptr(self):
         return int(self.L.sph_stream(self.h) or 0)
+
+    def grid_x_subdivision(self):
+        return int(self.L.sph_grid_x_subdivision(self.h))
 
     def grid(self):
         d = np.zeros(3, np.int32)

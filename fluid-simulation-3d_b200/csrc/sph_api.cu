@@ -5,6 +5,7 @@
 // all enqueued on the context's stream; six CUDA-event timers mirror getElapsedTime* (:184-212).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -57,6 +58,8 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->rr = r * r;
     P->cull_hi = nextafterf((float)((double)p.sqr_radius * (1.0 + 5e-7)), INFINITY);
     for (int a = 0; a < 3; a++) { P->gmin[a] = c->gmin[a]; P->gdim[a] = c->gdim[a]; }
+    P->xsub = c->xsub;
+    P->xwin = (float)(sqrt((double)p.sqr_radius) * (1.0 + 1e-5));
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
     P->row0 = 0; P->row1 = n; P->n_a = n;
@@ -78,7 +81,7 @@ static int update_grid_geometry(SphContext* c)
         if (q > 1e8) return fail(c, SPH_ERR_INVALID, "bound / interaction_radius too large for the grid table");
         const int hi = (int)q + 2, lo = -(int)q - 3;
         c->gmin[a] = lo;
-        c->gdim[a] = hi - lo + 1;
+        c->gdim[a] = (hi - lo + 1) * (a == 0 ? c->xsub : 1);          // x is subdivided (sph_device.cuh: grid_cell)
         cells *= (uint64_t)c->gdim[a];
     }
     if (cells > (1ull << 31))
@@ -180,6 +183,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
 
     SphContext* c = new SphContext();
+    if (const char* xs = getenv("SPH_XSUB")) { const int v = atoi(xs); if (v == 1 || v == 2 || v == 4 || v == 8) c->xsub = v; }
     c->device = device;
     c->cap = capacity;
     sph_default_params(&c->params);
@@ -263,6 +267,8 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
 void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
+
+int sph_grid_x_subdivision(const SphContext* c) { return c ? c->xsub : 0; }
 
 int sph_get_grid(const SphContext* c, int32_t* dims3, int32_t* origin3)
 {

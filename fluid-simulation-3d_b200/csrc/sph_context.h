@@ -48,6 +48,7 @@ struct SphContext {
     int gmin[3] = {0, 0, 0};
     int gdim[3] = {1, 1, 1};
     uint32_t ncell = 1;
+    int xsub = 4;                // x subdivision of the GRID table cells (power of two)
 
     // slab-decomposed multi-GPU (sph_multi.cu)
     ncclComm* comm = nullptr;

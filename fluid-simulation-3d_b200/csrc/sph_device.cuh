@@ -39,13 +39,63 @@ __device__ __forceinline__ uint32_t key_of_hash(uint32_t h, const DevParams& P)
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__device__ __forceinline__ int3 grid_cell(int3 c, const DevParams& P)
+// GRID table cell of a predicted position: (fine x, y, z).  y and z are the reference's cells
+// floor(p / r) (:499-503); x is subdivided xsub = 2^k times -- floor((p.x / r) * xsub), exact nesting because
+// the scale is a power of two -- so that a row's x window can be cut to the particle's own reach instead of
+// three whole cells.  Everything is clamped into the table (border cells collect what lies beyond).
+__device__ __forceinline__ int3 grid_cell(const float px, const float py, const float pz, const DevParams& P)
 {
+    const float tx = __fdiv_rn(px, P.r);
+    const int xf = __float2int_rz(floorf(tx * (float)P.xsub));
+    const int cy = __float2int_rz(floorf(__fdiv_rn(py, P.r)));
+    const int cz = __float2int_rz(floorf(__fdiv_rn(pz, P.r)));
     int3 g;
-    g.x = clampi(c.x - P.gmin[0], 0, P.gdim[0] - 1);
-    g.y = clampi(c.y - P.gmin[1], 0, P.gdim[1] - 1);
-    g.z = clampi(clampi(c.z - P.gmin[2], 0, P.gz_global - 1) - P.zlo, 0, P.gdim[2] - 1);
+    g.x = clampi(xf - P.gmin[0] * P.xsub, 0, P.gdim[0] - 1);
+    g.y = clampi(cy - P.gmin[1], 0, P.gdim[1] - 1);
+    g.z = clampi(clampi(cz - P.gmin[2], 0, P.gz_global - 1) - P.zlo, 0, P.gdim[2] - 1);
     return g;
+}
+
+// The candidate window of a particle: its cell, the fine-x range [x0, x1] to read in each (y,z) row, and a
+// 9-bit mask of the rows (dz+1)*3 + (dy+1) that can hold a neighbour at all.
+//  * x: [p.x - w, p.x + w] with w = sqrt(sqrRadius) widened past any rounding, intersected with the
+//    reference's three cells (so a radius smaller than the cull still sees exactly the reference's 27 cells, Q2);
+//  * rows: a row is skipped when the particle is farther than w from the row's (y,z) slab (the corner rows,
+//    21 % of the time) -- no particle there can pass d^2 <= sqrRadius.
+struct Win { int3 g; int x0, x1; uint32_t rows; };
+
+__device__ __forceinline__ Win window_of(const float px, const float py, const float pz, const DevParams& P)
+{
+    Win W;
+    W.g = grid_cell(px, py, pz, P);
+    const float S = (float)P.xsub;
+    const float slack = fabsf(px) * 3e-7f;
+    const int cx = __float2int_rz(floorf(__fdiv_rn(px, P.r)));
+    int lo = __float2int_rz(floorf(__fdiv_rn(px - P.xwin - slack, P.r) * S));
+    int hi = __float2int_rz(floorf(__fdiv_rn(px + P.xwin + slack, P.r) * S));
+    lo = max(lo, (cx - 1) * P.xsub);
+    hi = min(hi, (cx + 2) * P.xsub - 1);
+    W.x0 = clampi(lo - P.gmin[0] * P.xsub, 0, P.gdim[0] - 1);
+    W.x1 = clampi(hi - P.gmin[0] * P.xsub, 0, P.gdim[0] - 1);
+    // distance of the particle to the neighbouring slabs of its own cell, in y and z
+    const int cy = __float2int_rz(floorf(__fdiv_rn(py, P.r)));
+    const int cz = __float2int_rz(floorf(__fdiv_rn(pz, P.r)));
+    const float w = P.xwin + (fabsf(py) + fabsf(pz)) * 3e-7f + 1e-6f;
+    const float w2 = w * w;
+    const float ylo = fmaxf(py - (float)cy * P.r, 0.0f), yhi = fmaxf((float)(cy + 1) * P.r - py, 0.0f);
+    const float zlo = fmaxf(pz - (float)cz * P.r, 0.0f), zhi = fmaxf((float)(cz + 1) * P.r - pz, 0.0f);
+    uint32_t rows = 0x1FFu;
+    // only when the cell was not clamped into the table (then the geometry above does not describe the cell)
+    const bool inside = (cy - P.gmin[1] == W.g.y) && (clampi(cz - P.gmin[2], 0, P.gz_global - 1) - P.zlo == W.g.z) &&
+                        (cz - P.gmin[2] >= 0) && (cz - P.gmin[2] < P.gz_global);
+    if (inside) {
+        if (ylo * ylo + zlo * zlo > w2) rows &= ~(1u << 0);     // (dy,dz) = (-1,-1)
+        if (yhi * yhi + zlo * zlo > w2) rows &= ~(1u << 2);     // (+1,-1)
+        if (ylo * ylo + zhi * zhi > w2) rows &= ~(1u << 6);     // (-1,+1)
+        if (yhi * yhi + zhi * zhi > w2) rows &= ~(1u << 8);     // (+1,+1)
+    }
+    W.rows = rows;
+    return W;
 }
 __device__ __forceinline__ uint32_t grid_key(int3 g, const DevParams& P)
 {

@@ -61,6 +61,10 @@ __device__ __forceinline__ void walk_particle(const GatherArgs& A, const DevPara
 }
 
 constexpr int kWalkThreads = 128;
+#ifndef SPH_LIST_UNROLL
+#define SPH_LIST_UNROLL 4
+#endif
+constexpr int kListUnroll = SPH_LIST_UNROLL;   // neighbour-list entries in flight per thread
 
 template <int MODE, int PASS>
 __global__ void __launch_bounds__(kWalkThreads)
@@ -87,13 +91,14 @@ constexpr int SEG = 16;    // candidates between two flush checks
 
 template <int MODE>
 __device__ __forceinline__ void row_bounds(const GatherArgs& A, const DevParams& P, const int3 c, const int3 g,
-                                           const int x0, const int x1, const int r, uint32_t& b, uint32_t& e, float& hf)
+                                           const int x0, const int x1, const uint32_t rows, const int r,
+                                           uint32_t& b, uint32_t& e, float& hf)
 {
     b = e = 0;
     hf = 0.0f;
     if (MODE == SPH_TABLE_GRID) {                          // 9 rows (dy, dz) x one contiguous x window
         const int z = g.z + r / 3 - 1, y = g.y + r % 3 - 1;
-        if (z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
+        if (!((rows >> r) & 1u) || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
         const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
         b = __ldg(&A.table[row + x0]);
         e = __ldg(&A.table[row + x1 + 1]);
@@ -145,14 +150,16 @@ k_density_list(const GatherArgs A, const DevParams P)
     };
 
     const int3 c = cell_of(s.p.x, s.p.y, s.p.z, P.r);
-    const int3 g = grid_cell(c, P);
-    const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
+    Win W = {};
+    if (MODE == SPH_TABLE_GRID) W = window_of(s.p.x, s.p.y, s.p.z, P);
+    const int3 g = W.g;
+    const int x0 = W.x0, x1 = W.x1;
     constexpr int ROWS = (MODE == SPH_TABLE_GRID) ? 9 : 27;
     #pragma unroll 1
     for (int r = 0; r < ROWS; r++) {
         uint32_t b, e;
         float hf;
-        row_bounds<MODE>(A, P, c, g, x0, x1, r, b, e, hf);
+        row_bounds<MODE>(A, P, c, g, x0, x1, W.rows, r, b, e, hf);
         const uint32_t segs = (__reduce_max_sync(0xffffffffu, e - b) + SEG - 1) / SEG;
         #pragma unroll 1
         for (uint32_t sg = 0; sg < segs; sg++) {
@@ -198,15 +205,16 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
         walk_particle<MODE, PASS>(A, P, s, acc);
     } else {
         const uint32_t* __restrict__ col = A.list_idx + i;
-        for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
-            uint32_t j[4];
-            Fetched f[4];
+        constexpr int U = kListUnroll;
+        for (uint32_t k0 = 0; k0 < cnt; k0 += U) {
+            uint32_t j[U];
+            Fetched f[U];
             #pragma unroll
-            for (int u = 0; u < 4; u++) j[u] = (k0 + u < cnt) ? __ldg(&col[(size_t)(k0 + u) * A.list_stride]) : s.i;
+            for (int u = 0; u < U; u++) j[u] = (k0 + u < cnt) ? __ldg(&col[(size_t)(k0 + u) * A.list_stride]) : s.i;
             #pragma unroll
-            for (int u = 0; u < 4; u++) f[u] = fetch<PASS>(A, j[u]);
+            for (int u = 0; u < U; u++) f[u] = fetch<PASS>(A, j[u]);
             #pragma unroll
-            for (int u = 0; u < 4; u++) (void)eval<PASS>(P, s, j[u], f[u], acc);   // padding entries are the particle itself: skipped
+            for (int u = 0; u < U; u++) (void)eval<PASS>(P, s, j[u], f[u], acc);   // padding entries are the particle itself: skipped
         }
     }
     finish<PASS>(A, P, s, acc, dt);
@@ -214,12 +222,13 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
 
 // 9 row windows of a cell: rows (dy, dz), x window [xa, xb]
 __device__ __forceinline__ void row_range(const uint32_t* __restrict__ table, const DevParams& P, const int3 g,
-                                          const int xa, const int xb, const int r9, uint32_t& b, uint32_t& e)
+                                          const int xa, const int xb, const uint32_t rows, const int r9,
+                                          uint32_t& b, uint32_t& e)
 {
     const int dz = r9 / 3 - 1, dy = r9 % 3 - 1;
     const int z = g.z + dz, y = g.y + dy;
     b = e = 0;
-    if (r9 >= 9 || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
+    if (r9 >= 9 || !((rows >> r9) & 1u) || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
     const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
     b = __ldg(&table[row + xa]);
     e = __ldg(&table[row + xb + 1]);
@@ -236,15 +245,16 @@ k_gather2(const GatherArgs A, const DevParams P, const float dt)
     const bool valid0 = i0r <= last, valid1 = i1r <= last;
     const Self s0 = load_self<PASS>(A, P, valid0 ? i0r : last);
     Self s1 = load_self<PASS>(A, P, valid1 ? i1r : last);
-    const int3 g0 = grid_cell(cell_of(s0.p.x, s0.p.y, s0.p.z, P.r), P);
-    const int3 g1 = grid_cell(cell_of(s1.p.x, s1.p.y, s1.p.z, P.r), P);
+    const Win W0 = window_of(s0.p.x, s0.p.y, s0.p.z, P), W1 = window_of(s1.p.x, s1.p.y, s1.p.z, P);
+    const int3 g0 = W0.g, g1 = W1.g;
     const bool straddle = valid1 && (g0.y != g1.y || g0.z != g1.z);
     const bool pair = valid1 && !straddle;
+    const uint32_t rows01 = pair ? (W0.rows | W1.rows) : W0.rows;
     // a particle that is not processed in the packed loop is parked far away: it never passes the cull
     const float far = 1.0e18f;
     const uint64_t px = pk(s0.p.x, pair ? s1.p.x : far), py = pk(s0.p.y, pair ? s1.p.y : far), pz = pk(s0.p.z, pair ? s1.p.z : far);
-    const int xa = max((pair ? min(g0.x, g1.x) : g0.x) - 1, 0);
-    const int xb = min((pair ? max(g0.x, g1.x) : g0.x) + 1, P.gdim[0] - 1);
+    const int xa = pair ? min(W0.x0, W1.x0) : W0.x0;
+    const int xb = pair ? max(W0.x1, W1.x1) : W0.x1;
     Acc a0 = {0.0f, 0.0f, 0.0f, 0u}, a1 = {0.0f, 0.0f, 0.0f, 0u};
     uint32_t n0 = 0, n1 = 0;
     const uint32_t nlast = P.n - 1;
@@ -270,12 +280,12 @@ k_gather2(const GatherArgs A, const DevParams P, const float dt)
     // counts, not the sum of per-row maxima).  The next row's range is fetched one row ahead.
     int r = 0;
     uint32_t j, e, bn, en;
-    row_range(A.table, P, g0, xa, xb, 0, j, e);
-    row_range(A.table, P, g0, xa, xb, 1, bn, en);
+    row_range(A.table, P, g0, xa, xb, rows01, 0, j, e);
+    row_range(A.table, P, g0, xa, xb, rows01, 1, bn, en);
     auto advance = [&]() {
         do {
             r++; j = bn; e = en;
-            row_range(A.table, P, g0, xa, xb, r + 1, bn, en);
+            row_range(A.table, P, g0, xa, xb, rows01, r + 1, bn, en);
         } while (r < 9 && j >= e);
     };
     if (j >= e) advance();
@@ -311,13 +321,14 @@ k_gather2(const GatherArgs A, const DevParams P, const float dt)
         todo &= todo - 1;
         const uint32_t ic = __shfl_sync(0xffffffffu, s1.i, src);
         const Self sc = load_self<PASS>(A, P, ic);
-        const int3 gc = grid_cell(cell_of(sc.p.x, sc.p.y, sc.p.z, P.r), P);
-        const int ca = max(gc.x - 1, 0), cb = min(gc.x + 1, P.gdim[0] - 1);
+        const Win Wc = window_of(sc.p.x, sc.p.y, sc.p.z, P);
+        const int3 gc = Wc.g;
+        const int ca = Wc.x0, cb = Wc.x1;
         Acc ac = {0.0f, 0.0f, 0.0f, 0u};
         #pragma unroll 1
         for (int r9 = 0; r9 < 9; r9++) {
             uint32_t b, e;
-            row_range(A.table, P, gc, ca, cb, r9, b, e);
+            row_range(A.table, P, gc, ca, cb, Wc.rows, r9, b, e);
             for (uint32_t j = b + lane; j < e; j += 32) term<PASS>(A, P, sc, j, ac);
         }
         #pragma unroll
@@ -349,14 +360,15 @@ k_density_pair(const GatherArgs A, const DevParams P)
     const bool valid0 = i0r <= last, valid1 = i1r <= last;
     const Self s0 = load_self<PASS_DENSITY>(A, P, valid0 ? i0r : last);
     const Self s1 = load_self<PASS_DENSITY>(A, P, valid1 ? i1r : last);
-    const int3 g0 = grid_cell(cell_of(s0.p.x, s0.p.y, s0.p.z, P.r), P);
-    const int3 g1 = grid_cell(cell_of(s1.p.x, s1.p.y, s1.p.z, P.r), P);
+    const Win W0 = window_of(s0.p.x, s0.p.y, s0.p.z, P), W1 = window_of(s1.p.x, s1.p.y, s1.p.z, P);
+    const int3 g0 = W0.g, g1 = W1.g;
     const bool straddle = valid1 && (g0.y != g1.y || g0.z != g1.z);
     const bool pair = valid1 && !straddle;
+    const uint32_t rows01 = pair ? (W0.rows | W1.rows) : W0.rows;
     const float far = 1.0e18f;       // a particle that is not processed here never passes the cull
     const uint64_t px = pk(s0.p.x, pair ? s1.p.x : far), py = pk(s0.p.y, pair ? s1.p.y : far), pz = pk(s0.p.z, pair ? s1.p.z : far);
-    const int xa = max((pair ? min(g0.x, g1.x) : g0.x) - 1, 0);
-    const int xb = min((pair ? max(g0.x, g1.x) : g0.x) + 1, P.gdim[0] - 1);
+    const int xa = pair ? min(W0.x0, W1.x0) : W0.x0;
+    const int xb = pair ? max(W0.x1, W1.x1) : W0.x1;
     const uint32_t K = A.list_k;
     const size_t stride = A.list_stride;
     uint32_t* col0 = A.list_idx + s0.i;
@@ -368,7 +380,7 @@ k_density_pair(const GatherArgs A, const DevParams P)
     #pragma unroll 1
     for (int r9 = 0; r9 < 9; r9++) {
         uint32_t b, e;
-        row_range(A.table, P, g0, xa, xb, r9, b, e);
+        row_range(A.table, P, g0, xa, xb, rows01, r9, b, e);
         const uint32_t chunks = (__reduce_max_sync(0xffffffffu, e - b) + GCH - 1) / GCH;
         #pragma unroll 1
         for (uint32_t c = 0; c < chunks; c++) {
@@ -424,15 +436,16 @@ k_density_pair(const GatherArgs A, const DevParams P)
         todo &= todo - 1;
         const uint32_t ic = __shfl_sync(0xffffffffu, s1.i, src);
         const Self sc = load_self<PASS_DENSITY>(A, P, ic);
-        const int3 gc = grid_cell(cell_of(sc.p.x, sc.p.y, sc.p.z, P.r), P);
-        const int ca = max(gc.x - 1, 0), cb = min(gc.x + 1, P.gdim[0] - 1);
+        const Win Wc = window_of(sc.p.x, sc.p.y, sc.p.z, P);
+        const int3 gc = Wc.g;
+        const int ca = Wc.x0, cb = Wc.x1;
         uint32_t* colc = A.list_idx + ic;
         Acc ac = {0.0f, 0.0f, 0.0f, 0u};
         uint32_t nc = 0;
         #pragma unroll 1
         for (int r9 = 0; r9 < 9; r9++) {
             uint32_t b, e;
-            row_range(A.table, P, gc, ca, cb, r9, b, e);
+            row_range(A.table, P, gc, ca, cb, Wc.rows, r9, b, e);
             for (uint32_t jb = b; jb < e; jb += 32) {
                 const uint32_t j = jb + lane;
                 bool ok = false;

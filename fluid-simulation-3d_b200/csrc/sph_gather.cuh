@@ -212,8 +212,9 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pr
             }
         }
     } else {
-        const int3 g = grid_cell(c, P);
-        const int x0 = max(g.x - 1, 0), x1 = min(g.x + 1, P.gdim[0] - 1);
+        const Win W = window_of(pi.x, pi.y, pi.z, P);
+        const int3 g = W.g;
+        const int x0 = W.x0, x1 = W.x1;
         #pragma unroll 1
         for (int dz = -1; dz <= 1; dz++) {
             const int z = g.z + dz;
@@ -221,7 +222,7 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pr
             #pragma unroll 1
             for (int dy = -1; dy <= 1; dy++) {
                 const int y = g.y + dy;
-                if (y < 0 || y >= P.gdim[1]) continue;
+                if (y < 0 || y >= P.gdim[1] || !((W.rows >> ((dz + 1) * 3 + dy + 1)) & 1u)) continue;
                 const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
                 const uint32_t b = __ldg(&tstart[row + x0]);
                 const uint32_t e = __ldg(&tstart[row + x1 + 1]);

@@ -22,8 +22,10 @@ struct DevParams {
     float    rr;            // r*r
     float    cull_hi;       // sqr_r * (1 + 5e-7) rounded up: conservative prefilter for the FMA-fused d^2 (sph_gather.cu)
     // GRID table: cell g = clamp(floor(pred/r) - gmin, 0, gdim-1); key = (gz*gdim.y + gy)*gdim.x + gx
-    int      gmin[3];
-    int      gdim[3];
+    int      gmin[3];       // first reference cell of the table per axis
+    int      gdim[3];       // table extent: fine x cells (reference cells * xsub), y cells, z cells
+    int      xsub;          // subdivision of the cell in x (power of two)
+    float    xwin;          // half width of the x window: sqrt(sqr_r) * (1 + 1e-5)
     uint32_t ncell;
     // REFERENCE_HASH table: key = hash % n via Lemire fastmod, M = 2^64 / n + 1
     uint64_t modM;

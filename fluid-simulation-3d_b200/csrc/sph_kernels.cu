@@ -55,12 +55,12 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
             cls[s] = k;
         }
         if (k & (CLS_MIG_LO | CLS_MIG_HI)) { key[s] = P.ncell; return; }      // leaves this rank: sorts past the table
-        int3 g = grid_cell(c, P);
+        int3 g = grid_cell(pr.x, pr.y, pr.z, P);
         g.z = clampi(gz, P.own_lo, P.own_hi - 1) - P.zlo;                     // (a row that cannot migrate is kept in range)
         key[s] = grid_key(g, P);
         return;
     }
-    key[s] = grid_key(grid_cell(c, P), P);
+    key[s] = grid_key(grid_cell(pr.x, pr.y, pr.z, P), P);
 }
 
 // slab mode: keys of the ghost rows (predicted positions received from / kept for the neighbour ranks)
@@ -70,7 +70,7 @@ k_ghost_key(const float4* __restrict__ ghost_pred, uint32_t* __restrict__ key, c
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= rows) return;
     const float4 q = ghost_pred[s];
-    key[s] = grid_key(grid_cell(cell_of(q.x, q.y, q.z, P.r), P), P);
+    key[s] = grid_key(grid_cell(q.x, q.y, q.z, P), P);
 }
 
 // ---- S2 tables -------------------------------------------------------------
@@ -123,10 +123,11 @@ k_build_table_grid(const uint32_t* __restrict__ key_sorted, uint32_t* __restrict
             gap_list[1 + 3 * slot] = o; gap_list[2 + 3 * slot] = min(o + kGapSegment, hi); gap_list[3 + 3 * slot] = s;
         }
         len = 0;
-    } else if (len <= 2) {
-        // the common case inside the fluid (next occupied cell is adjacent): write it here
-        if (len >= 1) table[lo] = s;
-        if (len == 2) table[lo + 1] = s;
+    } else if (len <= 8) {
+        // the common case inside the fluid (the next occupied fine cell is a few entries away): write it here
+        #pragma unroll
+        for (uint32_t t = 0; t < 8; t++)
+            if (t < len) table[lo + t] = s;
         len = 0;
     }
     uint32_t todo = __ballot_sync(0xffffffffu, len > 0);

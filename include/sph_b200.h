@@ -149,6 +149,8 @@ uint64_t sph_launch_count(const SphContext* ctx);
 void* sph_stream(const SphContext* ctx);
 /* grid-table geometry: dims[3], origin cell[3] (for tests) */
 int  sph_get_grid(const SphContext* ctx, int32_t* dims3, int32_t* origin3);
+/* GRID table: the cell is subdivided this many times in x (dims3[0] counts the fine cells) */
+int  sph_grid_x_subdivision(const SphContext* ctx);
 
 /* -- host memory helpers ---------------------------------------------------- */
 /* Page-lock / unlock a caller-owned host range in place (cudaHostRegister) so uploads and downloads

@@ -34,9 +34,16 @@ def canonical_order(sorted_idx, sorted_key):
     return sorted_idx[order]
 
 
-def grid_keys(cells, dims, origin):
-    gc = np.clip(cells.astype(np.int64) - origin.astype(np.int64), 0, dims.astype(np.int64) - 1)
-    return ((gc[:, 2] * dims[1] + gc[:, 1]) * dims[0] + gc[:, 0]).astype(np.uint32)
+def grid_keys(pred, cells, dims, origin, xsub, r):
+    """GRID key of every particle: y, z = the reference's cells; x = the cell subdivided xsub times,
+    floor((pred.x / r) * xsub) in fp32 like the device (sph_device.cuh: grid_cell)."""
+    d = dims.astype(np.int64)
+    tx = pred[:, 0].astype(np.float32) / np.float32(r)
+    xf = np.floor(tx * np.float32(xsub)).astype(np.int64)
+    gx = np.clip(xf - int(origin[0]) * xsub, 0, d[0] - 1)
+    gy = np.clip(cells[:, 1].astype(np.int64) - int(origin[1]), 0, d[1] - 1)
+    gz = np.clip(cells[:, 2].astype(np.int64) - int(origin[2]), 0, d[2] - 1)
+    return ((gz * d[1] + gy) * d[0] + gx).astype(np.uint32)
 
 
 def assert_close(name, got, ref, scale, rel=REL):
@@ -86,7 +93,7 @@ def check_step(pkg, scene, mode, dt, report=None):
             assert np.array_equal(s_key, k[s_idx]), "sorted key vs per-particle key"
         else:
             dims, origin = sim.grid()
-            gk = grid_keys(cells, dims, origin)
+            gk = grid_keys(pred, cells, dims, origin, sim.grid_x_subdivision(), float(sim.get_params().interaction_radius))
             assert np.array_equal(s_key, gk[s_idx]), "grid key of sorted rows"
             ncell = int(dims[0]) * int(dims[1]) * int(dims[2])
             assert table.size == ncell + 1 and table[0] == 0 and table[-1] == n
