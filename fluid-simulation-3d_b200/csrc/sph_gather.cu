@@ -86,6 +86,12 @@ k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
 // for the ~16 % of candidates that are neighbours, converged -- and writes the neighbour-list column the
 // pressure / viscosity passes replay.  Rows and segments are warp-uniform loop levels (redux.sync), so the
 // flush is collective and happens at most once per SEG candidates whatever the density.
+__device__ __forceinline__ void sts_if(uint32_t* p, const uint32_t v, const bool c)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.shared.b32 [%0], %1; }" ::"r"(a), "r"(v), "r"((int)c) : "memory");
+}
+
 constexpr int KS = 48;     // stack entries per thread
 constexpr int SEG = 16;    // candidates between two flush checks
 
@@ -175,9 +181,10 @@ k_density_list(const GatherArgs A, const DevParams P)
                 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     float ox, oy, oz;
-                    bool ok = (jb + u < je) && !(sqr_dist(q[u], s.p, ox, oy, oz) > P.sqr_r);   // :357, exact (Q8)
-                    if (MODE == SPH_TABLE_REFERENCE_HASH) ok = ok && (q[u].w == hf);
-                    if (ok) stk[ns][tid] = jb + u;
+                    // branch-free: bitwise &, predicated store
+                    bool ok = (jb + u < je) & !(sqr_dist(q[u], s.p, ox, oy, oz) > P.sqr_r);    // :357, exact (Q8)
+                    if (MODE == SPH_TABLE_REFERENCE_HASH) ok = ok & (q[u].w == hf);
+                    sts_if(&stk[ns][tid], jb + u, ok);
                     ns += ok;
                 }
             }
@@ -206,11 +213,18 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
     } else {
         const uint32_t* __restrict__ col = A.list_idx + i;
         constexpr int U = kListUnroll;
+        // software pipeline: the list entries of chunk c+1 are requested before chunk c's rows are fetched,
+        // so the (cold, HBM-resident) list read overlaps the (L1/L2-resident) particle rows of the chunk before
+        uint32_t jn[U];
+        #pragma unroll
+        for (int u = 0; u < U; u++) jn[u] = (u < cnt) ? __ldg(&col[(size_t)u * A.list_stride]) : s.i;
         for (uint32_t k0 = 0; k0 < cnt; k0 += U) {
             uint32_t j[U];
             Fetched f[U];
             #pragma unroll
-            for (int u = 0; u < U; u++) j[u] = (k0 + u < cnt) ? __ldg(&col[(size_t)(k0 + u) * A.list_stride]) : s.i;
+            for (int u = 0; u < U; u++) j[u] = jn[u];
+            #pragma unroll
+            for (int u = 0; u < U; u++) jn[u] = (k0 + U + u < cnt) ? __ldg(&col[(size_t)(k0 + U + u) * A.list_stride]) : s.i;
             #pragma unroll
             for (int u = 0; u < U; u++) f[u] = fetch<PASS>(A, j[u]);
             #pragma unroll

@@ -57,7 +57,11 @@ def main():
         t = json.load(open(tp)) if os.path.exists(tp) else {}
         e = t.setdefault(cfg, {})
         for d in summary:
-            name = d['kernel'].split('<')[0].split('::')[-1].replace('k_', '')
+            kn = d['kernel']
+            if 'density' in kn or kn.endswith(', 0>'): name = 'density'
+            elif kn.endswith(', 1>') or 'pressure' in kn: name = 'pressure'
+            elif kn.endswith(', 2>') or 'viscosity' in kn: name = 'viscosity'
+            else: name = kn.split('<')[0].split('::')[-1].replace('k_', '')
             e[name] = d['dram_bytes_total']
         json.dump(t, open(tp, 'w'), indent=1)
     print(open(out + '.txt').read())
