@@ -96,7 +96,9 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
 {
     __shared__ uint32_t cnt[kSortWarps][256];
     __shared__ uint32_t base[256];
+    __shared__ uint32_t texcl[256];
     __shared__ uint32_t wsum[kSortWarps];
+    __shared__ uint32_t skey[kTile], sval[kTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     {   // digit base = exclusive scan of the 256 digit totals (thread d owns digit d)
@@ -138,24 +140,50 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
             __syncwarp();
         }
         __syncthreads();
-        {   // per digit: exclusive scan across the warps of this tile, then advance the block's running base
+        // per digit d (thread d): exclusive scan across the warps of this tile; tile count; then an exclusive
+        // scan of the 256 tile counts gives each digit's first slot inside the tile (texcl)
+        uint32_t run = 0;
+        {
             const int d = threadIdx.x;
-            uint32_t run = 0;
             #pragma unroll
-            for (int w = 0; w < kSortWarps; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run + base[d]; run += c; }
-            base[d] += run;   // only thread d touches base[d] / cnt[*][d] here
+            for (int w = 0; w < kSortWarps; w++) { uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+            uint32_t inc = run;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t2;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            uint32_t wbase = 0;
+            #pragma unroll
+            for (int w = 0; w < kSortWarps; w++) if (w < warp) wbase += wsum[w];
+            texcl[d] = wbase + inc - run;
         }
         __syncthreads();
+        // stage the tile in shared memory in digit order, then write it out linearly: consecutive threads
+        // write consecutive slots of the same digit's run -> coalesced segments instead of 4-byte scatters
         #pragma unroll
         for (int r = 0; r < kItems; r++) {
             const uint64_t idx = tile_base + (uint64_t)warp * (32 * kItems) + r * 32 + lane;
             if (idx < n) {
                 const uint32_t d = (key[r] >> shift) & 0xFFu;
-                const uint32_t dst = cnt[warp][d] + rank[r];
-                keys_out[dst] = key[r];
-                vals_out[dst] = kIdentity ? (uint32_t)idx : vals_in[idx];
+                const uint32_t lp = texcl[d] + cnt[warp][d] + rank[r];
+                skey[lp] = key[r];
+                sval[lp] = kIdentity ? (uint32_t)idx : vals_in[idx];
             }
         }
+        __syncthreads();
+        const uint32_t tile_n = (uint32_t)min((uint64_t)kTile, (uint64_t)n - tile_base);
+        for (uint32_t q = threadIdx.x; q < tile_n; q += kSortThreads) {
+            const uint32_t k = skey[q];
+            const uint32_t d = (k >> shift) & 0xFFu;
+            const uint32_t dst = base[d] + (q - texcl[d]);
+            keys_out[dst] = k;
+            vals_out[dst] = sval[q];
+        }
+        __syncthreads();
+        base[threadIdx.x] += run;   // advance the block's running global offset of digit d
         __syncthreads();
     }
 }
