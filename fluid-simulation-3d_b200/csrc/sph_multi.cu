@@ -20,6 +20,8 @@
 #include <nccl.h>
 #include <dlfcn.h>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -87,6 +89,7 @@ struct SlabState {
     float4* keep[2] = {nullptr, nullptr};         // [xcap] migrants that stay visible as ghosts, lo / hi
     float4* ghost_pred = nullptr;                 // [gcap] recv_lo | keep_lo | recv_hi | keep_hi
     uint32_t* block_counts = nullptr;             // [6][nblocks]
+    uint8_t* block_any = nullptr;                 // [nblocks] block has at least one row in some list
     uint32_t* dev_small = nullptr;                // 64 u32: totals[6], recv counts[4], picks[8], peer counts[4]
     uint32_t* host_small = nullptr;               // pinned mirror
     uint32_t nblocks_cap = 0;
@@ -94,6 +97,11 @@ struct SlabState {
     uint32_t o0 = 0, o1 = 0;                      // owned rows of the sorted arrays in the last step
     uint32_t stats[5] = {0, 0, 0, 0, 0};
     bool have_planes = false;
+    // SPH_SLAB_TIMING=1: finer timers of the spatial stage (events on the stream + host clock around the syncs)
+    bool prof = false;
+    cudaEvent_t pe[8] = {};
+    double pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t psteps = 0, pseen = 0;
 };
 
 namespace {
@@ -138,28 +146,40 @@ __device__ __forceinline__ bool lands_adjacent(const float4 p, const float4 v0, 
     return gz == P.own_lo - 1 || gz == P.own_hi;
 }
 
+constexpr int kPackIters = 16;                       // a block packs kPackIters * kPackThreads consecutive rows
+constexpr uint32_t kPackSpan = kPackIters * kPackThreads;
+
+// per block: how many of its rows go into each of the six lists (+ a flag "anything at all")
 __global__ void __launch_bounds__(kPackThreads)
 k_slab_count(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
-             uint32_t* __restrict__ block_counts, const uint32_t rows, const uint32_t nblocks, const DevParams P,
-             const float dt)
+             uint32_t* __restrict__ block_counts, uint8_t* __restrict__ block_any, const uint32_t rows,
+             const uint32_t nblocks, const DevParams P, const float dt)
 {
     __shared__ uint32_t cnt[NLISTS];
     if (threadIdx.x < NLISTS) cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    uint8_t k = 0;
-    bool keep = false;
-    if (s < rows) {
-        k = cls[s];
-        if (k & (CLS_MIG_LO | CLS_MIG_HI)) { float4 pr; keep = lands_adjacent(pos[s], vel[s], P, dt, &pr); }
-    }
-    #pragma unroll
-    for (int l = 0; l < NLISTS; l++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, in_list(k, l, keep));
-        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt[l], __popc(b));
+    for (int it = 0; it < kPackIters; it++) {
+        const uint32_t s = blockIdx.x * kPackSpan + it * kPackThreads + threadIdx.x;
+        uint8_t k = 0;
+        bool keep = false;
+        if (s < rows) {
+            k = cls[s];
+            if (k & (CLS_MIG_LO | CLS_MIG_HI)) { float4 pr; keep = lands_adjacent(pos[s], vel[s], P, dt, &pr); }
+        }
+        if (!__any_sync(0xffffffffu, k != 0)) continue;
+        #pragma unroll
+        for (int l = 0; l < NLISTS; l++) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, in_list(k, l, keep));
+            if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&cnt[l], __popc(bal));
+        }
     }
     __syncthreads();
     if (threadIdx.x < NLISTS) block_counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x == 0) {
+        uint32_t any = 0;
+        for (int l = 0; l < NLISTS; l++) any |= cnt[l];
+        block_any[blockIdx.x] = any ? 1 : 0;
+    }
 }
 
 // one block per list: exclusive scan of its row of block counts, total to totals[list]
@@ -194,43 +214,57 @@ k_slab_scan(uint32_t* __restrict__ block_counts, uint32_t* __restrict__ totals, 
 // order-preserving pack: list l, entry rank = (#members in earlier blocks) + (#members before me in this block)
 __global__ void __launch_bounds__(kPackThreads)
 k_slab_pack(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
-            const uint32_t* __restrict__ block_offsets, float4* __restrict__ mig_lo, float4* __restrict__ mig_hi,
+            const uint32_t* __restrict__ block_offsets, const uint8_t* __restrict__ block_any,
+            float4* __restrict__ mig_lo, float4* __restrict__ mig_hi,
             float4* __restrict__ ghost_lo, float4* __restrict__ ghost_hi, float4* __restrict__ keep_lo,
             float4* __restrict__ keep_hi, const uint32_t rows, const uint32_t nblocks, const uint32_t xcap,
             const DevParams P, const float dt)
 {
+    if (!block_any[blockIdx.x]) return;              // interior blocks: nothing leaves, nothing is a ghost
     __shared__ uint32_t wcnt[NLISTS][kPackThreads / 32];
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t run[NLISTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t k = 0;
-    bool keep = false;
-    float4 p = make_float4(0, 0, 0, 0), v = p, pr = p;
-    if (s < rows) {
-        k = cls[s];
-        if (k) { p = pos[s]; v = vel[s]; keep = lands_adjacent(p, v, P, dt, &pr); }
-    }
-    uint32_t ball[NLISTS];
-    #pragma unroll
-    for (int l = 0; l < NLISTS; l++) {
-        ball[l] = __ballot_sync(0xffffffffu, in_list(k, l, keep));
-        if (lane == 0) wcnt[l][warp] = __popc(ball[l]);
-    }
+    if (threadIdx.x < NLISTS) run[threadIdx.x] = block_offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
     __syncthreads();
-    #pragma unroll
-    for (int l = 0; l < NLISTS; l++) {
-        if (!in_list(k, l, keep)) continue;
-        uint32_t off = block_offsets[(size_t)l * nblocks + blockIdx.x];
-        for (int w = 0; w < warp; w++) off += wcnt[l][w];
-        off += __popc(ball[l] & ((1u << lane) - 1u));
-        if (off >= xcap) continue;                       // overflow is detected on the host from the totals
-        switch (l) {
-        case L_MIG_LO: mig_lo[off] = p; mig_lo[xcap + off] = v; break;
-        case L_MIG_HI: mig_hi[off] = p; mig_hi[xcap + off] = v; break;
-        case L_GHOST_LO: ghost_lo[off] = pr; break;
-        case L_GHOST_HI: ghost_hi[off] = pr; break;
-        case L_KEEP_LO: keep_lo[off] = pr; break;
-        default: keep_hi[off] = pr; break;
+    for (int it = 0; it < kPackIters; it++) {
+        const uint32_t s = blockIdx.x * kPackSpan + it * kPackThreads + threadIdx.x;
+        uint8_t k = 0;
+        bool keep = false;
+        float4 p = make_float4(0, 0, 0, 0), v = p, pr = p;
+        if (s < rows) {
+            k = cls[s];
+            if (k) { p = pos[s]; v = vel[s]; keep = lands_adjacent(p, v, P, dt, &pr); }
         }
+        uint32_t ball[NLISTS];
+        #pragma unroll
+        for (int l = 0; l < NLISTS; l++) {
+            ball[l] = __ballot_sync(0xffffffffu, in_list(k, l, keep));
+            if (lane == 0) wcnt[l][warp] = __popc(ball[l]);
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int l = 0; l < NLISTS; l++) {
+            if (!in_list(k, l, keep)) continue;
+            uint32_t off = run[l];
+            for (int w = 0; w < warp; w++) off += wcnt[l][w];
+            off += __popc(ball[l] & ((1u << lane) - 1u));
+            if (off >= xcap) continue;                       // overflow is detected on the host from the totals
+            switch (l) {
+            case L_MIG_LO: mig_lo[off] = p; mig_lo[xcap + off] = v; break;
+            case L_MIG_HI: mig_hi[off] = p; mig_hi[xcap + off] = v; break;
+            case L_GHOST_LO: ghost_lo[off] = pr; break;
+            case L_GHOST_HI: ghost_hi[off] = pr; break;
+            case L_KEEP_LO: keep_lo[off] = pr; break;
+            default: keep_hi[off] = pr; break;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NLISTS) {
+            uint32_t t = 0;
+            for (int w = 0; w < kPackThreads / 32; w++) t += wcnt[threadIdx.x][w];
+            run[threadIdx.x] += t;
+        }
+        __syncthreads();
     }
 }
 
@@ -256,8 +290,14 @@ void multi_teardown(SphContext* c)
     if (c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
     SlabState* s = c->slab;
     if (!s) return;
+    if (s->prof && s->psteps) {
+        fprintf(stderr, "[slab rank %d] spatial sub-stages, ms/step over %llu steps: pack %.3f | count xchg %.3f | (host wait %.3f) | payload xchg %.3f | keys+sort %.3f | table+reorder %.3f | pick+check xchg %.3f | (host wait %.3f)\n",
+                c->rank, (unsigned long long)s->psteps, s->pacc[0] / s->psteps, s->pacc[1] / s->psteps, s->pacc[6] / s->psteps,
+                s->pacc[2] / s->psteps, s->pacc[3] / s->psteps, s->pacc[4] / s->psteps, s->pacc[5] / s->psteps, s->pacc[7] / s->psteps);
+        for (auto& e : s->pe) if (e) cudaEventDestroy(e);
+    }
     void* ptrs[] = {s->cls, s->mig_send[0], s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0], s->keep[1],
-                    s->ghost_pred, s->block_counts, s->dev_small};
+                    s->ghost_pred, s->block_counts, s->block_any, s->dev_small};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->host_small) cudaFreeHost(s->host_small);
     delete s;
@@ -302,28 +342,35 @@ int multi_step(SphContext* c, float dt)
     launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
 
+    #define SLAB_MARK(i) do { if (s->prof) cudaEventRecord(s->pe[i], st); } while (0)
+    auto host_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    SLAB_MARK(0);
     // (2) order-preserving pack of the six lists
-    const uint32_t nblocks = n_old ? (n_old + kPackThreads - 1) / kPackThreads : 1;
+    const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
     uint32_t* totals = s->dev_small;            // [6]
     uint32_t* rcounts = s->dev_small + 8;       // [4] from lo: (mig, ghost), from hi: (mig, ghost)
     uint32_t* picks = s->dev_small + 16;        // [8]
     uint32_t* peer = s->dev_small + 24;         // [2] boundary lengths of the neighbours' layers
     SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
     if (n_old) {
-        k_slab_count<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, n_old, nblocks, P, dt);
+        k_slab_count<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, n_old, nblocks, P, dt);
         k_slab_scan<<<NLISTS, kPackThreads, 0, st>>>(s->block_counts, totals, nblocks);
-        k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->mig_send[0],
+        k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, s->mig_send[0],
                                                       s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0],
                                                       s->keep[1], n_old, nblocks, s->xcap, P, dt);
         c->launches += 3;
     }
+    SLAB_MARK(1);
     // (3a) counts to / from the neighbours
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) { SPH_NCCL(c, ncclSend(totals + 0, 2, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 0, 2, ncclUint32, lo, comm, st)); }
     if (has_hi) { SPH_NCCL(c, ncclSend(totals + 2, 2, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 2, 2, ncclUint32, hi, comm, st)); }
     SPH_NCCL(c, ncclGroupEnd());
     SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SLAB_MARK(2);
+    const double h0 = host_now();
     SPH_CUDA(c, cudaStreamSynchronize(st));
+    const double h1 = host_now();
     const uint32_t* T = s->host_small;
     const uint32_t* R = s->host_small + 8;
     for (int l = 0; l < NLISTS; l++)
@@ -367,6 +414,7 @@ int multi_step(SphContext* c, float dt)
     if (T[L_KEEP_LO]) SPH_CUDA(c, cudaMemcpyAsync(g_keep_lo, s->keep[0], (size_t)T[L_KEEP_LO] * 16, cudaMemcpyDeviceToDevice, st));
     if (T[L_KEEP_HI]) SPH_CUDA(c, cudaMemcpyAsync(g_keep_hi, s->keep[1], (size_t)T[L_KEEP_HI] * 16, cudaMemcpyDeviceToDevice, st));
 
+    SLAB_MARK(3);
     // (4) keys of the arrivals (they may not migrate again this step) and of the ghosts; one sort of everything
     const uint32_t n_all = n_a + n_ghost;
     slab_params(c, &P, n_all);
@@ -375,6 +423,7 @@ int multi_step(SphContext* c, float dt)
     launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, &c->launches);
     const int bits = ceil_log2_u64((uint64_t)P.ncell + 1);
     c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, n_all, bits, c->counts, &c->launches);
+    SLAB_MARK(4);
     const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
     const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
     // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
@@ -382,6 +431,7 @@ int multi_step(SphContext* c, float dt)
     PT.ncell = P.ncell + 1;
     launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
     launch_reorder(st, perm, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    SLAB_MARK(5);
     // owned rows and boundary layers of the sorted arrays
     const uint32_t plane = (uint32_t)P.gdim[0] * (uint32_t)P.gdim[1];
     const uint32_t l_own_lo = (uint32_t)(P.own_lo - P.zlo), l_own_hi = (uint32_t)(P.own_hi - P.zlo);
@@ -394,7 +444,16 @@ int multi_step(SphContext* c, float dt)
     if (has_hi) { SPH_NCCL(c, ncclSend(picks + 6, 1, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(peer + 1, 1, ncclUint32, hi, comm, st)); }
     SPH_NCCL(c, ncclGroupEnd());
     SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SLAB_MARK(6);
+    const double h2 = host_now();
     SPH_CUDA(c, cudaStreamSynchronize(st));
+    const double h3 = host_now();
+    if (s->prof && ++s->pseen > 3) {
+        float ms;
+        for (int i = 0; i < 6; i++) { cudaEventElapsedTime(&ms, s->pe[i], s->pe[i + 1]); s->pacc[i] += ms; }
+        s->pacc[6] += h1 - h0; s->pacc[7] += h3 - h2;
+        s->psteps++;
+    }
     const uint32_t* K = s->host_small + 16;
     const uint32_t o0 = K[0], b_lo_end = K[1], b_hi_begin = K[2], o1 = K[3], live_end = K[4];
     const uint32_t peer_lo = s->host_small[24], peer_hi = s->host_small[25];
@@ -483,7 +542,7 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
     c->slab = s;
     s->xcap = c->cap / 8 > 65536 ? c->cap / 8 : (c->cap < 65536 ? c->cap : 65536);
     s->gcap = 4 * s->xcap;
-    s->nblocks_cap = (c->cap + kPackThreads - 1) / kPackThreads;
+    s->nblocks_cap = (c->cap + kPackSpan - 1) / kPackSpan + 1;
     SPH_CUDA(c, cudaMalloc(&s->cls, c->cap));
     for (int d = 0; d < 2; d++) {
         SPH_CUDA(c, cudaMalloc(&s->mig_send[d], (size_t)s->xcap * 32));
@@ -492,8 +551,13 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
     }
     SPH_CUDA(c, cudaMalloc(&s->ghost_pred, (size_t)s->gcap * 16));
     SPH_CUDA(c, cudaMalloc(&s->block_counts, (size_t)NLISTS * s->nblocks_cap * 4));
+    SPH_CUDA(c, cudaMalloc(&s->block_any, s->nblocks_cap));
     SPH_CUDA(c, cudaMalloc(&s->dev_small, 64 * sizeof(uint32_t)));
     SPH_CUDA(c, cudaMallocHost(&s->host_small, 64 * sizeof(uint32_t)));
+    if (const char* e = getenv("SPH_SLAB_TIMING")) {
+        s->prof = e[0] == '1';
+        if (s->prof) for (auto& ev : s->pe) SPH_CUDA(c, cudaEventCreate(&ev));
+    }
     return SPH_OK;
 }
 
