@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
-    "sph_get_grid", "sph_grid_x_subdivision", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
+    "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
     "sph_upload_owned", "sph_download_owned", "sph_comm_stats",
 ]
 
@@ -119,6 +119,8 @@ def load_library():
     L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
     L.sph_grid_x_subdivision.argtypes = [vp]
+    L.sph_save_state.argtypes = [vp, C.c_char_p]
+    L.sph_load_state.argtypes = [vp, C.c_char_p]
     L.sph_host_register.argtypes = [vp, C.c_size_t]
     L.sph_host_unregister.argtypes = [vp]
     L.sph_comm_id_bytes.restype = C.c_size_t
@@ -297,6 +299,12 @@ class FluidSimulation:
         o = np.zeros(3, np.int32)
         self._check(self.L.sph_get_grid(self.h, _ptr(d), _ptr(o)))
         return d, o
+
+    def save_state(self, path):
+        self._check(self.L.sph_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path):
+        self._check(self.L.sph_load_state(self.h, os.fsencode(path)))
 
     # convenience mirrors of the reference getters
     def positions(self): return self.download("positions")

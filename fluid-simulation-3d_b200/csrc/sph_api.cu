@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "sph_context.h"
 
@@ -117,6 +118,17 @@ int ensure_tables(SphContext* c, const DevParams& P)
 
 int ensure_list(SphContext* c, NbrList* L)
 {
+    if (!c->h_overflow) {
+        SPH_CUDA(c, cudaHostAlloc((void**)&c->h_overflow, sizeof(uint32_t), cudaHostAllocMapped));
+        *c->h_overflow = 0;
+        SPH_CUDA(c, cudaHostGetDevicePointer((void**)&c->d_overflow, c->h_overflow, 0));
+    }
+    // auto-grow: the value may lag the kernels by a step or two (read without synchronising); overflowing
+    // particles are exact meanwhile (the later passes walk the table for them), only slower
+    if (c->list_auto && c->list_k && *c->h_overflow > c->list_k) {
+        const uint32_t want = (*c->h_overflow * 5u / 4u + 15u) & ~15u;
+        c->list_k = want > 4096u ? 4096u : want;
+    }
     if (c->list_k && c->list_k_alloc < c->list_k) {
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
         if (c->nlist) cudaFree(c->nlist);
@@ -127,6 +139,7 @@ int ensure_list(SphContext* c, NbrList* L)
     }
     L->idx = c->list_k ? c->nlist : nullptr;
     L->cnt = c->lcount;
+    L->overflow = c->d_overflow;
     L->ncount = c->ncount;
     L->k = c->list_k;
     L->stride = c->cap;
@@ -140,6 +153,7 @@ static void free_all(SphContext* c)
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
                     c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
 }
@@ -262,6 +276,8 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
     if (!c) return SPH_ERR_INVALID;
     if (entries > 4096) return fail(c, SPH_ERR_INVALID, "neighbour list capacity above 4096 entries per particle");
     c->list_k = entries;
+    c->list_auto = false;                                  // an explicit capacity is kept as is
+    if (c->h_overflow) *c->h_overflow = 0;
     return SPH_OK;
 }
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
@@ -503,6 +519,49 @@ int sph_get_particle(SphContext* c, uint32_t index, float* out10)
     SPH_CUDA(c, cudaMemcpyAsync(out10, d, 10 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     SPH_CUDA(c, cudaStreamSynchronize(c->st));
     return SPH_OK;
+}
+
+int sph_save_state(SphContext* c, const char* path)
+{
+    if (!c || !path) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_save_state: single-GPU contexts only (gather with sph_download_owned)");
+    std::vector<float> pos((size_t)c->n * 3), vel((size_t)c->n * 3);
+    int rc = sph_download(c, SPH_FIELD_POSITIONS, pos.data(), pos.size() * 4);
+    if (rc != SPH_OK) return rc;
+    rc = sph_download(c, SPH_FIELD_VELOCITIES, vel.data(), vel.size() * 4);
+    if (rc != SPH_OK) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(c, SPH_ERR_INVALID, std::string("sph_save_state: cannot open ") + path);
+    const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '1'};
+    const uint32_t n = c->n;
+    bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&c->params, sizeof(SphParams), 1, f) == 1;
+    ok = ok && (n == 0 || (fwrite(pos.data(), 12, n, f) == n && fwrite(vel.data(), 12, n, f) == n));
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SPH_OK : fail(c, SPH_ERR_INVALID, "sph_save_state: short write");
+}
+
+int sph_load_state(SphContext* c, const char* path)
+{
+    if (!c || !path) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_load_state: single-GPU contexts only");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, SPH_ERR_INVALID, std::string("sph_load_state: cannot open ") + path);
+    char magic[8];
+    uint32_t n = 0;
+    SphParams p;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "SPHB2001", 8) == 0 && fread(&n, 4, 1, f) == 1 &&
+              fread(&p, sizeof(SphParams), 1, f) == 1;
+    if (!ok) { fclose(f); return fail(c, SPH_ERR_INVALID, "sph_load_state: not a snapshot file"); }
+    if (n > c->cap) { fclose(f); return fail(c, SPH_ERR_CAPACITY, "sph_load_state: snapshot exceeds capacity"); }
+    std::vector<float> pos((size_t)n * 3), vel((size_t)n * 3);
+    ok = n == 0 || (fread(pos.data(), 12, n, f) == n && fread(vel.data(), 12, n, f) == n);
+    fclose(f);
+    if (!ok) return fail(c, SPH_ERR_INVALID, "sph_load_state: truncated snapshot");
+    int rc = sph_set_params(c, &p);
+    if (rc != SPH_OK) return rc;
+    rc = sph_upload_state(c, n, pos.data(), vel.data());
+    if (rc != SPH_OK) return rc;
+    return sph_synchronize(c);                          // the host vectors die here
 }
 
 int sph_host_register(void* ptr, size_t bytes)

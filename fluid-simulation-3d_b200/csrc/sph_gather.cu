@@ -194,6 +194,7 @@ k_density_list(const GatherArgs A, const DevParams P)
     if (valid) {
         finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
         if (A.list_cnt) A.list_cnt[i] = n;
+        if (n > K && A.list_overflow) atomicMax_system(A.list_overflow, n);   // rare: tells the host to grow the list
     }
 }
 
@@ -442,6 +443,7 @@ k_density_pair(const GatherArgs A, const DevParams P)
     if (pair && n1 > K) { a1 = {0.0f, 0.0f, 0.0f, 0u}; walk_particle<SPH_TABLE_GRID, PASS_DENSITY>(W, P, s1, a1); }
     if (valid0) { finish<PASS_DENSITY>(A, P, s0, a0, 0.0f); A.list_cnt[s0.i] = n0; }
     if (pair) { finish<PASS_DENSITY>(A, P, s1, a1, 0.0f); A.list_cnt[s1.i] = n1; }
+    if (A.list_overflow && ((valid0 && n0 > K) || (pair && n1 > K))) atomicMax_system(A.list_overflow, max(n0, n1));
 
     // second particles that live in another (y,z) row than their partner: whole warp on one particle
     uint32_t todo = __ballot_sync(0xffffffffu, straddle);
@@ -541,6 +543,7 @@ static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const 
     A.pred = pred_s; A.table = tstart; A.tend = tend;
     if (gather_variant() == 0 && L.idx && L.k) { A.list_idx = L.idx; A.list_k = L.k; A.list_stride = L.stride; }
     A.list_cnt = L.cnt;
+    A.list_overflow = L.overflow;
     return A;
 }
 

@@ -69,6 +69,7 @@ struct NbrList {
     uint32_t* idx;      // nullptr: no list, every pass walks the table
     uint32_t* cnt;      // [rows] list length (may exceed k: overflowed; may include <= 1e-6 borderline extras)
     uint32_t* ncount;   // [rows] exact neighbour count incl. self (always written by the density pass)
+    uint32_t* overflow; // host-mapped: largest list length that did not fit (0 = none)
     uint32_t  k;        // entries per row before a row counts as overflowed
     uint32_t  stride;
 };

@@ -113,8 +113,9 @@ int  sph_set_stage_timing(SphContext* ctx, int enabled);
 /* 1: also keep neighbour counts during the density pass (debug tap, off by default) */
 int  sph_set_neighbour_count_tap(SphContext* ctx, int enabled);
 /* Entries per particle of the neighbour list the density pass records for the pressure and viscosity
- * passes (default 64; 0 = no list, every pass walks the table).  A particle with more neighbours than
- * this is still exact: the later passes walk the table for it. */
+ * passes (0 = no list, every pass walks the table).  A particle with more neighbours than this is still
+ * exact: the later passes walk the table for it.  Without this call the capacity starts at 64 and grows
+ * by itself when the density pass meets denser particles. */
 int  sph_set_neighbour_list_capacity(SphContext* ctx, uint32_t entries);
 
 /* -- state ---------------------------------------------------------------- */
@@ -151,6 +152,12 @@ void* sph_stream(const SphContext* ctx);
 int  sph_get_grid(const SphContext* ctx, int32_t* dims3, int32_t* origin3);
 /* GRID table: the cell is subdivided this many times in x (dims3[0] counts the fine cells) */
 int  sph_grid_x_subdivision(const SphContext* ctx);
+
+/* -- state snapshots (the reference has none: Reset re-spawns, physicsWorld.cc:112) ---- */
+/* Little-endian file: "SPHB2001", u32 n, SphParams, then n x (pos3, vel3) fp32 in particle index order.
+ * Loading replaces parameters and state (n must fit the capacity). */
+int  sph_save_state(SphContext* ctx, const char* path);
+int  sph_load_state(SphContext* ctx, const char* path);
 
 /* -- host memory helpers ---------------------------------------------------- */
 /* Page-lock / unlock a caller-owned host range in place (cudaHostRegister) so uploads and downloads
