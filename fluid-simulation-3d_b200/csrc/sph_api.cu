@@ -119,9 +119,10 @@ int ensure_tables(SphContext* c, const DevParams& P)
 int ensure_list(SphContext* c, NbrList* L)
 {
     if (!c->h_overflow) {
-        SPH_CUDA(c, cudaHostAlloc((void**)&c->h_overflow, sizeof(uint32_t), cudaHostAllocMapped));
+        SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, sizeof(uint32_t)));
         *c->h_overflow = 0;
-        SPH_CUDA(c, cudaHostGetDevicePointer((void**)&c->d_overflow, c->h_overflow, 0));
+        SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, sizeof(uint32_t)));
+        SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, sizeof(uint32_t), c->st));
     }
     // auto-grow: the value may lag the kernels by a step or two (read without synchronising); overflowing
     // particles are exact meanwhile (the later passes walk the table for them), only slower
@@ -154,6 +155,7 @@ static void free_all(SphContext* c)
                     c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
+    if (c->d_overflow) cudaFree(c->d_overflow);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
 }
@@ -277,7 +279,7 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
     if (entries > 4096) return fail(c, SPH_ERR_INVALID, "neighbour list capacity above 4096 entries per particle");
     c->list_k = entries;
     c->list_auto = false;                                  // an explicit capacity is kept as is
-    if (c->h_overflow) *c->h_overflow = 0;
+    if (c->h_overflow) { *c->h_overflow = 0; cudaMemsetAsync(c->d_overflow, 0, sizeof(uint32_t), c->st); }
     return SPH_OK;
 }
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
@@ -341,6 +343,7 @@ static int run_step(SphContext* c, float dt, bool advance)
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (advance) {

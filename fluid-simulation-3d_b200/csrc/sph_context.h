@@ -28,8 +28,8 @@ struct SphContext {
     uint32_t list_k = 64;        // entries per row (0: lists off)
     uint32_t list_k_alloc = 0;
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
-    uint32_t* h_overflow = nullptr;  // pinned + mapped: written by the density kernel (atomicMax_system)
-    uint32_t* d_overflow = nullptr;  // its device alias
+    uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
+    uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
     uint32_t *tstart = nullptr, *tend = nullptr;
     size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
     uint32_t* gap_list = nullptr;

@@ -79,6 +79,15 @@ k_gather_walk(const GatherArgs A, const DevParams P, const float dt)
     if (PASS == PASS_DENSITY && A.list_cnt) A.list_cnt[i] = acc.cnt;
 }
 
+// The longest list that did not fit, for the host's auto-grow: one atomic per WARP at most, and only while the
+// value still rises (a plain read first), so a scene where every particle overflows costs nothing.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void report_overflow(const GatherArgs& A, const uint32_t n_over)
+{
+    const uint32_t m = __reduce_max_sync(0xffffffffu, n_over);
+    if (m && A.list_overflow && (threadIdx.x & 31) == 0 && m > *(volatile uint32_t*)A.list_overflow) atomicMax(A.list_overflow, m);
+}
+
 // ---- density pass, two-phase, one thread per particle (default) ------------------------------------
 // Phase A walks the table and applies ONLY the reference's exact predicate; survivors are pushed on a
 // small per-thread shared-memory stack with a predicated store (no divergent branch, 4 candidate loads
@@ -194,8 +203,8 @@ k_density_list(const GatherArgs A, const DevParams P)
     if (valid) {
         finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
         if (A.list_cnt) A.list_cnt[i] = n;
-        if (n > K && A.list_overflow) atomicMax_system(A.list_overflow, n);   // rare: tells the host to grow the list
     }
+    report_overflow(A, (valid && n > K) ? n : 0u);
 }
 
 // ---- neighbour-list passes: pressure and viscosity replay the exact neighbour set recorded by the
@@ -443,7 +452,7 @@ k_density_pair(const GatherArgs A, const DevParams P)
     if (pair && n1 > K) { a1 = {0.0f, 0.0f, 0.0f, 0u}; walk_particle<SPH_TABLE_GRID, PASS_DENSITY>(W, P, s1, a1); }
     if (valid0) { finish<PASS_DENSITY>(A, P, s0, a0, 0.0f); A.list_cnt[s0.i] = n0; }
     if (pair) { finish<PASS_DENSITY>(A, P, s1, a1, 0.0f); A.list_cnt[s1.i] = n1; }
-    if (A.list_overflow && ((valid0 && n0 > K) || (pair && n1 > K))) atomicMax_system(A.list_overflow, max(n0, n1));
+    report_overflow(A, max((valid0 && n0 > K) ? n0 : 0u, (pair && n1 > K) ? n1 : 0u));
 
     // second particles that live in another (y,z) row than their partner: whole warp on one particle
     uint32_t todo = __ballot_sync(0xffffffffu, straddle);

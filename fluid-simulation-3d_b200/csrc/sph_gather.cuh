@@ -22,7 +22,7 @@ struct GatherArgs {
     uint32_t* list_idx;
     uint32_t* list_cnt;
     uint32_t list_k, list_stride;
-    uint32_t* list_overflow;   // host-mapped word: largest list length seen above list_k (drives the auto-grow)
+    uint32_t* list_overflow;   // device word: largest list length seen above list_k (drives the host's auto-grow)
     float4* dens_out;          // density pass: (rho, near rho, 1/rho, 1/near rho)
     uint32_t* ncount;          // density pass, optional
     const float4* dens;        // pressure pass

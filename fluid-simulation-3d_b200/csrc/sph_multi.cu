@@ -470,6 +470,7 @@ int multi_step(SphContext* c, float dt)
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) {

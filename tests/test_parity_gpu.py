@@ -53,3 +53,15 @@ def test_gravity_off_defaults(pkg, scenes, mode):
     sc = scenes.small_dam_break(12)
     sc["params"] = dict(bound=sc["bound"])          # reference defaults: gravity off (physicsWorld.h:105)
     check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("radius", [0.25, 0.5])
+def test_q2_radius_differs_from_cutoff(pkg, scenes, mode, radius):
+    """SURVEY App.A Q2: setInteractionRadius changes the cell size and the kernel support but NOT the
+    d^2 cull (sqrRadius is a const member, physicsWorld.h:96).  With r = 0.25 the reference therefore
+    misses neighbours that lie within 0.35 but outside its 27 smaller cells -- and so must we."""
+    sc = scenes.small_dam_break(14)
+    sc["params"] = dict(sc["params"], interaction_radius=radius)
+    out = check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
+    assert out["mean_neighbours"] > 3

