@@ -233,7 +233,6 @@ def bench_single(args, pkg, scenes, torch, dev):
     sim.synchronize()
     torch.cuda.synchronize()
     launches = sim.launch_count() - l0
-    clk = clocks.stop()
     ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(ms.sum())
     value = n * args.steps / (total_ms * 1e-3) / 1e6
@@ -262,6 +261,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         sim.download_ptr("out_positions", h_out.data_ptr(), n * 16)   # returns when the host buffer is filled
     e2e_s = time.perf_counter() - t0
     e2e = n * args.steps / e2e_s / 1e6
+    clk = clocks.stop()          # sampled across the timed, steady-state and end-to-end loops (all under load)
 
     peak, peak_src = measured_peaks()
     names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
@@ -269,6 +269,14 @@ def bench_single(args, pkg, scenes, torch, dev):
     dom = max(gather, key=gather.get)
     dom_ms = gather[dom]
     achieved = A_BYTES[dom] * n / (dom_ms * 1e-3) / 1e9
+    # the two purely streaming kernels, by the bytes they really move (sph_kernels.cu): predict_key reads pos+vel
+    # (32 B) and writes the key (4 B); integrate reads pos+vel (32 B) and writes pos+vel (32 B)
+    resident = n * 170 < 100e6
+    streaming = {}
+    for kname, bytes_pp, t_ms in (("k_predict_key", 36, stage[0]), ("k_integrate", 64, stage[5])):
+        gbs = bytes_pp * n / (t_ms * 1e-3) / 1e9
+        streaming[kname] = {"bytes_per_particle": bytes_pp, "achieved": gbs, "frac": gbs / peak, "kernel_ms": float(t_ms),
+                            "note": "working set fits the 126 MB L2 at this size: served above the HBM peak" if resident else "HBM-resident"}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
     if os.path.exists(tp):
@@ -292,6 +300,9 @@ def bench_single(args, pkg, scenes, torch, dev):
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),
+                     "binding_roof": "L1 wavefronts + instruction issue, not HBM: the gather re-reads neighbours from L1/L2 by design "
+                                     "(ncu: profiles/r01_gather_final_C2.txt)",
+                     "streaming_kernels": streaming,
                      "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
                               "algorithmic_bytes_per_particle": A_BYTES["step"]}},
         "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16,

@@ -19,7 +19,7 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 8;                          // keys per thread per tile
 constexpr int kTile = kSortThreads * kItems;       // 2048 keys
-constexpr uint32_t kMaxSortBlocks = 148 * 8;
+constexpr uint32_t kMaxSortBlocks = 148 * 6;     // one resident wave of the scatter kernel (6 blocks per SM)
 
 struct SortGeom { uint32_t nblocks, tiles_per_block; };
 
@@ -88,7 +88,7 @@ k_radix_rowscan(uint32_t* __restrict__ counts, uint32_t* __restrict__ totals, ui
 }
 
 template <bool kIdentity>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 6)
 k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ totals, uint32_t n, int shift,
