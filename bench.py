@@ -316,6 +316,24 @@ def bench_single(args, pkg, scenes, torch, dev):
         r = cpu_reference_run(name if name in scenes.CONFIGS else "C2_dambreak_1M", steps=2, warmup=1, budget_s=20.0)
         result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
                                   "sample": r["sample"], "host_cores": os.cpu_count()}
+        # a second, clearly labelled line: the C restatement with OpenMP on every host core (the reference's
+        # own std::execution::par falls back to one thread here because TBB is not installed)
+        try:
+            ob = graft.load_oracle()
+            cores = os.cpu_count() or 1
+            o = ob.PortOracle(n, threads=cores, **sc["params"])
+            o.set_state(sc["pos"], sc["vel"])
+            o.step(dt, jacobi=True)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                o.step(dt, jacobi=True)
+            tt = (time.perf_counter() - t0) / 2
+            ob.PortOracle.lib().oracle_set_threads(1)
+            result["cpu_baseline"]["port_openmp"] = {"value": n / tt / 1e6, "unit": "M updates/s", "cores": cores, "kind": "port",
+                                                     "sample": "full %s, 2 steps after 1 warm-up, snapshot viscosity" % name}
+            o.close()
+        except Exception as e:                                  # never let the extra line break the bench
+            result["cpu_baseline"]["port_openmp"] = {"error": str(e)}
     return result
 
 

@@ -56,7 +56,14 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
         }
         if (k & (CLS_MIG_LO | CLS_MIG_HI)) { key[s] = P.ncell; return; }      // leaves this rank: sorts past the table
         int3 g = grid_cell(pr.x, pr.y, pr.z, P);
-        g.z = clampi(gz, P.own_lo, P.own_hi - 1) - P.zlo;                     // (a row that cannot migrate is kept in range)
+        // A row that may not migrate (it arrived this step) but whose layer lies beyond this whole slab -- it moved
+        // more than a slab in one step -- is parked one layer INSIDE the slab: the boundary layers must hold exactly
+        // the rows the neighbour rank mirrors as ghosts.  It finds no neighbours there (the cull is by distance),
+        // moves ballistically for this step and migrates onward in the next one.
+        int gzc = gz;
+        if (gz < P.own_lo) gzc = min(P.own_lo + 1, P.own_hi - 1);
+        else if (gz >= P.own_hi) gzc = max(P.own_hi - 2, P.own_lo);
+        g.z = gzc - P.zlo;
         key[s] = grid_key(g, P);
         return;
     }

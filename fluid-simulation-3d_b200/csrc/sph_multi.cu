@@ -575,7 +575,7 @@ int sph_comm_set_planes(SphContext* c, const float* planes)
     }
     L[0] = 0; L[c->nranks] = GZ;
     for (int k = 0; k < c->nranks; k++)
-        if (L[k + 1] - L[k] < 2) return fail(c, SPH_ERR_INVALID, "sph_comm_set_planes: every slab needs at least two cell layers");
+        if (L[k + 1] - L[k] < 3) return fail(c, SPH_ERR_INVALID, "sph_comm_set_planes: every slab needs at least three cell layers");
     s->layers = L;
     s->have_planes = true;
     c->planes.assign(planes, planes + c->nranks + 1);

@@ -21,7 +21,7 @@ def layer_of(z, r, gmin_z, gz):
 
 
 def choose_layers(z_sample, nranks, r, gmin_z, gz):
-    """Cut layers [0, gz) into nranks contiguous groups with ~equal particle counts (>= 2 layers each)."""
+    """Cut layers [0, gz) into nranks contiguous groups with ~equal particle counts (>= 3 layers each)."""
     lay = layer_of(z_sample, r, gmin_z, gz)
     hist = np.bincount(lay, minlength=int(gz)).astype(np.float64)
     cum = np.concatenate([[0.0], np.cumsum(hist)])
@@ -32,13 +32,13 @@ def choose_layers(z_sample, nranks, r, gmin_z, gz):
         cut = int(np.searchsorted(cum, target, side="left"))
         if cut > 0 and abs(cum[cut - 1] - target) <= abs(cum[min(cut, gz)] - target):
             cut -= 1
-        cut = max(cut, L[-1] + 2)
-        cut = min(cut, int(gz) - 2 * (nranks - k))
+        cut = max(cut, L[-1] + 3)
+        cut = min(cut, int(gz) - 3 * (nranks - k))
         L.append(cut)
     L.append(int(gz))
     for k in range(nranks):
-        if L[k + 1] - L[k] < 2:
-            raise ValueError("cannot give every rank two cell layers: %r" % (L,))
+        if L[k + 1] - L[k] < 3:
+            raise ValueError("cannot give every rank three cell layers: %r" % (L,))
     return L
 
 

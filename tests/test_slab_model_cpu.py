@@ -68,7 +68,7 @@ def test_partition_helpers():
     gmin_z, gz = -17, 34
     for world in (2, 4, 8):
         L = sm.choose_layers(z, world, 0.35, gmin_z, gz)
-        assert L[0] == 0 and L[-1] == gz and all(b - a >= 2 for a, b in zip(L, L[1:]))
+        assert L[0] == 0 and L[-1] == gz and all(b - a >= 3 for a, b in zip(L, L[1:]))
         own = sm.owner_of(z, L, 0.35, gmin_z, gz)
         cnt = np.bincount(own, minlength=world)
         assert cnt.min() > 0.6 * len(z) / world and cnt.max() < 1.4 * len(z) / world
