@@ -213,8 +213,8 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     ALLOC(c->A_pos, cap * 16); ALLOC(c->A_vel, cap * 16);
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
-    ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 16);
-    ALLOC(c->dens, cap * 16);
+    ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 32);
+    ALLOC(c->dens, cap * 32);
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
     ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
     ALLOC(c->ncount, cap * 4);
@@ -359,7 +359,6 @@ static int run_step(SphContext* c, float dt, bool advance)
         // keep "every per-particle array shares the device order": adopt the sorted order
         SPH_CUDA(c, cudaMemcpyAsync(c->A_pos, c->S_pos, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
         SPH_CUDA(c, cudaMemcpyAsync(c->A_vel, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
-        SPH_CUDA(c, cudaMemcpyAsync(c->velp, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
     }
     SPH_CUDA(c, cudaGetLastError());
     c->step_valid = true;

@@ -19,8 +19,9 @@ struct SphContext {
     // persistent state, device order
     float4 *A_pos = nullptr, *A_vel = nullptr;
     // per-step arrays, sorted order of the step
-    float4 *S_pos = nullptr, *S_vel = nullptr, *pred = nullptr, *velp = nullptr;
-    float4* dens = nullptr;      // (rho, near rho, 1/rho, 1/near rho)
+    float4 *S_pos = nullptr, *S_vel = nullptr, *pred = nullptr;
+    sphb200::Rec8* velp = nullptr;   // velocity records: v' after pressure
+    sphb200::Rec8* dens = nullptr;   // density records (sph_internal.h: Rec8)
     uint32_t *key_a = nullptr, *key_b = nullptr, *perm_a = nullptr, *perm_b = nullptr;
     uint32_t* ncount = nullptr;  // neighbour count incl. self of every row (density pass); also the list lengths
     uint32_t* lcount = nullptr;  // list lengths

@@ -54,7 +54,7 @@ __device__ __forceinline__ void walk_particle(const GatherArgs& A, const DevPara
         if (PASS != PASS_DENSITY) {
             float ox, oy, oz;
             if (sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r) return;      // do not fetch the aux row of a non-neighbour
-            f.aux = (PASS == PASS_PRESSURE) ? __ldg(&A.dens[j]) : __ldg(&A.velp[j]);
+            f = fetch<PASS>(A, j);
         }
         accept<PASS>(A, P, s, j, f, acc);
     });
@@ -557,7 +557,7 @@ static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const 
 }
 
 void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
-                    float4* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
+                    Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.dens_out = dens; A.ncount = L.ncount;
@@ -576,8 +576,8 @@ void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstar
     } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);           // SPH_DENSITY=walk / no list
 }
 
-void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, Rec8* vel_p, const NbrList& L, const DevParams& P,
                      float dt, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
@@ -586,7 +586,7 @@ void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, 
     else launch_walk_or_list<PASS_PRESSURE>(st, A, P, dt, A.list_idx != nullptr, launches);
 }
 
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const Rec8* vel_p, const uint32_t* tstart,
                       const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
                       uint64_t* launches)
 {

@@ -23,12 +23,12 @@ struct GatherArgs {
     uint32_t* list_cnt;
     uint32_t list_k, list_stride;
     uint32_t* list_overflow;   // device word: largest list length seen above list_k (drives the host's auto-grow)
-    float4* dens_out;          // density pass: (rho, near rho, 1/rho, 1/near rho)
+    Rec8* dens_out;            // density pass: density records
     uint32_t* ncount;          // density pass, optional
-    const float4* dens;        // pressure pass
+    const Rec8* dens;          // pressure pass
     const float4* vel_s;       // pressure pass: own velocity after S1
-    float4* velp_out;          // pressure pass
-    const float4* velp;        // viscosity pass: post-pressure snapshot
+    Rec8* velp_out;            // pressure pass: velocity records
+    const Rec8* velp;          // viscosity pass: post-pressure snapshot
     float4* velv_out;          // viscosity pass
 };
 
@@ -69,6 +69,15 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 }
 
 // ---- per-particle state ---------------------------------------------------------
+__device__ __forceinline__ Rec8 ld256(const Rec8* p)
+{
+    Rec8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+
 struct Self {
     float4 p;        // predicted position
     uint32_t i;      // sorted row
@@ -90,14 +99,14 @@ __device__ __forceinline__ Self load_self(const GatherArgs& A, const DevParams& 
     s.c0 = s.c1 = s.rho = 0.0f;
     s.v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (PASS == PASS_PRESSURE) {
-        const float4 d = A.dens[i];
-        const float pressure = (d.x - P.rho0) * P.k;      // :371
+        const Rec8 d = A.dens[i];
+        const float pressure = (d.lo.w - P.rho0) * P.k;   // :371
         s.c0 = pressure - P.k * P.rho0;
-        s.c1 = d.y * P.kn;                                  // :372
-        s.rho = d.x;
+        s.c1 = d.hi.x * P.kn;                               // :372
+        s.rho = d.lo.w;
         s.v = A.vel_s[i];
     } else if (PASS == PASS_VISCOSITY) {
-        s.v = A.velp[i];
+        { const Rec8 r = A.velp[i]; s.v = make_float4(r.lo.w, r.hi.x, r.hi.y, 0.0f); }
     }
     return s;
 }
@@ -113,10 +122,18 @@ template <int PASS>
 __device__ __forceinline__ Fetched fetch(const GatherArgs& A, const uint32_t j)
 {
     Fetched f;
-    f.q = __ldg(&A.pred[j]);
-    if (PASS == PASS_PRESSURE) f.aux = __ldg(&A.dens[j]);
-    else if (PASS == PASS_VISCOSITY) f.aux = __ldg(&A.velp[j]);
-    else f.aux = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (PASS == PASS_PRESSURE) {            // (rho, near rho, 1/rho, 1/near rho)
+        const Rec8 r = ld256(&A.dens[j]);
+        f.q = r.lo;
+        f.aux = make_float4(r.lo.w, r.hi.x, r.hi.y, r.hi.z);
+    } else if (PASS == PASS_VISCOSITY) {    // post-pressure velocity
+        const Rec8 r = ld256(&A.velp[j]);
+        f.q = r.lo;
+        f.aux = make_float4(r.lo.w, r.hi.x, r.hi.y, 0.0f);
+    } else {
+        f.q = __ldg(&A.pred[j]);
+        f.aux = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     return f;
 }
 
@@ -176,11 +193,17 @@ template <int PASS>
 __device__ __forceinline__ void finish(const GatherArgs& A, const DevParams& P, const Self& s, const Acc& acc, const float dt)
 {
     if (PASS == PASS_DENSITY) {
-        A.dens_out[s.i] = make_float4(acc.a, acc.b, __fdiv_rn(1.0f, acc.a), __fdiv_rn(1.0f, acc.b));
+        Rec8 r;
+        r.lo = make_float4(s.p.x, s.p.y, s.p.z, acc.a);
+        r.hi = make_float4(acc.b, __fdiv_rn(1.0f, acc.a), __fdiv_rn(1.0f, acc.b), 0.0f);
+        A.dens_out[s.i] = r;
         if (A.ncount) A.ncount[s.i] = acc.cnt;
     } else if (PASS == PASS_PRESSURE) {
         const float k = dt / s.rho;                        // :421
-        A.velp_out[s.i] = make_float4(fmaf(acc.a, k, s.v.x), fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f);
+        Rec8 r;
+        r.lo = make_float4(s.p.x, s.p.y, s.p.z, fmaf(acc.a, k, s.v.x));
+        r.hi = make_float4(fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f, 0.0f);
+        A.velp_out[s.i] = r;
     } else {
         const float k = P.mu * dt;                         // :463
         A.velv_out[s.i] = make_float4(fmaf(acc.a, k, s.v.x), fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f);

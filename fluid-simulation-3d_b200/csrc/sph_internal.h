@@ -39,6 +39,13 @@ struct DevParams {
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
 };
 
+// 32-byte per-particle records read with ONE 256-bit load (LDG.E.256 on sm_100a) by the list passes:
+//   density record  lo = (pred.x, pred.y, pred.z, rho)   hi = (near rho, 1/rho, 1/near rho, 0)
+//   velocity record lo = (pred.x, pred.y, pred.z, v'.x)  hi = (v'.y, v'.z, 0, 0)          (v' = after pressure)
+// Position and per-pass payload of a neighbour sit in the same sector, so a neighbour costs one load
+// instruction and one line instead of two of each.
+struct __align__(32) Rec8 { float4 lo, hi; };
+
 // slab mode: classification of an owned row by the z layer of its predicted position
 enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8 };
 
@@ -74,11 +81,11 @@ struct NbrList {
     uint32_t  stride;
 };
 void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
-                    float4* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
-void launch_pressure(cudaStream_t st, const float4* pred_s, const float4* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+                    Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
+void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, Rec8* vel_p, const NbrList& L, const DevParams& P,
                      float dt, uint64_t* launches);
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const Rec8* vel_p, const uint32_t* tstart,
                       const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
                       uint64_t* launches);
 void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,
@@ -89,7 +96,7 @@ void launch_pack_state(cudaStream_t st, const float* pos3, const float* vel3, co
                        float4* pos, float4* vel, uint32_t n, uint64_t* launches);
 void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void* src2, void* out,
                    uint32_t n, const DevParams& P, bool by_id, uint64_t* launches);
-void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float4* dens, uint32_t n,
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const Rec8* dens, uint32_t n,
                           uint32_t id, float* out10, uint64_t* launches);
 void launch_export_ids(cudaStream_t st, const float4* id_src, uint32_t* out, uint32_t n, uint64_t* launches);
 

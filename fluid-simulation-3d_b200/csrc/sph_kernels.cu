@@ -248,8 +248,13 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
     if (s >= n) return;
     const uint32_t dst = by_id ? __float_as_uint(id_src[s].w) : s;
     switch (field) {
+    case SPH_FIELD_VEL_AFTER_PRESSURE: {             // velocity record: lo.w, hi.x, hi.y
+        const Rec8 a = ((const Rec8*)src)[s];
+        float* o = (float*)out + 3 * (size_t)dst;
+        o[0] = a.lo.w; o[1] = a.hi.x; o[2] = a.hi.y;
+    } break;
     case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED:
-    case SPH_FIELD_VEL_AFTER_PRESSURE: case SPH_FIELD_VEL_AFTER_VISCOSITY: {
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: {
         const float4 a = ((const float4*)src)[s];
         float* o = (float*)out + 3 * (size_t)dst;
         o[0] = a.x; o[1] = a.y; o[2] = a.z;
@@ -259,7 +264,7 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
         ((float4*)out)[dst] = make_float4(a.x, a.y, a.z, 0.34f);          // :107
     } break;
     case SPH_FIELD_DENSITIES:
-        { const float4 d = ((const float4*)src)[s]; ((float2*)out)[dst] = make_float2(d.x, d.y); }
+        { const Rec8 d = ((const Rec8*)src)[s]; ((float2*)out)[dst] = make_float2(d.lo.w, d.hi.x); }   // density record
         break;
     case SPH_FIELD_HASH: case SPH_FIELD_KEY: {       // pure functions of the predicted position (:477-479)
         const float4 a = ((const float4*)src)[s];
@@ -283,7 +288,7 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
 
 // getPosition/getVelocity/getDensity/getNearDensity/getSpeed/getSpeedNormalzied (:149-182) for one id
 __global__ void __launch_bounds__(256)
-k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const float4* __restrict__ dens,
+k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const Rec8* __restrict__ dens,
                 const uint32_t n, const uint32_t id, float* __restrict__ out10)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,7 +298,7 @@ k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, 
     const float4 v = vel[s];
     const float len = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
     out10[0] = p.x; out10[1] = p.y; out10[2] = p.z; out10[3] = v.x; out10[4] = v.y; out10[5] = v.z;
-    if (dens) { const float4 d = dens[s]; out10[6] = d.x; out10[7] = d.y; }
+    if (dens) { const Rec8 d = dens[s]; out10[6] = d.lo.w; out10[7] = d.hi.x; }
     out10[8] = len;
     out10[9] = fminf(fmaxf(len, 0.0f), 1.5f) / 1.5f;
 }
@@ -373,7 +378,7 @@ void launch_export(cudaStream_t st, int field, const float4* id_src, const void*
     ++*launches;
 }
 
-void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const float4* dens, uint32_t n,
+void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const Rec8* dens, uint32_t n,
                           uint32_t id, float* out10, uint64_t* launches)
 {
     if (n == 0) return;

@@ -474,12 +474,12 @@ int multi_step(SphContext* c, float dt)
     c->ncount_valid = true;
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) {
-        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 4, ncclFloat, lo, comm, st));
-        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 4, ncclFloat, lo, comm, st));
+        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, st));
+        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 8, ncclFloat, lo, comm, st));
     }
     if (has_hi) {
-        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 4, ncclFloat, hi, comm, st));
-        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 4, ncclFloat, hi, comm, st));
+        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, st));
+        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, st));
     }
     SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
@@ -488,12 +488,12 @@ int multi_step(SphContext* c, float dt)
     launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
     SPH_NCCL(c, ncclGroupStart());
     if (has_lo) {
-        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->velp + o0, (size_t)(b_lo_end - o0) * 4, ncclFloat, lo, comm, st));
-        if (o0) SPH_NCCL(c, ncclRecv(c->velp, (size_t)o0 * 4, ncclFloat, lo, comm, st));
+        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->velp + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, st));
+        if (o0) SPH_NCCL(c, ncclRecv(c->velp, (size_t)o0 * 8, ncclFloat, lo, comm, st));
     }
     if (has_hi) {
-        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->velp + b_hi_begin, (size_t)(o1 - b_hi_begin) * 4, ncclFloat, hi, comm, st));
-        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->velp + o1, (size_t)(live_end - o1) * 4, ncclFloat, hi, comm, st));
+        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->velp + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, st));
+        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->velp + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, st));
     }
     SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
