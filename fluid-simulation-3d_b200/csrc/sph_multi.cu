@@ -97,6 +97,8 @@ struct SlabState {
     uint32_t o0 = 0, o1 = 0;                      // owned rows of the sorted arrays in the last step
     uint32_t stats[5] = {0, 0, 0, 0, 0};
     bool have_planes = false;
+    cudaStream_t halo_stream = nullptr;           // halos 2 and 3 travel here, overlapped with interior compute
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
     // SPH_SLAB_TIMING=1: finer timers of the spatial stage (events on the stream + host clock around the syncs)
     bool prof = false;
     cudaEvent_t pe[8] = {};
@@ -300,6 +302,9 @@ void multi_teardown(SphContext* c)
                     s->ghost_pred, s->block_counts, s->block_any, s->dev_small};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->host_small) cudaFreeHost(s->host_small);
+    if (s->halo_stream) { cudaStreamSynchronize(s->halo_stream); cudaStreamDestroy(s->halo_stream); }
+    if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
+    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
     delete s;
     c->slab = nullptr;
 }
@@ -465,39 +470,51 @@ int multi_step(SphContext* c, float dt)
     P.row0 = o0; P.row1 = o1;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
 
-    // (5) density on owned rows, halo of densities
+    // (5) gather passes.  Each pass runs its two BOUNDARY layers first; their results go to the neighbours
+    // on the halo stream while the interior rows (which never touch a ghost row) are computed, so the halo
+    // the NEXT pass needs arrives during this pass's interior work.
     NbrList L;
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
-    launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    const uint32_t hi_begin = b_hi_begin > b_lo_end ? b_hi_begin : b_lo_end;      // thin slab: the layers may coincide
+    const uint32_t seg[3][2] = {{o0, b_lo_end}, {hi_begin, o1}, {b_lo_end, hi_begin}};   // lo layer, hi layer, interior
+    cudaStream_t hs = s->halo_stream;
+    auto halo = [&](Rec8* rows) -> int {                  // boundary layers out, ghost layers in (contiguous ranges)
+        SPH_CUDA(c, cudaEventRecord(s->ev_boundary, st));
+        SPH_CUDA(c, cudaStreamWaitEvent(hs, s->ev_boundary, 0));
+        SPH_NCCL(c, ncclGroupStart());
+        if (has_lo) {
+            if (b_lo_end > o0) SPH_NCCL(c, ncclSend(rows + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, hs));
+            if (o0) SPH_NCCL(c, ncclRecv(rows, (size_t)o0 * 8, ncclFloat, lo, comm, hs));
+        }
+        if (has_hi) {
+            if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(rows + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, hs));
+            if (live_end > o1) SPH_NCCL(c, ncclRecv(rows + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, hs));
+        }
+        SPH_NCCL(c, ncclGroupEnd());
+        SPH_CUDA(c, cudaEventRecord(s->ev_halo, hs));
+        return SPH_OK;
+    };
+    DevParams Q = P;
+    for (int g = 0; g < 3; g++) {
+        Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
+        launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, Q, &c->launches);
+        if (g == 1) { rc = halo(c->dens); if (rc != SPH_OK) return rc; }
+    }
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
-    SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) {
-        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->dens + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, st));
-        if (o0) SPH_NCCL(c, ncclRecv(c->dens, (size_t)o0 * 8, ncclFloat, lo, comm, st));
-    }
-    if (has_hi) {
-        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->dens + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, st));
-        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->dens + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, st));
-    }
-    SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
 
-    // pressure, halo of post-pressure velocities
-    launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
-    SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) {
-        if (b_lo_end > o0) SPH_NCCL(c, ncclSend(c->velp + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, st));
-        if (o0) SPH_NCCL(c, ncclRecv(c->velp, (size_t)o0 * 8, ncclFloat, lo, comm, st));
+    // pressure: the boundary layers need the ghost densities that were travelling during the interior density work
+    SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_halo, 0));
+    for (int g = 0; g < 3; g++) {
+        Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
+        launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, Q, dt, &c->launches);
+        if (g == 1) { rc = halo(c->velp); if (rc != SPH_OK) return rc; }
     }
-    if (has_hi) {
-        if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(c->velp + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, st));
-        if (live_end > o1) SPH_NCCL(c, ncclRecv(c->velp + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, st));
-    }
-    SPH_NCCL(c, ncclGroupEnd());
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
 
+    SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_halo, 0));    // ghost post-pressure velocities are in
     launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, L, P, dt, &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
     launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
@@ -555,6 +572,9 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
     SPH_CUDA(c, cudaMalloc(&s->block_any, s->nblocks_cap));
     SPH_CUDA(c, cudaMalloc(&s->dev_small, 64 * sizeof(uint32_t)));
     SPH_CUDA(c, cudaMallocHost(&s->host_small, 64 * sizeof(uint32_t)));
+    SPH_CUDA(c, cudaStreamCreateWithFlags(&s->halo_stream, cudaStreamNonBlocking));
+    SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
+    SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
     if (const char* e = getenv("SPH_SLAB_TIMING")) {
         s->prof = e[0] == '1';
         if (s->prof) for (auto& ev : s->pe) SPH_CUDA(c, cudaEventCreate(&ev));
