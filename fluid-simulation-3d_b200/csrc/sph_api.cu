@@ -40,6 +40,13 @@ static int ceil_log2(uint64_t v)
     return b;
 }
 
+// SPH_SORT=radix keeps the LSD radix sort + table build for the GRID table (the REFERENCE_HASH table always uses it)
+bool counting_sort_enabled()
+{
+    static const bool on = [] { const char* e = getenv("SPH_SORT"); return !(e && e[0] == 'r'); }();
+    return on;
+}
+
 int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
 {
     const SphParams& p = c->params;
@@ -93,7 +100,8 @@ static int update_grid_geometry(SphContext* c)
 
 int ensure_tables(SphContext* c, const DevParams& P)
 {
-    const size_t need = (P.mode == SPH_TABLE_GRID) ? (size_t)P.ncell + 2 : (size_t)c->cap + 1;
+    // GRID: prefix table over ncell (+1 departed bucket in slab mode) + end, zero-padded for the in-place scan
+    const size_t need = (P.mode == SPH_TABLE_GRID) ? scan_pad((size_t)P.ncell + 3) : (size_t)c->cap + 1;
     if (need > c->table_cap) {
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
         if (c->tstart) cudaFree(c->tstart);
@@ -102,6 +110,14 @@ int ensure_tables(SphContext* c, const DevParams& P)
         c->table_cap = need;
     }
     if (P.mode == SPH_TABLE_GRID) {
+        const size_t sneed = scan_temp_entries(need);
+        if (sneed > c->scan_cap) {
+            SPH_CUDA(c, cudaStreamSynchronize(c->st));
+            if (c->scan_tmp) cudaFree(c->scan_tmp);
+            c->scan_tmp = nullptr; c->scan_cap = 0;
+            SPH_CUDA(c, cudaMalloc(&c->scan_tmp, sneed * sizeof(uint32_t)));
+            c->scan_cap = sneed;
+        }
         const size_t gneed = 1 + 3 * ((size_t)P.ncell / 1024 + (size_t)P.ncell / 16384 + 8);   // worst case of k_build_table_grid's worklist
         if (gneed > c->gap_cap) {
             SPH_CUDA(c, cudaStreamSynchronize(c->st));
@@ -152,7 +168,7 @@ int ensure_list(SphContext* c, NbrList* L)
 static void free_all(SphContext* c)
 {
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
-                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     if (c->d_overflow) cudaFree(c->d_overflow);
@@ -329,15 +345,30 @@ static int run_step(SphContext* c, float dt, bool advance)
     const bool timing = c->timing && advance;
     cudaStream_t st = c->st;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
-    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, &c->launches);
-    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
-    const int bits = ceil_log2(P.mode == SPH_TABLE_GRID ? (uint64_t)P.ncell : (uint64_t)P.n);
-    c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, P.n, bits, c->counts,
-                                       &c->launches);
-    const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
-    const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
-    launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
-    launch_reorder(st, perm, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    if (P.mode == SPH_TABLE_GRID && counting_sort_enabled()) {
+        // counting sort over the table (a one-pass radix sort whose digit is the whole key): tickets in the cell
+        // counters, in-place scan -> prefix table, placement; the reorder restores the canonical (stable) order
+        const size_t padded = scan_pad((size_t)P.ncell + 3);
+        SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, padded * sizeof(uint32_t), st));
+        launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, c->tstart, c->perm_b, &c->launches);
+        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+        exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
+        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, &c->launches);
+        launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred,
+                       P, dt, &c->launches);
+        c->sorted_where = 1;
+    } else {
+        launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, nullptr, nullptr, &c->launches);
+        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+        const int bits = ceil_log2(P.mode == SPH_TABLE_GRID ? (uint64_t)P.ncell : (uint64_t)P.n);
+        c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, P.n, bits, c->counts,
+                                           &c->launches);
+        const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
+        const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
+        launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
+        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, P, dt,
+                       &c->launches);
+    }
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
     NbrList L;
     rc = ensure_list(c, &L);

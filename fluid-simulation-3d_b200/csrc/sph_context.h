@@ -33,6 +33,8 @@ struct SphContext {
     uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
     uint32_t *tstart = nullptr, *tend = nullptr;
     size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
+    uint32_t* scan_tmp = nullptr; // block sums of the table scan (counting sort)
+    size_t scan_cap = 0;
     uint32_t* gap_list = nullptr;
     size_t gap_cap = 0;
     uint32_t* counts = nullptr;  // radix sort digit matrix
@@ -76,6 +78,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P);
 int ensure_tables(SphContext* c, const DevParams& P);
 int export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n);
 int ensure_list(SphContext* c, NbrList* L);
+bool counting_sort_enabled();
 
 // sph_multi.cu
 int multi_step(SphContext* c, float dt);

@@ -62,15 +62,24 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
                      bool vals_identity, uint32_t n, int bits, uint32_t* counts, uint64_t* launches);
 
 // ---- sph_kernels.cu -------------------------------------------------------
+// count / rank non-null: counting sort of the GRID table (the row takes a ticket in its cell's counter)
 void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
-                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint64_t* launches);
+                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint32_t* count, uint32_t* rank,
+                        uint64_t* launches);
 void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
-                      uint64_t* launches);
+                      uint32_t* count, uint32_t* rank, uint64_t* launches);
+void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,
+                  uint32_t n, uint64_t* launches);
+// sph_sort.cu: in-place exclusive scan of a zero-padded array (multiple of 4096 entries)
+size_t scan_pad(size_t entries);
+size_t scan_temp_entries(size_t entries);
+void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, uint32_t* blocksums, uint64_t* launches);
 void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* table_start, uint32_t* table_end,
                         uint32_t* gap_list, const DevParams& P, uint64_t* launches);
-void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
-                    const float4* ghost_pred, float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P,
-                    float dt, uint64_t* launches);
+// key / table non-null: counting-sort path (perm = slot -> some row of the cell; canonical order restored here)
+void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, const uint32_t* table, uint32_t* key_sorted,
+                    const float4* pos, const float4* vel, const float4* ghost_pred, float4* pos_s, float4* vel_s,
+                    float4* pred_s, const DevParams& P, float dt, uint64_t* launches);
 // neighbour list recorded by the density pass (k-major: entry k of row i at idx[k*stride + i])
 struct NbrList {
     uint32_t* idx;      // nullptr: no list, every pass walks the table

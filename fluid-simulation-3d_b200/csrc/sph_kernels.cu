@@ -27,8 +27,12 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
-              uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt)
+              uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt,
+              uint32_t* __restrict__ count, uint32_t* __restrict__ rank)
 {
+    // counting sort (GRID table): the row takes a ticket in its cell's counter; the tickets are made
+    // canonical (ascending source row) later, in k_reorder_binned
+    #define SPH_EMIT_KEY(K) do { const uint32_t k__ = (K); key[s] = k__; if (count) rank[s] = atomicAdd(&count[k__], 1u); } while (0)
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= rows) return;
     const float4 p = pos[s];
@@ -37,7 +41,7 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
     predict(p, v, pr, P, dt);
     const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
     if (P.mode == SPH_TABLE_REFERENCE_HASH) {
-        key[s] = key_of_hash(hash_cell(c.x, c.y, c.z), P);
+        SPH_EMIT_KEY(key_of_hash(hash_cell(c.x, c.y, c.z), P));
         return;
     }
     if (P.slab) {
@@ -54,7 +58,7 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
             }
             cls[s] = k;
         }
-        if (k & (CLS_MIG_LO | CLS_MIG_HI)) { key[s] = P.ncell; return; }      // leaves this rank: sorts past the table
+        if (k & (CLS_MIG_LO | CLS_MIG_HI)) { SPH_EMIT_KEY(P.ncell); return; }  // leaves this rank: sorts past the table
         int3 g = grid_cell(pr.x, pr.y, pr.z, P);
         // A row that may not migrate (it arrived this step) but whose layer lies beyond this whole slab -- it moved
         // more than a slab in one step -- is parked one layer INSIDE the slab: the boundary layers must hold exactly
@@ -64,20 +68,33 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
         if (gz < P.own_lo) gzc = min(P.own_lo + 1, P.own_hi - 1);
         else if (gz >= P.own_hi) gzc = max(P.own_hi - 2, P.own_lo);
         g.z = gzc - P.zlo;
-        key[s] = grid_key(g, P);
+        SPH_EMIT_KEY(grid_key(g, P));
         return;
     }
-    key[s] = grid_key(grid_cell(pr.x, pr.y, pr.z, P), P);
+    SPH_EMIT_KEY(grid_key(grid_cell(pr.x, pr.y, pr.z, P), P));
+    #undef SPH_EMIT_KEY
 }
 
 // slab mode: keys of the ghost rows (predicted positions received from / kept for the neighbour ranks)
 __global__ void __launch_bounds__(256)
-k_ghost_key(const float4* __restrict__ ghost_pred, uint32_t* __restrict__ key, const uint32_t rows, const DevParams P)
+k_ghost_key(const float4* __restrict__ ghost_pred, uint32_t* __restrict__ key, const uint32_t rows, const DevParams P,
+            uint32_t* __restrict__ count, uint32_t* __restrict__ rank)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= rows) return;
     const float4 q = ghost_pred[s];
-    key[s] = grid_key(grid_cell(q.x, q.y, q.z, P), P);
+    const uint32_t k = grid_key(grid_cell(q.x, q.y, q.z, P), P);
+    key[s] = k;
+    if (count) rank[s] = atomicAdd(&count[k], 1u);
+}
+
+// counting sort, placement: slot of row s = first slot of its cell + its ticket
+__global__ void __launch_bounds__(256)
+k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ table,
+        uint32_t* __restrict__ slot_row, const uint32_t n)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) slot_row[table[key[s]] + rank[s]] = s;
 }
 
 // ---- S2 tables -------------------------------------------------------------
@@ -159,14 +176,40 @@ k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
 }
 
 // ---- reorder ----------------------------------------------------------------
+// Source row of sorted slot s.  Radix path: perm[s].  Counting-sort path (key != nullptr): the tickets handed out by
+// atomicAdd put a cell's rows into its slots in arbitrary order; the canonical (= stable sort) order is ascending
+// source row, so slot number r of the cell takes the r-th smallest source row of the cell's slots.  Cells hold a
+// handful of rows; a cell with more than kMaxCanonical rows (clamped border cells in a blow-up) keeps ticket order.
+constexpr uint32_t kMaxCanonical = 1024;
+
+__device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
+                                               const uint32_t* __restrict__ table, const uint32_t s, uint32_t* key_sorted)
+{
+    const uint32_t s0 = perm[s];
+    if (!key) return s0;
+    const uint32_t k = key[s0];
+    if (key_sorted) key_sorted[s] = k;
+    const uint32_t b = table[k], m = table[k + 1] - b;
+    if (m == 1u || m > kMaxCanonical) return s0;
+    const uint32_t r = s - b;
+    for (uint32_t t = 0; t < m; t++) {                       // the entry with exactly r smaller entries
+        const uint32_t v = perm[b + t];
+        uint32_t less = 0;
+        for (uint32_t u = 0; u < m; u++) less += perm[b + u] < v;
+        if (less == r) return v;
+    }
+    return s0;
+}
+
 __global__ void __launch_bounds__(256)
-k_reorder(const uint32_t* __restrict__ perm, const float4* __restrict__ pos, const float4* __restrict__ vel,
+k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, const uint32_t* __restrict__ table,
+          uint32_t* __restrict__ key_sorted, const float4* __restrict__ pos, const float4* __restrict__ vel,
           const float4* __restrict__ ghost_pred, float4* __restrict__ pos_s, float4* __restrict__ vel_s,
           float4* __restrict__ pred_s, const DevParams P, const float dt)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n) return;
-    const uint32_t src = perm[s];
+    const uint32_t src = source_row(perm, key, table, s, key_sorted);
     if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
         const float4 q = ghost_pred[src - P.n_a];
         const int3 c = cell_of(q.x, q.y, q.z, P.r);
@@ -316,18 +359,19 @@ inline uint32_t blocks_for(uint32_t n, int threads) { return (n + threads - 1) /
 
 // ---- launchers ---------------------------------------------------------------
 void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
-                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint64_t* launches)
+                        uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint32_t* count, uint32_t* rank,
+                        uint64_t* launches)
 {
     if (rows == 0) return;
-    k_predict_key<<<blocks_for(rows, 256), 256, 0, st>>>(pos, vel, key, cls, rows, may_migrate, P, dt);
+    k_predict_key<<<blocks_for(rows, 256), 256, 0, st>>>(pos, vel, key, cls, rows, may_migrate, P, dt, count, rank);
     ++*launches;
 }
 
 void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
-                      uint64_t* launches)
+                      uint32_t* count, uint32_t* rank, uint64_t* launches)
 {
     if (rows == 0) return;
-    k_ghost_key<<<blocks_for(rows, 256), 256, 0, st>>>(ghost_pred, key, rows, P);
+    k_ghost_key<<<blocks_for(rows, 256), 256, 0, st>>>(ghost_pred, key, rows, P, count, rank);
     ++*launches;
 }
 
@@ -345,12 +389,20 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
     }
 }
 
-void launch_reorder(cudaStream_t st, const uint32_t* perm, const float4* pos, const float4* vel,
-                    const float4* ghost_pred, float4* pos_s, float4* vel_s, float4* pred_s, const DevParams& P,
-                    float dt, uint64_t* launches)
+void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,
+                  uint32_t n, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_place<<<blocks_for(n, 256), 256, 0, st>>>(key, rank, table, slot_row, n);
+    ++*launches;
+}
+
+void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, const uint32_t* table, uint32_t* key_sorted,
+                    const float4* pos, const float4* vel, const float4* ghost_pred, float4* pos_s, float4* vel_s,
+                    float4* pred_s, const DevParams& P, float dt, uint64_t* launches)
 {
     if (P.n == 0) return;
-    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, pos, vel, ghost_pred, pos_s, vel_s, pred_s, P, dt);
+    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, key, table, key_sorted, pos, vel, ghost_pred, pos_s, vel_s, pred_s, P, dt);
     ++*launches;
 }
 

@@ -344,7 +344,11 @@ int multi_step(SphContext* c, float dt)
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
 
     // (1) predict + classify + key of the resident rows
-    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, &c->launches);
+    const bool binned = counting_sort_enabled();
+    const size_t padded = scan_pad((size_t)P.ncell + 3);
+    if (binned) SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, padded * sizeof(uint32_t), st));
+    launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, binned ? c->tstart : nullptr, c->perm_b,
+                       &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
 
     #define SLAB_MARK(i) do { if (s->prof) cudaEventRecord(s->pe[i], st); } while (0)
@@ -424,18 +428,29 @@ int multi_step(SphContext* c, float dt)
     const uint32_t n_all = n_a + n_ghost;
     slab_params(c, &P, n_all);
     P.n_a = n_a;
-    launch_predict_key(st, c->A_pos + n_old, c->A_vel + n_old, c->key_a + n_old, nullptr, n_a - n_old, false, P, dt, &c->launches);
-    launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, &c->launches);
-    const int bits = ceil_log2_u64((uint64_t)P.ncell + 1);
-    c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, n_all, bits, c->counts, &c->launches);
-    SLAB_MARK(4);
-    const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
-    const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
-    // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
-    DevParams PT = P;
-    PT.ncell = P.ncell + 1;
-    launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
-    launch_reorder(st, perm, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, P, dt, &c->launches);
+    launch_predict_key(st, c->A_pos + n_old, c->A_vel + n_old, c->key_a + n_old, nullptr, n_a - n_old, false, P, dt,
+                       binned ? c->tstart : nullptr, c->perm_b + n_old, &c->launches);
+    launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, binned ? c->tstart : nullptr, c->perm_b + n_a, &c->launches);
+    if (binned) {
+        // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
+        exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
+        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, n_all, &c->launches);
+        SLAB_MARK(4);
+        launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel,
+                       c->pred, P, dt, &c->launches);
+        c->sorted_where = 1;
+    } else {
+        const int bits = ceil_log2_u64((uint64_t)P.ncell + 1);
+        c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, n_all, bits, c->counts, &c->launches);
+        SLAB_MARK(4);
+        const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
+        const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
+        DevParams PT = P;
+        PT.ncell = P.ncell + 1;
+        launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
+        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, P, dt,
+                       &c->launches);
+    }
     SLAB_MARK(5);
     // owned rows and boundary layers of the sorted arrays
     const uint32_t plane = (uint32_t)P.gdim[0] * (uint32_t)P.gdim[1];

@@ -224,3 +224,102 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
 }
 
 }  // namespace sphb200
+
+// ---- device-wide exclusive scan (in place) ---------------------------------------------------------
+// Used by the counting sort of the GRID table: per-cell counts -> prefix table t[c] = rows with key < c.
+// Reduce-then-scan in three launches over 4096-entry blocks; `data` must be padded to a multiple of 4096
+// entries (zeros).  Traffic: 2 reads + 1 write of the table.
+namespace sphb200 {
+namespace {
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 16;                                 // entries per thread
+constexpr int kScanBlock = kScanThreads * kScanPer;          // 4096
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_reduce(const uint4* __restrict__ data, uint32_t* __restrict__ blocksums)
+{
+    __shared__ uint32_t wsum[kScanThreads / 32];
+    const uint4* p = data + (size_t)blockIdx.x * (kScanBlock / 4);
+    uint32_t s = 0;
+    #pragma unroll
+    for (int k = 0; k < kScanPer / 4; k++) { const uint4 v = p[k * kScanThreads + threadIdx.x]; s += v.x + v.y + v.z + v.w; }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) t += wsum[w];
+        blocksums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_top(uint32_t* __restrict__ blocksums, const uint32_t nb)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nb ? blocksums[i] : 0u;
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += wsum[w];
+        const uint32_t carry = carry_s;
+        if (i < nb) blocksums[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wbase + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_apply(uint4* __restrict__ data, const uint32_t* __restrict__ blocksums)
+{
+    __shared__ uint32_t wsum[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread t owns 16 CONSECUTIVE entries: uint4 words [4t, 4t+4) of the block
+    uint4* p = data + (size_t)blockIdx.x * (kScanBlock / 4) + (size_t)threadIdx.x * (kScanPer / 4);
+    uint4 v[kScanPer / 4];
+    uint32_t s = 0;
+    #pragma unroll
+    for (int k = 0; k < kScanPer / 4; k++) { v[k] = p[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+    uint32_t inc = s;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t run = blocksums[blockIdx.x] + inc - s;
+    for (int w = 0; w < warp; w++) run += wsum[w];
+    #pragma unroll
+    for (int k = 0; k < kScanPer / 4; k++) {
+        uint4 o;
+        o.x = run; run += v[k].x;
+        o.y = run; run += v[k].y;
+        o.z = run; run += v[k].z;
+        o.w = run; run += v[k].w;
+        p[k] = o;
+    }
+}
+}  // namespace
+
+size_t scan_pad(size_t entries) { return (entries + kScanBlock - 1) / kScanBlock * kScanBlock; }
+size_t scan_temp_entries(size_t entries) { return scan_pad(entries) / kScanBlock + 1; }
+
+void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, uint32_t* blocksums, uint64_t* launches)
+{
+    const uint32_t nb = (uint32_t)(padded_entries / kScanBlock);
+    if (nb == 0) return;
+    k_scan_reduce<<<nb, kScanThreads, 0, st>>>((const uint4*)data, blocksums);
+    k_scan_top<<<1, 1024, 0, st>>>(blocksums, nb);
+    k_scan_apply<<<nb, kScanThreads, 0, st>>>((uint4*)data, blocksums);
+    if (launches) *launches += 3;
+}
+}  // namespace sphb200
