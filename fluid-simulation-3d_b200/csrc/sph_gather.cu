@@ -491,6 +491,136 @@ k_density_pair(const GatherArgs A, const DevParams P)
     }
 }
 
+// ---- density pass, two particles per thread + packed fp32x2 cull + shared-memory stacks (SPH_DENSITY=pair2) ----
+// Same two-phase structure as k_density_list, but every candidate row is loaded ONCE for two consecutive
+// particles and culled with 6 packed instructions (FADD2 x3, FMUL2, FFMA2 x2) against the conservatively widened
+// cull_hi; phase B applies the reference's exact predicate.  Halves the candidate loads per test (the single-
+// particle kernel is bound by L1 wavefronts) and the cull instructions per test.
+constexpr int KS2 = 24;    // stack entries per particle
+constexpr int SEG2 = 8;    // candidates between two flush checks
+
+__global__ void __launch_bounds__(GT)
+k_density_pair2(const GatherArgs A, const DevParams P)
+{
+    __shared__ uint32_t stk[2][KS2][GT];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t last = P.row1 - 1;
+    const uint32_t i0r = P.row0 + 2u * (blockIdx.x * GT + tid), i1r = i0r + 1u;
+    const bool valid0 = i0r <= last, valid1 = i1r <= last;
+    const Self s0 = load_self<PASS_DENSITY>(A, P, valid0 ? i0r : last);
+    const Self s1 = load_self<PASS_DENSITY>(A, P, valid1 ? i1r : last);
+    const Win W0 = window_of(s0.p.x, s0.p.y, s0.p.z, P), W1 = window_of(s1.p.x, s1.p.y, s1.p.z, P);
+    const bool straddle = valid1 && (W0.g.y != W1.g.y || W0.g.z != W1.g.z);
+    const bool pair = valid1 && !straddle;
+    const uint32_t rows01 = pair ? (W0.rows | W1.rows) : W0.rows;
+    const float far = 1.0e18f;       // a particle that is not processed here never passes the cull
+    const uint64_t px = pk(s0.p.x, pair ? s1.p.x : far), py = pk(s0.p.y, pair ? s1.p.y : far), pz = pk(s0.p.z, pair ? s1.p.z : far);
+    const int xa = pair ? min(W0.x0, W1.x0) : W0.x0;
+    const int xb = pair ? max(W0.x1, W1.x1) : W0.x1;
+    const uint32_t K = A.list_k;
+    const size_t stride = A.list_stride;
+    uint32_t* col0 = A.list_idx + s0.i;
+    uint32_t* col1 = A.list_idx + s1.i;
+    uint32_t n0 = 0, n1 = 0, ns0 = 0, ns1 = 0;
+    Acc a0 = {0.0f, 0.0f, 0.0f, 0u}, a1 = {0.0f, 0.0f, 0.0f, 0u};
+    const float cull_hi = P.cull_hi;
+
+    auto flush = [&]() {
+        const uint32_t m = max(ns0, ns1);
+        for (uint32_t k0 = 0; k0 < m; k0 += 2) {
+            uint32_t j0[2], j1[2];
+            Fetched f0[2], f1[2];
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                j0[u] = (k0 + u < ns0) ? stk[0][k0 + u][tid] : s0.i;
+                j1[u] = (k0 + u < ns1) ? stk[1][k0 + u][tid] : s1.i;
+            }
+            #pragma unroll
+            for (int u = 0; u < 2; u++) { f0[u] = fetch<PASS_DENSITY>(A, j0[u]); f1[u] = fetch<PASS_DENSITY>(A, j1[u]); }
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                // the list records the survivors of the conservative cull; every later pass re-applies the exact predicate
+                if (k0 + u < ns0) { (void)eval<PASS_DENSITY>(P, s0, j0[u], f0[u], a0); if (valid0 && n0 + k0 + u < K) col0[(size_t)(n0 + k0 + u) * stride] = j0[u]; }
+                if (k0 + u < ns1) { (void)eval<PASS_DENSITY>(P, s1, j1[u], f1[u], a1); if (pair && n1 + k0 + u < K) col1[(size_t)(n1 + k0 + u) * stride] = j1[u]; }
+            }
+        }
+        n0 += ns0; n1 += ns1;
+        ns0 = ns1 = 0;
+    };
+
+    #pragma unroll 1
+    for (int r9 = 0; r9 < 9; r9++) {
+        uint32_t b, e;
+        row_range(A.table, P, W0.g, xa, xb, rows01, r9, b, e);
+        const uint32_t segs = (__reduce_max_sync(0xffffffffu, e - b) + SEG2 - 1) / SEG2;
+        #pragma unroll 1
+        for (uint32_t sg = 0; sg < segs; sg++) {
+            if (__any_sync(0xffffffffu, max(ns0, ns1) > KS2 - SEG2)) flush();
+            const uint32_t j0 = b + sg * SEG2;
+            const uint32_t je = min(j0 + SEG2, e);
+            #pragma unroll 1
+            for (uint32_t jb = j0; jb < je; jb += 4) {
+                const float4* qp = A.pred + jb;            // padded array: up to 3 rows past `e` are readable
+                float4 q[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = __ldg(qp + u);
+                #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t ox = sub2(pk(q[u].x, q[u].x), px), oy = sub2(pk(q[u].y, q[u].y), py), oz = sub2(pk(q[u].z, q[u].z), pz);
+                    const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
+                    float d0, d1;
+                    upk(d2, d0, d1);
+                    const bool in = jb + u < je;
+                    const bool ok0 = in & !(d0 > cull_hi), ok1 = in & !(d1 > cull_hi);
+                    sts_if(&stk[0][ns0][tid], jb + u, ok0);
+                    sts_if(&stk[1][ns1][tid], jb + u, ok1);
+                    ns0 += ok0; ns1 += ok1;
+                }
+            }
+        }
+    }
+    flush();
+    if (valid0) { finish<PASS_DENSITY>(A, P, s0, a0, 0.0f); A.list_cnt[s0.i] = n0; }
+    if (pair) { finish<PASS_DENSITY>(A, P, s1, a1, 0.0f); A.list_cnt[s1.i] = n1; }
+    report_overflow(A, max((valid0 && n0 > K) ? n0 : 0u, (pair && n1 > K) ? n1 : 0u));
+
+    // second particles that live in another (y,z) row than their partner: whole warp on one particle
+    uint32_t todo = __ballot_sync(0xffffffffu, straddle);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t ic = __shfl_sync(0xffffffffu, s1.i, src);
+        const Self sc = load_self<PASS_DENSITY>(A, P, ic);
+        const Win Wc = window_of(sc.p.x, sc.p.y, sc.p.z, P);
+        uint32_t* colc = A.list_idx + ic;
+        Acc ac = {0.0f, 0.0f, 0.0f, 0u};
+        uint32_t nc = 0;
+        #pragma unroll 1
+        for (int r9 = 0; r9 < 9; r9++) {
+            uint32_t b, e;
+            row_range(A.table, P, Wc.g, Wc.x0, Wc.x1, Wc.rows, r9, b, e);
+            for (uint32_t jb = b; jb < e; jb += 32) {
+                const uint32_t j = jb + lane;
+                bool ok = false;
+                if (j < e) { const Fetched f = fetch<PASS_DENSITY>(A, j); ok = eval<PASS_DENSITY>(P, sc, j, f, ac); }
+                const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+                const uint32_t pos = nc + __popc(mask & ((1u << lane) - 1u));
+                if (ok && pos < K) colc[(size_t)pos * stride] = j;
+                nc += __popc(mask);
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ac.a += __shfl_xor_sync(0xffffffffu, ac.a, o);
+            ac.b += __shfl_xor_sync(0xffffffffu, ac.b, o);
+            ac.cnt += __shfl_xor_sync(0xffffffffu, ac.cnt, o);
+        }
+        if (lane == src) { finish<PASS_DENSITY>(A, P, sc, ac, 0.0f); A.list_cnt[ic] = nc; }
+        report_overflow(A, (lane == src && nc > K) ? nc : 0u);
+    }
+}
+
 template <int PASS>
 void launch(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
 {
@@ -526,6 +656,7 @@ static int density_variant()
         const char* e = getenv("SPH_DENSITY");
         if (e && e[0] == 'p') return 1;
         if (e && e[0] == 'w') return 2;
+        if (e && e[0] == '2') return 3;
         return 0;
     }();
     return v;
@@ -562,7 +693,12 @@ void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstar
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.dens_out = dens; A.ncount = L.ncount;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
-    else if (A.list_idx && density_variant() == 1 && P.mode == SPH_TABLE_GRID) {       // SPH_DENSITY=pair
+    else if (A.list_idx && density_variant() == 3 && P.mode == SPH_TABLE_GRID) {       // SPH_DENSITY=2: pair2
+        if (P.row1 <= P.row0) return;
+        const uint32_t threads = (P.row1 - P.row0 + 1) / 2;
+        k_density_pair2<<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P);
+        ++*launches;
+    } else if (A.list_idx && density_variant() == 1 && P.mode == SPH_TABLE_GRID) {     // SPH_DENSITY=pair
         if (P.row1 <= P.row0) return;
         const uint32_t threads = (P.row1 - P.row0 + 1) / 2;
         k_density_pair<<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P);

@@ -26,8 +26,8 @@ print("VARIANT_OK")
 """
 
 
-@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}],
-                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density"])
+@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}, {"SPH_DENSITY": "2"}, {"SPH_SORT": "radix"}],
+                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density", "list_with_pair2_density", "radix_sort_grid"])
 def test_enumeration_variants_match_oracle(env):
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, os.path.join(ROOT, "tests"))], env=e, cwd=ROOT,
