@@ -1,25 +1,28 @@
-// sph_gather.cu -- the three neighbour-gather passes for the GRID table, second generation.
+// sph_gather.cu -- the three neighbour-gather passes (density, pressure, viscosity) and their launchers.
 //
 //   density   S3  physicsWorld.cc:304-311, 325-365      pressure  S4  :367-422
 //   viscosity S5  :424-464 (snapshot semantics)          kernels   engine/physics/kernels.h:25-82
 //
-// ncu on the first version (thread per particle, scalar math; profiles/r01_gather_v1_C2.txt) showed the
-// passes are INSTRUCTION-ISSUE bound (76-87 % issue-active, L1 61 %), not HBM bound, so this version
-// minimises instructions per (particle, candidate) test:
+// The physics of a (particle, neighbour) pair lives once, in sph_gather.cuh (load_self / fetch / eval / finish);
+// the kernels here differ only in how they enumerate candidates.  What runs by default:
 //
-//  * TWO particles per thread, tested against each candidate with sm_100a packed fp32x2 math
-//    (FADD2 / FMUL2 / FFMA2: one instruction per pair of lanes' worth of work) -- 6 packed instructions
-//    + 1 shared 16-byte load per candidate for both particles.
-//  * TWO PHASES.  Phase A culls with the FMA-fused d^2 against a conservatively widened radius
-//    (cull_hi) and pushes survivors on a per-particle shared-memory stack; phase B pops them and
-//    applies the reference's EXACT predicate  d^2 = (ox*ox + oy*oy) + oz*oz (no FMA), !(d^2 > sqrRadius)
-//    before evaluating the smoothing kernels, so neighbour sets stay bit-exact while the 84 % of
-//    candidates that fail never reach the expensive code and the evaluation runs without divergence.
-//  * All loops are made warp-uniform (redux.sync max of the row lengths), so stack flushes are
-//    collective and the warp stays converged.
-//  * The two particles of a thread are consecutive sorted rows and share the 9 row windows (x window =
-//    union of both).  The rare thread whose two rows lie in different (y,z) rows hands its second
-//    particle to a warp-cooperative pass (32 lanes stride the candidates, shuffle reduction).
+//   k_density_list   two-phase density: phase A walks the table (9 row windows of the GRID table, or the 27 buckets
+//                    of the REFERENCE_HASH table), applies only the reference's exact predicate, branch-free, and
+//                    pushes survivors on a small shared-memory stack; phase B pops them, evaluates the smoothing
+//                    kernels converged and writes the particle's NEIGHBOUR LIST column.  Rows and 16-candidate
+//                    segments are warp-uniform loop levels (redux.sync), so the flush is collective.
+//   k_gather_list    pressure and viscosity replay the list (same predicted positions + same predicate => same
+//                    set): ~18 entries instead of ~100 candidates, one 256-bit record load per neighbour.
+//                    A particle whose list overflowed walks the table instead (walk_particle).
+//
+// ncu (profiles/): every variant of these passes is bound by L1 wavefronts and instruction issue, not by HBM --
+// the gather re-reads neighbours from L1/L2 by design.  Variants kept for A/B runs, all parity-tested
+// (tests/test_variants_gpu.py), selected with SPH_GATHER / SPH_DENSITY:
+//   k_gather_walk    generation 1: every pass walks the table (SPH_GATHER=v1; also the no-list configuration)
+//   k_gather2        packed fp32x2 two-particles-per-thread two-phase cull in every pass (SPH_GATHER=v2)
+//   k_density_pair / k_density_pair2   packed two-particle density feeding the list (SPH_DENSITY=pair / 2).
+//                    FADD2/FMUL2/FFMA2 halve the cull instructions, but a warp then spans 64 particles, its loads
+//                    touch ~1.7x more lines and the union windows waste slots: 190-205 us vs 140 us at 1 M particles.
 #include <cstdlib>
 
 #include "sph_gather.cuh"
