@@ -64,7 +64,8 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->s3 = 45 / (powf(r, 6) * kPi);
     P->sv = 315 / (64 * kPi * powf(fabsf(r), 9));
     P->rr = r * r;
-    P->cull_hi = nextafterf((float)((double)p.sqr_radius * (1.0 + 5e-7)), INFINITY);
+    P->cull_hi = nextafterf((float)((double)p.sqr_radius * (1.0 + 1e-6)), INFINITY);
+    P->cull_lo = nextafterf((float)((double)p.sqr_radius * (1.0 - 1e-6)), -INFINITY);
     for (int a = 0; a < 3; a++) { P->gmin[a] = c->gmin[a]; P->gdim[a] = c->gdim[a]; }
     P->xsub = c->xsub;
     P->xwin = (float)(sqrt((double)p.sqr_radius) * (1.0 + 1e-5));
@@ -167,7 +168,7 @@ int ensure_list(SphContext* c, NbrList* L)
 
 static void free_all(SphContext* c)
 {
-    void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->velp, c->dens, c->key_a, c->key_b,
+    void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->predpk, c->velp, c->dens, c->key_a, c->key_b,
                     c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
@@ -231,6 +232,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
     ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 32);
     ALLOC(c->dens, cap * 32);
+    ALLOC(c->predpk, (cap + 8) * 16);
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
     ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
     ALLOC(c->ncount, cap * 4);
@@ -355,7 +357,7 @@ static int run_step(SphContext* c, float dt, bool advance)
         exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
         launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, &c->launches);
         launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred,
-                       P, dt, &c->launches);
+                       c->predpk, P, dt, &c->launches);
         c->sorted_where = 1;
     } else {
         launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, nullptr, nullptr, &c->launches);
@@ -366,14 +368,14 @@ static int run_step(SphContext* c, float dt, bool advance)
         const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
         const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
         launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
-        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, P, dt,
+        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt,
                        &c->launches);
     }
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
     NbrList L;
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
-    launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, P, &c->launches);
+    launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));

@@ -239,9 +239,12 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
             #pragma unroll
             for (int u = 0; u < U; u++) jn[u] = (k0 + U + u < cnt) ? __ldg(&col[(size_t)(k0 + U + u) * A.list_stride]) : s.i;
             #pragma unroll
-            for (int u = 0; u < U; u++) f[u] = fetch<PASS>(A, j[u]);
+            for (int u = 0; u < U; u++) {            // the particle itself (its own entry, and the padding) is not fetched
+                f[u].q = s.p;
+                if (j[u] != s.i) f[u] = fetch<PASS>(A, j[u]);
+            }
             #pragma unroll
-            for (int u = 0; u < U; u++) (void)eval<PASS>(P, s, j[u], f[u], acc);   // padding entries are the particle itself: skipped
+            for (int u = 0; u < U; u++) (void)eval<PASS>(P, s, j[u], f[u], acc);   // ... and skipped
         }
     }
     finish<PASS>(A, P, s, acc, dt);
@@ -624,6 +627,145 @@ k_density_pair2(const GatherArgs A, const DevParams P)
     }
 }
 
+// ---- density pass, packed candidate pairs (default for the GRID table) ---------------------------------------
+// One thread per particle, as k_density_list, but
+//  * the candidates come from the PAIR-INTERLEAVED copy of the predicted positions (PredPair, sph_internal.h): one
+//    256-bit load brings two candidates as three aligned register pairs, and their d^2 costs 6 packed instructions
+//    (3 FADD2, FMUL2, 2 FFMA2) instead of 16 scalar ones -- half the L1 wavefronts and a third of the math per
+//    candidate.  The FMA-fused d^2 decides everything outside a 2e-6 wide band around sqrRadius; inside the band the
+//    reference's exact predicate is evaluated on the plain rows (phase B, ~1e-6 of the candidates);
+//  * every thread walks its <= 9 row windows as ONE flat sequence of aligned pairs (bounds fetched up front, kept in
+//    shared memory), so a warp runs for the longest TOTAL of its lanes, not for the sum of per-row maxima;
+//  * the stack keeps (row, d^2): phase B needs no second look at the candidate -- no gather loads at all;
+//  * phase B writes list row k for the whole warp at once (short lanes pad with their own index, which the
+//    pressure / viscosity passes skip), so list writes stay coalesced across flushes and list lengths are
+//    warp-uniform.
+constexpr int PKS = 24;    // stack entries per thread
+
+__global__ void __launch_bounds__(kWalkThreads)
+k_density_pk(const GatherArgs A, const DevParams P)
+{
+    __shared__ uint2 stk[PKS][kWalkThreads];       // survivors: (row, bits of the FMA-fused d^2)
+    constexpr uint32_t kRow = kWalkThreads * 8;    // bytes between two stack rows of a thread
+    const int tid = threadIdx.x;
+    const uint32_t iraw = P.row0 + blockIdx.x * blockDim.x + tid;
+    const bool valid = iraw < P.row1;
+    const uint32_t i = valid ? iraw : P.row1 - 1;  // idle tail threads shadow the last row (they join the collectives)
+    const Self s = load_self<PASS_DENSITY>(A, P, i);
+    const uint32_t K = A.list_k;
+    const size_t stride = A.list_stride;
+    uint32_t* col = A.list_idx + i;
+    uint32_t kbase = 0;                            // list rows written so far (warp-uniform)
+    (void)stride;
+    Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+    const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(&stk[0][tid]);
+    uint32_t sa = sa0;
+
+    // phase B: list row k of the whole warp at once; lanes with fewer survivors pad with their own index.  The sums
+    // are scaled by the kernel volumes once, in the end.
+    uint32_t* lp = col;
+    const uint32_t klim = valid ? K : 0u;
+    auto flush = [&]() {
+        const uint32_t ns = (sa - sa0) / kRow;
+        const uint32_t m = __reduce_max_sync(0xffffffffu, ns);
+        #pragma unroll 2
+        for (uint32_t k = 0; k < m; k++) {
+            const uint2 en = stk[k][tid];
+            float d2 = __uint_as_float(en.y);
+            bool nb = k < ns;
+            if (nb && d2 >= P.cull_lo) {           // inside the band: the reference's exact predicate (:357, Q8)
+                float ox, oy, oz;
+                d2 = sqr_dist(__ldg(&A.pred[en.x]), s.p, ox, oy, oz);
+                nb = !(d2 > P.sqr_r);
+            }
+            const float w = nb ? fmaxf(P.r - sqrt_approx(d2), 0.0f) : 0.0f;   // kernels.h:27,39: zero unless d < r
+            acc.cnt += nb;
+            acc.a = fmaf(w, w, acc.a);
+            acc.b = fmaf(w * w, w, acc.b);
+            if (kbase < klim) *lp = nb ? en.x : i;
+            lp += stride;
+            kbase++;
+        }
+        sa = sa0;
+    };
+
+    const Win W = window_of(s.p.x, s.p.y, s.p.z, P);
+    const Rec8* __restrict__ pairs = reinterpret_cast<const Rec8*>(A.predpk);
+    const uint32_t last_pair = (P.n - 1u) >> 1;
+    const uint64_t px = pk(s.p.x, s.p.x), py = pk(s.p.y, s.p.y), pz = pk(s.p.z, s.p.z);
+    const float cull_hi = P.cull_hi;
+
+    // cull one pair: rows (cj, cj + 1), the first at position t of a window of `len` rows (t = -1 when the window
+    // starts on an odd row).  Row cj is inside iff 0 <= t < len (one unsigned compare), row cj + 1 iff t < len - 1.
+    auto cull = [&](const Rec8& c, const int t, const int len, const uint32_t cj) {
+        const uint64_t ox = sub2(pk(c.lo.x, c.lo.y), px), oy = sub2(pk(c.lo.z, c.lo.w), py), oz = sub2(pk(c.hi.x, c.hi.y), pz);
+        const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
+        float d0, d1;
+        upk(d2, d0, d1);
+        asm volatile("{ .reg .pred p, q;\n"
+                     " setp.gt.f32 p, %3, %5;\n"
+                     " setp.lt.and.u32 q, %1, %2, !p;\n"
+                     " @q st.shared.v2.b32 [%0], {%7, %3};\n"
+                     " @q add.u32 %0, %0, %9;\n"
+                     " setp.gt.f32 p, %4, %5;\n"
+                     " setp.lt.and.s32 q, %1, %6, !p;\n"
+                     " @q st.shared.v2.b32 [%0], {%8, %4};\n"
+                     " @q add.u32 %0, %0, %9; }"
+                     : "+r"(sa)
+                     : "r"(t), "r"(len), "f"(d0), "f"(d1), "f"(cull_hi), "r"(len - 1), "r"(cj), "r"(cj + 1u), "n"(kRow)
+                     : "memory");
+    };
+
+    // 9 row windows; the bounds of the next row are requested while this one is culled.  Rows and 2-pair chunks
+    // are warp-uniform loop levels.
+    uint32_t vm = W.rows;                          // rows that exist and can hold a neighbour
+    #pragma unroll
+    for (int a3 = 0; a3 < 3; a3++) {
+        if ((uint32_t)(W.g.y + a3 - 1) >= (uint32_t)P.gdim[1]) vm &= ~(0x49u << a3);
+        if ((uint32_t)(W.g.z + a3 - 1) >= (uint32_t)P.gdim[2]) vm &= ~(0x7u << (3 * a3));
+    }
+    const uint32_t gd0 = (uint32_t)P.gdim[0];
+    const int64_t zstep = (int64_t)P.gdim[1] * gd0 - 3 * (int64_t)gd0;
+    const uint32_t* tp = A.table + ((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0;
+    const uint32_t xspan = (uint32_t)(W.x1 - W.x0) + 1u;
+    auto bounds = [&](const int r9, uint32_t& b, uint32_t& e) {
+        b = e = 0;
+        if ((vm >> r9) & 1u) { b = __ldg(tp); e = __ldg(tp + xspan); }
+        tp += gd0;
+    };
+    uint32_t bn, en;
+    bounds(0, bn, en);
+    int dyc = 1;
+    #pragma unroll 1
+    for (int r9 = 0; r9 < 9; r9++) {
+        const uint32_t b = bn, e = en;
+        if (dyc == 3) { dyc = 0; tp += zstep; }
+        dyc++;
+        bounds(r9 + 1, bn, en);
+        const int len = (int)(e - b);
+        const uint32_t p0 = b >> 1;                                    // first pair of the window
+        const uint32_t np = len ? ((e + 1u) >> 1) - p0 : 0u;
+        const uint32_t iters = __reduce_max_sync(0xffffffffu, np);
+        int t = -(int)(b & 1u);
+        #pragma unroll 1
+        for (uint32_t it = 0; it < iters; it += 2, t += 4) {
+            if (__any_sync(0xffffffffu, sa - sa0 > (PKS - 4) * kRow)) flush();
+            const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
+            const Rec8 c0 = ld256(pairs + q0), c1 = ld256(pairs + q1);
+            cull(c0, t, len, 2u * (p0 + it));
+            cull(c1, t + 2, len, 2u * (p0 + it) + 2u);
+        }
+    }
+    flush();
+    if (valid) {
+        acc.a *= P.vol2;
+        acc.b *= P.vol3;
+        finish<PASS_DENSITY>(A, P, s, acc, 0.0f);
+        A.list_cnt[i] = kbase;
+    }
+    report_overflow(A, (valid && kbase > K) ? kbase : 0u);
+}
+
 template <int PASS>
 void launch(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
 {
@@ -651,8 +793,9 @@ static int gather_variant()
     return v;
 }
 
-// SPH_DENSITY selects the density kernel when the neighbour list is on: default two-phase list kernel,
-// "pair" = packed two-particles-per-thread cull (GRID only), "walk" = single-phase walk.
+// SPH_DENSITY selects the density kernel when the neighbour list is on: default k_density_pk on the GRID table and
+// k_density_list on the REFERENCE_HASH table; "list" = k_density_list on both, "pair" / "2" = packed
+// two-particles-per-thread culls (GRID only), "walk" = single-phase walk.
 static int density_variant()
 {
     static const int v = [] {
@@ -660,6 +803,7 @@ static int density_variant()
         if (e && e[0] == 'p') return 1;
         if (e && e[0] == 'w') return 2;
         if (e && e[0] == '2') return 3;
+        if (e && e[0] == 'l') return 4;      // "list": the scalar two-phase kernel on the GRID table too
         return 0;
     }();
     return v;
@@ -690,10 +834,11 @@ static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const 
     return A;
 }
 
-void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
+void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
                     Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.predpk = pred_pk;
     A.dens_out = dens; A.ncount = L.ncount;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
     else if (A.list_idx && density_variant() == 3 && P.mode == SPH_TABLE_GRID) {       // SPH_DENSITY=2: pair2
@@ -706,10 +851,11 @@ void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstar
         const uint32_t threads = (P.row1 - P.row0 + 1) / 2;
         k_density_pair<<<(threads + GT - 1) / GT, GT, 0, st>>>(A, P);
         ++*launches;
-    } else if (A.list_idx && density_variant() == 0) {                                  // default: two-phase list density
+    } else if (A.list_idx && (density_variant() == 0 || density_variant() == 4)) {     // default: two-phase list density
         if (P.row1 <= P.row0) return;
         const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
-        if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
+        if (P.mode == SPH_TABLE_GRID && density_variant() == 0 && pred_pk) k_density_pk<<<blocks, kWalkThreads, 0, st>>>(A, P);
+        else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
         else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);
         ++*launches;
     } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);           // SPH_DENSITY=walk / no list

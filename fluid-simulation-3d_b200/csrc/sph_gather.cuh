@@ -15,6 +15,7 @@ enum { PASS_DENSITY = 0, PASS_PRESSURE = 1, PASS_VISCOSITY = 2 };
 
 struct GatherArgs {
     const float4* pred;        // sorted predicted positions (+ float(hash) in w)
+    const float4* predpk;      // the same rows pair-interleaved (PredPair, sph_internal.h): density pass, GRID table
     const uint32_t* table;     // GRID prefix table / REFERENCE_HASH startIndices
     const uint32_t* tend;      // REFERENCE_HASH bucket ends
     // neighbour list recorded by the density pass: entry k of row i at list_idx[k * list_stride + i],

@@ -20,7 +20,11 @@ struct DevParams {
     float    s2, s3;        // SmoothingDerivativePow2 / Pow3 scales
     float    sv;            // SmoothingViscoPoly6 scale
     float    rr;            // r*r
-    float    cull_hi;       // sqr_r * (1 + 5e-7) rounded up: conservative prefilter for the FMA-fused d^2 (sph_gather.cu)
+    // The packed cull computes d^2 with FMAs (3 roundings) where the reference's (x*x + y*y) + z*z has 5: the two
+    // differ by < 8 * 2^-24 = 4.8e-7 relative.  d^2' > cull_hi: certainly not a neighbour; d^2' < cull_lo: certainly
+    // one; in between (a ~2e-6 wide band) the exact predicate is evaluated on the plain rows.
+    float    cull_hi;       // sqr_r * (1 + 1e-6) rounded up
+    float    cull_lo;       // sqr_r * (1 - 1e-6) rounded down
     // GRID table: cell g = clamp(floor(pred/r) - gmin, 0, gdim-1); key = (gz*gdim.y + gy)*gdim.x + gx
     int      gmin[3];       // first reference cell of the table per axis
     int      gdim[3];       // table extent: fine x cells (reference cells * xsub), y cells, z cells
@@ -45,6 +49,11 @@ struct DevParams {
 // Position and per-pass payload of a neighbour sit in the same sector, so a neighbour costs one load
 // instruction and one line instead of two of each.
 struct __align__(32) Rec8 { float4 lo, hi; };
+
+// Pair-interleaved predicted positions (`predpk`): rows 2m and 2m+1 share one 32-byte record
+//   lo = (x0, x1, y0, y1)   hi = (z0, z1, w0, w1)
+// so that ONE 256-bit load hands the density pass two candidates as three aligned register pairs, ready for the
+// packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2).  Written by k_reorder next to the plain `pred` rows.
 
 // slab mode: classification of an owned row by the z layer of its predicted position
 enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8 };
@@ -79,7 +88,7 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
 // key / table non-null: counting-sort path (perm = slot -> some row of the cell; canonical order restored here)
 void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, const uint32_t* table, uint32_t* key_sorted,
                     const float4* pos, const float4* vel, const float4* ghost_pred, float4* pos_s, float4* vel_s,
-                    float4* pred_s, const DevParams& P, float dt, uint64_t* launches);
+                    float4* pred_s, float4* pred_pk, const DevParams& P, float dt, uint64_t* launches);
 // neighbour list recorded by the density pass (k-major: entry k of row i at idx[k*stride + i])
 struct NbrList {
     uint32_t* idx;      // nullptr: no list, every pass walks the table
@@ -89,7 +98,7 @@ struct NbrList {
     uint32_t  k;        // entries per row before a row counts as overflowed
     uint32_t  stride;
 };
-void launch_density(cudaStream_t st, const float4* pred_s, const uint32_t* tstart, const uint32_t* tend,
+void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
                     Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
 void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
                      const uint32_t* tstart, const uint32_t* tend, Rec8* vel_p, const NbrList& L, const DevParams& P,

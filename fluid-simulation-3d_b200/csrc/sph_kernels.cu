@@ -205,28 +205,39 @@ __global__ void __launch_bounds__(256)
 k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, const uint32_t* __restrict__ table,
           uint32_t* __restrict__ key_sorted, const float4* __restrict__ pos, const float4* __restrict__ vel,
           const float4* __restrict__ ghost_pred, float4* __restrict__ pos_s, float4* __restrict__ vel_s,
-          float4* __restrict__ pred_s, const DevParams P, const float dt)
+          float4* __restrict__ pred_s, float4* __restrict__ pred_pk, const DevParams P, const float dt)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
-    const uint32_t src = source_row(perm, key, table, s, key_sorted);
-    if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
-        const float4 q = ghost_pred[src - P.n_a];
-        const int3 c = cell_of(q.x, q.y, q.z, P.r);
-        pred_s[s] = make_float4(q.x, q.y, q.z, __uint2float_rn(hash_cell(c.x, c.y, c.z)));
-        pos_s[s] = make_float4(q.x, q.y, q.z, __uint_as_float(0xFFFFFFFFu));
-        vel_s[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        return;
+    const bool valid = s < P.n;                    // no early return: the pair-interleaved copy is written with shuffles
+    float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (valid) {
+        const uint32_t src = source_row(perm, key, table, s, key_sorted);
+        if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
+            const float4 gq = ghost_pred[src - P.n_a];
+            const int3 c = cell_of(gq.x, gq.y, gq.z, P.r);
+            q = make_float4(gq.x, gq.y, gq.z, __uint2float_rn(hash_cell(c.x, c.y, c.z)));
+            pos_s[s] = make_float4(gq.x, gq.y, gq.z, __uint_as_float(0xFFFFFFFFu));
+            vel_s[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else {
+            const float4 p = pos[src];
+            float4 v = vel[src];
+            float3 pr;
+            predict(p, v, pr, P, dt);          // bit-identical to k_predict_key: same inputs, same operations
+            const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
+            const uint32_t h = hash_cell(c.x, c.y, c.z);
+            pos_s[s] = p;
+            vel_s[s] = v;
+            q = make_float4(pr.x, pr.y, pr.z, __uint2float_rn(h));   // spatialLookup[].y is float(hash) (:480)
+        }
+        pred_s[s] = q;
     }
-    const float4 p = pos[src];
-    float4 v = vel[src];
-    float3 pr;
-    predict(p, v, pr, P, dt);          // bit-identical to k_predict_key: same inputs, same operations
-    const int3 c = cell_of(pr.x, pr.y, pr.z, P.r);
-    const uint32_t h = hash_cell(c.x, c.y, c.z);
-    pos_s[s] = p;
-    vel_s[s] = v;
-    pred_s[s] = make_float4(pr.x, pr.y, pr.z, __uint2float_rn(h));   // spatialLookup[].y is float(hash) (:480)
+    // PredPair record of rows (2m, 2m+1): the even row's thread writes lo = (x0, x1, y0, y1), the odd row's thread
+    // hi = (z0, z1, w0, w1) -- thread s writes float4 number s of the array, fully coalesced.  The partner of the
+    // last row of an odd-sized array contributes zeros (that slot is past every window, so it is never accepted).
+    const float ax = __shfl_xor_sync(0xffffffffu, q.x, 1), ay = __shfl_xor_sync(0xffffffffu, q.y, 1);
+    const float az = __shfl_xor_sync(0xffffffffu, q.z, 1), aw = __shfl_xor_sync(0xffffffffu, q.w, 1);
+    if (pred_pk && s < ((P.n + 1u) & ~1u))
+        pred_pk[s] = (s & 1u) ? make_float4(az, q.z, aw, q.w) : make_float4(q.x, ax, q.y, ay);
 }
 
 // S6 (:84-107)
@@ -399,10 +410,10 @@ void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, co
 
 void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, const uint32_t* table, uint32_t* key_sorted,
                     const float4* pos, const float4* vel, const float4* ghost_pred, float4* pos_s, float4* vel_s,
-                    float4* pred_s, const DevParams& P, float dt, uint64_t* launches)
+                    float4* pred_s, float4* pred_pk, const DevParams& P, float dt, uint64_t* launches)
 {
     if (P.n == 0) return;
-    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, key, table, key_sorted, pos, vel, ghost_pred, pos_s, vel_s, pred_s, P, dt);
+    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, key, table, key_sorted, pos, vel, ghost_pred, pos_s, vel_s, pred_s, pred_pk, P, dt);
     ++*launches;
 }
 

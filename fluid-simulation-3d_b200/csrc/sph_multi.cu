@@ -436,8 +436,7 @@ int multi_step(SphContext* c, float dt)
         exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
         launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, n_all, &c->launches);
         SLAB_MARK(4);
-        launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel,
-                       c->pred, P, dt, &c->launches);
+        launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt, &c->launches);
         c->sorted_where = 1;
     } else {
         const int bits = ceil_log2_u64((uint64_t)P.ncell + 1);
@@ -448,7 +447,7 @@ int multi_step(SphContext* c, float dt)
         DevParams PT = P;
         PT.ncell = P.ncell + 1;
         launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
-        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, P, dt,
+        launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt,
                        &c->launches);
     }
     SLAB_MARK(5);
@@ -513,7 +512,7 @@ int multi_step(SphContext* c, float dt)
     DevParams Q = P;
     for (int g = 0; g < 3; g++) {
         Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
-        launch_density(st, c->pred, c->tstart, c->tend, c->dens, L, Q, &c->launches);
+        launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, Q, &c->launches);
         if (g == 1) { rc = halo(c->dens); if (rc != SPH_OK) return rc; }
     }
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
