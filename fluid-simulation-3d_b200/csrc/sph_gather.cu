@@ -640,12 +640,15 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 //  * phase B writes list row k for the whole warp at once (short lanes pad with their own index, which the
 //    pressure / viscosity passes skip), so list writes stay coalesced across flushes and list lengths are
 //    warp-uniform.
-constexpr int PKS = 24;    // stack entries per thread
+constexpr int PKS = 24;         // stack entries per thread: sparse scenes (one or two flushes per particle)
+constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
 
 __global__ void __launch_bounds__(kWalkThreads)
-k_density_pk(const GatherArgs A, const DevParams P)
+k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
 {
-    __shared__ uint2 stk[PKS][kWalkThreads];       // survivors: (row, bits of the FMA-fused d^2)
+    extern __shared__ uint2 stk_raw[];             // [stack_rows][kWalkThreads] survivors: (row, bits of the FMA-fused d^2)
+    uint2 (*stk)[kWalkThreads] = reinterpret_cast<uint2 (*)[kWalkThreads]>(stk_raw);
+    const uint32_t full_mark = (stack_rows - 4u) * (kWalkThreads * 8u);
     constexpr uint32_t kRow = kWalkThreads * 8;    // bytes between two stack rows of a thread
     const int tid = threadIdx.x;
     const uint32_t iraw = P.row0 + blockIdx.x * blockDim.x + tid;
@@ -661,15 +664,21 @@ k_density_pk(const GatherArgs A, const DevParams P)
     const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(&stk[0][tid]);
     uint32_t sa = sa0;
 
-    // phase B: list row k of the whole warp at once; lanes with fewer survivors pad with their own index.  The sums
-    // are scaled by the kernel volumes once, in the end.
+    // phase B: list row k of the whole warp at once (coalesced).  A flush in mid-walk writes only as many rows as
+    // EVERY lane can fill -- or as many as it takes to get the fullest lane down to half a stack, lanes that run
+    // short then pad with their own index -- and the entries that stay are moved to the bottom of the stack.  The
+    // last flush writes everything, so a warp's list length is the longest true list of its lanes unless the
+    // lanes' counts drift apart by more than half a stack.  The sums are scaled by the kernel volumes in the end.
     uint32_t* lp = col;
     const uint32_t klim = valid ? K : 0u;
-    auto flush = [&]() {
+    const uint32_t keep = stack_rows / 2u;
+    auto flush = [&](const bool last) {
         const uint32_t ns = (sa - sa0) / kRow;
-        const uint32_t m = __reduce_max_sync(0xffffffffu, ns);
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, ns);
+        uint32_t rows = mx;
+        if (!last) rows = max(__reduce_min_sync(0xffffffffu, ns), mx > keep ? mx - keep : 0u);
         #pragma unroll 2
-        for (uint32_t k = 0; k < m; k++) {
+        for (uint32_t k = 0; k < rows; k++) {
             const uint2 en = stk[k][tid];
             float d2 = __uint_as_float(en.y);
             bool nb = k < ns;
@@ -686,7 +695,9 @@ k_density_pk(const GatherArgs A, const DevParams P)
             lp += stride;
             kbase++;
         }
-        sa = sa0;
+        if (last) return;
+        for (uint32_t k = rows; k < mx; k++) stk[k - rows][tid] = stk[k][tid];
+        sa = sa0 + (ns > rows ? ns - rows : 0u) * kRow;
     };
 
     const Win W = window_of(s.p.x, s.p.y, s.p.z, P);
@@ -749,14 +760,14 @@ k_density_pk(const GatherArgs A, const DevParams P)
         int t = -(int)(b & 1u);
         #pragma unroll 1
         for (uint32_t it = 0; it < iters; it += 2, t += 4) {
-            if (__any_sync(0xffffffffu, sa - sa0 > (PKS - 4) * kRow)) flush();
+            if (__any_sync(0xffffffffu, sa - sa0 > full_mark)) flush(false);
             const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
             const Rec8 c0 = ld256(pairs + q0), c1 = ld256(pairs + q1);
             cull(c0, t, len, 2u * (p0 + it));
             cull(c1, t + 2, len, 2u * (p0 + it) + 2u);
         }
     }
-    flush();
+    flush(true);
     if (valid) {
         acc.a *= P.vol2;
         acc.b *= P.vol3;
@@ -854,7 +865,12 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
     } else if (A.list_idx && (density_variant() == 0 || density_variant() == 4)) {     // default: two-phase list density
         if (P.row1 <= P.row0) return;
         const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
-        if (P.mode == SPH_TABLE_GRID && density_variant() == 0 && pred_pk) k_density_pk<<<blocks, kWalkThreads, 0, st>>>(A, P);
+        if (P.mode == SPH_TABLE_GRID && density_variant() == 0 && pred_pk) {
+            static const bool big_ok = cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            PKS_DENSE * kWalkThreads * 8) == cudaSuccess;
+            const uint32_t rows = (A.list_k > 64 && big_ok) ? PKS_DENSE : PKS;
+            k_density_pk<<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows);
+        }
         else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
         else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);
         ++*launches;
