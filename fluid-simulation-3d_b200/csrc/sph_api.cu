@@ -151,11 +151,13 @@ int ensure_list(SphContext* c, NbrList* L)
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
         if (c->nlist) cudaFree(c->nlist);
         c->nlist = nullptr; c->list_k_alloc = 0;
-        cudaError_t e = cudaMalloc(&c->nlist, (size_t)c->list_k * c->cap * sizeof(uint32_t));
+        // rows [0, k) hold the neighbour indices, rows [k, 2k) the viscosity weights of the same entries
+        cudaError_t e = cudaMalloc(&c->nlist, 2 * (size_t)c->list_k * c->cap * sizeof(uint32_t));
         if (e != cudaSuccess) { cudaGetLastError(); c->list_k = 0; }        // no room: fall back to walking every pass
         else c->list_k_alloc = c->list_k;
     }
     L->idx = c->list_k ? c->nlist : nullptr;
+    L->w = c->list_k ? reinterpret_cast<float*>(c->nlist + (size_t)c->list_k_alloc * c->cap) : nullptr;
     L->cnt = c->lcount;
     L->overflow = c->d_overflow;
     L->ncount = c->ncount;
@@ -230,7 +232,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     ALLOC(c->A_pos, cap * 16); ALLOC(c->A_vel, cap * 16);
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
-    ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 32);
+    ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 16);
     ALLOC(c->dens, cap * 32);
     ALLOC(c->predpk, (cap + 8) * 16);
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);

@@ -21,7 +21,7 @@ struct SphContext {
     // per-step arrays, sorted order of the step
     float4 *S_pos = nullptr, *S_vel = nullptr, *pred = nullptr;
     float4* predpk = nullptr;        // predicted positions, pair-interleaved (sph_internal.h: PredPair), read by the density pass
-    sphb200::Rec8* velp = nullptr;   // velocity records: v' after pressure
+    float4* velp = nullptr;          // v' = velocity after the pressure pass (snapshot read by the viscosity pass)
     sphb200::Rec8* dens = nullptr;   // density records (sph_internal.h: Rec8)
     uint32_t *key_a = nullptr, *key_b = nullptr, *perm_a = nullptr, *perm_b = nullptr;
     uint32_t* ncount = nullptr;  // neighbour count incl. self of every row (density pass); also the list lengths

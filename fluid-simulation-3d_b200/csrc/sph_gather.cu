@@ -250,6 +250,62 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
     finish<PASS>(A, P, s, acc, dt);
 }
 
+// ---- viscosity pass over the list WITH weights (default on the GRID table) --------------------------------------
+// k_density_pk leaves, next to every list entry j, the viscosity kernel value of the pair (exact neighbour set:
+// band candidates were re-tested; padding entries and entries at d >= r carry weight 0).  The pass then needs no
+// positions at all: per entry one coalesced index, one coalesced weight and ONE 16-byte gather of v'_j.  The
+// particle's own entry contributes (v'_i - v'_i) * w = 0, exactly like the reference's `continue` (:450).
+template <int MODE>
+__global__ void __launch_bounds__(kWalkThreads)
+k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
+{
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
+    const uint32_t cnt = A.list_cnt[i];
+    if (cnt > A.list_k) {                                  // overflowed list: walk the table like generation 1
+        const Self s = load_self<PASS_VISCOSITY>(A, P, i);
+        Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+        walk_particle<MODE, PASS_VISCOSITY>(A, P, s, acc);
+        finish<PASS_VISCOSITY>(A, P, s, acc, dt);
+        return;
+    }
+    const float4 vi = A.velp[i];
+    const uint32_t* __restrict__ col = A.list_idx + i;
+    const float* __restrict__ colw = A.list_w + i;
+    const size_t stride = A.list_stride;
+    constexpr int U = kListUnroll;
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    uint32_t jn[U];
+    float wn[U];
+    #pragma unroll
+    for (int u = 0; u < U; u++) {
+        jn[u] = (u < cnt) ? __ldg(&col[(size_t)u * stride]) : i;
+        wn[u] = (u < cnt) ? __ldg(&colw[(size_t)u * stride]) : 0.0f;
+    }
+    for (uint32_t k0 = 0; k0 < cnt; k0 += U) {
+        uint32_t j[U];
+        float w[U];
+        float4 v[U];
+        #pragma unroll
+        for (int u = 0; u < U; u++) { j[u] = jn[u]; w[u] = wn[u]; }
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+            jn[u] = (k0 + U + u < cnt) ? __ldg(&col[(size_t)(k0 + U + u) * stride]) : i;
+            wn[u] = (k0 + U + u < cnt) ? __ldg(&colw[(size_t)(k0 + U + u) * stride]) : 0.0f;
+        }
+        #pragma unroll
+        for (int u = 0; u < U; u++) { v[u] = vi; if (j[u] != i) v[u] = __ldg(&A.velp[j[u]]); }
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+            ax = fmaf(v[u].x - vi.x, w[u], ax);
+            ay = fmaf(v[u].y - vi.y, w[u], ay);
+            az = fmaf(v[u].z - vi.z, w[u], az);
+        }
+    }
+    const float k = P.mu * dt;                             // :463
+    A.velv_out[i] = make_float4(fmaf(ax, k, vi.x), fmaf(ay, k, vi.y), fmaf(az, k, vi.z), 0.0f);
+}
+
 // 9 row windows of a cell: rows (dy, dz), x window [xa, xb]
 __device__ __forceinline__ void row_range(const uint32_t* __restrict__ table, const DevParams& P, const int3 g,
                                           const int xa, const int xb, const uint32_t rows, const int r9,
@@ -670,6 +726,7 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
     // last flush writes everything, so a warp's list length is the longest true list of its lanes unless the
     // lanes' counts drift apart by more than half a stack.  The sums are scaled by the kernel volumes in the end.
     uint32_t* lp = col;
+    float* lw = A.list_w + i;                      // viscosity weight of the entry, same row / column as the index
     const uint32_t klim = valid ? K : 0u;
     const uint32_t keep = stack_rows / 2u;
     auto flush = [&](const bool last) {
@@ -691,8 +748,11 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
             acc.cnt += nb;
             acc.a = fmaf(w, w, acc.a);
             acc.b = fmaf(w * w, w, acc.b);
-            if (kbase < klim) *lp = nb ? en.x : i;
+            // SmoothingViscoPoly6 of the pair (kernels.h:73-82): (r^2 - d^2)^3 * scale where d < r, else 0; 0 for padding
+            const float u = nb ? fmaxf(P.rr - d2, 0.0f) : 0.0f;
+            if (kbase < klim) { *lp = nb ? en.x : i; *lw = u * u * (u * P.sv); }
             lp += stride;
+            lw += stride;
             kbase++;
         }
         if (last) return;
@@ -835,6 +895,12 @@ static void launch_walk_or_list(cudaStream_t st, GatherArgs A, const DevParams& 
     ++*launches;
 }
 
+// the packed density kernel (and only it) leaves the viscosity weights next to the list entries
+static bool density_is_pk(const NbrList& L, const DevParams& P)
+{
+    return gather_variant() == 0 && density_variant() == 0 && P.mode == SPH_TABLE_GRID && L.idx && L.k && L.w;
+}
+
 static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const uint32_t* tend, const NbrList& L)
 {
     GatherArgs A = {};
@@ -865,7 +931,8 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
     } else if (A.list_idx && (density_variant() == 0 || density_variant() == 4)) {     // default: two-phase list density
         if (P.row1 <= P.row0) return;
         const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
-        if (P.mode == SPH_TABLE_GRID && density_variant() == 0 && pred_pk) {
+        if (density_is_pk(L, P) && pred_pk) {
+            A.list_w = L.w;
             static const bool big_ok = cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                             PKS_DENSE * kWalkThreads * 8) == cudaSuccess;
             const uint32_t rows = (A.list_k > 64 && big_ok) ? PKS_DENSE : PKS;
@@ -878,7 +945,7 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
 }
 
 void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, Rec8* vel_p, const NbrList& L, const DevParams& P,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
                      float dt, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
@@ -887,13 +954,18 @@ void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, co
     else launch_walk_or_list<PASS_PRESSURE>(st, A, P, dt, A.list_idx != nullptr, launches);
 }
 
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const Rec8* vel_p, const uint32_t* tstart,
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
                       const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
                       uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.velp = vel_p; A.velv_out = vel_v;
-    if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_VISCOSITY>(st, A, P, dt, launches);
+    if (density_is_pk(L, P) && !getenv("SPH_VISC_NOW")) {        // weights recorded by k_density_pk
+        if (P.row1 <= P.row0) return;
+        A.list_w = L.w;
+        k_viscosity_w<SPH_TABLE_GRID><<<(P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, st>>>(A, P, dt);
+        ++*launches;
+    } else if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_VISCOSITY>(st, A, P, dt, launches);
     else launch_walk_or_list<PASS_VISCOSITY>(st, A, P, dt, A.list_idx != nullptr, launches);
 }
 

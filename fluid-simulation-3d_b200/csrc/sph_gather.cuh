@@ -21,6 +21,7 @@ struct GatherArgs {
     // neighbour list recorded by the density pass: entry k of row i at list_idx[k * list_stride + i],
     // list_cnt[i] entries (a count above list_k means "overflowed: walk the table instead")
     uint32_t* list_idx;
+    float* list_w;             // viscosity weights of the entries (k_density_pk); nullptr: the viscosity pass computes them
     uint32_t* list_cnt;
     uint32_t list_k, list_stride;
     uint32_t* list_overflow;   // device word: largest list length seen above list_k (drives the host's auto-grow)
@@ -28,8 +29,8 @@ struct GatherArgs {
     uint32_t* ncount;          // density pass, optional
     const Rec8* dens;          // pressure pass
     const float4* vel_s;       // pressure pass: own velocity after S1
-    Rec8* velp_out;            // pressure pass: velocity records
-    const Rec8* velp;          // viscosity pass: post-pressure snapshot
+    float4* velp_out;          // pressure pass: v' (velocity after pressure)
+    const float4* velp;        // viscosity pass: post-pressure snapshot
     float4* velv_out;          // viscosity pass
 };
 
@@ -107,7 +108,7 @@ __device__ __forceinline__ Self load_self(const GatherArgs& A, const DevParams& 
         s.rho = d.lo.w;
         s.v = A.vel_s[i];
     } else if (PASS == PASS_VISCOSITY) {
-        { const Rec8 r = A.velp[i]; s.v = make_float4(r.lo.w, r.hi.x, r.hi.y, 0.0f); }
+        s.v = A.velp[i];
     }
     return s;
 }
@@ -128,9 +129,8 @@ __device__ __forceinline__ Fetched fetch(const GatherArgs& A, const uint32_t j)
         f.q = r.lo;
         f.aux = make_float4(r.lo.w, r.hi.x, r.hi.y, r.hi.z);
     } else if (PASS == PASS_VISCOSITY) {    // post-pressure velocity
-        const Rec8 r = ld256(&A.velp[j]);
-        f.q = r.lo;
-        f.aux = make_float4(r.lo.w, r.hi.x, r.hi.y, 0.0f);
+        f.q = __ldg(&A.pred[j]);
+        f.aux = __ldg(&A.velp[j]);
     } else {
         f.q = __ldg(&A.pred[j]);
         f.aux = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -201,10 +201,7 @@ __device__ __forceinline__ void finish(const GatherArgs& A, const DevParams& P, 
         if (A.ncount) A.ncount[s.i] = acc.cnt;
     } else if (PASS == PASS_PRESSURE) {
         const float k = dt / s.rho;                        // :421
-        Rec8 r;
-        r.lo = make_float4(s.p.x, s.p.y, s.p.z, fmaf(acc.a, k, s.v.x));
-        r.hi = make_float4(fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f, 0.0f);
-        A.velp_out[s.i] = r;
+        A.velp_out[s.i] = make_float4(fmaf(acc.a, k, s.v.x), fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f);
     } else {
         const float k = P.mu * dt;                         // :463
         A.velv_out[s.i] = make_float4(fmaf(acc.a, k, s.v.x), fmaf(acc.b, k, s.v.y), fmaf(acc.c, k, s.v.z), 0.0f);

@@ -43,9 +43,8 @@ struct DevParams {
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
 };
 
-// 32-byte per-particle records read with ONE 256-bit load (LDG.E.256 on sm_100a) by the list passes:
+// 32-byte per-particle record read with ONE 256-bit load (LDG.E.256 on sm_100a) by the pressure pass:
 //   density record  lo = (pred.x, pred.y, pred.z, rho)   hi = (near rho, 1/rho, 1/near rho, 0)
-//   velocity record lo = (pred.x, pred.y, pred.z, v'.x)  hi = (v'.y, v'.z, 0, 0)          (v' = after pressure)
 // Position and per-pass payload of a neighbour sit in the same sector, so a neighbour costs one load
 // instruction and one line instead of two of each.
 struct __align__(32) Rec8 { float4 lo, hi; };
@@ -92,6 +91,7 @@ void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, 
 // neighbour list recorded by the density pass (k-major: entry k of row i at idx[k*stride + i])
 struct NbrList {
     uint32_t* idx;      // nullptr: no list, every pass walks the table
+    float*    w;        // viscosity weight of every entry, same geometry as idx (filled by k_density_pk only)
     uint32_t* cnt;      // [rows] list length (may exceed k: overflowed; may include <= 1e-6 borderline extras)
     uint32_t* ncount;   // [rows] exact neighbour count incl. self (always written by the density pass)
     uint32_t* overflow; // host-mapped: largest list length that did not fit (0 = none)
@@ -101,9 +101,9 @@ struct NbrList {
 void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
                     Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
 void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, Rec8* vel_p, const NbrList& L, const DevParams& P,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
                      float dt, uint64_t* launches);
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const Rec8* vel_p, const uint32_t* tstart,
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
                       const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
                       uint64_t* launches);
 void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v, float4* pos_out, float4* vel_out,

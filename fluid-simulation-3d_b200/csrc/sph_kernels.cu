@@ -302,12 +302,7 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
     if (s >= n) return;
     const uint32_t dst = by_id ? __float_as_uint(id_src[s].w) : s;
     switch (field) {
-    case SPH_FIELD_VEL_AFTER_PRESSURE: {             // velocity record: lo.w, hi.x, hi.y
-        const Rec8 a = ((const Rec8*)src)[s];
-        float* o = (float*)out + 3 * (size_t)dst;
-        o[0] = a.lo.w; o[1] = a.hi.x; o[2] = a.hi.y;
-    } break;
-    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED:
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED: case SPH_FIELD_VEL_AFTER_PRESSURE:
     case SPH_FIELD_VEL_AFTER_VISCOSITY: {
         const float4 a = ((const float4*)src)[s];
         float* o = (float*)out + 3 * (size_t)dst;

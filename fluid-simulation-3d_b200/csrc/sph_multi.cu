@@ -493,17 +493,18 @@ int multi_step(SphContext* c, float dt)
     const uint32_t hi_begin = b_hi_begin > b_lo_end ? b_hi_begin : b_lo_end;      // thin slab: the layers may coincide
     const uint32_t seg[3][2] = {{o0, b_lo_end}, {hi_begin, o1}, {b_lo_end, hi_begin}};   // lo layer, hi layer, interior
     cudaStream_t hs = s->halo_stream;
-    auto halo = [&](Rec8* rows) -> int {                  // boundary layers out, ghost layers in (contiguous ranges)
+    auto halo = [&](void* base, const size_t fpr) -> int {   // boundary layers out, ghost layers in (contiguous ranges of rows of `fpr` floats)
+        float* rows = static_cast<float*>(base);
         SPH_CUDA(c, cudaEventRecord(s->ev_boundary, st));
         SPH_CUDA(c, cudaStreamWaitEvent(hs, s->ev_boundary, 0));
         SPH_NCCL(c, ncclGroupStart());
         if (has_lo) {
-            if (b_lo_end > o0) SPH_NCCL(c, ncclSend(rows + o0, (size_t)(b_lo_end - o0) * 8, ncclFloat, lo, comm, hs));
-            if (o0) SPH_NCCL(c, ncclRecv(rows, (size_t)o0 * 8, ncclFloat, lo, comm, hs));
+            if (b_lo_end > o0) SPH_NCCL(c, ncclSend(rows + o0 * fpr, (size_t)(b_lo_end - o0) * fpr, ncclFloat, lo, comm, hs));
+            if (o0) SPH_NCCL(c, ncclRecv(rows, (size_t)o0 * fpr, ncclFloat, lo, comm, hs));
         }
         if (has_hi) {
-            if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(rows + b_hi_begin, (size_t)(o1 - b_hi_begin) * 8, ncclFloat, hi, comm, hs));
-            if (live_end > o1) SPH_NCCL(c, ncclRecv(rows + o1, (size_t)(live_end - o1) * 8, ncclFloat, hi, comm, hs));
+            if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(rows + b_hi_begin * fpr, (size_t)(o1 - b_hi_begin) * fpr, ncclFloat, hi, comm, hs));
+            if (live_end > o1) SPH_NCCL(c, ncclRecv(rows + o1 * fpr, (size_t)(live_end - o1) * fpr, ncclFloat, hi, comm, hs));
         }
         SPH_NCCL(c, ncclGroupEnd());
         SPH_CUDA(c, cudaEventRecord(s->ev_halo, hs));
@@ -513,7 +514,7 @@ int multi_step(SphContext* c, float dt)
     for (int g = 0; g < 3; g++) {
         Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
         launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, Q, &c->launches);
-        if (g == 1) { rc = halo(c->dens); if (rc != SPH_OK) return rc; }
+        if (g == 1) { rc = halo(c->dens, 8); if (rc != SPH_OK) return rc; }
     }
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
@@ -524,7 +525,7 @@ int multi_step(SphContext* c, float dt)
     for (int g = 0; g < 3; g++) {
         Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
         launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, Q, dt, &c->launches);
-        if (g == 1) { rc = halo(c->velp); if (rc != SPH_OK) return rc; }
+        if (g == 1) { rc = halo(c->velp, 4); if (rc != SPH_OK) return rc; }
     }
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
 
