@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsph_b200.so")
+# SPH_B200_LIB: load another build of the same library (A/B runs of kernel variants; development only)
+LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(HERE, "libsph_b200.so")
 
 SPH_OK = 0
 TABLE_GRID, TABLE_REFERENCE_HASH = 0, 1

@@ -68,6 +68,9 @@ constexpr int kWalkThreads = 128;
 #define SPH_LIST_UNROLL 4
 #endif
 constexpr int kListUnroll = SPH_LIST_UNROLL;   // neighbour-list entries in flight per thread
+#ifndef SPH_VISC_UNROLL
+#define SPH_VISC_UNROLL 4
+#endif
 
 template <int MODE, int PASS>
 __global__ void __launch_bounds__(kWalkThreads)
@@ -273,7 +276,7 @@ k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
     const uint32_t* __restrict__ col = A.list_idx + i;
     const float* __restrict__ colw = A.list_w + i;
     const size_t stride = A.list_stride;
-    constexpr int U = kListUnroll;
+    constexpr int U = SPH_VISC_UNROLL;
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
     uint32_t jn[U];
     float wn[U];
