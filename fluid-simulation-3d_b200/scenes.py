@@ -73,6 +73,8 @@ CONFIGS = {
     "C2_dambreak_1M": (100, 100, 100, 0xC2),
     "C3_dambreak_8M": (200, 200, 200, 0xC3),
     "C4_dambreak_64M": (400, 400, 400, 0xC4),
+    # a quarter of C4 in z: on 2 GPUs each rank holds what a rank of C4 holds on 8 (400 x 400 x 50 lattice sites)
+    "C4q_dambreak_16M": (400, 400, 100, 0xC4),
 }
 
 

@@ -26,8 +26,10 @@ print("VARIANT_OK")
 """
 
 
-@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}, {"SPH_DENSITY": "2"}, {"SPH_SORT": "radix"}],
-                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density", "list_with_pair2_density", "radix_sort_grid"])
+@pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}, {"SPH_DENSITY": "2"}, {"SPH_SORT": "radix"},
+                                 {"SPH_DENSITY": "list"}, {"SPH_VISC_NOW": "1"}],
+                         ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density", "list_with_pair2_density", "radix_sort_grid",
+                              "scalar_list_density_on_grid", "packed_density_viscosity_without_weights"])
 def test_enumeration_variants_match_oracle(env):
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, os.path.join(ROOT, "tests"))], env=e, cwd=ROOT,
@@ -51,6 +53,63 @@ def test_neighbour_list_overflow_and_disabled(pkg, cap):
             helpers.check_step(pkg, scenes.small_dam_break(12), mode, scenes.DT)
     finally:
         pkg.FluidSimulation.__init__ = orig
+
+
+def test_long_lists_dense_stack(pkg):
+    """List capacity above 64 selects the deep survivor stack of the packed density kernel; the dense column has
+    ~90 neighbours per particle, so every warp goes through several partial flushes."""
+    from fluid_simulation_3d_b200 import scenes
+    import helpers
+    orig = pkg.FluidSimulation.__init__
+
+    def patched(self, *a, **k):
+        orig(self, *a, **k)
+        self.set_neighbour_list_capacity(192)
+    pkg.FluidSimulation.__init__ = patched
+    try:
+        out = helpers.check_step(pkg, scenes.small_column(14, 40, 14), pkg.TABLE_GRID, scenes.DT)
+        assert out["mean_neighbours"] > 50
+    finally:
+        pkg.FluidSimulation.__init__ = orig
+
+
+@pytest.mark.parametrize("mode", ["grid", "reference_hash"])
+def test_pairs_on_the_cull_boundary(pkg, mode):
+    """Isolated pairs whose squared distance sits within a few ulp of sqrRadius (below, on and above it): the packed
+    cull's FMA-fused d^2 cannot decide these, the exact predicate `!(d2 > sqrRadius)` (physicsWorld.cc:357) must.
+    Neighbour counts are compared bit-exactly with the oracle by check_step."""
+    from fluid_simulation_3d_b200 import scenes
+    import helpers
+    rng = np.random.default_rng(11)
+    m = 14
+    g3 = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    centre = ((g3 - (m - 1) / 2.0) * 1.25 + (rng.random(g3.shape) - 0.5) * 0.2).astype(np.float32)
+    d = rng.normal(size=g3.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    scale = np.float32(0.35) * (1.0 + rng.integers(-6, 7, size=(len(g3), 1)) * 1.0e-7)
+    other = (centre.astype(np.float64) + d * scale).astype(np.float32)
+    pos = np.concatenate([centre, other]).astype(np.float32)
+    # how many of the pairs are neighbours by the reference's own arithmetic: it must be a real mix
+    o = other - centre
+    d2 = (o[:, 0] * o[:, 0] + o[:, 1] * o[:, 1]) + o[:, 2] * o[:, 2]
+    inside = int((~(d2 > np.float32(0.35) * np.float32(0.35))).sum())
+    assert len(g3) // 5 < inside < 4 * len(g3) // 5
+    sc = dict(pos=pos, vel=np.zeros_like(pos), n=len(pos), params=dict(gravity=0, bound=(20.0, 20.0, 20.0)))
+    # integers and densities only: with the partner exactly on the kernel support the reference's pressure and
+    # viscosity terms are exactly zero, so their cancellation-free scale (the float tolerance) is zero too
+    sim = pkg.FluidSimulation(sc["n"], device=0, table_mode=pkg.TABLE_GRID if mode == "grid" else pkg.TABLE_REFERENCE_HASH, **sc["params"])
+    try:
+        sim.set_neighbour_count_tap(True)
+        sim.upload_state(sc["pos"], sc["vel"])
+        sim.step(scenes.DT)
+        ref, _, _ = helpers.oracle_step(sc, scenes.DT)
+        nc, nc_ref = sim.download("neighbour_count"), ref.neighbour_counts()
+        assert np.array_equal(nc, nc_ref), "neighbour counts: %d differ" % int((nc != nc_ref).sum())
+        assert int((nc == 2).sum()) == 2 * inside and int((nc == 1).sum()) == 2 * (len(g3) - inside)
+        helpers.assert_close("density", sim.download("densities"), ref.densities(), 0.0)
+        assert np.all(np.isfinite(sim.download("velocities")))
+    finally:
+        sim.close()
 
 
 def test_multi_step_tracks_oracle(pkg, ob):
