@@ -300,8 +300,9 @@ def bench_single(args, pkg, scenes, torch, dev):
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),
-                     "binding_roof": "L1 wavefronts + instruction issue, not HBM: the gather re-reads neighbours from L1/L2 by design "
-                                     "(ncu: profiles/r01_gather_final_C2.txt)",
+                     "binding_roof": "L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M), not HBM: every lane streams "
+                                     "its own 16-byte candidates and the gather re-reads neighbours from L1/L2 by design "
+                                     "(ncu: profiles/r01_gather_final_C2.txt, r01_gather_final_C3.txt; DESIGN.md section 5)",
                      "streaming_kernels": streaming,
                      "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
                               "algorithmic_bytes_per_particle": A_BYTES["step"]}},
