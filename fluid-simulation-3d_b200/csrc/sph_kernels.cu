@@ -183,12 +183,16 @@ k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
 constexpr uint32_t kMaxCanonical = 1024;
 
 __device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
-                                               const uint32_t* __restrict__ table, const uint32_t s, uint32_t* key_sorted)
+                                               const uint32_t* __restrict__ table, const uint32_t s, uint32_t* key_sorted,
+                                               const uint32_t ncell)
 {
     const uint32_t s0 = perm[s];
     if (!key) return s0;
     const uint32_t k = key[s0];
     if (key_sorted) key_sorted[s] = k;
+    // slab mode: key == ncell collects the rows that leave this rank; they are dropped after the step, their order
+    // is irrelevant -- and there can be hundreds of them, which the O(m^2)-per-thread ranking below must never see
+    if (k >= ncell) return s0;
     const uint32_t b = table[k], m = table[k + 1] - b;
     if (m == 1u || m > kMaxCanonical) return s0;
     const uint32_t r = s - b;
@@ -211,7 +215,7 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
     const bool valid = s < P.n;                    // no early return: the pair-interleaved copy is written with shuffles
     float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (valid) {
-        const uint32_t src = source_row(perm, key, table, s, key_sorted);
+        const uint32_t src = source_row(perm, key, table, s, key_sorted, P.ncell);
         if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
             const float4 gq = ghost_pred[src - P.n_a];
             const int3 c = cell_of(gq.x, gq.y, gq.z, P.r);
