@@ -6,14 +6,15 @@
 // The physics of a (particle, neighbour) pair lives once, in sph_gather.cuh (load_self / fetch / eval / finish);
 // the kernels here differ only in how they enumerate candidates.  What runs by default:
 //
-//   k_density_list   two-phase density: phase A walks the table (9 row windows of the GRID table, or the 27 buckets
-//                    of the REFERENCE_HASH table), applies only the reference's exact predicate, branch-free, and
-//                    pushes survivors on a small shared-memory stack; phase B pops them, evaluates the smoothing
-//                    kernels converged and writes the particle's NEIGHBOUR LIST column.  Rows and 16-candidate
-//                    segments are warp-uniform loop levels (redux.sync), so the flush is collective.
-//   k_gather_list    pressure and viscosity replay the list (same predicted positions + same predicate => same
-//                    set): ~18 entries instead of ~100 candidates, one 256-bit record load per neighbour.
+//   k_density_pk     GRID table: two-phase density over packed candidate pairs (see the kernel): phase A culls two
+//                    candidates per 256-bit load with FFMA2 math and pushes survivors (row, d^2) on a small
+//                    shared-memory stack; phase B pops them converged, sums the kernels, writes the NEIGHBOUR LIST
+//                    rows and the viscosity weight of every entry.
+//   k_density_list   REFERENCE_HASH table (27 bucket walks, hash filter): the same two phases with scalar exact math.
+//   k_gather_list    the pressure pass replays the list (same predicted positions + same predicate => same set):
+//                    ~18 entries instead of ~100 candidates, one 256-bit record load per neighbour.
 //                    A particle whose list overflowed walks the table instead (walk_particle).
+//   k_viscosity_w    the viscosity pass over the recorded weights: per entry one 16-byte gather of v'_j.
 //
 // ncu (profiles/): every variant of these passes is bound by L1 wavefronts and instruction issue, not by HBM --
 // the gather re-reads neighbours from L1/L2 by design.  Variants kept for A/B runs, all parity-tested
@@ -690,15 +691,18 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 // One thread per particle, as k_density_list, but
 //  * the candidates come from the PAIR-INTERLEAVED copy of the predicted positions (PredPair, sph_internal.h): one
 //    256-bit load brings two candidates as three aligned register pairs, and their d^2 costs 6 packed instructions
-//    (3 FADD2, FMUL2, 2 FFMA2) instead of 16 scalar ones -- half the L1 wavefronts and a third of the math per
-//    candidate.  The FMA-fused d^2 decides everything outside a 2e-6 wide band around sqrRadius; inside the band the
-//    reference's exact predicate is evaluated on the plain rows (phase B, ~1e-6 of the candidates);
-//  * every thread walks its <= 9 row windows as ONE flat sequence of aligned pairs (bounds fetched up front, kept in
-//    shared memory), so a warp runs for the longest TOTAL of its lanes, not for the sum of per-row maxima;
-//  * the stack keeps (row, d^2): phase B needs no second look at the candidate -- no gather loads at all;
-//  * phase B writes list row k for the whole warp at once (short lanes pad with their own index, which the
-//    pressure / viscosity passes skip), so list writes stay coalesced across flushes and list lengths are
-//    warp-uniform.
+//    (3 FADD2, FMUL2, 2 FFMA2) instead of 16 scalar ones.  The FMA-fused d^2 decides everything outside a 2e-6 wide
+//    band around sqrRadius; inside the band the reference's exact predicate is evaluated on the plain rows
+//    (phase B, ~1e-6 of the candidates);
+//  * rows and 2-pair chunks are warp-uniform loop levels; the bounds of the next row window are requested while
+//    the current one is culled;
+//  * the stack keeps (row, d^2): phase B needs no second look at the candidate -- no gather loads at all -- and it
+//    also leaves the viscosity kernel value of every entry next to the index (k_viscosity_w);
+//  * phase B writes list row k for the whole warp at once (lanes that run short pad with their own index, which
+//    the pressure / viscosity passes skip), so list writes stay coalesced and list lengths are warp-uniform.
+// ncu: bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M particles): a 256-bit
+// load is served in 8 passes of 4 lanes, >= 1 wavefront each, i.e. >= 4 wavefronts per warp-candidate (measured
+// 5.25) -- the 16 bytes per lane per candidate are the cost, however they are loaded.
 constexpr int PKS = 24;         // stack entries per thread: sparse scenes (one or two flushes per particle)
 constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
 
