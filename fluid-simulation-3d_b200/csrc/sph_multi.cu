@@ -587,7 +587,12 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
     SPH_CUDA(c, cudaMalloc(&s->block_any, s->nblocks_cap));
     SPH_CUDA(c, cudaMalloc(&s->dev_small, 64 * sizeof(uint32_t)));
     SPH_CUDA(c, cudaMallocHost(&s->host_small, 64 * sizeof(uint32_t)));
-    SPH_CUDA(c, cudaStreamCreateWithFlags(&s->halo_stream, cudaStreamNonBlocking));
+    {   // highest priority: the halo's NCCL kernel must get SM slots ahead of the queued blocks of the interior pass
+        int lo_p = 0, hi_p = 0;
+        SPH_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        const char* e = getenv("SPH_HALO_PRIO");
+        SPH_CUDA(c, cudaStreamCreateWithPriority(&s->halo_stream, cudaStreamNonBlocking, (e && e[0] == '0') ? lo_p : hi_p));
+    }
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
     if (const char* e = getenv("SPH_SLAB_TIMING")) {
