@@ -65,6 +65,15 @@ __device__ __forceinline__ void walk_particle(const GatherArgs& A, const DevPara
 }
 
 constexpr int kWalkThreads = 128;
+// The neighbour list streams through once per pass (176 MB at 1 M particles, more than the L2): mark its traffic
+// evict-first so that it does not push the particle records, which every pass re-reads, out of the L2.
+#ifdef SPH_LIST_PLAIN
+#define LIST_LD(p) __ldg(p)
+#define LIST_ST(p, v) (*(p) = (v))
+#else
+#define LIST_LD(p) __ldcs(p)
+#define LIST_ST(p, v) __stcs((p), (v))
+#endif
 #ifndef SPH_LIST_UNROLL
 #define SPH_LIST_UNROLL 4
 #endif
@@ -234,14 +243,14 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
         // so the (cold, HBM-resident) list read overlaps the (L1/L2-resident) particle rows of the chunk before
         uint32_t jn[U];
         #pragma unroll
-        for (int u = 0; u < U; u++) jn[u] = (u < cnt) ? __ldg(&col[(size_t)u * A.list_stride]) : s.i;
+        for (int u = 0; u < U; u++) jn[u] = (u < cnt) ? LIST_LD(&col[(size_t)u * A.list_stride]) : s.i;
         for (uint32_t k0 = 0; k0 < cnt; k0 += U) {
             uint32_t j[U];
             Fetched f[U];
             #pragma unroll
             for (int u = 0; u < U; u++) j[u] = jn[u];
             #pragma unroll
-            for (int u = 0; u < U; u++) jn[u] = (k0 + U + u < cnt) ? __ldg(&col[(size_t)(k0 + U + u) * A.list_stride]) : s.i;
+            for (int u = 0; u < U; u++) jn[u] = (k0 + U + u < cnt) ? LIST_LD(&col[(size_t)(k0 + U + u) * A.list_stride]) : s.i;
             #pragma unroll
             for (int u = 0; u < U; u++) {            // the particle itself (its own entry, and the padding) is not fetched
                 f[u].q = s.p;
@@ -283,8 +292,8 @@ k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
     float wn[U];
     #pragma unroll
     for (int u = 0; u < U; u++) {
-        jn[u] = (u < cnt) ? __ldg(&col[(size_t)u * stride]) : i;
-        wn[u] = (u < cnt) ? __ldg(&colw[(size_t)u * stride]) : 0.0f;
+        jn[u] = (u < cnt) ? LIST_LD(&col[(size_t)u * stride]) : i;
+        wn[u] = (u < cnt) ? LIST_LD(&colw[(size_t)u * stride]) : 0.0f;
     }
     for (uint32_t k0 = 0; k0 < cnt; k0 += U) {
         uint32_t j[U];
@@ -294,8 +303,8 @@ k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
         for (int u = 0; u < U; u++) { j[u] = jn[u]; w[u] = wn[u]; }
         #pragma unroll
         for (int u = 0; u < U; u++) {
-            jn[u] = (k0 + U + u < cnt) ? __ldg(&col[(size_t)(k0 + U + u) * stride]) : i;
-            wn[u] = (k0 + U + u < cnt) ? __ldg(&colw[(size_t)(k0 + U + u) * stride]) : 0.0f;
+            jn[u] = (k0 + U + u < cnt) ? LIST_LD(&col[(size_t)(k0 + U + u) * stride]) : i;
+            wn[u] = (k0 + U + u < cnt) ? LIST_LD(&colw[(size_t)(k0 + U + u) * stride]) : 0.0f;
         }
         #pragma unroll
         for (int u = 0; u < U; u++) { v[u] = vi; if (j[u] != i) v[u] = __ldg(&A.velp[j[u]]); }
@@ -757,7 +766,7 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
             acc.b = fmaf(w * w, w, acc.b);
             // SmoothingViscoPoly6 of the pair (kernels.h:73-82): (r^2 - d^2)^3 * scale where d < r, else 0; 0 for padding
             const float u = nb ? fmaxf(P.rr - d2, 0.0f) : 0.0f;
-            if (kbase < klim) { *lp = nb ? en.x : i; *lw = u * u * (u * P.sv); }
+            if (kbase < klim) { LIST_ST(lp, nb ? en.x : i); LIST_ST(lw, u * u * (u * P.sv)); }
             lp += stride;
             lw += stride;
             kbase++;
@@ -940,9 +949,12 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
         const uint32_t blocks = (P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads;
         if (density_is_pk(L, P) && pred_pk) {
             A.list_w = L.w;
-            static const bool big_ok = cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                            PKS_DENSE * kWalkThreads * 8) == cudaSuccess;
-            const uint32_t rows = (A.list_k > 64 && big_ok) ? PKS_DENSE : PKS;
+            // the deep stack needs the opt-in above 48 KB; the attribute is per device, so it is (re)set whenever used
+            uint32_t rows = PKS;
+            if (A.list_k > 64) {
+                if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
+                else cudaGetLastError();
+            }
             k_density_pk<<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows);
         }
         else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
