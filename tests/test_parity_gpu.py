@@ -65,3 +65,16 @@ def test_q2_radius_differs_from_cutoff(pkg, scenes, mode, radius):
     sc["params"] = dict(sc["params"], interaction_radius=radius)
     out = check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
     assert out["mean_neighbours"] > 3
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n", [1, 3, 33, 1001])
+def test_tiny_and_odd_counts(pkg, scenes, mode, n):
+    """Odd particle counts exercise the half-filled last record of the pair-interleaved positions; 1 and 3 the
+    degenerate launches (one warp, mostly idle lanes)."""
+    rng = np.random.default_rng(100 + n)
+    bound = (3.0, 3.0, 3.0)
+    pos = ((rng.random((n, 3)) - 0.5) * 1.2).astype(np.float32)
+    vel = ((rng.random((n, 3)) - 0.5) * 2.0).astype(np.float32)
+    sc = dict(pos=pos, vel=vel, n=n, params=dict(gravity=1, viscosity_strength=0.5, bound=bound))
+    check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
