@@ -95,6 +95,8 @@ struct SlabState {
     uint32_t nblocks_cap = 0;
     std::vector<int> layers;                      // nranks + 1 global layer indices
     uint32_t o0 = 0, o1 = 0;                      // owned rows of the sorted arrays in the last step
+    uint32_t expect[5] = {0, 0, 0, 0, 0};         // row ranges derived on the host, checked against the table one step later
+    bool verify_pending = false;
     uint32_t stats[5] = {0, 0, 0, 0, 0};
     bool have_planes = false;
     cudaStream_t halo_stream = nullptr;           // halos 2 and 3 travel here, overlapped with interior compute
@@ -108,7 +110,8 @@ struct SlabState {
 
 namespace {
 
-enum { L_MIG_LO = 0, L_GHOST_LO = 1, L_MIG_HI = 2, L_GHOST_HI = 3, L_KEEP_LO = 4, L_KEEP_HI = 5, NLISTS = 6 };
+// the three lists of a side are contiguous, so a side's counts travel as one message
+enum { L_MIG_LO = 0, L_GHOST_LO = 1, L_KEEP_LO = 2, L_MIG_HI = 3, L_GHOST_HI = 4, L_KEEP_HI = 5, NLISTS = 6 };
 constexpr int kPackThreads = 256;
 
 #define SPH_NCCL(c, call)                                                                   \
@@ -357,7 +360,7 @@ int multi_step(SphContext* c, float dt)
     // (2) order-preserving pack of the six lists
     const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
     uint32_t* totals = s->dev_small;            // [6]
-    uint32_t* rcounts = s->dev_small + 8;       // [4] from lo: (mig, ghost), from hi: (mig, ghost)
+    uint32_t* rcounts = s->dev_small + 8;       // [6] from lo: its (mig, ghost, keep) towards me, then the same from hi
     uint32_t* picks = s->dev_small + 16;        // [8]
     uint32_t* peer = s->dev_small + 24;         // [2] boundary lengths of the neighbours' layers
     SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
@@ -372,8 +375,8 @@ int multi_step(SphContext* c, float dt)
     SLAB_MARK(1);
     // (3a) counts to / from the neighbours
     SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) { SPH_NCCL(c, ncclSend(totals + 0, 2, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 0, 2, ncclUint32, lo, comm, st)); }
-    if (has_hi) { SPH_NCCL(c, ncclSend(totals + 2, 2, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 2, 2, ncclUint32, hi, comm, st)); }
+    if (has_lo) { SPH_NCCL(c, ncclSend(totals + L_MIG_LO, 3, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 0, 3, ncclUint32, lo, comm, st)); }
+    if (has_hi) { SPH_NCCL(c, ncclSend(totals + L_MIG_HI, 3, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 3, 3, ncclUint32, hi, comm, st)); }
     SPH_NCCL(c, ncclGroupEnd());
     SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SLAB_MARK(2);
@@ -384,7 +387,17 @@ int multi_step(SphContext* c, float dt)
     const uint32_t* R = s->host_small + 8;
     for (int l = 0; l < NLISTS; l++)
         if (T[l] > s->xcap) return fail(c, SPH_ERR_CAPACITY, "slab mode: exchange buffer too small (raise capacity)");
-    const uint32_t mig_in_lo = R[0], ghost_in_lo = R[1], mig_in_hi = R[2], ghost_in_hi = R[3];
+    const uint32_t mig_in_lo = R[0], ghost_in_lo = R[1], mig_in_hi = R[3], ghost_in_hi = R[4];
+    const uint32_t kept_by_lo = R[2], kept_by_hi = R[5];   // arrivals the neighbour still mirrors: they lie in my boundary layers
+    // deferred check of the previous step's row ranges (computed on the host, see below) against the table
+    if (s->verify_pending) {
+        s->verify_pending = false;
+        const uint32_t* V = s->host_small + 16;
+        for (int q = 0; q < 5; q++)
+            if (V[q] != s->expect[q] && !(q == 1 && !has_lo) && !(q == 2 && !has_hi))      // no neighbour: no boundary layer on that side
+                return fail(c, SPH_ERR_INVALID, "slab mode: row ranges derived from the exchanged counts disagree with the table (range " +
+                                                    std::to_string(q) + ": " + std::to_string(s->expect[q]) + " vs " + std::to_string(V[q]) + ")");
+    }
     const uint32_t n_a = n_old + mig_in_lo + mig_in_hi;                 // resident + arrived (departed rows still inside)
     const uint32_t n_ghost = ghost_in_lo + T[L_KEEP_LO] + ghost_in_hi + T[L_KEEP_HI];
     if ((uint64_t)n_a + n_ghost > c->cap || n_ghost > s->gcap)
@@ -457,29 +470,51 @@ int multi_step(SphContext* c, float dt)
     k_slab_pick<<<1, 32, 0, st>>>(c->tstart, picks, l_own_lo * plane, (l_own_lo + 1) * plane, (l_own_hi - 1) * plane,
                                   l_own_hi * plane, P.ncell);
     ++c->launches;
-    // cross-check: the neighbour's boundary layer must be exactly as long as my ghost layer
-    SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) { SPH_NCCL(c, ncclSend(picks + 5, 1, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(peer + 0, 1, ncclUint32, lo, comm, st)); }
-    if (has_hi) { SPH_NCCL(c, ncclSend(picks + 6, 1, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(peer + 1, 1, ncclUint32, hi, comm, st)); }
-    SPH_NCCL(c, ncclGroupEnd());
-    SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SLAB_MARK(6);
+    // Row ranges of the sorted arrays.  With at least three owned layers they follow from the exchanged counts --
+    //   ghost-lo layer  = ghosts received from lo + my migrants to lo that I keep mirroring
+    //   lo boundary     = my rows flagged ghost-for-lo + the arrivals lo still mirrors          (same on the hi side)
+    //   departed        = my migrants
+    // -- so the step needs no second host synchronisation; the table's own answer (k_slab_pick) is copied back
+    // asynchronously and compared at the next step's synchronisation.  Thin slabs (boundary layers may coincide) and
+    // SPH_SLAB_CHECK=1 read the table now and cross-check the layer lengths with the neighbours, as before.
+    static const bool force_check = [] { const char* e = getenv("SPH_SLAB_CHECK"); return e && e[0] == '1'; }();
+    uint32_t o0, b_lo_end, b_hi_begin, o1, live_end;
     const double h2 = host_now();
-    SPH_CUDA(c, cudaStreamSynchronize(st));
+    if (!force_check && P.own_hi - P.own_lo >= 3) {
+        o0 = ghost_in_lo + T[L_KEEP_LO];
+        live_end = n_all - (T[L_MIG_LO] + T[L_MIG_HI]);
+        o1 = live_end - (ghost_in_hi + T[L_KEEP_HI]);
+        b_lo_end = o0 + T[L_GHOST_LO] + kept_by_lo;
+        b_hi_begin = o1 - (T[L_GHOST_HI] + kept_by_hi);
+        SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        s->expect[0] = o0; s->expect[1] = b_lo_end; s->expect[2] = b_hi_begin; s->expect[3] = o1; s->expect[4] = live_end;
+        s->verify_pending = true;
+        SLAB_MARK(6);
+    } else {
+        // cross-check: the neighbour's boundary layer must be exactly as long as my ghost layer
+        SPH_NCCL(c, ncclGroupStart());
+        if (has_lo) { SPH_NCCL(c, ncclSend(picks + 5, 1, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(peer + 0, 1, ncclUint32, lo, comm, st)); }
+        if (has_hi) { SPH_NCCL(c, ncclSend(picks + 6, 1, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(peer + 1, 1, ncclUint32, hi, comm, st)); }
+        SPH_NCCL(c, ncclGroupEnd());
+        SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SLAB_MARK(6);
+        SPH_CUDA(c, cudaStreamSynchronize(st));
+        const uint32_t* K = s->host_small + 16;
+        o0 = K[0]; b_lo_end = K[1]; b_hi_begin = K[2]; o1 = K[3]; live_end = K[4];
+        const uint32_t peer_lo = s->host_small[24], peer_hi = s->host_small[25];
+        if ((has_lo && peer_lo != o0) || (has_hi && peer_hi != live_end - o1))
+            return fail(c, SPH_ERR_INVALID, "slab mode: ghost layer and neighbour boundary layer disagree (" +
+                                                std::to_string(o0) + " vs " + std::to_string(peer_lo) + ", " +
+                                                std::to_string(live_end - o1) + " vs " + std::to_string(peer_hi) + ")");
+    }
     const double h3 = host_now();
     if (s->prof && ++s->pseen > 3) {
+        SPH_CUDA(c, cudaEventSynchronize(s->pe[6]));
         float ms;
         for (int i = 0; i < 6; i++) { cudaEventElapsedTime(&ms, s->pe[i], s->pe[i + 1]); s->pacc[i] += ms; }
         s->pacc[6] += h1 - h0; s->pacc[7] += h3 - h2;
         s->psteps++;
     }
-    const uint32_t* K = s->host_small + 16;
-    const uint32_t o0 = K[0], b_lo_end = K[1], b_hi_begin = K[2], o1 = K[3], live_end = K[4];
-    const uint32_t peer_lo = s->host_small[24], peer_hi = s->host_small[25];
-    if ((has_lo && peer_lo != o0) || (has_hi && peer_hi != live_end - o1))
-        return fail(c, SPH_ERR_INVALID, "slab mode: ghost layer and neighbour boundary layer disagree (" +
-                                            std::to_string(o0) + " vs " + std::to_string(peer_lo) + ", " +
-                                            std::to_string(live_end - o1) + " vs " + std::to_string(peer_hi) + ")");
     s->o0 = o0; s->o1 = o1;
     P.row0 = o0; P.row1 = o1;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
