@@ -715,10 +715,15 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 constexpr int PKS = 24;         // stack entries per thread: sparse scenes (one or two flushes per particle)
 constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
 
+// STAGED (SPH_DENSITY=staged, an A/B variant): the block first copies the union of its threads' row windows into
+// shared memory and the walk reads its candidates from there.  It answers "would staging the neighbourhood in
+// shared memory lift the L1 roof?" with a measurement: no -- shared memory is served by the same data pipe.
+template <bool STAGED>
 __global__ void __launch_bounds__(kWalkThreads)
-k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
+k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, const uint32_t stage_pairs)
 {
     extern __shared__ uint2 stk_raw[];             // [stack_rows][kWalkThreads] survivors: (row, bits of the FMA-fused d^2)
+                                                   // STAGED: followed by stage_pairs 32-byte pair records
     uint2 (*stk)[kWalkThreads] = reinterpret_cast<uint2 (*)[kWalkThreads]>(stk_raw);
     const uint32_t full_mark = (stack_rows - 4u) * (kWalkThreads * 8u);
     constexpr uint32_t kRow = kWalkThreads * 8;    // bytes between two stack rows of a thread
@@ -813,32 +818,79 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
     }
     const uint32_t gd0 = (uint32_t)P.gdim[0];
     const int64_t zstep = (int64_t)P.gdim[1] * gd0 - 3 * (int64_t)gd0;
-    const uint32_t* tp = A.table + ((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0;
+    const uint32_t* const tp0 = A.table + ((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0;
+    const uint32_t* tp = tp0;
     const uint32_t xspan = (uint32_t)(W.x1 - W.x0) + 1u;
+    int dyc = 0;
     auto bounds = [&](const int r9, uint32_t& b, uint32_t& e) {
         b = e = 0;
         if ((vm >> r9) & 1u) { b = __ldg(tp); e = __ldg(tp + xspan); }
         tp += gd0;
+        if (++dyc == 3) { dyc = 0; tp += zstep; }
     };
+
+    // STAGED: union of the block's windows per row -> shared memory
+    __shared__ uint32_t s_lo[9], s_hi[9], s_off[10];
+    const float4* stage = reinterpret_cast<const float4*>(stk_raw + (size_t)stack_rows * kWalkThreads);
+    bool staged = false;
+    if (STAGED) {
+        if (tid < 9) { s_lo[tid] = 0xFFFFFFFFu; s_hi[tid] = 0u; }
+        __syncthreads();
+        #pragma unroll 1
+        for (int r9 = 0; r9 < 9; r9++) {
+            uint32_t b, e;
+            bounds(r9, b, e);
+            const uint32_t lo = __reduce_min_sync(0xffffffffu, e > b ? (b >> 1) : 0xFFFFFFFFu);
+            const uint32_t hi = __reduce_max_sync(0xffffffffu, e > b ? ((e + 1u) >> 1) : 0u);
+            if ((tid & 31) == 0 && hi > lo) { atomicMin(&s_lo[r9], lo); atomicMax(&s_hi[r9], hi); }
+        }
+        tp = tp0; dyc = 0;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t off = 0;
+            for (int r9 = 0; r9 < 9; r9++) { s_off[r9] = off; off += s_hi[r9] > s_lo[r9] ? s_hi[r9] - s_lo[r9] : 0u; }
+            s_off[9] = off;
+        }
+        __syncthreads();
+        staged = s_off[9] <= stage_pairs;          // a block whose union does not fit reads global memory as usual
+        if (staged) {
+            float4* dst = const_cast<float4*>(stage);
+            const float4* src = A.predpk;
+            #pragma unroll 1
+            for (int r9 = 0; r9 < 9; r9++) {
+                const uint32_t lo = s_lo[r9], hi = s_hi[r9], off = s_off[r9];
+                if (hi <= lo) continue;
+                for (uint32_t q = 2u * lo + tid; q < 2u * hi; q += kWalkThreads) dst[2u * off + (q - 2u * lo)] = __ldg(&src[q]);
+            }
+        }
+        __syncthreads();
+    }
+
     uint32_t bn, en;
     bounds(0, bn, en);
-    int dyc = 1;
     #pragma unroll 1
     for (int r9 = 0; r9 < 9; r9++) {
         const uint32_t b = bn, e = en;
-        if (dyc == 3) { dyc = 0; tp += zstep; }
-        dyc++;
         bounds(r9 + 1, bn, en);
         const int len = (int)(e - b);
         const uint32_t p0 = b >> 1;                                    // first pair of the window
         const uint32_t np = len ? ((e + 1u) >> 1) - p0 : 0u;
         const uint32_t iters = __reduce_max_sync(0xffffffffu, np);
         int t = -(int)(b & 1u);
+        const uint32_t slo = STAGED ? s_lo[r9] : 0u, shi = STAGED ? s_hi[r9] : 0u;
+        const float4* srow = stage + 2u * (STAGED ? s_off[r9] : 0u);
         #pragma unroll 1
         for (uint32_t it = 0; it < iters; it += 2, t += 4) {
             if (__any_sync(0xffffffffu, sa - sa0 > full_mark)) flush(false);
-            const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
-            const Rec8 c0 = ld256(pairs + q0), c1 = ld256(pairs + q1);
+            Rec8 c0, c1;
+            if (STAGED && staged) {                // lanes past their own window re-read the staged run's last pair
+                const uint32_t q0 = min(max(p0 + it, slo), shi - 1u) - slo, q1 = min(max(p0 + it + 1u, slo), shi - 1u) - slo;
+                c0.lo = srow[2u * q0]; c0.hi = srow[2u * q0 + 1u];
+                c1.lo = srow[2u * q1]; c1.hi = srow[2u * q1 + 1u];
+            } else {
+                const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
+                c0 = ld256(pairs + q0); c1 = ld256(pairs + q1);
+            }
             cull(c0, t, len, 2u * (p0 + it));
             cull(c1, t + 2, len, 2u * (p0 + it) + 2u);
         }
@@ -952,10 +1004,16 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
             // the deep stack needs the opt-in above 48 KB; the attribute is per device, so it is (re)set whenever used
             uint32_t rows = PKS;
             if (A.list_k > 64) {
-                if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
+                if (cudaFuncSetAttribute(k_density_pk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
                 else cudaGetLastError();
             }
-            k_density_pk<<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows);
+            static const int stage_pairs = [] { const char* e = getenv("SPH_STAGE_PAIRS"); return e ? atoi(e) : 0; }();
+            if (stage_pairs > 0 && rows == PKS) {  // SPH_STAGE_PAIRS=n: the shared-memory staged variant, n pair records per block
+                const size_t bytes = (size_t)rows * kWalkThreads * 8 + (size_t)stage_pairs * 32;
+                cudaFuncSetAttribute(k_density_pk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                k_density_pk<true><<<blocks, kWalkThreads, bytes, st>>>(A, P, rows, (uint32_t)stage_pairs);
+            } else
+                k_density_pk<false><<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows, 0u);
         }
         else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
         else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);
