@@ -11,8 +11,9 @@ A "step" is one FluidSimulation::Update(dt) (engine/physics/physicsWorld.cc:39-1
 One JSON line on rank 0:
   value     whole-job M particle-updates/s, state resident in HBM, CUDA events on the solver's stream,
             L2 flushed between timed steps (the flush is outside the event pairs)
-  e2e       the same metric through the host-facing call sequence with HOST (pinned) buffers:
-            sph_upload_state (H2D positions+velocities) -> sph_step -> sph_download(OutPositions) (D2H)
+  e2e       the same metric through the host-facing call sequence with HOST (pinned) buffers, every frame:
+            H2D positions+velocities -> sph_step -> D2H OutPositions, through the pipelined calls
+            (sph_upload_state_begin/_commit, sph_download_begin/_wait); e2e.blocking = the serial calls
   roofline  dominant kernel: algorithmic bytes / its CUDA-event duration / measured HBM peak
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host, bounded sample
 --impl reference times the reference CPU implementation alone (rank 0 only).
@@ -306,6 +307,28 @@ def bench_single(args, pkg, scenes, torch, dev):
         sim.upload_state_ptr(n, h_pos.data_ptr(), h_vel.data_ptr())
         sim.step(dt)
         sim.download_ptr("out_positions", h_out.data_ptr(), n * 16)   # returns when the host buffer is filled
+    e2e_blocking_s = time.perf_counter() - t0
+    # the same frames through the pipelined calls (include/sph_b200.h): every frame still uploads its 24 B/particle of
+    # input and downloads its 16 B/particle of OutPositions inside the timed region, but the upload of frame k+1 and the
+    # download of frame k-1 travel on their own copy streams while frame k is computed
+    h_out2 = [h_out, torch.empty((n, 4), dtype=torch.float32).pin_memory()]
+
+    def pipelined(frames):
+        sim.upload_state_begin(n, h_pos.data_ptr(), h_vel.data_ptr())
+        for k in range(frames):
+            sim.upload_state_commit()
+            if k + 1 < frames:
+                sim.upload_state_begin(n, h_pos.data_ptr(), h_vel.data_ptr())
+            sim.step(dt)
+            if k:
+                sim.download_wait()                      # frame k-1's OutPositions are in host memory
+            sim.download_begin("out_positions", h_out2[k & 1].data_ptr(), n * 16)
+        sim.download_wait()
+        sim.synchronize()
+
+    pipelined(3)
+    t0 = time.perf_counter()
+    pipelined(args.steps)
     e2e_s = time.perf_counter() - t0
     e2e = n * args.steps / e2e_s / 1e6
     clk = clocks.stop()          # sampled across the timed, steady-state and end-to-end loops (all under load)
@@ -355,7 +378,10 @@ def bench_single(args, pkg, scenes, torch, dev):
                               "algorithmic_bytes_per_particle": A_BYTES["step"]}},
         "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "path": "sph_upload_state(pinned pos3+vel3) -> sph_step -> sph_download(OUT_POSITIONS, pinned)"},
+                "path": "per frame: sph_upload_state_begin/_commit(pinned pos3+vel3) -> sph_step -> sph_download_begin/_wait("
+                        "OUT_POSITIONS, pinned); copies on their own streams overlap the neighbouring frames' steps",
+                "blocking": {"value": n * args.steps / e2e_blocking_s / 1e6, "ms_per_step": e2e_blocking_s / args.steps * 1e3,
+                             "path": "sph_upload_state -> sph_step -> sph_download(OUT_POSITIONS), one stream, serial"}},
         "gpu_launches": int(launches),
         "clocks": clk,
     }

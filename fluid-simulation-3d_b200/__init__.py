@@ -35,7 +35,9 @@ ABI_SYMBOLS = [
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
-    "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister", "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
+    "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
+    "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
+    "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
     "sph_upload_owned", "sph_download_owned", "sph_comm_stats",
 ]
 
@@ -124,6 +126,10 @@ def load_library():
     L.sph_load_state.argtypes = [vp, C.c_char_p]
     L.sph_host_register.argtypes = [vp, C.c_size_t]
     L.sph_host_unregister.argtypes = [vp]
+    L.sph_upload_state_begin.argtypes = [vp, u32, vp, vp]
+    L.sph_upload_state_commit.argtypes = [vp]
+    L.sph_download_begin.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.sph_download_wait.argtypes = [vp]
     L.sph_comm_id_bytes.restype = C.c_size_t
     L.sph_comm_get_id.argtypes = [vp, C.c_size_t]
     L.sph_comm_init.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
@@ -238,6 +244,20 @@ class FluidSimulation:
     def upload_state_ptr(self, n, pos_ptr, vel_ptr):
         """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         self._check(self.L.sph_upload_state(self.h, int(n), C.c_void_p(pos_ptr), C.c_void_p(vel_ptr) if vel_ptr else None))
+
+    # -- pipelined transfers (raw host pointers; the buffers must outlive the copies)
+    def upload_state_begin(self, n, pos_ptr, vel_ptr=None):
+        self._check(self.L.sph_upload_state_begin(self.h, int(n), C.c_void_p(pos_ptr), C.c_void_p(vel_ptr) if vel_ptr else None))
+
+    def upload_state_commit(self):
+        self._check(self.L.sph_upload_state_commit(self.h))
+
+    def download_begin(self, field, host_ptr, nbytes):
+        fid = FIELDS[field] if isinstance(field, str) else int(field)
+        self._check(self.L.sph_download_begin(self.h, fid, C.c_void_p(host_ptr), int(nbytes)))
+
+    def download_wait(self):
+        self._check(self.L.sph_download_wait(self.h))
 
     # -- hot path
     def step(self, dt):                            # Update(dt)

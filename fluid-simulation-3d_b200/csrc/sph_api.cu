@@ -175,7 +175,12 @@ static void free_all(SphContext* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->stage_in) cudaFree(c->stage_in);
+    if (c->stage_out) cudaFree(c->stage_out);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_h2d, c->ev_pack, c->ev_export, c->ev_d2h}) if (e) cudaEventDestroy(e);
+    if (c->st_in) cudaStreamDestroy(c->st_in);
+    if (c->st_out) cudaStreamDestroy(c->st_out);
     if (c->st) cudaStreamDestroy(c->st);
 }
 
@@ -258,6 +263,8 @@ int sph_destroy(SphContext* c)
     if (!c) return SPH_OK;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st_in) cudaStreamSynchronize(c->st_in);
+    if (c->st_out) cudaStreamSynchronize(c->st_out);
     multi_teardown(c);
     free_all(c);
     delete c;
@@ -630,6 +637,117 @@ int sph_get_timings(SphContext* c, double* out6)
         }
     }
     for (int i = 0; i < 6; i++) out6[i] = c->timings[i];
+    return SPH_OK;
+}
+
+}  // extern "C"
+
+// ---- pipelined transfers ---------------------------------------------------------------------------
+// The blocking pair sph_upload_state / sph_download serialises PCIe and compute on one stream: at 1 M particles a
+// frame costs 0.44 ms (H2D 24 MB) + 0.37 ms (step) + 0.29 ms (D2H 16 MB).  With their own staging buffers and copy
+// streams the three overlap -- the upload of frame k+1 and the download of frame k-1 travel while frame k is
+// computed -- and the frame time drops to the longest of the three.  Orderings (events, no host waits except
+// sph_download_wait):
+//   st_in : [wait ev_pack: the previous pack has consumed stage_in]  H2D -> stage_in                    record ev_h2d
+//   st    : [wait ev_h2d] pack stage_in -> state   record ev_pack   ...step(s)...  export -> stage_out  record ev_export
+//   st_out: [wait ev_export] D2H stage_out -> host                                                      record ev_d2h
+static int ensure_pipeline(SphContext* c)
+{
+    if (c->st_in) return SPH_OK;
+    cudaStream_t si = nullptr, so = nullptr;
+    SPH_CUDA(c, cudaStreamCreateWithFlags(&si, cudaStreamNonBlocking));
+    cudaError_t e = cudaStreamCreateWithFlags(&so, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaStreamDestroy(si); return cuda_fail(c, e, "cudaStreamCreate (copy-out)"); }
+    cudaEvent_t* evs[4] = {&c->ev_h2d, &c->ev_pack, &c->ev_export, &c->ev_d2h};
+    for (cudaEvent_t* ev : evs) {
+        e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) { cudaStreamDestroy(si); cudaStreamDestroy(so); return cuda_fail(c, e, "cudaEventCreate (pipeline)"); }
+    }
+    c->st_in = si; c->st_out = so;
+    return SPH_OK;
+}
+
+extern "C" {
+
+int sph_upload_state_begin(SphContext* c, uint32_t n, const float* pos3, const float* vel3)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_upload_state_begin: single-GPU contexts only");
+    if (n > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_upload_state_begin: n exceeds capacity");
+    if (n && !pos3) return fail(c, SPH_ERR_INVALID, "sph_upload_state_begin: pos3 is NULL");
+    if (c->upload_pending) return fail(c, SPH_ERR_INVALID, "sph_upload_state_begin: an upload is already pending (commit it first)");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc != SPH_OK) return rc;
+    if (!c->stage_in) SPH_CUDA(c, cudaMalloc((void**)&c->stage_in, (size_t)c->cap * 24));
+    // the previous upload's pack kernel reads stage_in on the solver stream: do not overwrite it before that ran
+    if (c->pack_recorded) SPH_CUDA(c, cudaStreamWaitEvent(c->st_in, c->ev_pack, 0));
+    if (n) {
+        SPH_CUDA(c, cudaMemcpyAsync(c->stage_in, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st_in));
+        if (vel3) SPH_CUDA(c, cudaMemcpyAsync(c->stage_in + (size_t)c->cap * 12, vel3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st_in));
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_h2d, c->st_in));
+    c->upload_pending = true;
+    c->upload_has_vel = vel3 != nullptr;
+    c->upload_n = n;
+    return SPH_OK;
+}
+
+int sph_upload_state_commit(SphContext* c)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (!c->upload_pending) return fail(c, SPH_ERR_INVALID, "sph_upload_state_commit: no upload pending");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n = c->upload_n;
+    SPH_CUDA(c, cudaStreamWaitEvent(c->st, c->ev_h2d, 0));
+    if (n) {
+        const float* dpos = (const float*)c->stage_in;
+        const float* dvel = (const float*)(c->stage_in + (size_t)c->cap * 12);
+        launch_pack_state(c->st, dpos, c->upload_has_vel ? dvel : nullptr, nullptr, c->A_pos, c->A_vel, n, &c->launches);
+        SPH_CUDA(c, cudaGetLastError());
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_pack, c->st));
+    c->pack_recorded = true;
+    c->upload_pending = false;
+    c->n = n;
+    c->step_valid = false;
+    c->ncount_valid = false;
+    return SPH_OK;
+}
+
+int sph_download_begin(SphContext* c, int field, void* host, size_t host_bytes)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_download_begin: single-GPU contexts only");
+    if (c->download_pending) return fail(c, SPH_ERR_INVALID, "sph_download_begin: a download is already pending (wait for it first)");
+    const size_t need = field_bytes(field, c->n);
+    if (need == 0 && c->n) return fail(c, SPH_ERR_INVALID, "unknown field");
+    if (host_bytes < need) return fail(c, SPH_ERR_INVALID, "sph_download_begin: host buffer too small");
+    if (c->n && !host) return fail(c, SPH_ERR_INVALID, "sph_download_begin: host is NULL");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc != SPH_OK) return rc;
+    if (!c->stage_out) SPH_CUDA(c, cudaMalloc((void**)&c->stage_out, (size_t)c->cap * 16));
+    if (c->n) {
+        // the previous download was waited for (download_pending is false), so stage_out is free
+        rc = export_field(c, field, c->stage_out, true, c->n);
+        if (rc != SPH_OK) return rc;
+        SPH_CUDA(c, cudaEventRecord(c->ev_export, c->st));
+        SPH_CUDA(c, cudaStreamWaitEvent(c->st_out, c->ev_export, 0));
+        SPH_CUDA(c, cudaMemcpyAsync(host, c->stage_out, need, cudaMemcpyDeviceToHost, c->st_out));
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_d2h, c->st_out));
+    c->download_pending = true;
+    return SPH_OK;
+}
+
+int sph_download_wait(SphContext* c)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (!c->download_pending) return fail(c, SPH_ERR_INVALID, "sph_download_wait: no download pending");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    c->download_pending = false;
+    SPH_CUDA(c, cudaEventSynchronize(c->ev_d2h));
     return SPH_OK;
 }
 

@@ -41,6 +41,15 @@ struct SphContext {
     uint32_t* counts = nullptr;  // radix sort digit matrix
     size_t counts_cap = 0;
     unsigned char* stage = nullptr;   // device staging for upload / export (cap * 32 B)
+
+    // pipelined transfers (sph_upload_state_begin / _commit, sph_download_begin / _wait): their own staging
+    // buffers and copy streams, so a PCIe copy in either direction overlaps the step on `st`
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    unsigned char* stage_in = nullptr;    // cap * 24 B: pos3 | vel3 of the pending upload
+    unsigned char* stage_out = nullptr;   // cap * 16 B: the exported field of the pending download
+    cudaEvent_t ev_h2d = nullptr, ev_pack = nullptr, ev_export = nullptr, ev_d2h = nullptr;
+    bool upload_pending = false, upload_has_vel = false, pack_recorded = false, download_pending = false;
+    uint32_t upload_n = 0;
     int sorted_where = 0;        // 0: sorted keys in key_a, 1: key_b
     bool step_valid = false;     // per-step arrays describe the current device order
     bool ncount_valid = false;

@@ -165,6 +165,30 @@ int  sph_load_state(SphContext* ctx, const char* path);
 int  sph_host_register(void* ptr, size_t bytes);
 int  sph_host_unregister(void* ptr);
 
+/* -- pipelined transfers ------------------------------------------------------ */
+/* The reference's Update() leaves OutPositions in host memory every frame (physicsWorld.cc:107, consumed at
+ * fluidSimCPU.cc:58); a caller that also feeds new state every frame pays PCIe twice.  These four calls move both
+ * copies off the solver's stream (own staging buffers, own copy streams), so the upload of frame k+1 and the
+ * download of frame k-1 overlap the step of frame k:
+ *
+ *     sph_upload_state_begin(ctx, n, pos, vel);             // H2D starts, returns at once
+ *     for (k = 0; k < frames; k++) {
+ *         sph_upload_state_commit(ctx);                     // state := upload k, ordered after all enqueued work
+ *         if (k + 1 < frames) sph_upload_state_begin(...);  // frame k+1's input travels during frame k
+ *         sph_step(ctx, dt);
+ *         if (k) sph_download_wait(ctx);                    // frame k-1's result is in host memory now
+ *         sph_download_begin(ctx, SPH_FIELD_OUT_POSITIONS, out[k & 1], bytes);
+ *     }
+ *     sph_download_wait(ctx);
+ *
+ * Host buffers must stay valid (and should be page-locked: sph_host_register) until the matching commit has been
+ * followed by a sph_synchronize / sph_download_wait, resp. until sph_download_wait returns.  One upload and one
+ * download may be in flight per context.  Results are bit-identical to the blocking calls.  Single-GPU contexts. */
+int  sph_upload_state_begin(SphContext* ctx, uint32_t n, const float* pos3, const float* vel3);
+int  sph_upload_state_commit(SphContext* ctx);
+int  sph_download_begin(SphContext* ctx, int field, void* host, size_t host_bytes);
+int  sph_download_wait(SphContext* ctx);
+
 /* -- slab-decomposed multi-GPU (one context per rank / GPU) ---------------- */
 /* Size of the opaque rendezvous blob (an ncclUniqueId). Rank 0 fills it, the host runtime
  * broadcasts it (torch.distributed / MPI / file), every rank passes it to sph_comm_init. */
