@@ -32,7 +32,7 @@ TABLES = dict(sorted_index=0, sorted_key=1, start_indices=2, sorted_hash=3)
 ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
-    "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_upload_state",
+    "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_spawn_block", "sph_upload_state",
     "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
@@ -48,6 +48,13 @@ class SphParams(C.Structure):
                 ("target_density", C.c_float), ("pressure_multiplier", C.c_float),
                 ("near_pressure_multiplier", C.c_float), ("viscosity_strength", C.c_float),
                 ("gravity_scale", C.c_float), ("gravity", C.c_int32), ("bound", C.c_float * 3)]
+
+
+class SphBlockSpawn(C.Structure):
+    """Mirror of ``struct SphBlockSpawn`` (device-side scene spawn)."""
+    _fields_ = [("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32), ("reserved", C.c_uint32),
+                ("gap", C.c_double), ("origin", C.c_double * 3), ("jitter_amp", C.c_float),
+                ("velocity_scale", C.c_float), ("seed", C.c_uint64)]
 
 
 class SphError(RuntimeError):
@@ -105,6 +112,7 @@ def load_library():
     L.sph_set_neighbour_count_tap.argtypes = [vp, C.c_int]
     L.sph_set_neighbour_list_capacity.argtypes = [vp, u32]
     L.sph_spawn_grid.argtypes = [vp, u32]
+    L.sph_spawn_block.argtypes = [vp, C.POINTER(SphBlockSpawn)]
     L.sph_upload_state.argtypes = [vp, u32, vp, vp]
     L.sph_num_particles.argtypes = [vp]
     L.sph_num_particles.restype = u32
@@ -233,6 +241,12 @@ class FluidSimulation:
 
     def spawn_grid(self, n):                       # InitializeData
         self._check(self.L.sph_spawn_grid(self.h, int(n)))
+
+    def spawn_block(self, nx, ny, nz, gap, origin, jitter_amp=0.0, velocity_scale=0.0, seed=0):
+        """Device-side lattice block (scenes.device_spawn_args builds the arguments of a named scene)."""
+        b = SphBlockSpawn(int(nx), int(ny), int(nz), 0, float(gap), (C.c_double * 3)(*[float(x) for x in origin]),
+                          float(jitter_amp), float(velocity_scale), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        self._check(self.L.sph_spawn_block(self.h, C.byref(b)))
 
     def upload_state(self, pos, vel=None):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)

@@ -464,6 +464,26 @@ int sph_spawn_grid(SphContext* c, uint32_t n)
     return sph_synchronize(c);                           // pos is a local: the H2D copy must finish first
 }
 
+int sph_spawn_block(SphContext* c, const SphBlockSpawn* b)
+{
+    if (!c || !b) return SPH_ERR_INVALID;
+    if (c->nranks > 1) return fail(c, SPH_ERR_UNSUPPORTED, "sph_spawn_block: single-GPU contexts only (slab mode: sph_upload_owned)");
+    const uint64_t n64 = (uint64_t)b->nx * b->ny * b->nz;
+    if (n64 > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_spawn_block: nx*ny*nz exceeds capacity");
+    if (!std::isfinite(b->gap) || !(b->gap > 0.0)) return fail(c, SPH_ERR_INVALID, "sph_spawn_block: gap must be > 0");
+    for (int a = 0; a < 3; a++)
+        if (!std::isfinite(b->origin[a])) return fail(c, SPH_ERR_INVALID, "sph_spawn_block: origin must be finite");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n = (uint32_t)n64;
+    launch_spawn_block(c->st, c->A_pos, c->A_vel, b->nx, b->ny, b->nz, b->gap, b->origin, b->jitter_amp, b->velocity_scale,
+                       b->seed, n, &c->launches);
+    SPH_CUDA(c, cudaGetLastError());
+    c->n = n;
+    c->step_valid = false;
+    c->ncount_valid = false;
+    return SPH_OK;
+}
+
 static size_t field_bytes(int field, size_t n)
 {
     switch (field) {

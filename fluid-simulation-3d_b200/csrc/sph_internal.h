@@ -112,6 +112,8 @@ void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v,
 // upload / export helpers (original particle index order <-> device order)
 void launch_pack_state(cudaStream_t st, const float* pos3, const float* vel3, const uint32_t* ids,
                        float4* pos, float4* vel, uint32_t n, uint64_t* launches);
+void launch_spawn_block(cudaStream_t st, float4* pos, float4* vel, uint32_t nx, uint32_t ny, uint32_t nz, double gap,
+                        const double lo[3], float jitter_amp, float vel_scale, uint64_t seed, uint32_t n, uint64_t* launches);
 void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void* src2, void* out,
                    uint32_t n, const DevParams& P, bool by_id, uint64_t* launches);
 void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const Rec8* dens, uint32_t n,

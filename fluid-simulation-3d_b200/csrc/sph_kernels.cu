@@ -284,6 +284,44 @@ k_pack_state(const float* __restrict__ pos3, const float* __restrict__ vel3, con
     vel[i] = vel3 ? make_float4(vel3[3 * i], vel3[3 * i + 1], vel3[3 * i + 2], 0.0f) : make_float4(0, 0, 0, 0);
 }
 
+// ---- device-side scene spawn ---------------------------------------------------------------
+// Jittered lattice block written straight into the state arrays: no host array, no upload.  The arithmetic is the
+// synthetic-scene rule of SURVEY 8(d) (fluid-simulation-3d_b200/scenes.py: block) operation for operation -- lattice
+// site in fp64 then rounded to fp32, jitter / velocity from the counter-based generator splitmix64(seed ^ (3*id +
+// axis)) in fp32 -- so the device scene is bit-identical to the host one (tests/test_spawn_gpu.py).  Particle id <->
+// lattice site follows the reference's fill order (GridArrangement, physicsWorld.cc:526-530): y outer from the top
+// layer down, then x, then z.
+__device__ __forceinline__ float spawn_uniform01(const uint64_t seed, const uint64_t id, const uint32_t axis)
+{
+    uint64_t x = (seed ^ (id * 3ull + axis)) + 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return __fmul_rn((float)(uint32_t)(x >> 40), 1.0f / 16777216.0f);   // top 24 bits -> [0, 1), exact
+}
+
+__global__ void __launch_bounds__(256)
+k_spawn_block(float4* __restrict__ pos, float4* __restrict__ vel, const uint32_t nx, const uint32_t ny, const uint32_t nz,
+              const double gap, const double lox, const double loy, const double loz, const float jitter_amp,
+              const float vel_scale, const uint64_t seed, const uint32_t n)
+{
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const uint32_t iz = id % nz, ix = (id / nz) % nx, iy = id / (nz * nx);
+    float p[3];
+    p[0] = (float)__dadd_rn(lox, __dmul_rn((double)ix, gap));
+    p[1] = (float)__dadd_rn(loy, __dmul_rn((double)(ny - 1u - iy), gap));     // iy counts from the top layer down
+    p[2] = (float)__dadd_rn(loz, __dmul_rn((double)iz, gap));
+    float v[3] = {0.0f, 0.0f, 0.0f};
+    #pragma unroll
+    for (uint32_t a = 0; a < 3; a++) {
+        if (jitter_amp != 0.0f) p[a] = __fadd_rn(p[a], __fmul_rn(__fsub_rn(spawn_uniform01(seed, id, a), 0.5f), jitter_amp));
+        if (vel_scale != 0.0f) v[a] = __fmul_rn(__fsub_rn(spawn_uniform01(seed ^ 0x5EEDull, id, a), 0.5f), vel_scale);
+    }
+    pos[id] = make_float4(p[0], p[1], p[2], __uint_as_float(id));
+    vel[id] = make_float4(v[0], v[1], v[2], 0.0f);
+}
+
 __device__ __forceinline__ float4 speed_color(float t)
 {   // FluidSimCPU::updateColors (fluidSimCPU.cc:100-125)
     const float4 c1 = make_float4(0.0f, 0.75f, 1.0f, 1.0f), c2 = make_float4(0.0f, 1.0f, 0.0f, 1.0f);
@@ -421,6 +459,14 @@ void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v,
 {
     if (P.row1 <= P.row0) return;
     k_integrate<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    ++*launches;
+}
+
+void launch_spawn_block(cudaStream_t st, float4* pos, float4* vel, uint32_t nx, uint32_t ny, uint32_t nz, double gap,
+                        const double lo[3], float jitter_amp, float vel_scale, uint64_t seed, uint32_t n, uint64_t* launches)
+{
+    if (n == 0) return;
+    k_spawn_block<<<blocks_for(n, 256), 256, 0, st>>>(pos, vel, nx, ny, nz, gap, lo[0], lo[1], lo[2], jitter_amp, vel_scale, seed, n);
     ++*launches;
 }
 

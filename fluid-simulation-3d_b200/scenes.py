@@ -27,6 +27,24 @@ def uniform01(seed, ids, axis):
     return (bits.astype(np.float32) * np.float32(1.0 / (1 << 24))).astype(np.float32)
 
 
+def block_origin(nx, ny, nz, gap, bound, anchor="corner"):
+    """fp64 position of the lattice site with the smallest x, y, z (what sph_spawn_block takes as `origin`)."""
+    b = np.asarray(bound, dtype=np.float64)
+    ext = np.array([nx, ny, nz], dtype=np.float64) * gap
+    if anchor == "corner":
+        return -b / 2 + gap / 2
+    if anchor == "floor_center":
+        return np.array([-ext[0] / 2 + gap / 2, -b[1] / 2 + gap / 2, -ext[2] / 2 + gap / 2])
+    return -ext / 2 + gap / 2
+
+
+def device_spawn_args(nx, ny, nz, gap, bound, seed, anchor="corner", jitter=0.1, vel_amp=0.0):
+    """Arguments of FluidSimulation.spawn_block (sph_spawn_block) that reproduce block(...) bit for bit on the device."""
+    return dict(nx=nx, ny=ny, nz=nz, gap=float(gap), origin=[float(x) for x in block_origin(nx, ny, nz, gap, bound, anchor)],
+                jitter_amp=float(np.float32(2.0 * jitter * gap)) if jitter else 0.0,
+                velocity_scale=float(np.float32(2.0 * vel_amp)) if vel_amp else 0.0, seed=int(seed))
+
+
 def block(nx, ny, nz, gap, bound, seed, anchor="corner", jitter=0.1, vel_amp=0.0, ids=None):
     """Jittered lattice block.  anchor='corner': flush to the -x wall, the floor and the -z wall
     (min corner = -bound/2 + gap/2); 'floor_center': centred in x,z, standing on the floor;
@@ -38,14 +56,7 @@ def block(nx, ny, nz, gap, bound, seed, anchor="corner", jitter=0.1, vel_amp=0.0
     iz = (ids % np.uint64(nz)).astype(np.int64)
     ix = ((ids // np.uint64(nz)) % np.uint64(nx)).astype(np.int64)
     iy = (ids // np.uint64(nz * nx)).astype(np.int64)
-    b = np.asarray(bound, dtype=np.float64)
-    ext = np.array([nx, ny, nz], dtype=np.float64) * gap
-    if anchor == "corner":
-        lo = -b / 2 + gap / 2
-    elif anchor == "floor_center":
-        lo = np.array([-ext[0] / 2 + gap / 2, -b[1] / 2 + gap / 2, -ext[2] / 2 + gap / 2])
-    else:
-        lo = -ext / 2 + gap / 2
+    lo = block_origin(nx, ny, nz, gap, bound, anchor)
     pos = np.empty((ids.size, 3), dtype=np.float32)
     pos[:, 0] = (lo[0] + ix * gap).astype(np.float32)
     pos[:, 1] = (lo[1] + (ny - 1 - iy) * gap).astype(np.float32)   # iy counts from the top layer down
@@ -84,13 +95,15 @@ def config(name, ids=None):
         nx, ny, nz, seed = CONFIGS[name]
         pos, vel, bound = dam_break(nx, ny, nz, seed, ids=ids)
         return dict(pos=pos, vel=vel, bound=bound, n=nx * ny * nz, dims=(nx, ny, nz),
-                    params=dict(gravity=1, viscosity_strength=0.5, bound=bound))
+                    params=dict(gravity=1, viscosity_strength=0.5, bound=bound),
+                    spawn=device_spawn_args(nx, ny, nz, GAP0, bound, seed, anchor="corner"))
     if name == "C5_column_8M":
         nx, ny, nz, gap = 100, 800, 100, 0.1216
         bound = (36.5, 146.0, 36.5)
         pos, vel = block(nx, ny, nz, gap, bound, 0xC5, anchor="floor_center", vel_amp=0.5, ids=ids)
         return dict(pos=pos, vel=vel, bound=bound, n=nx * ny * nz, dims=(nx, ny, nz),
-                    params=dict(gravity=1, viscosity_strength=1.0, bound=bound))
+                    params=dict(gravity=1, viscosity_strength=1.0, bound=bound),
+                    spawn=device_spawn_args(nx, ny, nz, gap, bound, 0xC5, anchor="floor_center", vel_amp=0.5))
     raise KeyError(name)
 
 
@@ -98,7 +111,8 @@ def small_dam_break(n_side, seed=7, ids=None):
     """Scaled-down C2 (same rule) for parity tests the oracle finishes in seconds."""
     pos, vel, bound = dam_break(n_side, n_side, n_side, seed, ids=ids)
     return dict(pos=pos, vel=vel, bound=bound, n=n_side ** 3, dims=(n_side,) * 3,
-                params=dict(gravity=1, viscosity_strength=0.5, bound=bound))
+                params=dict(gravity=1, viscosity_strength=0.5, bound=bound),
+                spawn=device_spawn_args(n_side, n_side, n_side, GAP0, bound, seed, anchor="corner"))
 
 
 def small_column(nx, ny, nz, seed=0xC5):
@@ -107,4 +121,5 @@ def small_column(nx, ny, nz, seed=0xC5):
     bound = (max(4.0, nx * gap * 3), max(6.0, ny * gap * 1.5), max(4.0, nz * gap * 3))
     pos, vel = block(nx, ny, nz, gap, bound, seed, anchor="floor_center", vel_amp=0.5)
     return dict(pos=pos, vel=vel, bound=bound, n=nx * ny * nz, dims=(nx, ny, nz),
-                params=dict(gravity=1, viscosity_strength=1.0, bound=bound))
+                params=dict(gravity=1, viscosity_strength=1.0, bound=bound),
+                spawn=device_spawn_args(nx, ny, nz, gap, bound, seed, anchor="floor_center", vel_amp=0.5))

@@ -122,6 +122,23 @@ int  sph_set_neighbour_list_capacity(SphContext* ctx, uint32_t entries);
 /* InitializeData(n) (.cc:112-147): cube lattice spawn (GridArrangement :518-557), velocities zero,
  * then the initial lookup + densities.  */
 int  sph_spawn_grid(SphContext* ctx, uint32_t n);
+/* Device-side scene spawn (no host array, no upload): an nx*ny*nz lattice block, particle id = (iy*nx + ix)*nz + iz
+ * in the reference's fill order (GridArrangement :526-530: y outer from the TOP layer down, then x, then z):
+ *   pos = fp32(origin + (ix, ny-1-iy, iz) * gap)  [fp64 lattice, rounded once]
+ *         + (u(seed, id, axis) - 0.5) * jitter_amp,     vel = (u(seed ^ 0x5EED, id, axis) - 0.5) * velocity_scale
+ * with u = top 24 bits of splitmix64(seed ^ (3*id + axis)) / 2^24: counter-based, so the host generator
+ * (fluid-simulation-3d_b200/scenes.py) produces the same bits.  Velocities are zero when velocity_scale is 0.
+ * Asynchronous like sph_step.  Dam-break / column emitters are this call with the origin chosen against the bounds. */
+typedef struct SphBlockSpawn {
+    uint32_t nx, ny, nz;
+    uint32_t reserved;        /* 0 */
+    double   gap;             /* lattice spacing (reference spawn gap: 0.215, physicsWorld.cc:140) */
+    double   origin[3];       /* position of the lattice site with the smallest x, y, z */
+    float    jitter_amp;      /* full width of the uniform jitter per axis (0 = regular lattice) */
+    float    velocity_scale;  /* full width of the uniform initial velocity per axis (0 = at rest) */
+    uint64_t seed;
+} SphBlockSpawn;
+int  sph_spawn_block(SphContext* ctx, const SphBlockSpawn* block);
 /* Replace the particle state: positions[N][3], velocity[N][3] (NULL = zeros). */
 int  sph_upload_state(SphContext* ctx, uint32_t n, const float* pos3, const float* vel3);
 uint32_t sph_num_particles(const SphContext* ctx);
