@@ -2,6 +2,7 @@
 // the C ABI of libsph_b200.so.
 #include "FluidSimulation.h"
 
+#include <cmath>
 #include <stdexcept>
 
 namespace Physics
@@ -81,14 +82,30 @@ namespace Physics
 				check(sph_download(ctx, SPH_FIELD_POSITIONS, positions.data(), positions.size() * sizeof(vec3)), "sph_download");
 				check(sph_download(ctx, SPH_FIELD_OUT_POSITIONS, OutPositions.data(), OutPositions.size() * sizeof(vec4)), "sph_download");
 			}
-			cacheValid = false;
+			densitiesValid = true;
+			invalidateGetters();
 			timingsFresh = true;
 		}
+
+		void FluidSimulation::invalidateGetters()
+		{
+			cacheValid = false;
+			getterCalls = 0;
+			bulkFresh.store(false, std::memory_order_release);
+		}
+
+		void FluidSimulation::setMaxTimestep(float maxDt) { maxTimestep = (maxDt > 0.0f) ? maxDt : 0.0f; }
 
 		void FluidSimulation::Update(float deltatime)
 		{
 			if (!ctx || numParticles == 0) return;
-			check(sph_step(ctx, deltatime), "sph_step");
+			substeps = 1;
+			if (maxTimestep > 0.0f && deltatime > maxTimestep) {
+				const float q = std::ceil(deltatime / maxTimestep);
+				substeps = (q < 1.0f) ? 1u : (q > 1024.0f ? 1024u : (uint32)q);
+			}
+			if (substeps == 1) check(sph_step(ctx, deltatime), "sph_step");
+			else check(sph_step_n(ctx, deltatime / (float)substeps, substeps), "sph_step_n");
 			// Update() returns with the host-visible buffers complete: the renderer takes
 			// &OutPositions[0] right after (fluidSimCPU.cc:58)
 			if (mirrorOut)
@@ -96,7 +113,8 @@ namespace Physics
 			if (mirrorPos)
 				check(sph_download(ctx, SPH_FIELD_POSITIONS, positions.data(), positions.size() * sizeof(vec3)), "sph_download");
 			if (!mirrorOut && !mirrorPos) check(sph_synchronize(ctx), "sph_synchronize");
-			cacheValid = false;
+			densitiesValid = true;
+			invalidateGetters();
 			timingsFresh = false;
 		}
 
@@ -111,7 +129,8 @@ namespace Physics
 			}
 			check(sph_upload_state(ctx, numParticles, numParticles ? &positions[0].x : nullptr, velocities3), "sph_upload_state");
 			check(sph_synchronize(ctx), "sph_synchronize");
-			cacheValid = false;
+			densitiesValid = false;                      // the reference's densities would be stale too until the next Update
+			invalidateGetters();
 		}
 
 		void FluidSimulation::downloadVelocities(std::vector<vec3>& out)
@@ -131,20 +150,46 @@ namespace Physics
 		}
 
 		// per-particle getters: bounds-checked, zero when out of range (:151,157,163,168,174,180)
-		void FluidSimulation::readParticle(uint32 index)
+		void FluidSimulation::readParticle(uint32 index, float out[10])
 		{
-			if (cacheValid && cachedIndex == index) return;
-			for (float& f : cached) f = 0.0f;
-			if (ctx && index < numParticles) check(sph_get_particle(ctx, index, cached), "sph_get_particle");
-			cachedIndex = index;
-			cacheValid = true;
+			for (int k = 0; k < 10; k++) out[k] = 0.0f;
+			if (!ctx || index >= numParticles) return;
+			if (!bulkFresh.load(std::memory_order_acquire)) {
+				std::lock_guard<std::mutex> lock(getterMutex);
+				if (!bulkFresh.load(std::memory_order_relaxed)) {
+					if (!(cacheValid && cachedIndex == index) && getterCalls < kSingleReads) {
+						getterCalls++;
+						check(sph_get_particle(ctx, index, cached), "sph_get_particle");
+						cachedIndex = index;
+						cacheValid = true;
+					}
+					if (cacheValid && cachedIndex == index) {
+						for (int k = 0; k < 10; k++) out[k] = cached[k];
+						return;
+					}
+					// many getters this frame: one bulk read, then every getter is a host read
+					const size_t n = numParticles;
+					bulkPos.resize(n * 3); bulkVel.resize(n * 3); bulkDens.assign(n * 2, 0.0f);
+					check(sph_download(ctx, SPH_FIELD_POSITIONS, bulkPos.data(), bulkPos.size() * 4), "sph_download");
+					check(sph_download(ctx, SPH_FIELD_VELOCITIES, bulkVel.data(), bulkVel.size() * 4), "sph_download");
+					if (densitiesValid) check(sph_download(ctx, SPH_FIELD_DENSITIES, bulkDens.data(), bulkDens.size() * 4), "sph_download");
+					bulkFresh.store(true, std::memory_order_release);
+				}
+			}
+			const size_t i = index;
+			for (int k = 0; k < 3; k++) { out[k] = bulkPos[3 * i + k]; out[3 + k] = bulkVel[3 * i + k]; }
+			out[6] = bulkDens[2 * i]; out[7] = bulkDens[2 * i + 1];
+			// glm::length = sqrt(dot), dot = (x*x + y*y) + z*z (func_geometric.inl:48-55); :172-182
+			const float sp = std::sqrt((out[3] * out[3] + out[4] * out[4]) + out[5] * out[5]);
+			out[8] = sp;
+			out[9] = (sp < 0.0f ? 0.0f : (sp > 1.5f ? 1.5f : sp)) / 1.5f;
 		}
-		FluidSimulation::vec3 FluidSimulation::getPosition(uint32 i) { readParticle(i); return vec3(cached[0], cached[1], cached[2]); }
-		FluidSimulation::vec3 FluidSimulation::getVelocity(uint32 i) { readParticle(i); return vec3(cached[3], cached[4], cached[5]); }
-		float FluidSimulation::getDensity(uint32 i) { readParticle(i); return cached[6]; }
-		float FluidSimulation::getNearDensity(uint32 i) { readParticle(i); return cached[7]; }
-		float FluidSimulation::getSpeed(uint32 i) { readParticle(i); return cached[8]; }
-		float FluidSimulation::getSpeedNormalzied(uint32 i) { readParticle(i); return cached[9]; }
+		FluidSimulation::vec3 FluidSimulation::getPosition(uint32 i) { float o[10]; readParticle(i, o); return vec3(o[0], o[1], o[2]); }
+		FluidSimulation::vec3 FluidSimulation::getVelocity(uint32 i) { float o[10]; readParticle(i, o); return vec3(o[3], o[4], o[5]); }
+		float FluidSimulation::getDensity(uint32 i) { float o[10]; readParticle(i, o); return o[6]; }
+		float FluidSimulation::getNearDensity(uint32 i) { float o[10]; readParticle(i, o); return o[7]; }
+		float FluidSimulation::getSpeed(uint32 i) { float o[10]; readParticle(i, o); return o[8]; }
+		float FluidSimulation::getSpeedNormalzied(uint32 i) { float o[10]; readParticle(i, o); return o[9]; }
 
 		void FluidSimulation::refreshTimings()
 		{

@@ -10,7 +10,9 @@
 // stand-alone (this repo's tests) where vec3/vec4 are layout-compatible PODs.
 #pragma once
 
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -90,6 +92,12 @@ namespace Physics
 			void downloadVelocities(std::vector<vec3>& out);
 			void downloadDensities(std::vector<float>& rhoNearRhoPairs);
 			void downloadColors(std::vector<vec4>& out);   // FluidSimCPU::updateColors on the device
+			// Sub-stepping (the reference's README notes the pressure "going crazy" below
+			// 40 fps): Update(dt) with dt > maxDt runs ceil(dt / maxDt) equal steps.  0 (default) = one step,
+			// exactly the reference's behaviour.
+			void setMaxTimestep(float maxDt);
+			float getMaxTimestep() const { return maxTimestep; }
+			uint32 lastSubsteps() const { return substeps; }
 			SphContext* context() { return ctx; }
 			const std::string& lastError() const { return error; }
 
@@ -102,7 +110,7 @@ namespace Physics
 			void pushParams();
 			void check(int rc, const char* what);
 			void refreshTimings();
-			void readParticle(uint32 index);
+			void readParticle(uint32 index, float out10[10]);
 
 			SphContext* ctx = nullptr;
 			SphParams params = defaultParams();
@@ -115,9 +123,22 @@ namespace Physics
 			float simTime = 0.0f;
 			double timings[6] = {0, 0, 0, 0, 0, 0};
 			bool timingsFresh = true;
+			// Per-particle getters.  The first few calls of a frame are single-particle device reads; a caller that
+			// asks for many (FluidSimCPU::updateColors reads getSpeedNormalzied of EVERY particle from parallel
+			// threads, fluidSimCPU.cc:100-106) gets one bulk read into host mirrors, after which the getters are
+			// plain, thread-safe host reads until the next Update.
+			static constexpr uint32 kSingleReads = 8;
 			float cached[10] = {0};
 			uint32 cachedIndex = 0xFFFFFFFFu;
 			bool cacheValid = false;
+			uint32 getterCalls = 0;
+			bool densitiesValid = false;
+			std::atomic<bool> bulkFresh{false};
+			std::mutex getterMutex;
+			std::vector<float> bulkPos, bulkVel, bulkDens;
+			void invalidateGetters();
+			float maxTimestep = 0.0f;
+			uint32 substeps = 1;
 			void* pinnedOut = nullptr; size_t pinnedOutBytes = 0;
 			void* pinnedPos = nullptr; size_t pinnedPosBytes = 0;
 			std::string error;

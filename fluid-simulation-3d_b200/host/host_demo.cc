@@ -1,10 +1,14 @@
 // host/host_demo.cc -- headless driver of the host class, the way FluidSimCPU drives the reference
 // (fluidSimCPU.cc:9-46): InitializeData(n), then Update(dt) per frame.  Prints one line per run that
-// tests/test_host_class_gpu.py compares with the same scene run through the C ABI from Python.
+// tests/test_variants_gpu.py / tests/test_host_gpu.py compare with the same scene run through the C ABI from Python.
+//   host_demo n steps table_mode [class | adapter | getters | substeps]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include "FluidSimulation.h"
+#include <cmath>
+#include <thread>
+#include <vector>
+#include "FluidSimB200.h"
 
 static unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 0xcbf29ce484222325ull)
 {
@@ -13,13 +17,115 @@ static unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 
     return h;
 }
 
+// FluidSimB200 driven the way GameApp::Run drives a FluidSimBase (gameApp.cc:112-113,231,238,272):
+// initialize, then update + render per frame, one reset in between.
+struct Captured { unsigned long long pos = 0, col = 0; int count = -1, frames = 0; };
+static void capture(const FluidSimB200::Frame& f, Shader*, RenderUtils::Camera*, void* user)
+{
+    Captured* c = (Captured*)user;
+    c->count = f.count;
+    c->pos = fnv1a(f.positions, (size_t)f.count * 16);
+    c->col = fnv1a(f.colors, (size_t)f.count * 16);
+    c->frames++;
+}
+
+static int run_adapter(int n, int steps, int mode)
+{
+    auto& sim = Physics::Fluid::FluidSimulation::getInstance();
+    sim.setTableMode(mode);
+    sim.setGravity(true);
+    FluidSimB200 backend;
+    FluidSimBase* b = &backend;                          // through the base class, like the application
+    Captured cap;
+    backend.setPresenter(capture, &cap);
+    alignas(16) static char shader_stub[16], camera_stub[16];   // render()'s arguments are only passed through
+    Shader& sh = *reinterpret_cast<Shader*>(shader_stub);
+    RenderUtils::Camera& cam = *reinterpret_cast<RenderUtils::Camera*>(camera_stub);
+    b->initialize(n);
+    b->render(sh, cam);
+    printf("adapter init count=%d pos_fnv=%016llx col_fnv=%016llx\n", cap.count, cap.pos, cap.col);
+    b->update(0.016667f);
+    b->reset();                                          // back to the spawn state
+    for (int s = 0; s < steps; s++) { b->update(0.016667f); b->render(sh, cam); }
+    printf("adapter n=%d steps=%d frames=%d out_fnv=%016llx col_fnv=%016llx\n", n, steps, cap.frames, cap.pos, cap.col);
+    b->cleanup();
+    return 0;
+}
+
+// the per-particle getters: single device reads for the first few calls of a frame, then host mirrors that
+// FluidSimCPU::updateColors-style parallel loops can hit from any thread
+static int run_getters(int n, int steps, int mode)
+{
+    auto& sim = Physics::Fluid::FluidSimulation::getInstance();
+    sim.setTableMode(mode);
+    sim.setGravity(true);
+    sim.setHostMirrors(true, true);
+    sim.InitializeData(n);
+    for (int s = 0; s < steps; s++) sim.Update(0.016667f);
+    const uint32 probe[4] = {0u, (uint32)n / 3u, (uint32)n / 2u, (uint32)n - 1u};
+    float single[4][8];
+    for (int k = 0; k < 4; k++) {                        // <= kSingleReads distinct particles: device reads
+        const uint32 i = probe[k];
+        const auto p = sim.getPosition(i); const auto v = sim.getVelocity(i);
+        const float row[8] = {p.x, p.y, p.z, v.x, v.y, v.z, sim.getDensity(i), sim.getSpeedNormalzied(i)};
+        memcpy(single[k], row, sizeof(row));
+    }
+    std::vector<float> speedn((size_t)n), rho((size_t)n * 2), pos((size_t)n * 3);
+    auto work = [&](int t, int nt) {
+        for (int i = t; i < n; i += nt) {
+            speedn[i] = sim.getSpeedNormalzied((uint32)i);
+            rho[2 * (size_t)i] = sim.getDensity((uint32)i); rho[2 * (size_t)i + 1] = sim.getNearDensity((uint32)i);
+            const auto p = sim.getPosition((uint32)i);
+            pos[3 * (size_t)i] = p.x; pos[3 * (size_t)i + 1] = p.y; pos[3 * (size_t)i + 2] = p.z;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < 4; t++) th.emplace_back(work, t, 4);
+    for (auto& t : th) t.join();
+    double worst = 0.0;
+    for (int k = 0; k < 4; k++) {
+        const uint32 i = probe[k];
+        const auto p = sim.getPosition(i); const auto v = sim.getVelocity(i);
+        const float row[8] = {p.x, p.y, p.z, v.x, v.y, v.z, sim.getDensity(i), sim.getSpeedNormalzied(i)};
+        for (int c = 0; c < 8; c++) {
+            const double d = std::fabs((double)row[c] - (double)single[k][c]);
+            const double tol = (c == 7) ? 1e-6 : 0.0;    // the device's speed may be FMA-contracted
+            if (d > tol && d > worst) worst = d;
+        }
+    }
+    float sum = 0.0f;
+    for (int i = 0; i < n; i++) sum += speedn[i];
+    printf("getters n=%d steps=%d single_vs_bulk_worst=%g pos_fnv=%016llx mirror_fnv=%016llx dens_fnv=%016llx speed_sum=%.6f oob=%.1f\n",
+           n, steps, worst, fnv1a(pos.data(), pos.size() * 4), fnv1a(sim.positions.data(), sim.positions.size() * 12),
+           fnv1a(rho.data(), rho.size() * 4), sum, sim.getSpeedNormalzied((uint32)n));
+    return 0;
+}
+
+static int run_substeps(int n, int steps, int mode)
+{
+    auto& sim = Physics::Fluid::FluidSimulation::getInstance();
+    sim.setTableMode(mode);
+    sim.setGravity(true);
+    sim.setHostMirrors(true, true);
+    sim.InitializeData(n);
+    sim.setMaxTimestep(0.005f);
+    for (int s = 0; s < steps; s++) sim.Update(0.016667f);     // 4 sub-steps of 0.016667f / 4 each
+    printf("substeps n=%d steps=%d sub=%u pos_fnv=%016llx\n", n, steps, sim.lastSubsteps(),
+           fnv1a(sim.positions.data(), sim.positions.size() * 12));
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     int n = argc > 1 ? atoi(argv[1]) : 10000;
     int steps = argc > 2 ? atoi(argv[2]) : 3;
     int mode = argc > 3 ? atoi(argv[3]) : SPH_TABLE_GRID;
+    const char* what = argc > 4 ? argv[4] : "class";
     auto& sim = Physics::Fluid::FluidSimulation::getInstance();
     try {
+        if (!strcmp(what, "adapter")) return run_adapter(n, steps, mode);
+        if (!strcmp(what, "getters")) return run_getters(n, steps, mode);
+        if (!strcmp(what, "substeps")) return run_substeps(n, steps, mode);
         sim.setTableMode(mode);
         sim.setGravity(true);
         sim.setHostMirrors(true, true);

@@ -72,5 +72,18 @@ def test_host_class_library_links(pkg):
     out = subprocess.run(["nm", "-DC", "--defined-only", host], stdout=subprocess.PIPE, text=True).stdout
     for sym in ("Physics::Fluid::FluidSimulation::Update(float)", "Physics::Fluid::FluidSimulation::getInstance()",
                 "Physics::Fluid::FluidSimulation::InitializeData(int,", "Physics::Fluid::FluidSimulation::getSpeedNormalzied(",
-                "Physics::Fluid::FluidSimulation::setBound("):
+                "Physics::Fluid::FluidSimulation::setBound(", "Physics::Fluid::FluidSimulation::setMaxTimestep(float)",
+                "FluidSimB200::initialize(int)", "FluidSimB200::update(float)", "FluidSimB200::reset()", "FluidSimB200::cleanup()",
+                "FluidSimB200::render(Shader&, RenderUtils::Camera&)"):
         assert sym in out, sym
+
+
+def test_host_driver_fails_loudly_without_gpu():
+    """the C++ host layer has no CPU fallback either: without a device InitializeData throws"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
+    for what in ("class", "adapter"):
+        r = subprocess.run([demo, "100", "1", "0", what], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+        assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout
