@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_spawn_block", "sph_upload_state",
-    "sph_num_particles", "sph_step", "sph_step_n", "sph_synchronize", "sph_refresh_densities",
+    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
@@ -126,6 +126,8 @@ def load_library():
     L.sph_get_timings.argtypes = [vp, vp]
     L.sph_launch_count.argtypes = [vp]
     L.sph_launch_count.restype = C.c_uint64
+    L.sph_graph_replays.argtypes = [vp]
+    L.sph_graph_replays.restype = C.c_uint64
     L.sph_stream.argtypes = [vp]
     L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
@@ -322,6 +324,9 @@ class FluidSimulation:
 
     def launch_count(self):
         return int(self.L.sph_launch_count(self.h))
+
+    def graph_replays(self):
+        return int(self.L.sph_graph_replays(self.h))
 
     def stream_ptr(self):
         return int(self.L.sph_stream(self.h) or 0)

@@ -143,7 +143,7 @@ int ensure_list(SphContext* c, NbrList* L)
     }
     // auto-grow: the value may lag the kernels by a step or two (read without synchronising); overflowing
     // particles are exact meanwhile (the later passes walk the table for them), only slower
-    if (c->list_auto && c->list_k && *c->h_overflow > c->list_k) {
+    if (c->list_auto && c->list_k && !c->capturing && *c->h_overflow > c->list_k) {
         const uint32_t want = (*c->h_overflow * 5u / 4u + 15u) & ~15u;
         c->list_k = want > 4096u ? 4096u : want;
     }
@@ -175,6 +175,8 @@ static void free_all(SphContext* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
     if (c->stage_in) cudaFree(c->stage_in);
     if (c->stage_out) cudaFree(c->stage_out);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -311,6 +313,7 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
 }
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
+uint64_t sph_graph_replays(const SphContext* c) { return c ? c->graph_replays : 0; }
 void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
 
 int sph_grid_x_subdivision(const SphContext* c) { return c ? c->xsub : 0; }
@@ -344,7 +347,7 @@ int sph_upload_state(SphContext* c, uint32_t n, const float* pos3, const float* 
 }
 
 // the whole step; dt == 0 with `advance == false` is InitializeData's tail (lookup + densities only)
-static int run_step(SphContext* c, float dt, bool advance)
+static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = true)
 {
     SPH_CUDA(c, cudaSetDevice(c->device));
     DevParams P;
@@ -353,7 +356,7 @@ static int run_step(SphContext* c, float dt, bool advance)
     if (c->n == 0) return SPH_OK;
     rc = ensure_tables(c, P);
     if (rc != SPH_OK) return rc;
-    const bool timing = c->timing && advance;
+    const bool timing = c->timing && advance && allow_timing;
     cudaStream_t st = c->st;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
     if (P.mode == SPH_TABLE_GRID && counting_sort_enabled()) {
@@ -414,10 +417,90 @@ int sph_step(SphContext* c, float dt)
     return run_step(c, dt, true);
 }
 
+// ---- CUDA-graph replay inside sph_step_n ------------------------------------------------------------------------
+// A step is ~10 launches; at the reference's own scene sizes (10 k - 100 k particles) each kernel runs for a few
+// microseconds and the host's launch rate is the limit.  sph_step_n therefore records the launch sequence of one
+// step once (stream capture) and replays it: one cudaGraphLaunch per step.  The recording is valid for one StepKey
+// only; a changed particle count / dt / parameter / list capacity / buffer falls back to a plain step, which also
+// does whatever allocation the change needs, and the next step records again.  The last step of a call runs plainly
+// so that the stage timers (getElapsedTime*) describe a real step.  SPH_GRAPH=0 turns the replay off.
+static bool graphs_enabled()
+{
+    static const bool on = [] { const char* e = getenv("SPH_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+static SphContext::StepKey step_key(const SphContext* c, float dt)
+{
+    SphContext::StepKey k;
+    memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
+    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc;
+    k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
+    return k;
+}
+
+static void drop_graph(SphContext* c)
+{
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+    c->graph_valid = false;
+}
+
+// records one step; on any failure the context simply keeps stepping without graphs
+static bool record_step(SphContext* c, float dt)
+{
+    drop_graph(c);
+    if (cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_disabled = true; return false; }
+    const uint64_t l0 = c->launches;
+    c->capturing = true;
+    const int rc = run_step(c, dt, true, false);
+    c->capturing = false;
+    const uint64_t per_step = c->launches - l0;
+    c->launches = l0;                               // nothing ran yet
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->st, &g);
+    if (rc != SPH_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->graph_disabled = true;
+        return false;
+    }
+    cudaGraphExec_t x = nullptr;
+    if (cudaGraphInstantiate(&x, g, 0) != cudaSuccess || !x) {
+        cudaGraphDestroy(g);
+        cudaGetLastError();
+        c->graph_disabled = true;
+        return false;
+    }
+    c->graph = g; c->graph_exec = x; c->graph_launches = per_step;
+    c->graph_key = step_key(c, dt);
+    c->graph_valid = true;
+    return true;
+}
+
 int sph_step_n(SphContext* c, float dt, uint32_t nsteps)
 {
+    if (!c) return SPH_ERR_INVALID;
+    const bool replay = graphs_enabled() && !c->graph_disabled && c->nranks == 1 && nsteps >= 3 && c->n > 0;
     for (uint32_t i = 0; i < nsteps; i++) {
-        int rc = sph_step(c, dt);
+        const bool last = i + 1 == nsteps;
+        if (replay && !last && !c->graph_disabled) {
+            // a list that has to grow, or any change of configuration: plain step (it reallocates), record afterwards
+            const bool grow = c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k;
+            const SphContext::StepKey k = step_key(c, dt);
+            const bool match = c->graph_valid && memcmp(&k, &c->graph_key, sizeof(k)) == 0;
+            if (!grow && (match || (c->step_valid && i > 0 && record_step(c, dt)))) {
+                SPH_CUDA(c, cudaSetDevice(c->device));
+                SPH_CUDA(c, cudaGraphLaunch(c->graph_exec, c->st));
+                c->launches += c->graph_launches;
+                c->graph_replays++;
+                c->ncount_valid = true;
+                c->step_valid = true;
+                c->ev_recorded = false;
+                continue;
+            }
+        }
+        int rc = c->nranks > 1 ? multi_step(c, dt) : run_step(c, dt, true);
         if (rc != SPH_OK) return rc;
     }
     return SPH_OK;

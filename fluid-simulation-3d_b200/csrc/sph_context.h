@@ -50,6 +50,22 @@ struct SphContext {
     cudaEvent_t ev_h2d = nullptr, ev_pack = nullptr, ev_export = nullptr, ev_d2h = nullptr;
     bool upload_pending = false, upload_has_vel = false, pack_recorded = false, download_pending = false;
     uint32_t upload_n = 0;
+
+    // CUDA-graph replay of the step inside sph_step_n (launch-bound at the reference's own scene sizes): the captured
+    // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
+    // plain step and re-captures
+    struct StepKey {
+        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc; int nc_tap;
+        const void *nlist, *tstart, *scan_tmp, *tend;
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    StepKey graph_key = {};
+    bool graph_valid = false;
+    bool graph_disabled = false;     // SPH_GRAPH=0, or a capture failed once on this context
+    bool capturing = false;          // run_step is being recorded: no allocation, no list growth
+    uint64_t graph_launches = 0;     // kernels per replay
+    uint64_t graph_replays = 0;
     int sorted_where = 0;        // 0: sorted keys in key_a, 1: key_b
     bool step_valid = false;     // per-step arrays describe the current device order
     bool ncount_valid = false;

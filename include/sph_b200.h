@@ -148,7 +148,13 @@ uint32_t sph_num_particles(const SphContext* ctx);
  * (snapshot semantics), S6 integrate + box collision.  Asynchronous: returns when
  * the work is enqueued; sph_download / sph_synchronize wait for it. */
 int  sph_step(SphContext* ctx, float dt);
+/* nsteps consecutive Update(dt) calls (sub-stepping, offline pre-computation).  From the second step on the launch
+ * sequence of a step is replayed as ONE CUDA graph launch per step (the step is launch-bound at the reference's own
+ * scene sizes); results are bit-identical to nsteps calls of sph_step.  The last step runs plainly, so the stage
+ * timers describe it.  Environment SPH_GRAPH=0 disables the replay. */
 int  sph_step_n(SphContext* ctx, float dt, uint32_t nsteps);
+/* steps executed by graph replay since creation (diagnostic) */
+uint64_t sph_graph_replays(const SphContext* ctx);
 int  sph_synchronize(SphContext* ctx);
 /* rebuild lookup + densities for the current positions without advancing (InitializeData's tail, .cc:144-145) */
 int  sph_refresh_densities(SphContext* ctx);
