@@ -46,11 +46,12 @@ def test_step_n_graph_replay_equals_plain_steps(pkg, mode):
 
 def test_step_n_replay_with_growing_neighbour_lists(pkg):
     """a dense column overflows the default list capacity: the replay must hand over to a plain step that grows the
-    list, and stay exact meanwhile.  Pressure is switched off so that the scene stays calm (the column explodes within
-    three steps otherwise, and rounding-level differences would be amplified chaotically)."""
+    list, and stay exact meanwhile.  All three force multipliers are zero, so the particles drift ballistically and the
+    column stays dense (with forces on it explodes within three steps, and rounding-level differences between the
+    list and the table-walk path would be amplified chaotically); every pass still runs over the full lists."""
     from fluid_simulation_3d_b200 import scenes
     sc = scenes.small_column(10, 30, 10)
-    params = dict(sc["params"], pressure_multiplier=0.0, near_pressure_multiplier=0.0, gravity=0)
+    params = dict(sc["params"], pressure_multiplier=0.0, near_pressure_multiplier=0.0, viscosity_strength=0.0, gravity=0)
     a = pkg.FluidSimulation(sc["n"], **params)
     b = pkg.FluidSimulation(sc["n"], **params)
     for s in (a, b):
@@ -59,11 +60,11 @@ def test_step_n_replay_with_growing_neighbour_lists(pkg):
     a.step_n(scenes.DT, 8)
     for _ in range(8):
         b.step(scenes.DT)
+    assert a.graph_replays() >= 1
     na, nb = a.download("neighbour_count"), b.download("neighbour_count")
     assert nb.max() > 64                            # the default capacity did overflow
-    assert np.mean(na != nb) <= 1e-3
-    pa, pb = a.download("positions"), b.download("positions")
-    # list growth happens at different steps in the two runs (the overflow word is read without synchronising), and a
-    # particle served by the table walk rounds its viscosity weights differently from one served by its list
-    assert np.all(np.isfinite(pa)) and np.abs(pa - pb).max() <= 1e-4
+    assert np.array_equal(na, nb)
+    assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
+    da, db = a.download("densities"), b.download("densities")
+    assert np.all(np.abs(da - db) <= 1e-5 * np.maximum(np.abs(db), 1.0))
     a.close(); b.close()
