@@ -176,13 +176,35 @@ def cpu_reference_run(scene_name, steps, warmup, budget_s=25.0):
                 n=sc["n"])
 
 
+def cpu_reference_c1(steps, warmup):
+    """C1: the reference's default scene, whole (10 000 particles): InitializeData(10000), gravity on, Update(dt)."""
+    ob = graft.load_oracle()
+    kind = "reference" if ob.have_ref() else "port"
+    n = 10000
+    orc = ob.RefOracle(n, spawn=True, gravity=1) if kind == "reference" else ob.PortOracle(n, gravity=1)
+    if kind == "port":
+        orc.spawn_grid()
+    dt = float(np.float32(0.016667))
+    step = (lambda: orc.update(dt)) if kind == "reference" else (lambda: orc.step(dt, jacobi=True))
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    t = time.perf_counter() - t0
+    return dict(value=n * steps / t / 1e6, unit=METRIC, cores=1, kind=kind, ms_per_step=t / steps * 1e3, n=n,
+                sample="the whole C1 scene (InitializeData(10000), default bounds, gravity on), %d steps after %d warm-up, %s"
+                       % (steps, warmup, "unmodified reference Update() (serial PSTL: TBB absent)" if kind == "reference"
+                          else "C restatement, 1 thread"))
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     name = "C2_dambreak_1M" if args.gpus == 1 else "C4_dambreak_64M"
     if args.config:
         name = args.config
-    r = cpu_reference_run(name, args.steps, args.warmup, budget_s=120.0)
+    r = cpu_reference_c1(args.steps, args.warmup) if name == C1_NAME else cpu_reference_run(name, args.steps, args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "M updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -241,9 +263,24 @@ def main():
         dist.destroy_process_group()
 
 
+C1_NAME = "C1_default_10k"      # BASELINE.json configs[0]: exactly InitializeData(10000), default bounds, gravity on
+
+
+def c1_scene(pkg, dev):
+    """The reference's own default scene: the lattice of InitializeData(10000), positions read back
+    from sph_spawn_grid so that the end-to-end loop has host arrays like every other config."""
+    n = 10000
+    params = dict(gravity=1)
+    sim = pkg.FluidSimulation(n, device=dev, **params)
+    sim.spawn_grid(n)
+    pos = sim.download("positions").copy()
+    sim.close()
+    return dict(pos=pos, vel=np.zeros_like(pos), bound=(20.0, 20.0, 20.0), n=n, params=params)
+
+
 def bench_single(args, pkg, scenes, torch, dev):
     name = args.config or "C2_dambreak_1M"
-    sc = scenes.config(name)
+    sc = c1_scene(pkg, dev) if name == C1_NAME else scenes.config(name)
     n = sc["n"]
     mode = pkg.TABLE_GRID if args.table == "grid" else pkg.TABLE_REFERENCE_HASH
     sim = pkg.FluidSimulation(n, device=dev, table_mode=mode, **sc["params"])
@@ -289,12 +326,15 @@ def bench_single(args, pkg, scenes, torch, dev):
     # ---- steady state: K steps back to back, no flush (what a simulation loop sees)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sim.set_stage_timing(False)
+    steady_steps = max(args.steps, 200) if n <= 200000 else args.steps    # small scenes: enough steps to time
+    sim.step_n(dt, 4)                            # records the step's CUDA graph outside the timed region
+    r0 = sim.graph_replays()
     a.record(stream)
-    for _ in range(args.steps):
-        sim.step(dt)
+    sim.step_n(dt, steady_steps)
     b.record(stream)
     sim.synchronize()
-    steady_ms = a.elapsed_time(b) / args.steps
+    steady_ms = a.elapsed_time(b) / steady_steps
+    steady_replays = sim.graph_replays() - r0
     sim.set_stage_timing(True)
 
     # ---- end to end through host buffers: H2D state, step, D2H OutPositions, every step
@@ -364,14 +404,17 @@ def bench_single(args, pkg, scenes, torch, dev):
         "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
-                               "r=0.35, gravity on, mu=%.2f, dt=0.016667" % (name, n, tuple(round(x, 3) for x in sc["bound"]),
-                                                                          sc["params"]["viscosity_strength"]),
+        "config": {"workload": ("%s: %d particles, the reference's InitializeData lattice (gap 0.215, centred), bounds %s, "
+                                "r=0.35, gravity on, mu=%.2f, dt=0.016667" if name == C1_NAME else
+                                "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
+                                "r=0.35, gravity on, mu=%.2f, dt=0.016667") % (name, n, tuple(round(x, 3) for x in sc["bound"]),
+                                                                           sc["params"].get("viscosity_strength", 0.5)),
                    "particles": n, "table": args.table,
                    "l2": "flushed between timed steps (256 MiB fill outside the event pairs)" if flush is not None
                          else "not flushed"},
         "steady_state": {"value": n / (steady_ms * 1e-3) / 1e6, "ms_per_step": steady_ms,
-                         "note": "K steps back to back, no L2 flush, stage timers off"},
+                         "steps": steady_steps, "graph_replays": int(steady_replays),
+                         "note": "sph_step_n: steps back to back (CUDA-graph replay), no L2 flush, stage timers off"},
         "stage_ms": {k: float(v) for k, v in zip(names, stage)},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -391,7 +434,11 @@ def bench_single(args, pkg, scenes, torch, dev):
         "clocks": clk,
     }
     sim.close()
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and name == C1_NAME:
+        r = cpu_reference_c1(steps=100, warmup=20)
+        result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
+                                  "sample": r["sample"], "host_cores": os.cpu_count()}
+    elif not args.no_cpu_baseline:
         r = cpu_reference_run(name if name in scenes.CONFIGS else "C2_dambreak_1M", steps=2, warmup=1, budget_s=20.0)
         result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
                                   "sample": r["sample"], "host_cores": os.cpu_count()}
