@@ -46,6 +46,22 @@ def test_params_struct_layout_and_defaults(pkg):
     assert list(p.bound) == [20, 20, 20]
 
 
+def test_struct_layouts_match_a_c_compiler(pkg, tmp_path):
+    """the ctypes mirrors against what gcc lays out from the header itself (a plain-C translation unit: the header
+    must stay C, not C++)"""
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sph_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SphParams), offsetof(SphParams, bound),'
+                   ' sizeof(SphBlockSpawn), offsetof(SphBlockSpawn, gap), offsetof(SphBlockSpawn, origin),'
+                   ' offsetof(SphBlockSpawn, jitter_amp), offsetof(SphBlockSpawn, velocity_scale), offsetof(SphBlockSpawn, seed));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    B = pkg.SphBlockSpawn
+    assert got == [C.sizeof(pkg.SphParams), pkg.SphParams.bound.offset, C.sizeof(B), B.gap.offset, B.origin.offset,
+                   B.jitter_amp.offset, B.velocity_scale.offset, B.seed.offset]
+
+
 def test_create_without_gpu_fails_loudly(pkg):
     import torch
     if torch.cuda.is_available():
