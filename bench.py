@@ -400,6 +400,45 @@ def bench_single(args, pkg, scenes, torch, dev):
             traffic = json.load(open(tp)).get(name, {}).get(dom)
         except Exception:
             traffic = None
+    # all three gather kernels side by side: A-figure roofline, live duration, and (from the committed ncu captures of
+    # the same kernels) the measured DRAM traffic and the two SM-side roofs that actually bind them
+    ncu = {}
+    short = {"C2_dambreak_1M": "C2", "C3_dambreak_8M": "C3"}.get(name)
+    if short:
+        try:
+            for rec in json.load(open(os.path.join(ROOT, "profiles", "r01_gather_final_%s.json" % short))):
+                for key, frag in (("density", "k_density_pk"), ("pressure", "k_gather_list<0, 1>"), ("viscosity", "k_viscosity_w")):
+                    if frag in rec.get("kernel", ""):
+                        ncu[key] = rec
+        except Exception:
+            ncu = {}
+    tr_all = {}
+    try:
+        tr_all = json.load(open(tp)).get(name, {})
+    except Exception:
+        pass
+
+    def pct(rec, metric):
+        try:
+            return float(rec[metric].split()[0])
+        except Exception:
+            return None
+
+    gather_kernels = {}
+    for key in ("density", "pressure", "viscosity"):
+        t_ms = float(gather[key])
+        ach = A_BYTES[key] * n / (t_ms * 1e-3) / 1e9
+        row = {"algorithmic_bytes_per_particle": A_BYTES[key], "kernel_ms": t_ms, "achieved": ach, "frac": ach / peak}
+        if tr_all.get(key):
+            row["traffic"] = tr_all[key]
+            row["dram_gbs_live"] = tr_all[key] / (t_ms * 1e-3) / 1e9      # ncu's bytes per launch over the live duration
+            row["dram_frac_live"] = row["dram_gbs_live"] / peak
+        if key in ncu:
+            row["ncu"] = {"l1_data_pipe_pct": pct(ncu[key], "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                          "issue_active_pct": pct(ncu[key], "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          "dram_pct": pct(ncu[key], "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                          "source": "profiles/r01_gather_final_%s.json" % short}
+        gather_kernels[key] = row
     result = {
         "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -422,6 +461,7 @@ def bench_single(args, pkg, scenes, torch, dev):
                      "binding_roof": "L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M), not HBM: every lane streams "
                                      "its own 16-byte candidates and the gather re-reads neighbours from L1/L2 by design "
                                      "(ncu: profiles/r01_gather_final_C2.txt, r01_gather_final_C3.txt; DESIGN.md section 5)",
+                     "gather_kernels": gather_kernels,
                      "streaming_kernels": streaming,
                      "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
                               "algorithmic_bytes_per_particle": A_BYTES["step"]}},
