@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
     "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
-    "sph_upload_owned", "sph_download_owned", "sph_comm_stats",
+    "sph_upload_owned", "sph_download_owned", "sph_upload_owned_begin", "sph_download_owned_begin", "sph_comm_stats",
 ]
 
 
@@ -146,6 +146,8 @@ def load_library():
     L.sph_comm_set_planes.argtypes = [vp, vp]
     L.sph_upload_owned.argtypes = [vp, u32, vp, vp, vp]
     L.sph_download_owned.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(u32)]
+    L.sph_upload_owned_begin.argtypes = [vp, u32, vp, vp, vp]
+    L.sph_download_owned_begin.argtypes = [vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(u32)]
     L.sph_comm_stats.argtypes = [vp, vp]
     _lib = L
     return L

@@ -754,7 +754,7 @@ int sph_get_timings(SphContext* c, double* out6)
 //   st_in : [wait ev_pack: the previous pack has consumed stage_in]  H2D -> stage_in                    record ev_h2d
 //   st    : [wait ev_h2d] pack stage_in -> state   record ev_pack   ...step(s)...  export -> stage_out  record ev_export
 //   st_out: [wait ev_export] D2H stage_out -> host                                                      record ev_d2h
-static int ensure_pipeline(SphContext* c)
+int sphb200::ensure_pipeline(SphContext* c)
 {
     if (c->st_in) return SPH_OK;
     cudaStream_t si = nullptr, so = nullptr;
@@ -782,7 +782,7 @@ int sph_upload_state_begin(SphContext* c, uint32_t n, const float* pos3, const f
     SPH_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_pipeline(c);
     if (rc != SPH_OK) return rc;
-    if (!c->stage_in) SPH_CUDA(c, cudaMalloc((void**)&c->stage_in, (size_t)c->cap * 24));
+    if (!c->stage_in) SPH_CUDA(c, cudaMalloc((void**)&c->stage_in, (size_t)c->cap * 28));
     // the previous upload's pack kernel reads stage_in on the solver stream: do not overwrite it before that ran
     if (c->pack_recorded) SPH_CUDA(c, cudaStreamWaitEvent(c->st_in, c->ev_pack, 0));
     if (n) {
@@ -792,6 +792,7 @@ int sph_upload_state_begin(SphContext* c, uint32_t n, const float* pos3, const f
     SPH_CUDA(c, cudaEventRecord(c->ev_h2d, c->st_in));
     c->upload_pending = true;
     c->upload_has_vel = vel3 != nullptr;
+    c->upload_has_ids = false;
     c->upload_n = n;
     return SPH_OK;
 }
@@ -806,7 +807,9 @@ int sph_upload_state_commit(SphContext* c)
     if (n) {
         const float* dpos = (const float*)c->stage_in;
         const float* dvel = (const float*)(c->stage_in + (size_t)c->cap * 12);
-        launch_pack_state(c->st, dpos, c->upload_has_vel ? dvel : nullptr, nullptr, c->A_pos, c->A_vel, n, &c->launches);
+        const uint32_t* dids = (const uint32_t*)(c->stage_in + (size_t)c->cap * 24);
+        launch_pack_state(c->st, dpos, c->upload_has_vel ? dvel : nullptr, c->upload_has_ids ? dids : nullptr, c->A_pos, c->A_vel, n,
+                          &c->launches);
         SPH_CUDA(c, cudaGetLastError());
     }
     SPH_CUDA(c, cudaEventRecord(c->ev_pack, c->st));
@@ -815,6 +818,7 @@ int sph_upload_state_commit(SphContext* c)
     c->n = n;
     c->step_valid = false;
     c->ncount_valid = false;
+    multi_adopt_upload(c, n);
     return SPH_OK;
 }
 
@@ -830,7 +834,7 @@ int sph_download_begin(SphContext* c, int field, void* host, size_t host_bytes)
     SPH_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_pipeline(c);
     if (rc != SPH_OK) return rc;
-    if (!c->stage_out) SPH_CUDA(c, cudaMalloc((void**)&c->stage_out, (size_t)c->cap * 16));
+    if (!c->stage_out) SPH_CUDA(c, cudaMalloc((void**)&c->stage_out, (size_t)c->cap * 20));
     if (c->n) {
         // the previous download was waited for (download_pending is false), so stage_out is free
         rc = export_field(c, field, c->stage_out, true, c->n);

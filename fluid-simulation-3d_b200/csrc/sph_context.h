@@ -45,10 +45,10 @@ struct SphContext {
     // pipelined transfers (sph_upload_state_begin / _commit, sph_download_begin / _wait): their own staging
     // buffers and copy streams, so a PCIe copy in either direction overlaps the step on `st`
     cudaStream_t st_in = nullptr, st_out = nullptr;
-    unsigned char* stage_in = nullptr;    // cap * 24 B: pos3 | vel3 of the pending upload
-    unsigned char* stage_out = nullptr;   // cap * 16 B: the exported field of the pending download
+    unsigned char* stage_in = nullptr;    // cap * 28 B: pos3 | vel3 | global ids (slab mode) of the pending upload
+    unsigned char* stage_out = nullptr;   // cap * 20 B: the exported field (+ global ids, slab mode) of the pending download
     cudaEvent_t ev_h2d = nullptr, ev_pack = nullptr, ev_export = nullptr, ev_d2h = nullptr;
-    bool upload_pending = false, upload_has_vel = false, pack_recorded = false, download_pending = false;
+    bool upload_pending = false, upload_has_vel = false, upload_has_ids = false, pack_recorded = false, download_pending = false;
     uint32_t upload_n = 0;
 
     // CUDA-graph replay of the step inside sph_step_n (launch-bound at the reference's own scene sizes): the captured
@@ -105,9 +105,11 @@ int ensure_tables(SphContext* c, const DevParams& P);
 int export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n);
 int ensure_list(SphContext* c, NbrList* L);
 bool counting_sort_enabled();
+int ensure_pipeline(SphContext* c);      // copy streams + events of the pipelined transfers (sph_api.cu)
 
 // sph_multi.cu
 int multi_step(SphContext* c, float dt);
 void multi_teardown(SphContext* c);
+void multi_adopt_upload(SphContext* c, uint32_t n);   // slab mode: the owned rows are [0, n) again after an upload
 
 }  // namespace sphb200

@@ -290,6 +290,11 @@ int ceil_log2_u64(uint64_t v) { int b = 0; while ((1ull << b) < v && b < 63) b++
 
 namespace sphb200 {
 
+void multi_adopt_upload(SphContext* c, uint32_t n)
+{
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; }
+}
+
 void multi_teardown(SphContext* c)
 {
     if (c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }
@@ -681,6 +686,45 @@ int sph_upload_owned(SphContext* c, uint32_t n, const uint32_t* global_id, const
     return SPH_OK;
 }
 
+static size_t owned_field_bytes(int field)
+{
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED: case SPH_FIELD_VEL_AFTER_PRESSURE:
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: return 12;
+    case SPH_FIELD_OUT_POSITIONS: case SPH_FIELD_COLORS: return 16;
+    case SPH_FIELD_DENSITIES: return 8;
+    case SPH_FIELD_HASH: case SPH_FIELD_KEY: case SPH_FIELD_NEIGHBOUR_COUNT: case SPH_FIELD_SPEED_NORMALIZED: return 4;
+    default: return 0;
+    }
+}
+
+// export `field` of the owned rows, device order, into dev_out (enqueued on the solver's stream)
+static int owned_export(SphContext* c, int field, void* dev_out, uint32_t n)
+{
+    // per-step arrays live at sorted rows [o0, o1); the state arrays were compacted to [0, n)
+    const uint32_t off = c->slab ? c->slab->o0 : 0;
+    const void* src = nullptr;
+    bool needs_step = true;
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_OUT_POSITIONS: src = c->A_pos; needs_step = false; break;
+    case SPH_FIELD_VELOCITIES: case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: src = c->A_vel; needs_step = false; break;
+    case SPH_FIELD_DENSITIES: src = c->dens + off; break;
+    case SPH_FIELD_PREDICTED: case SPH_FIELD_HASH: case SPH_FIELD_KEY: src = c->pred + off; break;
+    case SPH_FIELD_VEL_AFTER_PRESSURE: src = c->velp + off; break;
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: src = c->S_vel + off; break;
+    case SPH_FIELD_NEIGHBOUR_COUNT:
+        if (!c->ncount_valid) return fail(c, SPH_ERR_INVALID, "neighbour counts not recorded");
+        src = c->ncount + off; break;
+    default: return fail(c, SPH_ERR_INVALID, "unknown field");
+    }
+    if (needs_step && !c->step_valid) return fail(c, SPH_ERR_INVALID, "field needs a step first");
+    DevParams P;
+    make_dev_params(c, n, &P);
+    launch_export(c->st, field, c->A_pos, src, nullptr, dev_out, n, P, false, &c->launches);
+    SPH_CUDA(c, cudaGetLastError());
+    return SPH_OK;
+}
+
 int sph_download_owned(SphContext* c, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n)
 {
     if (!c) return SPH_ERR_INVALID;
@@ -688,15 +732,8 @@ int sph_download_owned(SphContext* c, int field, uint32_t* global_id, void* host
     const uint32_t n = c->n;
     if (out_n) *out_n = n;
     if (!n) return SPH_OK;
-    size_t per = 0;
-    switch (field) {
-    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED: case SPH_FIELD_VEL_AFTER_PRESSURE:
-    case SPH_FIELD_VEL_AFTER_VISCOSITY: per = 12; break;
-    case SPH_FIELD_OUT_POSITIONS: case SPH_FIELD_COLORS: per = 16; break;
-    case SPH_FIELD_DENSITIES: per = 8; break;
-    case SPH_FIELD_HASH: case SPH_FIELD_KEY: case SPH_FIELD_NEIGHBOUR_COUNT: case SPH_FIELD_SPEED_NORMALIZED: per = 4; break;
-    default: return fail(c, SPH_ERR_INVALID, "unknown field");
-    }
+    const size_t per = owned_field_bytes(field);
+    if (!per) return fail(c, SPH_ERR_INVALID, "unknown field");
     if (host && host_bytes < per * n) return fail(c, SPH_ERR_INVALID, "sph_download_owned: host buffer too small");
     if (global_id) {
         launch_export_ids(c->st, c->A_pos, (uint32_t*)c->stage, n, &c->launches);
@@ -704,29 +741,65 @@ int sph_download_owned(SphContext* c, int field, uint32_t* global_id, void* host
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
     }
     if (host) {
-        // per-step arrays live at sorted rows [o0, o1); the state arrays were compacted to [0, n)
-        const uint32_t off = c->slab ? c->slab->o0 : 0;
-        const void* src = nullptr;
-        bool needs_step = true;
-        switch (field) {
-        case SPH_FIELD_POSITIONS: case SPH_FIELD_OUT_POSITIONS: src = c->A_pos; needs_step = false; break;
-        case SPH_FIELD_VELOCITIES: case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: src = c->A_vel; needs_step = false; break;
-        case SPH_FIELD_DENSITIES: src = c->dens + off; break;
-        case SPH_FIELD_PREDICTED: case SPH_FIELD_HASH: case SPH_FIELD_KEY: src = c->pred + off; break;
-        case SPH_FIELD_VEL_AFTER_PRESSURE: src = c->velp + off; break;
-        case SPH_FIELD_VEL_AFTER_VISCOSITY: src = c->S_vel + off; break;
-        case SPH_FIELD_NEIGHBOUR_COUNT:
-            if (!c->ncount_valid) return fail(c, SPH_ERR_INVALID, "neighbour counts not recorded");
-            src = c->ncount + off; break;
-        }
-        if (needs_step && !c->step_valid) return fail(c, SPH_ERR_INVALID, "field needs a step first");
-        DevParams P;
-        make_dev_params(c, n, &P);
-        launch_export(c->st, field, c->A_pos, src, nullptr, c->stage, n, P, false, &c->launches);
-        SPH_CUDA(c, cudaGetLastError());
+        int rc = owned_export(c, field, c->stage, n);
+        if (rc != SPH_OK) return rc;
         SPH_CUDA(c, cudaMemcpyAsync(host, c->stage, per * n, cudaMemcpyDeviceToHost, c->st));
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
     }
+    return SPH_OK;
+}
+
+// ---- pipelined transfers, slab mode (see sph_api.cu: same streams, events and staging buffers) -------------------
+int sph_upload_owned_begin(SphContext* c, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (n > c->cap) return fail(c, SPH_ERR_CAPACITY, "sph_upload_owned_begin: n exceeds capacity");
+    if (n && (!pos3 || !global_id)) return fail(c, SPH_ERR_INVALID, "sph_upload_owned_begin: NULL input");
+    if (c->upload_pending) return fail(c, SPH_ERR_INVALID, "sph_upload_owned_begin: an upload is already pending (commit it first)");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc != SPH_OK) return rc;
+    if (!c->stage_in) SPH_CUDA(c, cudaMalloc((void**)&c->stage_in, (size_t)c->cap * 28));
+    if (c->pack_recorded) SPH_CUDA(c, cudaStreamWaitEvent(c->st_in, c->ev_pack, 0));
+    if (n) {
+        SPH_CUDA(c, cudaMemcpyAsync(c->stage_in, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st_in));
+        if (vel3) SPH_CUDA(c, cudaMemcpyAsync(c->stage_in + (size_t)c->cap * 12, vel3, (size_t)n * 12, cudaMemcpyHostToDevice, c->st_in));
+        SPH_CUDA(c, cudaMemcpyAsync(c->stage_in + (size_t)c->cap * 24, global_id, (size_t)n * 4, cudaMemcpyHostToDevice, c->st_in));
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_h2d, c->st_in));
+    c->upload_pending = true;
+    c->upload_has_vel = vel3 != nullptr;
+    c->upload_has_ids = true;
+    c->upload_n = n;
+    return SPH_OK;
+}
+
+int sph_download_owned_begin(SphContext* c, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n)
+{
+    if (!c) return SPH_ERR_INVALID;
+    if (c->download_pending) return fail(c, SPH_ERR_INVALID, "sph_download_owned_begin: a download is already pending (wait for it first)");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n = c->n;
+    if (out_n) *out_n = n;
+    const size_t per = owned_field_bytes(field);
+    if (!per) return fail(c, SPH_ERR_INVALID, "unknown field");
+    if (n && !host) return fail(c, SPH_ERR_INVALID, "sph_download_owned_begin: host is NULL");
+    if (host_bytes < per * n) return fail(c, SPH_ERR_INVALID, "sph_download_owned_begin: host buffer too small");
+    int rc = ensure_pipeline(c);
+    if (rc != SPH_OK) return rc;
+    if (!c->stage_out) SPH_CUDA(c, cudaMalloc((void**)&c->stage_out, (size_t)c->cap * 20));
+    if (n) {
+        rc = owned_export(c, field, c->stage_out, n);
+        if (rc != SPH_OK) return rc;
+        uint32_t* dids = (uint32_t*)(c->stage_out + (size_t)c->cap * 16);
+        if (global_id) launch_export_ids(c->st, c->A_pos, dids, n, &c->launches);
+        SPH_CUDA(c, cudaEventRecord(c->ev_export, c->st));
+        SPH_CUDA(c, cudaStreamWaitEvent(c->st_out, c->ev_export, 0));
+        SPH_CUDA(c, cudaMemcpyAsync(host, c->stage_out, per * n, cudaMemcpyDeviceToHost, c->st_out));
+        if (global_id) SPH_CUDA(c, cudaMemcpyAsync(global_id, dids, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st_out));
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_d2h, c->st_out));
+    c->download_pending = true;
     return SPH_OK;
 }
 

@@ -224,6 +224,10 @@ int  sph_comm_set_planes(SphContext* ctx, const float* planes);
 int  sph_upload_owned(SphContext* ctx, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3);
 /* Download this rank's owned particles (device order): ids + requested field. */
 int  sph_download_owned(SphContext* ctx, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n);
+/* Pipelined forms of the two calls above (same rules as sph_upload_state_begin / sph_download_begin; committed with
+ * sph_upload_state_commit, completed with sph_download_wait).  out_n is this rank's owned count at the time of the call. */
+int  sph_upload_owned_begin(SphContext* ctx, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3);
+int  sph_download_owned_begin(SphContext* ctx, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n);
 /* counters of the last step: owned, ghosts received (lo, hi), migrated out (lo, hi) */
 int  sph_comm_stats(const SphContext* ctx, uint32_t* out5);
 

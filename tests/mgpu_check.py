@@ -124,6 +124,31 @@ def main():
     dist.barrier()
     if rank == 0:
         print("blow_up_12k: 6 steps, ids conserved", flush=True)
+    # (5) the pipelined transfer calls in slab mode: same frames through the blocking and the pipelined calls
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_multi_gpu import _slab_frames
+    sc = scenes.small_dam_break(20, seed=3)
+    res = []
+    for pipelined in (False, True):
+        idb = slab_driver.broadcast_id(pkg, dist, torch, rank, dev)
+        slab = slab_driver.SlabSimulation(pkg, sc["n"] + 4096, rank, world, dev, idb, **sc["params"])
+        gmin_z, gz = int(slab.origin[2]), int(slab.dims[2])
+        layers = slab_driver.choose_layers(sc["pos"][:, 2], world, slab.r, gmin_z, gz)
+        slab.set_layers(layers)
+        frames = []
+        for k in range(3):
+            f = scenes.small_dam_break(20, seed=3 + k)
+            own = slab_driver.owner_of(f["pos"][:, 2], layers, slab.r, gmin_z, gz) == rank
+            frames.append((np.nonzero(own)[0].astype(np.uint32), np.ascontiguousarray(f["pos"][own]), np.ascontiguousarray(f["vel"][own])))
+        res.append(_slab_frames(pkg, slab, frames, scenes.DT, pipelined))
+        slab.close()
+        dist.barrier()
+    for k, ((ia, a), (ib, b)) in enumerate(zip(*res)):
+        assert np.array_equal(ia, ib), "pipelined frame %d: ids differ on rank %d" % (k, rank)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "pipelined frame %d differs on rank %d" % (k, rank)
+    dist.barrier()
+    if rank == 0:
+        print("pipelined_owned_transfers: 3 frames bit-identical to the blocking calls", flush=True)
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_CHECK_OK")
