@@ -64,7 +64,10 @@ __device__ __forceinline__ void walk_particle(const GatherArgs& A, const DevPara
     });
 }
 
-constexpr int kWalkThreads = 128;
+#ifndef SPH_WALK_THREADS
+#define SPH_WALK_THREADS 128          // block size of the one-thread-per-particle gather kernels (tools/sweep_variants.sh)
+#endif
+constexpr int kWalkThreads = SPH_WALK_THREADS;
 // The neighbour list streams through once per pass (176 MB at 1 M particles, more than the L2): mark its traffic
 // evict-first so that it does not push the particle records, which every pass re-reads, out of the L2.
 #ifdef SPH_LIST_PLAIN
@@ -712,7 +715,10 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 // ncu: bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M particles): a 256-bit
 // load is served in 8 passes of 4 lanes, >= 1 wavefront each, i.e. >= 4 wavefronts per warp-candidate (measured
 // 5.25) -- the 16 bytes per lane per candidate are the cost, however they are loaded.
-constexpr int PKS = 24;         // stack entries per thread: sparse scenes (one or two flushes per particle)
+#ifndef SPH_PKS
+#define SPH_PKS 24
+#endif
+constexpr int PKS = SPH_PKS;    // stack entries per thread: sparse scenes (one or two flushes per particle)
 constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
 
 // STAGED (SPH_DENSITY=staged, an A/B variant): the block first copies the union of its threads' row windows into
