@@ -461,6 +461,11 @@ def bench_single(args, pkg, scenes, torch, dev):
                      "binding_roof": "L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M), not HBM: every lane streams "
                                      "its own 16-byte candidates and the gather re-reads neighbours from L1/L2 by design "
                                      "(ncu: profiles/r01_gather_final_C2.txt, r01_gather_final_C3.txt; DESIGN.md section 5)",
+                     "stages": {k: {"algorithmic_bytes_per_particle": a, "ms": float(t), "achieved": a * n / (float(t) * 1e-3) / 1e9,
+                                    "frac": a * n / (float(t) * 1e-3) / 1e9 / peak}
+                                for k, a, t in zip(names, (A_BYTES["predict_key"], A_BYTES["sort"] + A_BYTES["table"] + A_BYTES["reorder"],
+                                                           A_BYTES["density"], A_BYTES["pressure"], A_BYTES["viscosity"],
+                                                           A_BYTES["integrate"]), stage)},
                      "gather_kernels": gather_kernels,
                      "streaming_kernels": streaming,
                      "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
