@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--table", default="grid", choices=["grid", "refhash"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--rebalance", type=int, default=0, metavar="K",
+                    help="multi-GPU: sph_comm_rebalance every K steps (inside the timed region); 0 = planes stay where the initial quantile cut put them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

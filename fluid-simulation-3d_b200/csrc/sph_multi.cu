@@ -41,6 +41,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -61,7 +62,7 @@ void load_nccl()
     if (!g_nccl.field) { g_nccl.error = std::string("libnccl.so.2 lacks ") + name; return; }
     SPH_SYM(GetUniqueId, "ncclGetUniqueId") SPH_SYM(CommInitRank, "ncclCommInitRank") SPH_SYM(CommDestroy, "ncclCommDestroy")
     SPH_SYM(Send, "ncclSend") SPH_SYM(Recv, "ncclRecv") SPH_SYM(GroupStart, "ncclGroupStart") SPH_SYM(GroupEnd, "ncclGroupEnd")
-    SPH_SYM(GetErrorString, "ncclGetErrorString")
+    SPH_SYM(GetErrorString, "ncclGetErrorString") SPH_SYM(AllReduce, "ncclAllReduce")
 #undef SPH_SYM
     g_nccl.ok = true;
 }
@@ -76,6 +77,7 @@ const NcclApi& nccl()
 #define ncclCommDestroy nccl().CommDestroy
 #define ncclSend nccl().Send
 #define ncclRecv nccl().Recv
+#define ncclAllReduce nccl().AllReduce
 #define ncclGroupStart nccl().GroupStart
 #define ncclGroupEnd nccl().GroupEnd
 #define ncclGetErrorString nccl().GetErrorString
@@ -106,6 +108,12 @@ struct SlabState {
     cudaEvent_t pe[8] = {};
     double pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t psteps = 0, pseen = 0;
+    // re-balancing (sph_comm_rebalance): the layers the table of the last step was built for, histogram buffers
+    bool table_valid = false;
+    int t_zlo = 0, t_own_lo = 0, t_own_hi = 0;
+    uint32_t* hist_dev = nullptr;                 // [hist_cap] per-layer counts (+ 1 word: the smallest exchange buffer of any rank)
+    uint32_t* hist_host = nullptr;                // pinned mirror
+    uint32_t hist_cap = 0;
 };
 
 namespace {
@@ -286,13 +294,25 @@ __global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __rest
 
 int ceil_log2_u64(uint64_t v) { int b = 0; while ((1ull << b) < v && b < 63) b++; return b; }
 
+// re-balancing: rows per OWNED global z layer, read off the prefix table of the last step (layer l of the local table
+// spans the entries [l * plane, (l + 1) * plane)); the other layers of the global histogram stay zero on this rank
+__global__ void __launch_bounds__(256)
+k_layer_hist(const uint32_t* __restrict__ table, uint32_t* __restrict__ hist, const uint32_t plane, const int zlo,
+             const int own_lo, const int own_hi)
+{
+    const int g = own_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (g >= own_hi) return;
+    const size_t l = (size_t)(g - zlo);
+    hist[g] = table[(l + 1) * plane] - table[l * plane];
+}
+
 }  // namespace
 
 namespace sphb200 {
 
 void multi_adopt_upload(SphContext* c, uint32_t n)
 {
-    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; }
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; }
 }
 
 void multi_teardown(SphContext* c)
@@ -310,6 +330,8 @@ void multi_teardown(SphContext* c)
                     s->ghost_pred, s->block_counts, s->block_any, s->dev_small};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->host_small) cudaFreeHost(s->host_small);
+    if (s->hist_dev) cudaFree(s->hist_dev);
+    if (s->hist_host) cudaFreeHost(s->hist_host);
     if (s->halo_stream) { cudaStreamSynchronize(s->halo_stream); cudaStreamDestroy(s->halo_stream); }
     if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
@@ -579,6 +601,7 @@ int multi_step(SphContext* c, float dt)
     c->n = o1 - o0;
     c->step_valid = true;
     s->stats[0] = c->n; s->stats[1] = o0; s->stats[2] = live_end - o1; s->stats[3] = T[L_MIG_LO]; s->stats[4] = T[L_MIG_HI];
+    s->t_zlo = P.zlo; s->t_own_lo = P.own_lo; s->t_own_hi = P.own_hi; s->table_valid = true;
     return SPH_OK;
 }
 
@@ -662,6 +685,120 @@ int sph_comm_set_planes(SphContext* c, const float* planes)
     return SPH_OK;
 }
 
+int sph_comm_get_layers(const SphContext* c, int32_t* layers_out)
+{
+    if (!c || !layers_out || !c->slab || !c->slab->have_planes) return SPH_ERR_INVALID;
+    for (int k = 0; k <= c->nranks; k++) layers_out[k] = c->slab->layers[k];
+    return SPH_OK;
+}
+
+int sph_slab_balance_layers(const uint32_t* hist, int32_t gz, int32_t nranks, const int32_t* layers_old, uint32_t max_shift,
+                            uint64_t row_budget, int32_t* layers_new)
+{
+    constexpr int kMinLayers = 3;                   // sph_comm_set_planes: every slab needs three cell layers
+    if (!hist || !layers_new || nranks < 1 || gz < kMinLayers * nranks) return SPH_ERR_INVALID;
+    const int R = nranks;
+    std::vector<uint64_t> cum((size_t)gz + 1, 0);
+    for (int l = 0; l < gz; l++) cum[l + 1] = cum[l] + hist[l];
+    const uint64_t total = cum[gz];
+    if (layers_old) {
+        if (layers_old[0] != 0 || layers_old[R] != gz) return SPH_ERR_INVALID;
+        for (int k = 0; k < R; k++) if (layers_old[k + 1] - layers_old[k] < kMinLayers) return SPH_ERR_INVALID;
+    }
+    const int s = (int)(max_shift > 3u ? 3u : max_shift);       // a plane never crosses its old neighbours (single-hop migration)
+    std::vector<int> L((size_t)R + 1, 0);
+    L[R] = gz;
+    for (int k = 1; k < R; k++) {
+        // the layer boundary whose cumulative count is nearest to k/R of the total (exact integer arithmetic; the
+        // lower boundary on a tie)
+        const unsigned __int128 target = (unsigned __int128)total * (unsigned)k;
+        int lo = 0, hi = gz;                        // first boundary with cum * R >= target
+        while (lo < hi) { const int m = (lo + hi) / 2; if ((unsigned __int128)cum[m] * (unsigned)R >= target) hi = m; else lo = m + 1; }
+        int cut = lo;
+        if (cut > 0 && target - (unsigned __int128)cum[cut - 1] * (unsigned)R <= (unsigned __int128)cum[cut] * (unsigned)R - target) cut--;
+        if (layers_old) {
+            const int old = layers_old[k];
+            if (cut > old + s) cut = old + s;
+            if (cut < old - s) cut = old - s;
+            if (row_budget) {                        // rows that change owner through this plane
+                while (cut > old && cum[cut] - cum[old] > row_budget) cut--;
+                while (cut < old && cum[old] - cum[cut] > row_budget) cut++;
+            }
+        }
+        L[k] = cut;
+    }
+    for (int k = 1; k < R; k++) if (L[k] < L[k - 1] + kMinLayers) L[k] = L[k - 1] + kMinLayers;
+    for (int k = R - 1; k >= 1; k--) if (L[k] > L[k + 1] - kMinLayers) L[k] = L[k + 1] - kMinLayers;
+    if (layers_old) {
+        // the thickness passes can push a plane past what the limits allowed; then nothing moves this time
+        bool ok = true;
+        for (int k = 1; k < R && ok; k++) {
+            const int old = layers_old[k], d = L[k] > old ? L[k] - old : old - L[k];
+            const uint64_t moved = L[k] > old ? cum[L[k]] - cum[old] : cum[old] - cum[L[k]];
+            if (d > s || (row_budget && moved > row_budget)) ok = false;
+        }
+        if (!ok) for (int k = 1; k < R; k++) L[k] = layers_old[k];
+    }
+    for (int k = 0; k <= R; k++) layers_new[k] = L[k];
+    return SPH_OK;
+}
+
+int sph_comm_rebalance(SphContext* c, uint32_t max_shift, int32_t* layers_out, uint32_t* hist_out, size_t hist_entries, int* changed_out)
+{
+    if (!c) return SPH_ERR_INVALID;
+    SlabState* s = c->slab;
+    if (!s || !c->comm) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: call sph_comm_init first");
+    if (!s->have_planes) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: call sph_comm_set_planes first");
+    if (!s->table_valid) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: needs a completed sph_step (the histogram is read off its table)");
+    const int GZ = c->gdim[2];
+    if (hist_out && hist_entries < (size_t)GZ) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: hist_out too small");
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    cudaStream_t st = c->st;
+    if (s->hist_cap < (uint32_t)GZ + 1u) {
+        SPH_CUDA(c, cudaStreamSynchronize(st));
+        if (s->hist_dev) cudaFree(s->hist_dev);
+        if (s->hist_host) cudaFreeHost(s->hist_host);
+        s->hist_dev = nullptr; s->hist_host = nullptr; s->hist_cap = 0;
+        SPH_CUDA(c, cudaMalloc(&s->hist_dev, ((size_t)GZ + 1) * sizeof(uint32_t)));
+        SPH_CUDA(c, cudaMallocHost(&s->hist_host, ((size_t)GZ + 1) * sizeof(uint32_t)));
+        s->hist_cap = (uint32_t)GZ + 1u;
+    }
+    // global histogram: every rank fills its owned layers, the sum over ranks is the whole column.  One extra word,
+    // reduced with ncclMin, carries the smallest exchange buffer of any rank (it bounds the rows a plane may move).
+    SPH_CUDA(c, cudaMemsetAsync(s->hist_dev, 0, ((size_t)GZ + 1) * sizeof(uint32_t), st));
+    const int own = s->t_own_hi - s->t_own_lo;
+    const uint32_t plane = (uint32_t)c->gdim[0] * (uint32_t)c->gdim[1];
+    if (own > 0) {
+        k_layer_hist<<<(own + 255) / 256, 256, 0, st>>>(c->tstart, s->hist_dev, plane, s->t_zlo, s->t_own_lo, s->t_own_hi);
+        ++c->launches;
+    }
+    SPH_CUDA(c, cudaMemcpyAsync(s->hist_dev + GZ, &s->xcap, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SPH_NCCL(c, ncclAllReduce(s->hist_dev, s->hist_dev, (size_t)GZ, ncclUint32, ncclSum, comm, st));
+    SPH_NCCL(c, ncclAllReduce(s->hist_dev + GZ, s->hist_dev + GZ, 1, ncclUint32, ncclMin, comm, st));
+    SPH_CUDA(c, cudaMemcpyAsync(s->hist_host, s->hist_dev, ((size_t)GZ + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(c, cudaStreamSynchronize(st));
+    if (hist_out) memcpy(hist_out, s->hist_host, (size_t)GZ * sizeof(uint32_t));
+    std::vector<int32_t> fresh((size_t)c->nranks + 1);
+    bool changed = false;
+    if (max_shift && c->nranks > 1) {
+        // rows changing owner travel as migrants (+ one layer of them as kept ghosts): half an exchange buffer at most
+        const uint64_t budget = s->hist_host[GZ] / 2u;
+        const int rc = sph_slab_balance_layers(s->hist_host, GZ, c->nranks, s->layers.data(), max_shift, budget ? budget : 1u, fresh.data());
+        if (rc != SPH_OK) return fail(c, rc, "sph_comm_rebalance: the layer histogram cannot be cut (fewer than three layers per rank?)");
+        for (int k = 0; k <= c->nranks; k++) changed |= fresh[k] != s->layers[k];
+        if (changed) {
+            for (int k = 0; k <= c->nranks; k++) {
+                s->layers[k] = fresh[k];
+                c->planes[k] = ((float)(fresh[k] + c->gmin[2]) + 0.5f) * c->params.interaction_radius;   // a z inside the slab's first layer
+            }
+        }
+    }
+    if (layers_out) for (int k = 0; k <= c->nranks; k++) layers_out[k] = s->layers[k];
+    if (changed_out) *changed_out = changed ? 1 : 0;
+    return SPH_OK;
+}
+
 int sph_upload_owned(SphContext* c, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3)
 {
     if (!c) return SPH_ERR_INVALID;
@@ -682,7 +819,7 @@ int sph_upload_owned(SphContext* c, uint32_t n, const uint32_t* global_id, const
     c->n = n;
     c->step_valid = false;
     c->ncount_valid = false;
-    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; }
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; }
     return SPH_OK;
 }
 

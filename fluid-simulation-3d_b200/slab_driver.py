@@ -42,6 +42,20 @@ def choose_layers(z_sample, nranks, r, gmin_z, gz):
     return L
 
 
+def balance_layers(pkg, hist, nranks, layers_old=None, max_shift=1, row_budget=0):
+    """sph_slab_balance_layers (pure host function of libsph_b200.so): cut the per-layer particle histogram at the
+    particle-count quantiles, optionally constrained to stay near ``layers_old`` (re-balancing)."""
+    hist = np.ascontiguousarray(hist, np.uint32)
+    old = None if layers_old is None else np.ascontiguousarray(layers_old, np.int32)
+    new = np.zeros(nranks + 1, np.int32)
+    rc = pkg.load_library().sph_slab_balance_layers(C.c_void_p(hist.ctypes.data), hist.size, nranks,
+                                                    None if old is None else C.c_void_p(old.ctypes.data), int(max_shift),
+                                                    int(row_budget), C.c_void_p(new.ctypes.data))
+    if rc != 0:
+        raise ValueError("sph_slab_balance_layers: cannot cut %d layers for %d ranks (rc %d)" % (hist.size, nranks, rc))
+    return [int(x) for x in new]
+
+
 def planes_from_layers(L, r, gmin_z):
     """z value inside the first layer of each slab: the library floors it back to the same layer."""
     return np.array([(l + gmin_z + 0.5) * r for l in L], dtype=np.float32)
@@ -103,6 +117,22 @@ class SlabSimulation:
                                                       C.c_void_p(out.ctypes.data), out.nbytes, C.byref(cnt)))
         assert cnt.value == n
         return ids, out
+
+    def rebalance(self, max_shift=1):
+        """COLLECTIVE: move the slab planes towards the particle-count quantiles (sph_comm_rebalance).  Returns
+        (layers now in force, global per-layer histogram, whether any plane moved)."""
+        layers = np.zeros(self.nranks + 1, np.int32)
+        hist = np.zeros(int(self.dims[2]), np.uint32)
+        changed = C.c_int(0)
+        self.sim._check(self.sim.L.sph_comm_rebalance(self.sim.h, int(max_shift), C.c_void_p(layers.ctypes.data),
+                                                      C.c_void_p(hist.ctypes.data), hist.size, C.byref(changed)))
+        self.layers = [int(x) for x in layers]
+        return self.layers, hist, bool(changed.value)
+
+    def get_layers(self):
+        layers = np.zeros(self.nranks + 1, np.int32)
+        self.sim._check(self.sim.L.sph_comm_get_layers(self.sim.h, C.c_void_p(layers.ctypes.data)))
+        return [int(x) for x in layers]
 
     def stats(self):
         out = np.zeros(5, np.uint32)
@@ -172,8 +202,12 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
     dt = scenes.DT
     stream = torch.cuda.ExternalStream(slab.sim.stream_ptr(), device=dev)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev)
-    for _ in range(args.warmup):
+    rebalance_every = int(getattr(args, "rebalance", 0) or 0)
+    plane_moves = 0
+    for k in range(args.warmup):
         slab.step(dt)
+        if rebalance_every and (k + 1) % rebalance_every == 0:
+            plane_moves += int(slab.rebalance(1)[2])
     slab.sim.synchronize()
     torch.cuda.synchronize()
     dist.barrier()
@@ -182,7 +216,7 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
     l0 = slab.sim.launch_count()
     stage = np.zeros(6)
     total_ms = 0.0
-    for _ in range(args.steps):
+    for k in range(args.steps):
         if flush is not None:
             with torch.cuda.stream(stream):
                 flush.fill_(1)
@@ -191,6 +225,8 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         slab.step(dt)
+        if rebalance_every and (k + 1) % rebalance_every == 0:      # part of the job: timed
+            plane_moves += int(slab.rebalance(1)[2])
         b.record(stream)
         slab.sim.synchronize()
         stage += slab.sim.timings()
@@ -292,7 +328,9 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
                                "migration per step over NCCL" % (name, n_total, world, layers),
                    "particles": n_total, "table": "grid", "owned_total_after": int(owned.item()),
                    "l2": "flushed between timed steps" if flush is not None else "not flushed",
-                   "rank0_last_step": stats},
+                   "rank0_last_step": stats,
+                   "rebalance": ({"every": rebalance_every, "plane_moves": plane_moves, "layers_after": slab.layers}
+                                 if rebalance_every else "off (planes at the initial particle-count quantiles)")},
         "stage_ms": {k: float(v) for k, v in zip(names, stage)},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per": "rank (max over ranks)",

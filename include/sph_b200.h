@@ -231,6 +231,27 @@ int  sph_download_owned_begin(SphContext* ctx, int field, uint32_t* global_id, v
 /* counters of the last step: owned, ghosts received (lo, hi), migrated out (lo, hi) */
 int  sph_comm_stats(const SphContext* ctx, uint32_t* out5);
 
+/* -- slab re-balancing (planes at particle-count quantiles, re-balanced every K steps) ---- */
+/* The slabs are cut at cell-layer granularity; this returns the nranks+1 global layer indices in force
+ * (rank k owns layers [layers[k], layers[k+1]); layer 0 is the first layer of the grid table, sph_get_grid). */
+int  sph_comm_get_layers(const SphContext* ctx, int32_t* layers_out);
+/* COLLECTIVE (every rank calls it between the same two steps).  Builds the global histogram of particles per
+ * z layer from the tables of the last step (one tiny kernel + one ncclAllReduce of dims[2] counters), cuts it at the
+ * particle-count quantiles with sph_slab_balance_layers below -- every plane moves by at most max_shift layers
+ * (capped at 3, and at what the exchange buffers hold) -- and puts the new planes in force.  The next sph_step
+ * migrates the rows of the layers that changed owner through the ordinary migration path; results stay identical
+ * to the single-GPU step.  max_shift = 0 only measures.  layers_out (nranks+1), hist_out (hist_entries >= dims[2]
+ * counters, the global histogram) and changed_out may be NULL.  Needs a completed sph_step. */
+int  sph_comm_rebalance(SphContext* ctx, uint32_t max_shift, int32_t* layers_out, uint32_t* hist_out,
+                        size_t hist_entries, int* changed_out);
+/* Pure host function (no device, no context): cut hist[0, gz) into nranks contiguous runs of layers with particle
+ * counts as equal as layer granularity allows, every run at least three layers thick (the slab protocol's minimum).
+ * With layers_old != NULL every plane stays within max_shift layers of its old place, never crosses its old
+ * neighbours (migration is single-hop) and moves at most row_budget particles (0: unlimited); with layers_old ==
+ * NULL the cut is unconstrained.  Deterministic: every rank derives the same planes from the same histogram. */
+int  sph_slab_balance_layers(const uint32_t* hist, int32_t gz, int32_t nranks, const int32_t* layers_old,
+                             uint32_t max_shift, uint64_t row_budget, int32_t* layers_new);
+
 #ifdef __cplusplus
 }
 #endif

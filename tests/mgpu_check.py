@@ -27,7 +27,7 @@ def gather_by_id(dist, n_total, ids, arr):
     return out
 
 
-def run_scene(pkg, slabmod, scenes, dist, torch, rank, world, dev, sc, steps, label):
+def run_scene(pkg, slabmod, scenes, dist, torch, rank, world, dev, sc, steps, label, skew=0, rebalance=0):
     dt = scenes.DT
     n = sc["n"]
     idb = slabmod.broadcast_id(pkg, dist, torch, rank, dev)
@@ -35,9 +35,14 @@ def run_scene(pkg, slabmod, scenes, dist, torch, rank, world, dev, sc, steps, la
     gmin_z, gz = int(slab.origin[2]), int(slab.dims[2])
     pred0 = sc["pos"] + sc["vel"] * np.float32(1.0 / 120.0)
     layers = slabmod.choose_layers(pred0[:, 2], world, slab.r, gmin_z, gz)
+    if skew:        # deliberately unbalanced start (every inner plane `skew` layers up); sph_comm_rebalance has to walk it back
+        layers = [layers[0]] + [min(l + skew, gz - 3 * (world - k)) for k, l in enumerate(layers[1:-1], 1)] + [layers[-1]]
+    layers0 = list(layers)
     slab.set_layers(layers)
+    assert slab.get_layers() == layers
     own = slabmod.owner_of(sc["pos"][:, 2], layers, slab.r, gmin_z, gz) == rank
     ids = np.nonzero(own)[0].astype(np.uint32)
+    owned0 = int(own.sum())
     slab.sim.set_neighbour_count_tap(True)
     slab.upload_owned(ids, sc["pos"][own], sc["vel"][own])
     single = None
@@ -69,8 +74,28 @@ def run_scene(pkg, slabmod, scenes, dist, torch, rank, world, dev, sc, steps, la
                 err = np.abs(got - ref)
                 assert np.all(err <= tol), "%s step %d: %s worst %g (tol %g)" % (label, s, f, err.max(), tol[np.unravel_index(err.argmax(), err.shape)])
                 worst[f] = max(worst.get(f, 0.0), float((err / np.maximum(np.abs(ref), 1e-30 + scale * np.abs(ref).max())).max()))
+        if rebalance:
+            # COLLECTIVE: planes walk towards the particle-count quantiles, `rebalance` layers per call at most; the
+            # histogram it returns is the global one (sums to n) and equal on every rank
+            new_layers, hist, changed = slab.rebalance(rebalance)
+            assert int(hist.sum()) == n, "%s step %d: layer histogram sums to %d, not %d" % (label, s, int(hist.sum()), n)
+            assert all(abs(a - b) <= rebalance for a, b in zip(new_layers, layers)) and changed == (new_layers != layers)
+            assert slab.get_layers() == new_layers
+            layers = new_layers
     tot = torch.tensor([migrated], device="cuda:%d" % dev)
     dist.all_reduce(tot)
+    if rebalance:
+        cnt = torch.zeros(world, dtype=torch.int64, device="cuda:%d" % dev)
+        cnt[rank] = slab.stats()["owned"]
+        dist.all_reduce(cnt)
+        c0 = torch.zeros(world, dtype=torch.int64, device="cuda:%d" % dev)
+        c0[rank] = owned0
+        dist.all_reduce(c0)
+        spread0, spread1 = int(c0.max() - c0.min()), int(cnt.max() - cnt.min())
+        assert layers != layers0 and spread1 < spread0, "%s: re-balancing did not help: layers %r -> %r, owned %r -> %r" % (
+            label, layers0, layers, c0.tolist(), cnt.tolist())
+        if rank == 0:
+            print("%s: planes %r -> %r, owned per rank %r -> %r" % (label, layers0, layers, c0.tolist(), cnt.tolist()), flush=True)
     if rank == 0:
         print("%s: %d particles, %d ranks, layers %s, %d steps OK; migrations %d; worst rel err %s" % (
             label, n, world, layers, steps, int(tot.item()), {k: "%.1e" % v for k, v in worst.items()}), flush=True)
@@ -99,6 +124,11 @@ def main():
     run_scene(pkg, slab_driver, scenes, dist, torch, rank, world, dev, sc, 6, "fast_random_20k")
     # (3) dense column
     run_scene(pkg, slab_driver, scenes, dist, torch, rank, world, dev, scenes.small_column(12, 30, 40), 3, "column_12x30x40")
+    # (3b) re-balancing: planes start three layers off the quantiles and are moved back (two layers per call at most)
+    # after every step, so whole layers change owner through the migration path -- results still equal the single GPU
+    run_scene(pkg, slab_driver, scenes, dist, torch, rank, world, dev, scenes.small_dam_break(24, seed=7), 4, "rebalance_dam_break_24",
+              skew=3, rebalance=2)
+    run_scene(pkg, slab_driver, scenes, dist, torch, rank, world, dev, sc, 5, "rebalance_fast_random_20k", skew=4, rebalance=1)
     # (4) blow-up: particles fast enough to cross more than a whole slab in one step.  Values are not compared
     # (such a particle takes one ballistic step while it is handed on); the protocol must neither fail its
     # halo cross-check nor lose or duplicate particles.

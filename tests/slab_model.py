@@ -118,6 +118,7 @@ class SlabModel:
         dens = c.densities()
         self.ncount = c.neighbour_counts()[:n_own]
         o_lay = self.sm.layer_of(o_pred[:, 2], self.r, self.gmin_z, self.gz)
+        self.owned_layers = o_lay                       # what sph_comm_rebalance reads off the step's table
         b_lo = (o_lay == own_lo) & (rank > 0)
         b_hi = (o_lay == own_hi - 1) & (rank < world - 1)
         # (4) halo of densities, matched by id
@@ -144,7 +145,18 @@ class SlabModel:
         self.dens = c.densities()[:n_own]
 
 
-def run_rank(rank, world, port, scene, steps, dt, q):
+    def rebalance(self, pkg, max_shift):
+        """model of sph_comm_rebalance: global per-layer histogram of the last step's owned rows (sum over ranks),
+        cut by the library's own pure host function, new layers in force from the next step on"""
+        hist = torch.from_numpy(np.bincount(self.owned_layers, minlength=self.gz).astype(np.int64))
+        dist.all_reduce(hist)
+        new = self.sm.balance_layers(pkg, hist.numpy().astype(np.uint32), self.world, self.L, max_shift)
+        changed = list(new) != list(self.L)
+        self.L = list(new)
+        return changed
+
+
+def run_rank(rank, world, port, scene, steps, dt, q, rebalance_every=0, skew=0):
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -152,7 +164,7 @@ def run_rank(rank, world, port, scene, steps, dt, q):
     import __graft_entry__ as g
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     ob = g.load_oracle()
-    g.load_package()
+    pkg = g.load_package()
     from fluid_simulation_3d_b200 import slab_driver as sm
     r = 0.35
     half = np.float32(scene["params"]["bound"][2]) * np.float32(0.5)
@@ -160,15 +172,21 @@ def run_rank(rank, world, port, scene, steps, dt, q):
     gmin_z, gz = -qz - 3, (qz + 2) - (-qz - 3) + 1           # same geometry rule as the library (update_grid_geometry)
     pred0 = scene["pos"] + scene["vel"] * np.float32(1.0 / 120.0)
     layers = sm.choose_layers(pred0[:, 2], world, r, gmin_z, gz)
+    if skew:                                                 # deliberately unbalanced start: every inner plane `skew` layers up
+        layers = [layers[0]] + [min(l + skew, gz - 3 * (world - k)) for k, l in enumerate(layers[1:-1], 1)] + [layers[-1]]
+    layers0 = list(layers)
     own = sm.owner_of(scene["pos"][:, 2], layers, r, gmin_z, gz) == rank
     m = SlabModel(ob, sm, rank, world, layers, r, gmin_z, gz, scene["params"])
     m.upload(np.nonzero(own)[0], scene["pos"][own], scene["vel"][own])
     migrated = 0
-    for _ in range(steps):
+    moves = 0
+    for k in range(steps):
         m.step(dt)
         migrated += m.stats["migrated"]
+        if rebalance_every and (k + 1) % rebalance_every == 0 and k + 1 < steps:
+            moves += int(m.rebalance(pkg, 2))
     out = [None] * world
-    dist.all_gather_object(out, (m.ids, m.pos, m.vel, m.dens, m.ncount, migrated, layers))
+    dist.all_gather_object(out, (m.ids, m.pos, m.vel, m.dens, m.ncount, migrated, (layers0, list(m.L), moves)))
     if rank == 0:
         q.put(out)
     dist.barrier()

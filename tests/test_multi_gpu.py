@@ -36,6 +36,37 @@ def test_single_rank_slab_equals_plain_step(pkg):
     slab.close(); plain.close()
 
 
+def test_single_rank_layer_histogram_and_rebalance_call(pkg):
+    """sph_comm_rebalance on one rank: the histogram it reads off the step's table is the per-layer count of the
+    predicted positions, no plane can move, and it refuses to run before a step"""
+    from fluid_simulation_3d_b200 import scenes, slab_driver
+    sc = scenes.small_dam_break(18, seed=4)
+    idb = slab_driver.SlabSimulation.make_id(pkg)
+    slab = slab_driver.SlabSimulation(pkg, sc["n"] + 1024, 0, 1, 0, idb, **sc["params"])
+    gz = int(slab.dims[2])
+    slab.set_layers([0, gz])
+    slab.upload_owned(np.arange(sc["n"], dtype=np.uint32), sc["pos"], sc["vel"])
+    with pytest.raises(pkg.SphError):
+        slab.rebalance(1)                                   # no table yet
+    for _ in range(2):
+        slab.step(scenes.DT)
+    layers, hist, changed = slab.rebalance(2)
+    assert layers == [0, gz] and not changed and slab.get_layers() == [0, gz]
+    _, pred = slab.download_owned("predicted")
+    want = np.bincount(slab_driver.layer_of(pred[:, 2], slab.r, int(slab.origin[2]), gz), minlength=gz)
+    assert np.array_equal(hist, want.astype(np.uint32))
+    # the cut a 2- or 4-rank run would make from this histogram
+    for world in (2, 4):
+        L = slab_driver.balance_layers(pkg, hist, world)
+        own = np.diff(np.concatenate([[0], np.cumsum(want)])[L])
+        assert own.sum() == sc["n"] and own.max() - own.min() <= 2 * want.max()
+    slab.step(scenes.DT)                                    # and the step after a (no-op) re-balance still runs
+    slab.upload_owned(np.arange(sc["n"], dtype=np.uint32), sc["pos"], sc["vel"])
+    with pytest.raises(pkg.SphError):
+        slab.rebalance(1)                                   # a new state invalidates the table
+    slab.close()
+
+
 def _slab_frames(pkg, slab, frames, dt, pipelined):
     """every frame: upload the rank's owned state, step, read OutPositions + ids back; returns them sorted by id"""
     import ctypes as C
