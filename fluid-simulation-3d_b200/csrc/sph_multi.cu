@@ -749,8 +749,12 @@ int sph_comm_rebalance(SphContext* c, uint32_t max_shift, int32_t* layers_out, u
     SlabState* s = c->slab;
     if (!s || !c->comm) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: call sph_comm_init first");
     if (!s->have_planes) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: call sph_comm_set_planes first");
-    if (!s->table_valid) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: needs a completed sph_step (the histogram is read off its table)");
     const int GZ = c->gdim[2];
+    // the layers the last step's table was built for (a single-rank context steps through the plain path: whole grid)
+    bool table_valid = s->table_valid;
+    int t_zlo = s->t_zlo, t_own_lo = s->t_own_lo, t_own_hi = s->t_own_hi;
+    if (c->nranks == 1) { table_valid = c->step_valid && c->mode == SPH_TABLE_GRID; t_zlo = 0; t_own_lo = 0; t_own_hi = GZ; }
+    if (!table_valid) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: needs a completed sph_step (the histogram is read off its table)");
     if (hist_out && hist_entries < (size_t)GZ) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: hist_out too small");
     SPH_CUDA(c, cudaSetDevice(c->device));
     ncclComm_t comm = (ncclComm_t)c->comm;
@@ -767,10 +771,10 @@ int sph_comm_rebalance(SphContext* c, uint32_t max_shift, int32_t* layers_out, u
     // global histogram: every rank fills its owned layers, the sum over ranks is the whole column.  One extra word,
     // reduced with ncclMin, carries the smallest exchange buffer of any rank (it bounds the rows a plane may move).
     SPH_CUDA(c, cudaMemsetAsync(s->hist_dev, 0, ((size_t)GZ + 1) * sizeof(uint32_t), st));
-    const int own = s->t_own_hi - s->t_own_lo;
+    const int own = t_own_hi - t_own_lo;
     const uint32_t plane = (uint32_t)c->gdim[0] * (uint32_t)c->gdim[1];
     if (own > 0) {
-        k_layer_hist<<<(own + 255) / 256, 256, 0, st>>>(c->tstart, s->hist_dev, plane, s->t_zlo, s->t_own_lo, s->t_own_hi);
+        k_layer_hist<<<(own + 255) / 256, 256, 0, st>>>(c->tstart, s->hist_dev, plane, t_zlo, t_own_lo, t_own_hi);
         ++c->launches;
     }
     SPH_CUDA(c, cudaMemcpyAsync(s->hist_dev + GZ, &s->xcap, sizeof(uint32_t), cudaMemcpyHostToDevice, st));

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_single_rank_slab_equals_plain_step(pkg):
-    """nranks = 1: no neighbours, but the whole slab pipeline (classify, pack, ghost-aware sort) runs."""
+    """nranks = 1: a one-slab context (ids travel with the state, owned up/downloads) steps through the plain path."""
     from fluid_simulation_3d_b200 import scenes, slab_driver
     sc = scenes.small_dam_break(16)
     idb = slab_driver.SlabSimulation.make_id(pkg)
