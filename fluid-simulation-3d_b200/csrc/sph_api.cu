@@ -279,7 +279,9 @@ int sph_set_params(SphContext* c, const SphParams* p)
     const SphParams old = c->params;
     c->params = *p;
     int rc = update_grid_geometry(c);
-    if (rc != SPH_OK) { c->params = old; update_grid_geometry(c); return rc; }
+    // slab mode: the planes are world-space z values; a new radius or bound changes the layer grid under them
+    if (rc == SPH_OK) rc = multi_params_changed(c);
+    if (rc != SPH_OK) { const std::string m = c->err; c->params = old; update_grid_geometry(c); multi_params_changed(c); c->err = m; return rc; }
     return SPH_OK;
 }
 
@@ -714,7 +716,7 @@ int sph_load_state(SphContext* c, const char* path)
 int sph_host_register(void* ptr, size_t bytes)
 {
     if (!ptr || !bytes) return SPH_ERR_INVALID;
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable)   /* pinned for every device's context (multi-GPU hosts) */;
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SPH_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
     return SPH_OK;
 }

@@ -110,6 +110,7 @@ int ensure_pipeline(SphContext* c);      // copy streams + events of the pipelin
 // sph_multi.cu
 int multi_step(SphContext* c, float dt);
 void multi_teardown(SphContext* c);
+int multi_params_changed(SphContext* c);              // slab mode: re-derive the cell layers of the planes after sph_set_params
 void multi_adopt_upload(SphContext* c, uint32_t n);   // slab mode: the owned rows are [0, n) again after an upload
 
 }  // namespace sphb200

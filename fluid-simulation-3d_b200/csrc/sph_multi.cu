@@ -315,6 +315,14 @@ void multi_adopt_upload(SphContext* c, uint32_t n)
     if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; }
 }
 
+int multi_params_changed(SphContext* c)
+{
+    if (!c->slab || !c->slab->have_planes) return SPH_OK;
+    const std::vector<float> planes = c->planes;         // sph_comm_set_planes assigns c->planes
+    c->slab->table_valid = false;                        // the last table was laid out for the old layer grid
+    return sph_comm_set_planes(c, planes.data());
+}
+
 void multi_teardown(SphContext* c)
 {
     if (c->comm) { ncclCommDestroy((ncclComm_t)c->comm); c->comm = nullptr; }

@@ -1,6 +1,7 @@
 // host/FluidSimulation.cc -- see FluidSimulation.h.  Pure host C++: talks to the GPU only through
 // the C ABI of libsph_b200.so.
 #include "FluidSimulation.h"
+#include "SlabGroup.h"
 
 #include <cmath>
 #include <stdexcept>
@@ -15,11 +16,18 @@ namespace Physics
 			return instance;
 		}
 
-		FluidSimulation::~FluidSimulation()
+		FluidSimulation::FluidSimulation() {}
+		FluidSimulation::~FluidSimulation() { shutdown(); }
+
+		void FluidSimulation::shutdown()
 		{
-			if (pinnedOut) sph_host_unregister(pinnedOut);
-			if (pinnedPos) sph_host_unregister(pinnedPos);
-			if (ctx) sph_destroy(ctx);
+			if (pinnedOut) { sph_host_unregister(pinnedOut); pinnedOut = nullptr; }
+			if (pinnedPos) { sph_host_unregister(pinnedPos); pinnedPos = nullptr; }
+			group.reset();
+			if (ctx) { sph_destroy(ctx); ctx = nullptr; }
+			capacity = 0;
+			numParticles = 0;
+			invalidateGetters();
 		}
 
 		// The reference cannot fail (void returns, physicsWorld.cc); a GPU backend can, and a silent
@@ -51,10 +59,44 @@ namespace Physics
 		void FluidSimulation::pushParams()
 		{
 			if (ctx) check(sph_set_params(ctx, &params), "sph_set_params");
+			if (group) {
+				try { group->setParams(params); }
+				catch (const std::exception& e) { error = e.what(); throw; }
+			}
 		}
 
-		void FluidSimulation::setDevice(int cudaDevice) { device = cudaDevice; }
-		void FluidSimulation::setTableMode(int m) { tableMode = m; if (ctx) check(sph_set_table_mode(ctx, m), "sph_set_table_mode"); }
+		void FluidSimulation::setDevice(int cudaDevice) { device = cudaDevice; devices.clear(); }
+		void FluidSimulation::setDevices(const std::vector<int>& cudaDevices)
+		{
+			devices = cudaDevices;
+			if (!devices.empty()) device = devices[0];           // the spawn lattice is made on the first device
+			if (devices.size() == 1) devices.clear();
+			if (!devices.empty() && tableMode != SPH_TABLE_GRID) {
+				error = "setDevices: the slab decomposition uses the GRID table (the reference table is global)";
+				throw std::runtime_error(error);
+			}
+		}
+		std::vector<uint32> FluidSimulation::particlesPerDevice() const
+		{
+			if (group) return group->ownedCounts();
+			return std::vector<uint32>(1, numParticles);
+		}
+		void FluidSimulation::fetch(int field, void* out, size_t bytes, const char* what)
+		{
+			if (group) {
+				try { group->download(field, out, bytes); }
+				catch (const std::exception& e) { error = std::string(what) + ": " + e.what(); throw; }
+			} else check(sph_download(ctx, field, out, bytes), what);
+		}
+		void FluidSimulation::setTableMode(int m)
+		{
+			if (m != SPH_TABLE_GRID && (group || devices.size() > 1)) {
+				error = "setTableMode: the slab decomposition uses the GRID table";
+				throw std::runtime_error(error);
+			}
+			tableMode = m;
+			if (ctx) check(sph_set_table_mode(ctx, m), "sph_set_table_mode");
+		}
 		void FluidSimulation::setHostMirrors(bool outPositions, bool positionsToo) { mirrorOut = outPositions; mirrorPos = positionsToo; }
 
 		void FluidSimulation::InitializeData(int particleAmmount, vec3)
@@ -62,6 +104,7 @@ namespace Physics
 			// (the reference ignores Centre too: GridArrangement is called without it, :142)
 			if (particleAmmount < 0) particleAmmount = 0;
 			numParticles = (uint32)particleAmmount;
+			group.reset();
 			ensureContext(numParticles ? numParticles : 1);
 			if (pinnedOut) { sph_host_unregister(pinnedOut); pinnedOut = nullptr; }
 			if (pinnedPos) { sph_host_unregister(pinnedPos); pinnedPos = nullptr; }
@@ -85,6 +128,21 @@ namespace Physics
 			densitiesValid = true;
 			invalidateGetters();
 			timingsFresh = true;
+			if (devices.size() > 1 && numParticles) {
+				// The lattice, its lookup and its densities (:139-145) were just made on the first device; the slabs
+				// take the particles from here.  Until the first Update the getters answer from this spawn state.
+				const size_t n = numParticles;
+				bulkPos.resize(n * 3); bulkVel.assign(n * 3, 0.0f); bulkDens.resize(n * 2);
+				check(sph_download(ctx, SPH_FIELD_POSITIONS, bulkPos.data(), bulkPos.size() * 4), "sph_download");
+				check(sph_download(ctx, SPH_FIELD_DENSITIES, bulkDens.data(), bulkDens.size() * 4), "sph_download");
+				sph_destroy(ctx); ctx = nullptr; capacity = 0;
+				try {
+					group.reset(new sphb200::SlabGroup(devices, numParticles, params));
+					group->upload(numParticles, bulkPos.data(), nullptr);
+				} catch (const std::exception& e) { group.reset(); error = e.what(); throw; }
+				bulkFresh.store(true, std::memory_order_release);
+				updatesSinceRebalance = 0;
+			}
 		}
 
 		void FluidSimulation::invalidateGetters()
@@ -98,21 +156,25 @@ namespace Physics
 
 		void FluidSimulation::Update(float deltatime)
 		{
-			if (!ctx || numParticles == 0) return;
+			if ((!ctx && !group) || numParticles == 0) return;
 			substeps = 1;
 			if (maxTimestep > 0.0f && deltatime > maxTimestep) {
 				const float q = std::ceil(deltatime / maxTimestep);
 				substeps = (q < 1.0f) ? 1u : (q > 1024.0f ? 1024u : (uint32)q);
 			}
-			if (substeps == 1) check(sph_step(ctx, deltatime), "sph_step");
+			if (group) {
+				try {
+					group->step(substeps == 1 ? deltatime : deltatime / (float)substeps, substeps);
+					if (rebalanceEvery && ++updatesSinceRebalance >= rebalanceEvery) { updatesSinceRebalance = 0; group->rebalance(1); }
+				} catch (const std::exception& e) { error = e.what(); throw; }
+			}
+			else if (substeps == 1) check(sph_step(ctx, deltatime), "sph_step");
 			else check(sph_step_n(ctx, deltatime / (float)substeps, substeps), "sph_step_n");
 			// Update() returns with the host-visible buffers complete: the renderer takes
 			// &OutPositions[0] right after (fluidSimCPU.cc:58)
-			if (mirrorOut)
-				check(sph_download(ctx, SPH_FIELD_OUT_POSITIONS, OutPositions.data(), OutPositions.size() * sizeof(vec4)), "sph_download");
-			if (mirrorPos)
-				check(sph_download(ctx, SPH_FIELD_POSITIONS, positions.data(), positions.size() * sizeof(vec3)), "sph_download");
-			if (!mirrorOut && !mirrorPos) check(sph_synchronize(ctx), "sph_synchronize");
+			if (mirrorOut) fetch(SPH_FIELD_OUT_POSITIONS, OutPositions.data(), OutPositions.size() * sizeof(vec4), "sph_download");
+			if (mirrorPos) fetch(SPH_FIELD_POSITIONS, positions.data(), positions.size() * sizeof(vec3), "sph_download");
+			if (!mirrorOut && !mirrorPos && ctx) check(sph_synchronize(ctx), "sph_synchronize");
 			densitiesValid = true;
 			invalidateGetters();
 			timingsFresh = false;
@@ -120,15 +182,20 @@ namespace Physics
 
 		void FluidSimulation::uploadState(const float* velocities3)
 		{
-			if (!ctx) return;
+			if (!ctx && !group) return;
 			std::vector<float> vel;
 			if (!velocities3 && numParticles) {
 				vel.resize((size_t)numParticles * 3);
-				check(sph_download(ctx, SPH_FIELD_VELOCITIES, vel.data(), vel.size() * 4), "sph_download");
+				fetch(SPH_FIELD_VELOCITIES, vel.data(), vel.size() * 4, "sph_download");
 				velocities3 = vel.data();
 			}
-			check(sph_upload_state(ctx, numParticles, numParticles ? &positions[0].x : nullptr, velocities3), "sph_upload_state");
-			check(sph_synchronize(ctx), "sph_synchronize");
+			if (group) {
+				try { group->upload(numParticles, numParticles ? &positions[0].x : nullptr, velocities3); }
+				catch (const std::exception& e) { error = e.what(); throw; }
+			} else {
+				check(sph_upload_state(ctx, numParticles, numParticles ? &positions[0].x : nullptr, velocities3), "sph_upload_state");
+				check(sph_synchronize(ctx), "sph_synchronize");
+			}
 			densitiesValid = false;                      // the reference's densities would be stale too until the next Update
 			invalidateGetters();
 		}
@@ -136,28 +203,29 @@ namespace Physics
 		void FluidSimulation::downloadVelocities(std::vector<vec3>& out)
 		{
 			out.resize(numParticles);
-			if (ctx && numParticles) check(sph_download(ctx, SPH_FIELD_VELOCITIES, out.data(), out.size() * sizeof(vec3)), "sph_download");
+			if ((ctx || group) && numParticles) fetch(SPH_FIELD_VELOCITIES, out.data(), out.size() * sizeof(vec3), "sph_download");
 		}
 		void FluidSimulation::downloadDensities(std::vector<float>& out)
 		{
 			out.resize((size_t)numParticles * 2);
-			if (ctx && numParticles) check(sph_download(ctx, SPH_FIELD_DENSITIES, out.data(), out.size() * 4), "sph_download");
+			if ((ctx || group) && numParticles) fetch(SPH_FIELD_DENSITIES, out.data(), out.size() * 4, "sph_download");
 		}
 		void FluidSimulation::downloadColors(std::vector<vec4>& out)
 		{
 			out.resize(numParticles);
-			if (ctx && numParticles) check(sph_download(ctx, SPH_FIELD_COLORS, out.data(), out.size() * sizeof(vec4)), "sph_download");
+			if ((ctx || group) && numParticles) fetch(SPH_FIELD_COLORS, out.data(), out.size() * sizeof(vec4), "sph_download");
 		}
 
 		// per-particle getters: bounds-checked, zero when out of range (:151,157,163,168,174,180)
 		void FluidSimulation::readParticle(uint32 index, float out[10])
 		{
 			for (int k = 0; k < 10; k++) out[k] = 0.0f;
-			if (!ctx || index >= numParticles) return;
+			if ((!ctx && !group) || index >= numParticles) return;
 			if (!bulkFresh.load(std::memory_order_acquire)) {
 				std::lock_guard<std::mutex> lock(getterMutex);
 				if (!bulkFresh.load(std::memory_order_relaxed)) {
-					if (!(cacheValid && cachedIndex == index) && getterCalls < kSingleReads) {
+					// (several GPUs: a particle lives on whichever slab owns it now, so every read is the bulk read)
+					if (ctx && !(cacheValid && cachedIndex == index) && getterCalls < kSingleReads) {
 						getterCalls++;
 						check(sph_get_particle(ctx, index, cached), "sph_get_particle");
 						cachedIndex = index;
@@ -170,9 +238,9 @@ namespace Physics
 					// many getters this frame: one bulk read, then every getter is a host read
 					const size_t n = numParticles;
 					bulkPos.resize(n * 3); bulkVel.resize(n * 3); bulkDens.assign(n * 2, 0.0f);
-					check(sph_download(ctx, SPH_FIELD_POSITIONS, bulkPos.data(), bulkPos.size() * 4), "sph_download");
-					check(sph_download(ctx, SPH_FIELD_VELOCITIES, bulkVel.data(), bulkVel.size() * 4), "sph_download");
-					if (densitiesValid) check(sph_download(ctx, SPH_FIELD_DENSITIES, bulkDens.data(), bulkDens.size() * 4), "sph_download");
+					fetch(SPH_FIELD_POSITIONS, bulkPos.data(), bulkPos.size() * 4, "sph_download");
+					fetch(SPH_FIELD_VELOCITIES, bulkVel.data(), bulkVel.size() * 4, "sph_download");
+					if (densitiesValid) fetch(SPH_FIELD_DENSITIES, bulkDens.data(), bulkDens.size() * 4, "sph_download");
 					bulkFresh.store(true, std::memory_order_release);
 				}
 			}
@@ -193,8 +261,11 @@ namespace Physics
 
 		void FluidSimulation::refreshTimings()
 		{
-			if (timingsFresh || !ctx) return;
-			check(sph_get_timings(ctx, timings), "sph_get_timings");
+			if (timingsFresh || (!ctx && !group)) return;
+			if (group) {
+				try { group->timings(timings); }
+				catch (const std::exception& e) { error = e.what(); throw; }
+			} else check(sph_get_timings(ctx, timings), "sph_get_timings");
 			timingsFresh = true;
 		}
 		double FluidSimulation::getElapsedTimeGravity() { refreshTimings(); return timings[0]; }

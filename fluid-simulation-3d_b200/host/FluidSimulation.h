@@ -12,11 +12,14 @@
 
 #include <atomic>
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "sph_b200.h"
+
+namespace sphb200 { class SlabGroup; }
 
 #ifdef SPH_B200_USE_GLM
 namespace sphb200 { using vec3 = glm::vec3; using vec4 = glm::vec4; }
@@ -83,6 +86,18 @@ namespace Physics
 
 			// ---- B200 additions (no counterpart in the reference) ----
 			void setDevice(int cudaDevice);            // before InitializeData; default 0
+			// Several GPUs of the box (before InitializeData): the particles are slab-decomposed along z, one slab
+			// per device, stepped in lockstep from one host thread each with ghost halos and migration over NCCL
+			// (SlabGroup.h).  Everything else -- Update, the mirrors, getters, timers (the slowest slab per stage),
+			// parameters -- behaves as on one GPU; results agree with the single-GPU step within fp32 summation
+			// order.  GRID table only.  One device = setDevice.
+			void setDevices(const std::vector<int>& cudaDevices);
+			// Multi-GPU: move the slab planes towards the particle-count quantiles every N Updates (0 = never)
+			void setRebalanceInterval(uint32 everyNUpdates) { rebalanceEvery = everyNUpdates; }
+			std::vector<uint32> particlesPerDevice() const;
+			// Release every device resource now (the destructor does the same, but at static-destruction time the
+			// CUDA / NCCL runtimes may already be unloading): call before exit in multi-GPU programs.
+			void shutdown();
 			void setTableMode(int sphTableMode);       // SPH_TABLE_GRID (default) / SPH_TABLE_REFERENCE_HASH
 			// Which host mirrors Update() refreshes: OutPositions (what the renderer uploads,
 			// fluidSimCPU.cc:58) is on by default; `positions` costs a second copy and is off by default.
@@ -102,7 +117,7 @@ namespace Physics
 			const std::string& lastError() const { return error; }
 
 		private:
-			FluidSimulation() {}
+			FluidSimulation();
 			FluidSimulation(const FluidSimulation& cpy) = delete;
 			~FluidSimulation();
 
@@ -113,6 +128,11 @@ namespace Physics
 			void readParticle(uint32 index, float out10[10]);
 
 			SphContext* ctx = nullptr;
+			std::vector<int> devices;                            // more than one entry: slab mode through `group`
+			std::unique_ptr<sphb200::SlabGroup> group;
+			uint32 rebalanceEvery = 0, updatesSinceRebalance = 0;
+			bool multi() const { return group != nullptr; }
+			void fetch(int field, void* out, size_t bytes, const char* what);   // sph_download / SlabGroup::download
 			SphParams params = defaultParams();
 			static SphParams defaultParams() { SphParams p; sph_default_params(&p); return p; }
 			uint32 numParticles = 0;

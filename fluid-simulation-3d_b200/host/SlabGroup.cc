@@ -1,0 +1,214 @@
+// host/SlabGroup.cc -- see SlabGroup.h.  Pure host C++: talks to the GPUs only through the C ABI of libsph_b200.so.
+#include "SlabGroup.h"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+namespace sphb200 {
+
+void SlabGroup::check(SphContext* c, int rc, const char* what)
+{
+    if (rc == SPH_OK) return;
+    const char* msg = sph_last_error(c);
+    throw std::runtime_error(std::string(what) + ": " + (msg && *msg ? msg : "error " + std::to_string(rc)));
+}
+
+size_t SlabGroup::fieldBytes(int field)
+{
+    switch (field) {
+    case SPH_FIELD_POSITIONS: case SPH_FIELD_VELOCITIES: case SPH_FIELD_PREDICTED: case SPH_FIELD_VEL_AFTER_PRESSURE:
+    case SPH_FIELD_VEL_AFTER_VISCOSITY: return 12;
+    case SPH_FIELD_OUT_POSITIONS: case SPH_FIELD_COLORS: return 16;
+    case SPH_FIELD_DENSITIES: return 8;
+    case SPH_FIELD_HASH: case SPH_FIELD_KEY: case SPH_FIELD_NEIGHBOUR_COUNT: case SPH_FIELD_SPEED_NORMALIZED: return 4;
+    default: return 0;
+    }
+}
+
+void SlabGroup::parallel(const std::function<void(int)>& f)
+{
+    const int R = ranks();
+    std::vector<std::string> err((size_t)R);
+    std::vector<std::thread> th;
+    th.reserve((size_t)R);
+    for (int k = 0; k < R; k++)
+        th.emplace_back([&, k] {
+            try { f(k); } catch (const std::exception& e) { err[(size_t)k] = e.what()[0] ? e.what() : "error"; }
+        });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < R; k++)
+        if (!err[(size_t)k].empty()) throw std::runtime_error("rank " + std::to_string(k) + ": " + err[(size_t)k]);
+}
+
+SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const SphParams& params) : params_(params)
+{
+    const size_t R = devices.size();
+    if (R == 0) throw std::runtime_error("SlabGroup: no devices");
+    // a rank holds its owned rows, the rows arriving in a step and two ghost layers; slabs are cut at particle-count
+    // quantiles, so 1.5x the even share plus slack for thin scenes is ample (re-balancing keeps it that way)
+    const uint64_t share = (uint64_t)particles / R * 3 / 2 + 131072;
+    const uint64_t all = (uint64_t)particles + 4096;
+    cap_ = (uint32_t)(R == 1 ? (particles ? particles : 1) : (share < all ? share : all));
+    rank_.resize(R);
+    try {
+        for (size_t k = 0; k < R; k++) {
+            rank_[k].device = devices[k];
+            const int rc = sph_create(&rank_[k].ctx, devices[k], cap_);
+            if (rc != SPH_OK) {
+                const char* msg = sph_last_error(nullptr);
+                throw std::runtime_error(std::string("sph_create on device ") + std::to_string(devices[k]) + ": " + (msg ? msg : "?"));
+            }
+            check(rank_[k].ctx, sph_set_params(rank_[k].ctx, &params_), "sph_set_params");
+        }
+        std::vector<unsigned char> id(sph_comm_id_bytes());
+        check(nullptr, sph_comm_get_id(id.data(), id.size()), "sph_comm_get_id");
+        // ncclCommInitRank blocks until every rank has joined: one thread per rank
+        parallel([&](int k) { check(rank_[(size_t)k].ctx, sph_comm_init(rank_[(size_t)k].ctx, k, (int)R, id.data(), id.size()), "sph_comm_init"); });
+    } catch (...) {
+        for (auto& r : rank_) if (r.ctx) sph_destroy(r.ctx);
+        throw;
+    }
+}
+
+SlabGroup::~SlabGroup()
+{
+    // communicators are torn down together (ncclCommDestroy may wait for the peers)
+    try { parallel([&](int k) { if (rank_[(size_t)k].ctx) sph_destroy(rank_[(size_t)k].ctx); }); } catch (...) {}
+}
+
+void SlabGroup::setParams(const SphParams& p)
+{
+    params_ = p;
+    for (auto& r : rank_) check(r.ctx, sph_set_params(r.ctx, &params_), "sph_set_params");
+}
+
+void SlabGroup::upload(uint32_t n, const float* pos3, const float* vel3)
+{
+    const int R = ranks();
+    if (n && !pos3) throw std::runtime_error("SlabGroup::upload: positions missing");
+    int32_t dims[3], origin[3];
+    check(rank_[0].ctx, sph_get_grid(rank_[0].ctx, dims, origin), "sph_get_grid");
+    const int gz = dims[2], gmin_z = origin[2];
+    const float r = params_.interaction_radius;
+    // z cell layer of every particle, with the device's arithmetic: floor(z / r) in fp32 (sph_device.cuh: cell_of)
+    std::vector<int32_t> layer((size_t)n);
+    std::vector<uint32_t> hist((size_t)gz, 0u);
+    for (uint32_t i = 0; i < n; i++) {
+        int l = (int)std::floor(pos3[3 * (size_t)i + 2] / r) - gmin_z;
+        l = l < 0 ? 0 : (l > gz - 1 ? gz - 1 : l);
+        layer[i] = l;
+        hist[(size_t)l]++;
+    }
+    std::vector<int32_t> L((size_t)R + 1);
+    if (sph_slab_balance_layers(hist.data(), gz, R, nullptr, 0, 0, L.data()) != SPH_OK)
+        throw std::runtime_error("SlabGroup::upload: the box has fewer than three cell layers per GPU along z (" +
+                                 std::to_string(gz) + " layers, " + std::to_string(R) + " GPUs)");
+    std::vector<float> planes((size_t)R + 1);
+    for (int k = 0; k <= R; k++) planes[(size_t)k] = ((float)(L[(size_t)k] + gmin_z) + 0.5f) * r;   // a z inside the slab's first layer
+    std::vector<int> owner_of_layer((size_t)gz);
+    for (int k = 0; k < R; k++)
+        for (int l = L[(size_t)k]; l < L[(size_t)k + 1]; l++) owner_of_layer[(size_t)l] = k;
+    for (auto& rk : rank_) { rk.ids.clear(); rk.pos.clear(); rk.vel.clear(); }
+    for (uint32_t i = 0; i < n; i++) {
+        Rank& rk = rank_[(size_t)owner_of_layer[(size_t)layer[i]]];
+        rk.ids.push_back(i);
+        rk.pos.insert(rk.pos.end(), pos3 + 3 * (size_t)i, pos3 + 3 * (size_t)i + 3);
+        if (vel3) rk.vel.insert(rk.vel.end(), vel3 + 3 * (size_t)i, vel3 + 3 * (size_t)i + 3);
+    }
+    for (int k = 0; k < R; k++)
+        if (rank_[(size_t)k].ids.size() > cap_)
+            throw std::runtime_error("SlabGroup::upload: rank " + std::to_string(k) + " would own " +
+                                     std::to_string(rank_[(size_t)k].ids.size()) + " particles, capacity " + std::to_string(cap_));
+    parallel([&](int k) {
+        Rank& rk = rank_[(size_t)k];
+        check(rk.ctx, sph_comm_set_planes(rk.ctx, planes.data()), "sph_comm_set_planes");
+        check(rk.ctx, sph_upload_owned(rk.ctx, (uint32_t)rk.ids.size(), rk.ids.data(), rk.pos.data(), vel3 ? rk.vel.data() : nullptr),
+              "sph_upload_owned");
+        std::vector<float>().swap(rk.pos);
+        std::vector<float>().swap(rk.vel);
+    });
+    n_ = n;
+}
+
+void SlabGroup::step(float dt, uint32_t nsteps)
+{
+    parallel([&](int k) {
+        SphContext* c = rank_[(size_t)k].ctx;
+        if (nsteps <= 1) check(c, sph_step(c, dt), "sph_step");
+        else check(c, sph_step_n(c, dt, nsteps), "sph_step_n");
+    });
+}
+
+bool SlabGroup::rebalance(uint32_t max_shift)
+{
+    std::vector<int> changed((size_t)ranks(), 0);
+    parallel([&](int k) {
+        SphContext* c = rank_[(size_t)k].ctx;
+        check(c, sph_comm_rebalance(c, max_shift, nullptr, nullptr, 0, &changed[(size_t)k]), "sph_comm_rebalance");
+    });
+    return changed[0] != 0;
+}
+
+void SlabGroup::download(int field, void* out, size_t out_bytes)
+{
+    const size_t per = fieldBytes(field);
+    if (!per) throw std::runtime_error("SlabGroup::download: unknown field");
+    if (out_bytes < per * (size_t)n_) throw std::runtime_error("SlabGroup::download: output buffer too small");
+    std::vector<uint32_t> got((size_t)ranks(), 0u);
+    unsigned char* dst = static_cast<unsigned char*>(out);
+    parallel([&](int k) {
+        Rank& rk = rank_[(size_t)k];
+        const uint32_t m = sph_num_particles(rk.ctx);
+        rk.ids.resize(m);
+        rk.buf.resize((size_t)m * per);
+        uint32_t cnt = 0;
+        check(rk.ctx, sph_download_owned(rk.ctx, field, rk.ids.data(), rk.buf.data(), rk.buf.size(), &cnt), "sph_download_owned");
+        if (cnt != m) throw std::runtime_error("sph_download_owned: row count changed under the download");
+        // scatter by particle index (ranks own disjoint indices, so the threads never write the same element)
+        const unsigned char* src = rk.buf.data();
+        for (uint32_t i = 0; i < m; i++) {
+            const uint32_t id = rk.ids[i];
+            if (id >= n_) throw std::runtime_error("sph_download_owned: particle id out of range");
+            memcpy(dst + (size_t)id * per, src + (size_t)i * per, per);
+        }
+        got[(size_t)k] = m;
+    });
+    uint64_t total = 0;
+    for (uint32_t g : got) total += g;
+    if (total != n_) throw std::runtime_error("SlabGroup::download: the ranks own " + std::to_string(total) + " particles, expected " + std::to_string(n_));
+}
+
+void SlabGroup::timings(double out6[6])
+{
+    for (int i = 0; i < 6; i++) out6[i] = 0.0;
+    for (auto& r : rank_) {
+        double t[6];
+        check(r.ctx, sph_get_timings(r.ctx, t), "sph_get_timings");
+        for (int i = 0; i < 6; i++) if (t[i] > out6[i]) out6[i] = t[i];
+    }
+}
+
+std::vector<int32_t> SlabGroup::layers() const
+{
+    std::vector<int32_t> L((size_t)ranks() + 1, 0);
+    if (sph_comm_get_layers(rank_[0].ctx, L.data()) != SPH_OK) L.clear();
+    return L;
+}
+
+std::vector<uint32_t> SlabGroup::ownedCounts() const
+{
+    std::vector<uint32_t> c;
+    for (const auto& r : rank_) c.push_back(sph_num_particles(r.ctx));
+    return c;
+}
+
+uint64_t SlabGroup::launches() const
+{
+    uint64_t l = 0;
+    for (const auto& r : rank_) l += sph_launch_count(r.ctx);
+    return l;
+}
+
+}  // namespace sphb200

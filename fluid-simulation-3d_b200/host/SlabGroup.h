@@ -1,0 +1,61 @@
+// host/SlabGroup.h -- several GPUs of one box behind one solver object, in ONE process.
+//
+// The reference is a single-process application; its solver class cannot be spread over processes
+// without changing the application.  SlabGroup keeps the process model: it owns one C-ABI context per GPU
+// (include/sph_b200.h, slab mode), drives each from its own host thread -- the slab step exchanges ghosts and
+// migrants with its neighbours over NCCL, so all ranks must step at the same time -- and presents the particles
+// in the reference's index order again (every particle carries its index as a global id).  FluidSimulation uses it
+// when setDevices() names more than one GPU.  Pure host C++ on top of the C ABI, like the rest of host/.
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "sph_b200.h"
+
+namespace sphb200 {
+
+class SlabGroup {
+public:
+    // one slab per device, in the order given (slab k is the k-th z range); `particles` sizes the per-rank capacity
+    SlabGroup(const std::vector<int>& devices, uint32_t particles, const SphParams& params);
+    ~SlabGroup();
+    SlabGroup(const SlabGroup&) = delete;
+    SlabGroup& operator=(const SlabGroup&) = delete;
+
+    int ranks() const { return (int)rank_.size(); }
+    uint32_t particles() const { return n_; }
+    void setParams(const SphParams& p);
+    // Replace the whole state (index order, velocities may be null = zero).  Cuts the slabs at the particle-count
+    // quantiles of the z cell layers (sph_slab_balance_layers) and hands every rank its particles.
+    void upload(uint32_t n, const float* pos3, const float* vel3);
+    void step(float dt, uint32_t nsteps = 1);                     // all ranks in lockstep
+    // COLLECTIVE sph_comm_rebalance on every rank; returns whether a plane moved
+    bool rebalance(uint32_t max_shift = 1);
+    // gather a field into index order; `out` holds particles() elements of the field's size (sph_b200.h: SPH_FIELD_*)
+    void download(int field, void* out, size_t out_bytes);
+    void timings(double out6[6]);                                 // per stage: the slowest rank
+    std::vector<int32_t> layers() const;
+    std::vector<uint32_t> ownedCounts() const;
+    uint64_t launches() const;
+
+private:
+    struct Rank {
+        SphContext* ctx = nullptr;
+        int device = 0;
+        std::vector<uint32_t> ids;          // scratch: ids of the rows of the last download / the pending upload
+        std::vector<unsigned char> buf;     // scratch: field rows
+        std::vector<float> pos, vel;
+    };
+    void parallel(const std::function<void(int)>& f);             // f(rank) on one thread per rank; rethrows the first error
+    static void check(SphContext* c, int rc, const char* what);
+    static size_t fieldBytes(int field);
+    std::vector<Rank> rank_;
+    SphParams params_;
+    uint32_t n_ = 0;
+    uint32_t cap_ = 0;
+};
+
+}  // namespace sphb200

@@ -1,11 +1,12 @@
 // host/host_demo.cc -- headless driver of the host class, the way FluidSimCPU drives the reference
 // (fluidSimCPU.cc:9-46): InitializeData(n), then Update(dt) per frame.  Prints one line per run that
 // tests/test_variants_gpu.py / tests/test_host_gpu.py compare with the same scene run through the C ABI from Python.
-//   host_demo n steps table_mode [class | adapter | getters | substeps]
+//   host_demo n steps table_mode [class | adapter | getters | substeps | multi ndev]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <string>
 #include <thread>
 #include <vector>
 #include "FluidSimB200.h"
@@ -115,6 +116,54 @@ static int run_substeps(int n, int steps, int mode)
     return 0;
 }
 
+// the same scene on one GPU and slab-decomposed over ndev GPUs of the box, through the same class
+static int run_multi(int n, int steps, int ndev)
+{
+    auto& sim = Physics::Fluid::FluidSimulation::getInstance();
+    sim.setGravity(true);
+    sim.setHostMirrors(true, true);
+    sim.setDevice(0);
+    sim.InitializeData(n);
+    const float rho_spawn = sim.getDensity((uint32)n / 2u);
+    for (int s = 0; s < steps; s++) sim.Update(0.016667f);
+    const auto pos1 = sim.positions;
+    const auto out1 = sim.OutPositions;
+    std::vector<float> rho1;
+    sim.downloadDensities(rho1);
+    std::vector<int> devs;
+    for (int d = 0; d < ndev; d++) devs.push_back(d);
+    sim.setDevices(devs);
+    sim.setRebalanceInterval(2);
+    sim.InitializeData(n);                               // the reset path: same lattice, now handed to the slabs
+    const float rho_spawn_multi = sim.getDensity((uint32)n / 2u);      // valid before the first Update, like the reference
+    for (int s = 0; s < steps; s++) sim.Update(0.016667f);
+    double dpos = 0.0, dout = 0.0, drho = 0.0;
+    for (int i = 0; i < n; i++) {
+        dpos = std::fmax(dpos, std::fmax(std::fabs((double)sim.positions[i].x - pos1[i].x),
+                         std::fmax(std::fabs((double)sim.positions[i].y - pos1[i].y), std::fabs((double)sim.positions[i].z - pos1[i].z))));
+        dout = std::fmax(dout, std::fabs((double)sim.OutPositions[i].x - out1[i].x) + std::fabs((double)sim.OutPositions[i].w - out1[i].w));
+    }
+    std::vector<float> rho2;
+    sim.downloadDensities(rho2);
+    for (size_t i = 0; i < rho2.size(); i++) drho = std::fmax(drho, std::fabs((double)rho2[i] - rho1[i]) / std::fmax(1e-30, std::fabs((double)rho1[i])));
+    // getters: answered from the bulk mirrors, whichever slab owns the particle now
+    int getters_ok = 1;
+    const uint32 probe[3] = {0u, (uint32)n / 2u, (uint32)n - 1u};
+    for (uint32 i : probe) {
+        const auto p = sim.getPosition(i);
+        if (p.x != sim.positions[i].x || p.y != sim.positions[i].y || p.z != sim.positions[i].z) getters_ok = 0;
+        if (sim.getDensity(i) != rho2[2 * (size_t)i]) getters_ok = 0;
+    }
+    if (sim.getDensity((uint32)n) != 0.0f) getters_ok = 0;
+    unsigned long long owned = 0;
+    std::string per;
+    for (uint32 c : sim.particlesPerDevice()) { owned += c; per += (per.empty() ? "" : ",") + std::to_string(c); }
+    printf("multi n=%d ndev=%d steps=%d max_pos_diff=%.3g max_out_diff=%.3g max_rho_rel=%.3g spawn_rho=%.6f/%.6f getters_ok=%d owned=%llu per_device=[%s] density_ms=%.4f\n",
+           n, ndev, steps, dpos, dout, drho, rho_spawn, rho_spawn_multi, getters_ok, owned, per.c_str(), sim.getElapsedTimeDensity());
+    sim.shutdown();
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     int n = argc > 1 ? atoi(argv[1]) : 10000;
@@ -126,6 +175,7 @@ int main(int argc, char** argv)
         if (!strcmp(what, "adapter")) return run_adapter(n, steps, mode);
         if (!strcmp(what, "getters")) return run_getters(n, steps, mode);
         if (!strcmp(what, "substeps")) return run_substeps(n, steps, mode);
+        if (!strcmp(what, "multi")) return run_multi(n, steps, argc > 5 ? atoi(argv[5]) : 2);
         sim.setTableMode(mode);
         sim.setGravity(true);
         sim.setHostMirrors(true, true);

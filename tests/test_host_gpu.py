@@ -69,3 +69,26 @@ def test_substepping_equals_explicit_smaller_steps(pkg):
         sim.step_n(sub_dt, 4)
     assert got["pos_fnv"] == ob.fnv1a64(sim.download("positions"))
     sim.close()
+
+
+def test_host_class_over_two_gpus_matches_one_gpu():
+    """setDevices({0, 1}): the reference's class interface, slab-decomposed in ONE process (a host thread per GPU,
+    NCCL between them, planes re-balanced every second Update) against the same class on one GPU"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, steps = 20000, 4
+    r = subprocess.run([DEMO, str(n), str(steps), "0", "multi", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("multi n=")][0]
+    got = dict(kv.split("=", 1) for kv in line.split()[1:])
+    # fp32 summation order differs between the decompositions: 1e-5 of the box scale per step
+    assert float(got["max_pos_diff"]) <= 1e-5 * 10.0 * steps, line
+    assert float(got["max_out_diff"]) <= 1e-5 * 10.0 * steps, line
+    assert float(got["max_rho_rel"]) <= 1e-5 * steps, line
+    a, b = got["spawn_rho"].split("/")
+    assert a == b and float(a) > 0.0, line                      # densities valid before the first Update, same lattice
+    assert got["getters_ok"] == "1" and got["owned"] == str(n), line
+    per = [int(x) for x in got["per_device"].strip("[]").split(",")]
+    assert len(per) == 2 and min(per) > 0.3 * n, line
+    assert float(got["density_ms"]) > 0.0, line
