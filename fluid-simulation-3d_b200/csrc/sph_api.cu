@@ -241,7 +241,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
     ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 16);
     ALLOC(c->dens, cap * 32);
-    ALLOC(c->predpk, (cap + 8) * 16);
+    ALLOC(c->predpk, (cap + 8) * 16 + (size_t)kPairPad * 32);
     ALLOC(c->key_a, cap * 4);  ALLOC(c->key_b, cap * 4);
     ALLOC(c->perm_a, cap * 4); ALLOC(c->perm_b, cap * 4);
     ALLOC(c->ncount, cap * 4);

@@ -48,6 +48,9 @@ struct DevParams {
 // Position and per-pass payload of a neighbour sit in the same sector, so a neighbour costs one load
 // instruction and one line instead of two of each.
 struct __align__(32) Rec8 { float4 lo, hi; };
+// pair records of padding behind `predpk`: a density-pass warp may read this far past the last row's pair without
+// clamping its addresses (the slots are outside every window, so whatever they hold is rejected)
+constexpr uint32_t kPairPad = 2048;
 
 // Pair-interleaved predicted positions (`predpk`): rows 2m and 2m+1 share one 32-byte record
 //   lo = (x0, x1, y0, y1)   hi = (z0, z1, w0, w1)
