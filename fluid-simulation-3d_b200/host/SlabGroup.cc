@@ -27,19 +27,42 @@ size_t SlabGroup::fieldBytes(int field)
     }
 }
 
+void SlabGroup::workerLoop(int k)
+{
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int)>* job;
+        {
+            std::unique_lock<std::mutex> lock(mu_);
+            cvWork_.wait(lock, [&] { return quit_ || generation_ != seen; });
+            if (quit_) return;
+            seen = generation_;
+            job = job_;
+        }
+        std::string err;
+        try { (*job)(k); } catch (const std::exception& e) { err = e.what()[0] ? e.what() : "error"; } catch (...) { err = "unknown exception"; }
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            err_[(size_t)k] = err;
+            if (--pending_ == 0) cvDone_.notify_all();
+        }
+    }
+}
+
 void SlabGroup::parallel(const std::function<void(int)>& f)
 {
     const int R = ranks();
-    std::vector<std::string> err((size_t)R);
-    std::vector<std::thread> th;
-    th.reserve((size_t)R);
+    {
+        std::unique_lock<std::mutex> lock(mu_);
+        job_ = &f;
+        pending_ = R;
+        generation_++;
+        cvWork_.notify_all();
+        cvDone_.wait(lock, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
     for (int k = 0; k < R; k++)
-        th.emplace_back([&, k] {
-            try { f(k); } catch (const std::exception& e) { err[(size_t)k] = e.what()[0] ? e.what() : "error"; }
-        });
-    for (auto& t : th) t.join();
-    for (int k = 0; k < R; k++)
-        if (!err[(size_t)k].empty()) throw std::runtime_error("rank " + std::to_string(k) + ": " + err[(size_t)k]);
+        if (!err_[(size_t)k].empty()) throw std::runtime_error("rank " + std::to_string(k) + ": " + err_[(size_t)k]);
 }
 
 SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const SphParams& params) : params_(params)
@@ -52,6 +75,14 @@ SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const 
     const uint64_t all = (uint64_t)particles + 4096;
     cap_ = (uint32_t)(R == 1 ? (particles ? particles : 1) : (share < all ? share : all));
     rank_.resize(R);
+    err_.resize(R);
+    for (size_t k = 0; k < R; k++) workers_.emplace_back(&SlabGroup::workerLoop, this, (int)k);
+    auto stopWorkers = [&] {
+        { std::lock_guard<std::mutex> lock(mu_); quit_ = true; }
+        cvWork_.notify_all();
+        for (auto& t : workers_) t.join();
+        workers_.clear();
+    };
     try {
         for (size_t k = 0; k < R; k++) {
             rank_[k].device = devices[k];
@@ -67,6 +98,7 @@ SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const 
         // ncclCommInitRank blocks until every rank has joined: one thread per rank
         parallel([&](int k) { check(rank_[(size_t)k].ctx, sph_comm_init(rank_[(size_t)k].ctx, k, (int)R, id.data(), id.size()), "sph_comm_init"); });
     } catch (...) {
+        stopWorkers();
         for (auto& r : rank_) if (r.ctx) sph_destroy(r.ctx);
         throw;
     }
@@ -76,6 +108,9 @@ SlabGroup::~SlabGroup()
 {
     // communicators are torn down together (ncclCommDestroy may wait for the peers)
     try { parallel([&](int k) { if (rank_[(size_t)k].ctx) sph_destroy(rank_[(size_t)k].ctx); }); } catch (...) {}
+    { std::lock_guard<std::mutex> lock(mu_); quit_ = true; }
+    cvWork_.notify_all();
+    for (auto& t : workers_) t.join();
 }
 
 void SlabGroup::setParams(const SphParams& p)

@@ -8,9 +8,12 @@
 // when setDevices() names more than one GPU.  Pure host C++ on top of the C ABI, like the rest of host/.
 #pragma once
 
+#include <condition_variable>
 #include <cstdint>
 #include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sph_b200.h"
@@ -49,7 +52,18 @@ private:
         std::vector<unsigned char> buf;     // scratch: field rows
         std::vector<float> pos, vel;
     };
-    void parallel(const std::function<void(int)>& f);             // f(rank) on one thread per rank; rethrows the first error
+    // f(rank) on every rank's own worker thread at once; returns when all are done and rethrows the first error.
+    // The workers live as long as the group (a step is a few hundred microseconds: no thread start per call).
+    void parallel(const std::function<void(int)>& f);
+    void workerLoop(int k);
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cvWork_, cvDone_;
+    const std::function<void(int)>* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool quit_ = false;
+    std::vector<std::string> err_;
     static void check(SphContext* c, int rc, const char* what);
     static size_t fieldBytes(int field);
     std::vector<Rank> rank_;
