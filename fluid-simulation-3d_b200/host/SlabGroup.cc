@@ -92,6 +92,11 @@ SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const 
                 throw std::runtime_error(std::string("sph_create on device ") + std::to_string(devices[k]) + ": " + (msg ? msg : "?"));
             }
             check(rank_[k].ctx, sph_set_params(rank_[k].ctx, &params_), "sph_set_params");
+            // download scratch, page-locked once (a pageable D2H copy runs at a tenth of the PCIe rate)
+            rank_[k].ids.resize(cap_);
+            rank_[k].buf.resize((size_t)cap_ * 16);
+            sph_host_register(rank_[k].ids.data(), rank_[k].ids.size() * 4);
+            sph_host_register(rank_[k].buf.data(), rank_[k].buf.size());
         }
         std::vector<unsigned char> id(sph_comm_id_bytes());
         check(nullptr, sph_comm_get_id(id.data(), id.size()), "sph_comm_get_id");
@@ -99,7 +104,11 @@ SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const 
         parallel([&](int k) { check(rank_[(size_t)k].ctx, sph_comm_init(rank_[(size_t)k].ctx, k, (int)R, id.data(), id.size()), "sph_comm_init"); });
     } catch (...) {
         stopWorkers();
-        for (auto& r : rank_) if (r.ctx) sph_destroy(r.ctx);
+        for (auto& r : rank_) {
+            if (!r.ids.empty()) sph_host_unregister(r.ids.data());
+            if (!r.buf.empty()) sph_host_unregister(r.buf.data());
+            if (r.ctx) sph_destroy(r.ctx);
+        }
         throw;
     }
 }
@@ -107,6 +116,10 @@ SlabGroup::SlabGroup(const std::vector<int>& devices, uint32_t particles, const 
 SlabGroup::~SlabGroup()
 {
     // communicators are torn down together (ncclCommDestroy may wait for the peers)
+    for (auto& r : rank_) {
+        if (!r.ids.empty()) sph_host_unregister(r.ids.data());
+        if (!r.buf.empty()) sph_host_unregister(r.buf.data());
+    }
     try { parallel([&](int k) { if (rank_[(size_t)k].ctx) sph_destroy(rank_[(size_t)k].ctx); }); } catch (...) {}
     { std::lock_guard<std::mutex> lock(mu_); quit_ = true; }
     cvWork_.notify_all();
@@ -145,22 +158,23 @@ void SlabGroup::upload(uint32_t n, const float* pos3, const float* vel3)
     std::vector<int> owner_of_layer((size_t)gz);
     for (int k = 0; k < R; k++)
         for (int l = L[(size_t)k]; l < L[(size_t)k + 1]; l++) owner_of_layer[(size_t)l] = k;
-    for (auto& rk : rank_) { rk.ids.clear(); rk.pos.clear(); rk.vel.clear(); }
+    for (auto& rk : rank_) { rk.upIds.clear(); rk.pos.clear(); rk.vel.clear(); rk.idsFresh = false; }
     for (uint32_t i = 0; i < n; i++) {
         Rank& rk = rank_[(size_t)owner_of_layer[(size_t)layer[i]]];
-        rk.ids.push_back(i);
+        rk.upIds.push_back(i);
         rk.pos.insert(rk.pos.end(), pos3 + 3 * (size_t)i, pos3 + 3 * (size_t)i + 3);
         if (vel3) rk.vel.insert(rk.vel.end(), vel3 + 3 * (size_t)i, vel3 + 3 * (size_t)i + 3);
     }
     for (int k = 0; k < R; k++)
-        if (rank_[(size_t)k].ids.size() > cap_)
+        if (rank_[(size_t)k].upIds.size() > cap_)
             throw std::runtime_error("SlabGroup::upload: rank " + std::to_string(k) + " would own " +
-                                     std::to_string(rank_[(size_t)k].ids.size()) + " particles, capacity " + std::to_string(cap_));
+                                     std::to_string(rank_[(size_t)k].upIds.size()) + " particles, capacity " + std::to_string(cap_));
     parallel([&](int k) {
         Rank& rk = rank_[(size_t)k];
         check(rk.ctx, sph_comm_set_planes(rk.ctx, planes.data()), "sph_comm_set_planes");
-        check(rk.ctx, sph_upload_owned(rk.ctx, (uint32_t)rk.ids.size(), rk.ids.data(), rk.pos.data(), vel3 ? rk.vel.data() : nullptr),
+        check(rk.ctx, sph_upload_owned(rk.ctx, (uint32_t)rk.upIds.size(), rk.upIds.data(), rk.pos.data(), vel3 ? rk.vel.data() : nullptr),
               "sph_upload_owned");
+        std::vector<uint32_t>().swap(rk.upIds);
         std::vector<float>().swap(rk.pos);
         std::vector<float>().swap(rk.vel);
     });
@@ -171,6 +185,7 @@ void SlabGroup::step(float dt, uint32_t nsteps)
 {
     parallel([&](int k) {
         SphContext* c = rank_[(size_t)k].ctx;
+        rank_[(size_t)k].idsFresh = false;               // the step re-sorts the rows and may migrate some
         if (nsteps <= 1) check(c, sph_step(c, dt), "sph_step");
         else check(c, sph_step_n(c, dt, nsteps), "sph_step_n");
     });
@@ -196,17 +211,38 @@ void SlabGroup::download(int field, void* out, size_t out_bytes)
     parallel([&](int k) {
         Rank& rk = rank_[(size_t)k];
         const uint32_t m = sph_num_particles(rk.ctx);
-        rk.ids.resize(m);
-        rk.buf.resize((size_t)m * per);
+        if (m > cap_) throw std::runtime_error("sph_num_particles exceeds the rank's capacity");
         uint32_t cnt = 0;
-        check(rk.ctx, sph_download_owned(rk.ctx, field, rk.ids.data(), rk.buf.data(), rk.buf.size(), &cnt), "sph_download_owned");
-        if (cnt != m) throw std::runtime_error("sph_download_owned: row count changed under the download");
-        // scatter by particle index (ranks own disjoint indices, so the threads never write the same element)
-        const unsigned char* src = rk.buf.data();
-        for (uint32_t i = 0; i < m; i++) {
-            const uint32_t id = rk.ids[i];
-            if (id >= n_) throw std::runtime_error("sph_download_owned: particle id out of range");
-            memcpy(dst + (size_t)id * per, src + (size_t)i * per, per);
+        // the ids travel once per state, every field after that is one export + one copy
+        check(rk.ctx, sph_download_owned(rk.ctx, field, rk.idsFresh ? nullptr : rk.ids.data(), rk.buf.data(), (size_t)m * per, &cnt),
+              "sph_download_owned");
+        if (cnt != m || (rk.idsFresh && rk.owned != m)) throw std::runtime_error("sph_download_owned: row count changed under the download");
+        if (!rk.idsFresh) {
+            for (uint32_t i = 0; i < m; i++)
+                if (rk.ids[i] >= n_) throw std::runtime_error("sph_download_owned: particle id out of range");
+            rk.owned = m;
+            rk.idsFresh = true;
+        }
+        // scatter by particle index (the ranks own disjoint indices, so the threads never write the same element)
+        const uint32_t* ids = rk.ids.data();
+        if (per == 16) {
+            struct R16 { uint64_t a, b; };
+            const R16* src = reinterpret_cast<const R16*>(rk.buf.data());
+            R16* o = reinterpret_cast<R16*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else if (per == 12) {
+            struct R12 { uint32_t a, b, c; };
+            const R12* src = reinterpret_cast<const R12*>(rk.buf.data());
+            R12* o = reinterpret_cast<R12*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else if (per == 8) {
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(rk.buf.data());
+            uint64_t* o = reinterpret_cast<uint64_t*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rk.buf.data());
+            uint32_t* o = reinterpret_cast<uint32_t*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
         }
         got[(size_t)k] = m;
     });

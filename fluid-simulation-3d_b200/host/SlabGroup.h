@@ -48,8 +48,11 @@ private:
     struct Rank {
         SphContext* ctx = nullptr;
         int device = 0;
-        std::vector<uint32_t> ids;          // scratch: ids of the rows of the last download / the pending upload
-        std::vector<unsigned char> buf;     // scratch: field rows
+        std::vector<uint32_t> ids;          // ids of the owned rows, device order (page-locked; fetched once per state)
+        std::vector<unsigned char> buf;     // field rows of the current download (page-locked)
+        uint32_t owned = 0;                 // rows behind `ids`
+        bool idsFresh = false;
+        std::vector<uint32_t> upIds;        // scratch of upload()
         std::vector<float> pos, vel;
     };
     // f(rank) on every rank's own worker thread at once; returns when all are done and rethrows the first error.

@@ -127,8 +127,9 @@ static int run_multi(int n, int steps, int ndev)
     sim.InitializeData(n);
     const float rho_spawn = sim.getDensity((uint32)n / 2u);
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t1 = 0.0, tn = 0.0;                            // wall time of the Updates after the first (mirrors included)
-    for (int s = 0; s < steps; s++) { const double a = now(); sim.Update(0.016667f); if (s) t1 += now() - a; }
+    double t1 = 0.0, tn = 0.0;                            // wall time of the Updates after the warm-up ones (mirrors included)
+    const int skip = steps > 6 ? 3 : 1;                   // (the first re-balance sets up NCCL's all-reduce: a one-off of tens of ms)
+    for (int s = 0; s < steps; s++) { const double a = now(); sim.Update(0.016667f); if (s >= skip) t1 += now() - a; }
     const auto pos1 = sim.positions;
     const auto out1 = sim.OutPositions;
     std::vector<float> rho1;
@@ -139,7 +140,7 @@ static int run_multi(int n, int steps, int ndev)
     sim.setRebalanceInterval(2);
     sim.InitializeData(n);                               // the reset path: same lattice, now handed to the slabs
     const float rho_spawn_multi = sim.getDensity((uint32)n / 2u);      // valid before the first Update, like the reference
-    for (int s = 0; s < steps; s++) { const double a = now(); sim.Update(0.016667f); if (s) tn += now() - a; }
+    for (int s = 0; s < steps; s++) { const double a = now(); sim.Update(0.016667f); if (s >= skip) tn += now() - a; }
     double dpos = 0.0, dout = 0.0, drho = 0.0;
     for (int i = 0; i < n; i++) {
         dpos = std::fmax(dpos, std::fmax(std::fabs((double)sim.positions[i].x - pos1[i].x),
@@ -163,7 +164,7 @@ static int run_multi(int n, int steps, int ndev)
     for (uint32 c : sim.particlesPerDevice()) { owned += c; per += (per.empty() ? "" : ",") + std::to_string(c); }
     printf("multi n=%d ndev=%d steps=%d max_pos_diff=%.3g max_out_diff=%.3g max_rho_rel=%.3g spawn_rho=%.6f/%.6f getters_ok=%d owned=%llu per_device=[%s] density_ms=%.4f update_ms_1gpu=%.3f update_ms_ngpu=%.3f\n",
            n, ndev, steps, dpos, dout, drho, rho_spawn, rho_spawn_multi, getters_ok, owned, per.c_str(), sim.getElapsedTimeDensity(),
-           steps > 1 ? t1 / (steps - 1) : 0.0, steps > 1 ? tn / (steps - 1) : 0.0);
+           steps > skip ? t1 / (steps - skip) : 0.0, steps > skip ? tn / (steps - skip) : 0.0);
     sim.shutdown();
     return 0;
 }
