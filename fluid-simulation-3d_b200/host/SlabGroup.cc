@@ -223,46 +223,27 @@ void SlabGroup::download(int field, void* out, size_t out_bytes)
             rk.owned = m;
             rk.idsFresh = true;
         }
-        // scatter by particle index (the ranks own disjoint indices, so no two threads ever write the same element);
-        // big slabs split their rows over a share of the host's cores -- the random 4..16-byte writes, ~3 ns each on
-        // one thread, are what a multi-GPU Update() spends most of its time on
+        // scatter by particle index (the ranks own disjoint indices, so the threads never write the same element)
         const uint32_t* ids = rk.ids.data();
-        const unsigned char* srcb = rk.buf.data();
-        auto scatter = [=](uint32_t lo, uint32_t hi) {
-            if (per == 16) {
-                struct R16 { uint64_t a, b; };
-                const R16* src = reinterpret_cast<const R16*>(srcb);
-                R16* o = reinterpret_cast<R16*>(dst);
-                for (uint32_t i = lo; i < hi; i++) o[ids[i]] = src[i];
-            } else if (per == 12) {
-                struct R12 { uint32_t a, b, c; };
-                const R12* src = reinterpret_cast<const R12*>(srcb);
-                R12* o = reinterpret_cast<R12*>(dst);
-                for (uint32_t i = lo; i < hi; i++) o[ids[i]] = src[i];
-            } else if (per == 8) {
-                const uint64_t* src = reinterpret_cast<const uint64_t*>(srcb);
-                uint64_t* o = reinterpret_cast<uint64_t*>(dst);
-                for (uint32_t i = lo; i < hi; i++) o[ids[i]] = src[i];
-            } else {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(srcb);
-                uint32_t* o = reinterpret_cast<uint32_t*>(dst);
-                for (uint32_t i = lo; i < hi; i++) o[ids[i]] = src[i];
-            }
-        };
-        unsigned helpers = 0;
-        if (m >= 131072u) {
-            const unsigned hw = std::thread::hardware_concurrency();
-            const unsigned share = hw / (unsigned)ranks();
-            helpers = share > 1 ? (share > 8 ? 7 : share - 1) : 0;
+        if (per == 16) {
+            struct R16 { uint64_t a, b; };
+            const R16* src = reinterpret_cast<const R16*>(rk.buf.data());
+            R16* o = reinterpret_cast<R16*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else if (per == 12) {
+            struct R12 { uint32_t a, b, c; };
+            const R12* src = reinterpret_cast<const R12*>(rk.buf.data());
+            R12* o = reinterpret_cast<R12*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else if (per == 8) {
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(rk.buf.data());
+            uint64_t* o = reinterpret_cast<uint64_t*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
+        } else {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rk.buf.data());
+            uint32_t* o = reinterpret_cast<uint32_t*>(dst);
+            for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
         }
-        const uint32_t chunk = (m + helpers) / (helpers + 1);
-        std::vector<std::thread> extra;
-        for (unsigned t = 0; t < helpers; t++) {
-            const uint32_t lo = (t + 1) * chunk, hi = lo + chunk < m ? lo + chunk : m;
-            if (lo < hi) extra.emplace_back(scatter, lo, hi);
-        }
-        scatter(0, chunk < m ? chunk : m);
-        for (auto& t : extra) t.join();
         got[(size_t)k] = m;
     });
     uint64_t total = 0;
