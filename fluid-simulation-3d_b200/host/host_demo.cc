@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 #include "FluidSimB200.h"
+#include "SlabGroup.h"
 
 static unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 0xcbf29ce484222325ull)
 {
@@ -181,6 +182,15 @@ int main(int argc, char** argv)
         if (!strcmp(what, "getters")) return run_getters(n, steps, mode);
         if (!strcmp(what, "substeps")) return run_substeps(n, steps, mode);
         if (!strcmp(what, "multi")) return run_multi(n, steps, argc > 5 ? atoi(argv[5]) : 2);
+        if (!strcmp(what, "slabgroup")) {              // the group on its own: construction (and its failure path), nothing else
+            SphParams p;
+            sph_default_params(&p);
+            std::vector<int> devs;
+            for (int d = 0; d < (argc > 5 ? atoi(argv[5]) : 2); d++) devs.push_back(d);
+            sphb200::SlabGroup group(devs, (uint32_t)n, p);
+            printf("slabgroup ranks=%d\n", group.ranks());
+            return 0;
+        }
         sim.setTableMode(mode);
         sim.setGravity(true);
         sim.setHostMirrors(true, true);

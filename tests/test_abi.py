@@ -100,6 +100,8 @@ def test_host_driver_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
-    for what in ("class", "adapter"):
+    for what in ("class", "adapter", "multi", "slabgroup"):
+        # ("slabgroup" constructs the multi-GPU group directly: its worker threads must be stopped and joined on the
+        # failure path, or the process would terminate instead of reporting)
         r = subprocess.run([demo, "100", "1", "0", what], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
         assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout
