@@ -10,6 +10,26 @@ import __graft_entry__ as g
 REL = 1e-5
 
 
+def coincident_scene(seed=17):
+    """Particles that share an exact position: pairs and triples inside the fluid (equal velocities, so their
+    predicted positions coincide too), a few stacked in a wall corner the way the box clamp leaves them, and a small
+    cloud around them.  dist == 0 takes the reference's direction fallback (0, 1, 0) in the pressure pass
+    (physicsWorld.cc:414) and the full kernel weights everywhere else."""
+    rng = np.random.default_rng(seed)
+    bound = (3.0, 3.0, 3.0)
+    cloud = ((rng.random((90, 3)) - 0.5) * 1.4).astype(np.float32)
+    cvel = ((rng.random((90, 3)) - 0.5) * 2.0).astype(np.float32)
+    pos, vel = [cloud], [cvel]
+    for k in range(6):                                   # pairs and triples at the position (and velocity) of a cloud particle
+        reps = 1 + k % 2 + 1
+        pos.append(np.repeat(cloud[k:k + 1], reps, axis=0)); vel.append(np.repeat(cvel[k:k + 1], reps, axis=0))
+    corner = np.array([[-1.5, -1.5, 1.5]], np.float32)   # exactly on three walls: what the clamp writes (:88-106)
+    pos.append(np.repeat(corner, 4, axis=0)); vel.append(np.zeros((4, 3), np.float32))
+    pos.append(np.array([[0.4, -1.5, 0.2]] * 3, np.float32)); vel.append(np.array([[0.3, 0.0, -0.2]] * 3, np.float32))
+    pos = np.ascontiguousarray(np.concatenate(pos)); vel = np.ascontiguousarray(np.concatenate(vel))
+    return dict(pos=pos, vel=vel, n=len(pos), params=dict(gravity=1, viscosity_strength=0.6, bound=bound))
+
+
 def oracle_pair(n, params):
     """(value oracle, scale oracle).  Values come from the UNMODIFIED reference when oracle/_ref is
     built, else from the C restatement; the term scales always come from the restatement."""

@@ -186,6 +186,29 @@ def test_live_reference_vs_port_default_scene(ob):
 
 
 @needs_ref
+def test_live_reference_vs_port_coincident_particles(ob):
+    """dist == 0 (stacked particles): the restatement follows the unmodified reference bit for bit through the
+    (0, 1, 0) direction fallback (physicsWorld.cc:414) -- two steps, the second from the state the first one leaves"""
+    from helpers import coincident_scene
+    sc = coincident_scene()
+    dt = float(np.float32(0.016667))
+    r = ob.RefOracle(sc["n"], **sc["params"])
+    p = ob.PortOracle(sc["n"], **sc["params"])
+    r.set_state(sc["pos"], sc["vel"]); p.set_state(sc["pos"], sc["vel"])
+    pred0 = sc["pos"] + sc["vel"] * np.float32(1.0 / 120.0)
+    assert len(np.unique(pred0, axis=0)) < sc["n"] - 8            # the scene really stacks particles
+    for _ in range(2):
+        r.update(dt)
+        idx, _, _ = r.sorted_lookup()
+        p.stage_predict(dt); p.stage_spatial(forced_order=idx); p.stage_density(); p.stage_pressure(dt)
+        p.stage_viscosity(dt, jacobi=False); p.stage_integrate(dt)
+        assert np.all(np.isfinite(r.positions())) and np.all(np.isfinite(r.velocities()))
+        assert np.array_equal(bits(p.positions()), bits(r.positions()))
+        assert np.array_equal(bits(p.velocities()), bits(r.velocities()))
+        assert np.array_equal(bits(p.densities()), bits(r.densities()))
+
+
+@needs_ref
 def test_live_reference_getters_bounds(ob):
     r = ob.RefOracle(64, spawn=True)
     assert np.all(r.getter_probe(64) == 0) and np.all(r.getter_probe(2 ** 31) == 0)      # OOB -> zeros

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import __graft_entry__ as g
-from helpers import check_step
+from helpers import check_step, coincident_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -78,3 +78,14 @@ def test_tiny_and_odd_counts(pkg, scenes, mode, n):
     vel = ((rng.random((n, 3)) - 0.5) * 2.0).astype(np.float32)
     sc = dict(pos=pos, vel=vel, n=n, params=dict(gravity=1, viscosity_strength=0.5, bound=bound))
     check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_coincident_particles(pkg, scenes, mode):
+    """Particles at exactly the same (predicted) position -- stacked in a wall corner by the box clamp, or spawned on
+    top of each other: d == 0 passes every cull, takes the (0, 1, 0) direction fallback of the pressure pass
+    (physicsWorld.cc:414) and the peak kernel weights; the pair records, the band re-test and the list replay must
+    treat it like the reference."""
+    sc = coincident_scene()
+    out = check_step(pkg, sc, _mode(pkg, mode), scenes.DT)
+    assert out["mean_neighbours"] > 2
