@@ -130,6 +130,19 @@ def test_negative_cell_hash_wraps(ob):
     assert np.array_equal(k, (want_h % 4).astype(np.uint32))
 
 
+def test_q13_two_of_the_27_cells_never_share_a_float_hash():
+    """the reference would walk a bucket twice (and double-count its particles) if two of the 27
+    queried cells agreed in key AND in float(hash).  They cannot: the hashes of two cells of one 3x3x3 block differ by
+    at least 15823 (mod 2^32), and a u32 rounded to fp32 moves by at most 128 -- so the GRID table's exact cell walk
+    and the reference's bucket walk always visit the same particles."""
+    smallest = min(min(d, 2 ** 32 - d)
+                   for a in range(-2, 3) for b in range(-2, 3) for c in range(-2, 3) if (a, b, c) != (0, 0, 0)
+                   for d in [(a * 15823 + b * 9737333 + c * 440817757) % 2 ** 32])
+    assert smallest == 15823
+    worst_rounding = max(abs(int(np.float32(h)) - h) for h in (2 ** 32 - 129, 2 ** 31 + 128, 2 ** 31 - 65, 3000000001))
+    assert worst_rounding <= 128 and 2 * worst_rounding < smallest
+
+
 def test_empty_and_single_particle(ob):
     o = ob.PortOracle(1)
     o.set_state(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32))
