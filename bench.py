@@ -198,6 +198,29 @@ def cpu_reference_c1(steps, warmup):
                           else "C restatement, 1 thread"))
 
 
+def workload_text(name, n, bound, mu):
+    """the `config.workload` string of a single-GPU run; the reference arm names its workload with the same words"""
+    return (("%s: %d particles, the reference's InitializeData lattice (gap 0.215, centred), bounds %s, "
+             "r=0.35, gravity on, mu=%.2f, dt=0.016667" if name == C1_NAME else
+             "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
+             "r=0.35, gravity on, mu=%.2f, dt=0.016667") % (name, n, tuple(round(float(x), 3) for x in bound), mu))
+
+
+def reference_arm_workload(name, gpus):
+    """(workload text, full particle count) of the configuration the other arm runs, without generating it"""
+    graft.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    if name == C1_NAME:
+        return workload_text(name, 10000, (20.0, 20.0, 20.0), 0.5), 10000
+    if name in scenes.CONFIGS:
+        nx, ny, nz, _ = scenes.CONFIGS[name]
+        n = nx * ny * nz
+        if gpus > 1:
+            return "%s: %d particles, slab-decomposed along z over %d ranks" % (name, n, gpus), n
+        return workload_text(name, n, (3 * nx * scenes.GAP0, 1.5 * ny * scenes.GAP0, nz * scenes.GAP0 + scenes.GAP0), 0.5), n
+    return name, None
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -205,10 +228,12 @@ def run_reference_arm(args, rank):
     if args.config:
         name = args.config
     r = cpu_reference_c1(args.steps, args.warmup) if name == C1_NAME else cpu_reference_run(name, args.steps, args.warmup, budget_s=120.0)
+    text, n_full = reference_arm_workload(name, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "M updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "sample_particles": r["n"]},
+            "config": {"workload": text, "particles": n_full, "sample_particles": r["n"],
+                       "note": "the reference CPU step on a bounded sample of this workload (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
                              "sample": r["sample"], "host_cores": os.cpu_count()},
             "e2e": {"value": r["value"], "unit": "M updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -445,11 +470,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("%s: %d particles, the reference's InitializeData lattice (gap 0.215, centred), bounds %s, "
-                                "r=0.35, gravity on, mu=%.2f, dt=0.016667" if name == C1_NAME else
-                                "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
-                                "r=0.35, gravity on, mu=%.2f, dt=0.016667") % (name, n, tuple(round(x, 3) for x in sc["bound"]),
-                                                                           sc["params"].get("viscosity_strength", 0.5)),
+        "config": {"workload": workload_text(name, n, sc["bound"], sc["params"].get("viscosity_strength", 0.5)),
                    "particles": n, "table": args.table,
                    "l2": "flushed between timed steps (256 MiB fill outside the event pairs)" if flush is not None
                          else "not flushed"},
