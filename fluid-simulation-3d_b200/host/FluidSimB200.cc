@@ -1,4 +1,7 @@
 // host/FluidSimB200.cc -- see FluidSimB200.h.
+#ifdef SPH_B200_USE_GLM
+#include "config.h"                      // inside the reference tree: its prelude first, as fluidSimCPU.cc:1 does
+#endif
 #include "FluidSimB200.h"
 
 using Physics::Fluid::FluidSimulation;

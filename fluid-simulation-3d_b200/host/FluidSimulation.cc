@@ -1,5 +1,8 @@
 // host/FluidSimulation.cc -- see FluidSimulation.h.  Pure host C++: talks to the GPU only through
 // the C ABI of libsph_b200.so.
+#ifdef SPH_B200_USE_GLM
+#include "config.h"                      // inside the reference tree: its prelude first, as physicsWorld.cc:18 does (glm, uint32)
+#endif
 #include "FluidSimulation.h"
 #include "SlabGroup.h"
 
