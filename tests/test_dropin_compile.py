@@ -103,3 +103,29 @@ def test_fluidsimbase_backend_compiles_against_the_reference_headers():
            "-I", HOST, "-I", os.path.join(ROOT, "include"), os.path.join(HOST, "FluidSimB200.cc")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "engine")), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("caller", ["projects/Simulation/code/simulations/fluidSimCPU.cc", "projects/Simulation/code/gameApp.cc"])
+def test_the_reference_callers_compile_unmodified_against_the_host_class(tmp_path, caller):
+    """The two translation units of the reference that use the solver class -- the CPU adapter and the application with
+    its ImGui panels -- compiled where they lie, UNMODIFIED, with `physics/physicsWorld.h` resolved to a one-line header
+    that includes host/FluidSimulation.h (what INTEGRATION.md section 1 tells a maintainer to do).  Syntax and types
+    only: linking them needs the application's render library, GLFW and an OpenGL context."""
+    shim = tmp_path / "physics"
+    shim.mkdir()
+    (shim / "physicsWorld.h").write_text('#include "FluidSimulation.h"\n')
+    cmd = ["g++", "-std=c++20", "-fsyntax-only", "-w", "-DGLM_ENABLE_EXPERIMENTAL", "-DGLEW_NO_GLU", "-DGLFW_INCLUDE_NONE",
+           "-DSPH_B200_USE_GLM", "-DSPH_B200_HAVE_UINT32",
+           "-I", str(tmp_path),                                   # wins over engine/physics/physicsWorld.h
+           "-I", os.path.join(REF, "engine"), "-I", os.path.join(REF, "exts", "glm"), "-I", os.path.join(REF, "exts", "glm", "glm"),
+           "-I", os.path.join(REF, "exts", "glew", "include"), "-I", os.path.join(REF, "exts", "glfw", "include"),
+           "-I", os.path.join(REF, "exts", "imgui"), "-I", os.path.join(REF, "projects", "Simulation", "code"),
+           "-I", os.path.join(REF, "projects", "Simulation", "code", "simulations"),
+           "-I", HOST, "-I", os.path.join(ROOT, "include"), os.path.join(REF, caller)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:]
+    # and the shim really was the header in use: with the class hidden the same command must fail
+    (shim / "physicsWorld.h").write_text("namespace Physics { namespace Fluid { } }\n")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode != 0 and "FluidSimulation" in r.stdout
