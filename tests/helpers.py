@@ -139,3 +139,50 @@ def check_step(pkg, scene, mode, dt, report=None):
         return out
     finally:
         sim.close()
+
+
+def golden_params(gold):
+    p = gold["params"]
+    return dict(interaction_radius=p[0], target_density=p[1], pressure_multiplier=p[2], near_pressure_multiplier=p[3],
+                viscosity_strength=p[4], gravity_scale=p[5], gravity=int(p[6]), bound=tuple(p[7:10]))
+
+
+def golden_scales(gold):
+    """cancellation-free term scales of the fixture's step (from the restatement, which test_oracle.py pins to the
+    fixture bit for bit)"""
+    ob = g.load_oracle()
+    n, dt = gold["pos0"].shape[0], float(gold["dt"])
+    port = ob.PortOracle(n, **golden_params(gold))
+    port.set_state(gold["pos0"], gold["vel0"])
+    port.step(dt, jacobi=True)
+    return port.force_scales(dt)
+
+
+def compare_to_golden(get, gold, reference_table):
+    """One step's outputs against a committed fixture of the UNMODIFIED reference (tests/golden/*.npz, made by
+    make_golden.py): integers bit-exact, floats within REL of the stage scale.  `get(name)` returns the implementation's
+    array: predicted, hash, key, neighbour_count, densities, vel_after_pressure, vel_after_viscosity, positions,
+    velocities, out_positions and -- with the reference's table (`reference_table`) -- sorted_key, sorted_index,
+    start_indices."""
+    dt = float(gold["dt"])
+    ps, vs = golden_scales(gold)
+    assert np.array_equal(np.asarray(get("predicted")).view(np.uint32), gold["pred"].view(np.uint32)), "predicted positions not bit-exact"
+    assert np.array_equal(get("hash"), gold["hash"]), "hash"
+    assert np.array_equal(get("key"), gold["key"]), "key"
+    assert np.array_equal(get("neighbour_count"), gold["ncount"]), "neighbour counts"
+    if reference_table:
+        s_key, s_idx = get("sorted_key"), get("sorted_index")
+        assert np.array_equal(s_key, gold["sorted_key"]), "sorted key sequence"
+        assert np.array_equal(get("start_indices"), gold["start"]), "start table"
+        assert np.array_equal(canonical_order(s_idx, s_key), canonical_order(gold["sorted_idx"], gold["sorted_key"])), "sorted order (canonical ties)"
+    out = {}
+    out["density"] = assert_close("density", get("densities"), gold["dens"], 0.0)
+    out["vel_after_pressure"] = assert_close("vel_after_pressure", get("vel_after_pressure"), gold["vel_press"], ps[:, None])
+    out["vel_after_viscosity"] = assert_close("vel_after_viscosity", get("vel_after_viscosity"), gold["vel_visc"], (ps + vs)[:, None])
+    speed = np.abs(gold["vel_visc"]).max(axis=1, keepdims=True)
+    out["positions"] = assert_close("positions", get("positions"), gold["pos1"], speed * dt + (ps + vs)[:, None] * dt)
+    out["velocities"] = assert_close("velocities", get("velocities"), gold["vel1"], (ps + vs)[:, None])
+    o4 = np.asarray(get("out_positions"))
+    out["out_positions"] = assert_close("out_positions", o4[:, :3], gold["out1"][:, :3], speed * dt + (ps + vs)[:, None] * dt)
+    assert np.all(o4[:, 3] == np.float32(0.34)) and np.all(gold["out1"][:, 3] == np.float32(0.34))
+    return out

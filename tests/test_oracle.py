@@ -76,6 +76,28 @@ def test_port_own_sort_is_canonical_and_close(ob, path):
     assert np.allclose(o.positions(), gold["pos1"], rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_fixture_comparison_used_by_the_gpu_tests(ob, path):
+    """helpers.compare_to_golden is what tests/test_parity_gpu.py holds the CUDA step against; here the restatement
+    (own sort, own summation order) goes through it, so the comparison code itself is exercised without a GPU"""
+    from helpers import compare_to_golden, golden_params
+    gold = np.load(path)
+    o = ob.PortOracle(gold["pos0"].shape[0], **golden_params(gold))
+    o.set_state(gold["pos0"], gold["vel0"])
+    o.step(float(gold["dt"]), jacobi=True)
+    h, k, _ = o.hash_key()
+    si, _, sk = o.sorted_lookup()
+    got = dict(predicted=o.predicted(), hash=h, key=k, neighbour_count=o.neighbour_counts(), sorted_key=sk, sorted_index=si,
+               start_indices=o.start_indices(), densities=o.densities(), vel_after_pressure=o.vel_after_pressure(),
+               vel_after_viscosity=o.vel_after_viscosity(), positions=o.positions(), velocities=o.velocities(),
+               out_positions=o.out_positions())
+    worst = compare_to_golden(got.__getitem__, gold, reference_table=True)
+    assert max(worst.values()) <= 1e-5
+    bad = dict(got, densities=got["densities"] * np.float32(1.0001))            # and it does notice a 1e-4 error
+    with pytest.raises(AssertionError):
+        compare_to_golden(bad.__getitem__, gold, reference_table=True)
+
+
 def test_port_in_place_viscosity_matches_verbatim_update(ob):
     """Gauss-Seidel (index-order, in-place) viscosity of the port == the reference's verbatim Update()."""
     gold = np.load(os.path.join(HERE, "golden", "dambreak_12.npz"))
