@@ -369,6 +369,7 @@ int multi_step(SphContext* c, float dt)
     if (!s || !c->comm) return fail(c, SPH_ERR_INVALID, "slab mode: call sph_comm_init first");
     if (!s->have_planes) return fail(c, SPH_ERR_INVALID, "slab mode: call sph_comm_set_planes first");
     SPH_CUDA(c, cudaSetDevice(c->device));
+    s->table_valid = false;                     // until this step has rebuilt it (sph_comm_rebalance reads it)
     ncclComm_t comm = (ncclComm_t)c->comm;
     cudaStream_t st = c->st;
     const uint32_t n_old = c->n;
