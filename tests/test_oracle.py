@@ -78,7 +78,7 @@ def test_port_own_sort_is_canonical_and_close(ob, path):
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_fixture_comparison_used_by_the_gpu_tests(ob, path):
-    """helpers.compare_to_golden is what tests/test_parity_gpu.py holds the CUDA step against; here the restatement
+    """helpers.compare_to_golden is what tests/test_zgolden_gpu.py holds the CUDA step against; here the restatement
     (own sort, own summation order) goes through it, so the comparison code itself is exercised without a GPU"""
     from helpers import compare_to_golden, golden_params
     gold = np.load(path)
