@@ -105,3 +105,51 @@ def test_host_driver_fails_loudly_without_gpu():
         # failure path, or the process would terminate instead of reporting)
         r = subprocess.run([demo, "100", "1", "0", what], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
         assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout
+
+
+def test_every_entry_point_survives_null_arguments(pkg):
+    """the reference's class cannot be misused through a null pointer; a C ABI can.  Every handle-taking entry point
+    returns an error status (or a benign value from the pure queries) for a NULL context and NULL buffers -- no compute,
+    no device needed"""
+    L = pkg.load_library()
+    P, B = pkg.SphParams(), pkg.SphBlockSpawn()
+    status = {          # must report an error
+        "sph_create": lambda: L.sph_create(None, 0, 10),
+        "sph_set_params": lambda: L.sph_set_params(None, C.byref(P)), "sph_get_params": lambda: L.sph_get_params(None, C.byref(P)),
+        "sph_set_table_mode": lambda: L.sph_set_table_mode(None, 0), "sph_set_stage_timing": lambda: L.sph_set_stage_timing(None, 1),
+        "sph_set_neighbour_count_tap": lambda: L.sph_set_neighbour_count_tap(None, 1),
+        "sph_set_neighbour_list_capacity": lambda: L.sph_set_neighbour_list_capacity(None, 8),
+        "sph_spawn_grid": lambda: L.sph_spawn_grid(None, 10), "sph_spawn_block": lambda: L.sph_spawn_block(None, C.byref(B)),
+        "sph_upload_state": lambda: L.sph_upload_state(None, 0, None, None), "sph_step": lambda: L.sph_step(None, 0.01),
+        "sph_step_n": lambda: L.sph_step_n(None, 0.01, 3), "sph_synchronize": lambda: L.sph_synchronize(None),
+        "sph_refresh_densities": lambda: L.sph_refresh_densities(None), "sph_download": lambda: L.sph_download(None, 0, None, 0),
+        "sph_download_table": lambda: L.sph_download_table(None, 0, None, 0, None),
+        "sph_get_particle": lambda: L.sph_get_particle(None, 0, None), "sph_get_timings": lambda: L.sph_get_timings(None, None),
+        "sph_get_grid": lambda: L.sph_get_grid(None, None, None), "sph_save_state": lambda: L.sph_save_state(None, b"/tmp/none"),
+        "sph_load_state": lambda: L.sph_load_state(None, b"/tmp/none"), "sph_host_register": lambda: L.sph_host_register(None, 0),
+        "sph_host_unregister": lambda: L.sph_host_unregister(None),
+        "sph_upload_state_begin": lambda: L.sph_upload_state_begin(None, 0, None, None),
+        "sph_upload_state_commit": lambda: L.sph_upload_state_commit(None), "sph_download_begin": lambda: L.sph_download_begin(None, 0, None, 0),
+        "sph_download_wait": lambda: L.sph_download_wait(None), "sph_comm_get_id": lambda: L.sph_comm_get_id(None, 0),
+        "sph_comm_init": lambda: L.sph_comm_init(None, 0, 1, None, 0), "sph_comm_set_planes": lambda: L.sph_comm_set_planes(None, None),
+        "sph_upload_owned": lambda: L.sph_upload_owned(None, 0, None, None, None),
+        "sph_download_owned": lambda: L.sph_download_owned(None, 0, None, None, 0, None),
+        "sph_upload_owned_begin": lambda: L.sph_upload_owned_begin(None, 0, None, None, None),
+        "sph_download_owned_begin": lambda: L.sph_download_owned_begin(None, 0, None, None, 0, None),
+        "sph_comm_stats": lambda: L.sph_comm_stats(None, None), "sph_comm_get_layers": lambda: L.sph_comm_get_layers(None, None),
+        "sph_comm_rebalance": lambda: L.sph_comm_rebalance(None, 1, None, None, 0, None),
+        "sph_slab_balance_layers": lambda: L.sph_slab_balance_layers(None, 0, 0, None, 0, 0, None),
+    }
+    benign = {          # pure queries: a neutral answer
+        "sph_destroy": (lambda: L.sph_destroy(None), 0), "sph_get_table_mode": (lambda: L.sph_get_table_mode(None), -1),
+        "sph_num_particles": (lambda: L.sph_num_particles(None), 0), "sph_graph_replays": (lambda: L.sph_graph_replays(None), 0),
+        "sph_launch_count": (lambda: L.sph_launch_count(None), 0), "sph_stream": (lambda: L.sph_stream(None), None),
+        "sph_grid_x_subdivision": (lambda: L.sph_grid_x_subdivision(None), 0),
+    }
+    other = {"sph_default_params", "sph_last_error", "sph_abi_version", "sph_comm_id_bytes"}     # take no handle / checked elsewhere
+    assert set(status) | set(benign) | other == set(pkg.ABI_SYMBOLS)
+    for name, call in status.items():
+        assert call() != 0, name + " accepted NULL arguments"
+    for name, (call, want) in benign.items():
+        assert call() == want, name
+    assert L.sph_comm_id_bytes() >= 128 and isinstance(L.sph_last_error(None), bytes)
