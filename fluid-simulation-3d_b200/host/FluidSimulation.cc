@@ -84,6 +84,11 @@ namespace Physics
 			if (group) return group->ownedCounts();
 			return std::vector<uint32>(1, numParticles);
 		}
+		void FluidSimulation::multiGpuBreakdown(double out4[4])
+		{
+			for (int i = 0; i < 4; i++) out4[i] = 0.0;
+			if (group) { group->breakdown(out4); group->resetBreakdown(); }
+		}
 		void FluidSimulation::fetch(int field, void* out, size_t bytes, const char* what)
 		{
 			if (group) {

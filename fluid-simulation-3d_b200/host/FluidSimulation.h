@@ -95,6 +95,9 @@ namespace Physics
 			// Multi-GPU: move the slab planes towards the particle-count quantiles every N Updates (0 = never)
 			void setRebalanceInterval(uint32 everyNUpdates) { rebalanceEvery = everyNUpdates; }
 			std::vector<uint32> particlesPerDevice() const;
+			// Multi-GPU: host milliseconds since the last call, slowest slab per phase -- step, download (wait + export +
+			// copy), scatter into index order, re-balancing; zeros on one GPU
+			void multiGpuBreakdown(double out4[4]);
 			// Release every device resource now (the destructor does the same, but at static-destruction time the
 			// CUDA / NCCL runtimes may already be unloading): call before exit in multi-GPU programs.
 			void shutdown();

@@ -1,12 +1,18 @@
 // host/SlabGroup.cc -- see SlabGroup.h.  Pure host C++: talks to the GPUs only through the C ABI of libsph_b200.so.
 #include "SlabGroup.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
 
 namespace sphb200 {
+
+static double nowMs()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 void SlabGroup::check(SphContext* c, int rc, const char* what)
 {
@@ -186,8 +192,10 @@ void SlabGroup::step(float dt, uint32_t nsteps)
     parallel([&](int k) {
         SphContext* c = rank_[(size_t)k].ctx;
         rank_[(size_t)k].idsFresh = false;               // the step re-sorts the rows and may migrate some
+        const double t0 = nowMs();
         if (nsteps <= 1) check(c, sph_step(c, dt), "sph_step");
         else check(c, sph_step_n(c, dt, nsteps), "sph_step_n");
+        rank_[(size_t)k].ms[0] += nowMs() - t0;
     });
 }
 
@@ -196,7 +204,9 @@ bool SlabGroup::rebalance(uint32_t max_shift)
     std::vector<int> changed((size_t)ranks(), 0);
     parallel([&](int k) {
         SphContext* c = rank_[(size_t)k].ctx;
+        const double t0 = nowMs();
         check(c, sph_comm_rebalance(c, max_shift, nullptr, nullptr, 0, &changed[(size_t)k]), "sph_comm_rebalance");
+        rank_[(size_t)k].ms[3] += nowMs() - t0;
     });
     return changed[0] != 0;
 }
@@ -213,9 +223,12 @@ void SlabGroup::download(int field, void* out, size_t out_bytes)
         const uint32_t m = sph_num_particles(rk.ctx);
         if (m > cap_) throw std::runtime_error("sph_num_particles exceeds the rank's capacity");
         uint32_t cnt = 0;
+        const double t0 = nowMs();
         // the ids travel once per state, every field after that is one export + one copy
         check(rk.ctx, sph_download_owned(rk.ctx, field, rk.idsFresh ? nullptr : rk.ids.data(), rk.buf.data(), (size_t)m * per, &cnt),
               "sph_download_owned");
+        const double t1 = nowMs();
+        rk.ms[1] += t1 - t0;
         if (cnt != m || (rk.idsFresh && rk.owned != m)) throw std::runtime_error("sph_download_owned: row count changed under the download");
         if (!rk.idsFresh) {
             for (uint32_t i = 0; i < m; i++)
@@ -244,6 +257,7 @@ void SlabGroup::download(int field, void* out, size_t out_bytes)
             uint32_t* o = reinterpret_cast<uint32_t*>(dst);
             for (uint32_t i = 0; i < m; i++) o[ids[i]] = src[i];
         }
+        rk.ms[2] += nowMs() - t1;
         got[(size_t)k] = m;
     });
     uint64_t total = 0;
@@ -259,6 +273,19 @@ void SlabGroup::timings(double out6[6])
         check(r.ctx, sph_get_timings(r.ctx, t), "sph_get_timings");
         for (int i = 0; i < 6; i++) if (t[i] > out6[i]) out6[i] = t[i];
     }
+}
+
+void SlabGroup::breakdown(double out4[4]) const
+{
+    for (int i = 0; i < 4; i++) {
+        out4[i] = 0.0;
+        for (const auto& r : rank_) if (r.ms[i] > out4[i]) out4[i] = r.ms[i];
+    }
+}
+
+void SlabGroup::resetBreakdown()
+{
+    for (auto& r : rank_) for (double& v : r.ms) v = 0.0;
 }
 
 std::vector<int32_t> SlabGroup::layers() const

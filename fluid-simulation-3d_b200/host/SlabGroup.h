@@ -43,6 +43,11 @@ public:
     std::vector<int32_t> layers() const;
     std::vector<uint32_t> ownedCounts() const;
     uint64_t launches() const;
+    // Where the host time of the calls since the last resetBreakdown() went, in ms, slowest rank per phase:
+    // [0] step (sph_step: enqueue, the slab exchanges' host synchronisations), [1] waiting for the device + export +
+    // device-to-host copies of the downloads, [2] scattering the rows into index order, [3] re-balancing
+    void breakdown(double out4[4]) const;
+    void resetBreakdown();
 
 private:
     struct Rank {
@@ -52,6 +57,7 @@ private:
         std::vector<unsigned char> buf;     // field rows of the current download (page-locked)
         uint32_t owned = 0;                 // rows behind `ids`
         bool idsFresh = false;
+        double ms[4] = {0, 0, 0, 0};        // host time per phase (breakdown())
         std::vector<uint32_t> upIds;        // scratch of upload()
         std::vector<float> pos, vel;
     };

@@ -141,7 +141,12 @@ static int run_multi(int n, int steps, int ndev)
     sim.setRebalanceInterval(2);
     sim.InitializeData(n);                               // the reset path: same lattice, now handed to the slabs
     const float rho_spawn_multi = sim.getDensity((uint32)n / 2u);      // valid before the first Update, like the reference
-    for (int s = 0; s < steps; s++) { const double a = now(); sim.Update(0.016667f); if (s >= skip) tn += now() - a; }
+    double phase[4] = {0, 0, 0, 0};
+    for (int s = 0; s < steps; s++) {
+        if (s == skip) sim.multiGpuBreakdown(phase);      // drop the warm-up Updates from the per-phase sums
+        const double a = now(); sim.Update(0.016667f); if (s >= skip) tn += now() - a;
+    }
+    sim.multiGpuBreakdown(phase);
     double dpos = 0.0, dout = 0.0, drho = 0.0;
     for (int i = 0; i < n; i++) {
         dpos = std::fmax(dpos, std::fmax(std::fabs((double)sim.positions[i].x - pos1[i].x),
@@ -163,9 +168,12 @@ static int run_multi(int n, int steps, int ndev)
     unsigned long long owned = 0;
     std::string per;
     for (uint32 c : sim.particlesPerDevice()) { owned += c; per += (per.empty() ? "" : ",") + std::to_string(c); }
-    printf("multi n=%d ndev=%d steps=%d max_pos_diff=%.3g max_out_diff=%.3g max_rho_rel=%.3g spawn_rho=%.6f/%.6f getters_ok=%d owned=%llu per_device=[%s] density_ms=%.4f update_ms_1gpu=%.3f update_ms_ngpu=%.3f\n",
+    printf("multi n=%d ndev=%d steps=%d max_pos_diff=%.3g max_out_diff=%.3g max_rho_rel=%.3g spawn_rho=%.6f/%.6f getters_ok=%d owned=%llu per_device=[%s] density_ms=%.4f update_ms_1gpu=%.3f update_ms_ngpu=%.3f "
+           "ngpu_phase_ms=step:%.3f,download:%.3f,scatter:%.3f,rebalance:%.3f\n",
            n, ndev, steps, dpos, dout, drho, rho_spawn, rho_spawn_multi, getters_ok, owned, per.c_str(), sim.getElapsedTimeDensity(),
-           steps > skip ? t1 / (steps - skip) : 0.0, steps > skip ? tn / (steps - skip) : 0.0);
+           steps > skip ? t1 / (steps - skip) : 0.0, steps > skip ? tn / (steps - skip) : 0.0,
+           steps > skip ? phase[0] / (steps - skip) : 0.0, steps > skip ? phase[1] / (steps - skip) : 0.0,
+           steps > skip ? phase[2] / (steps - skip) : 0.0, steps > skip ? phase[3] / (steps - skip) : 0.0);
     sim.shutdown();
     return 0;
 }
