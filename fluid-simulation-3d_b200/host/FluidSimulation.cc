@@ -7,6 +7,8 @@
 #include "SlabGroup.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 #include <stdexcept>
 
 namespace Physics
@@ -208,6 +210,61 @@ namespace Physics
 			invalidateGetters();
 		}
 
+		// ---- snapshots: the C ABI's file format (sph_api.cu: sph_save_state), host-side so it serves every device layout
+		static bool writeSnapshotFileImpl(const std::string& path, uint32_t n, const SphParams& p, const float* pos3, const float* vel3)
+		{
+			FILE* f = fopen(path.c_str(), "wb");
+			if (!f) return false;
+			const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '1'};
+			bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&p, sizeof(SphParams), 1, f) == 1;
+			ok = ok && (n == 0 || (fwrite(pos3, 12, n, f) == n && fwrite(vel3, 12, n, f) == n));
+			return (fclose(f) == 0) && ok;
+		}
+		static bool readSnapshotFileImpl(const std::string& path, uint32_t& n, SphParams& p, std::vector<float>& pos3, std::vector<float>& vel3)
+		{
+			FILE* f = fopen(path.c_str(), "rb");
+			if (!f) return false;
+			char magic[8];
+			bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "SPHB2001", 8) == 0 && fread(&n, 4, 1, f) == 1 &&
+			          fread(&p, sizeof(SphParams), 1, f) == 1;
+			if (ok) {
+				pos3.resize((size_t)n * 3); vel3.resize((size_t)n * 3);
+				ok = n == 0 || (fread(pos3.data(), 12, n, f) == n && fread(vel3.data(), 12, n, f) == n);
+			}
+			fclose(f);
+			return ok;
+		}
+
+		void FluidSimulation::saveState(const std::string& path)
+		{
+			std::vector<float> pos((size_t)numParticles * 3), vel((size_t)numParticles * 3);
+			if ((ctx || group) && numParticles) {
+				fetch(SPH_FIELD_POSITIONS, pos.data(), pos.size() * 4, "sph_download");
+				fetch(SPH_FIELD_VELOCITIES, vel.data(), vel.size() * 4, "sph_download");
+			}
+			if (!writeSnapshotFileImpl(path, numParticles, params, pos.data(), vel.data())) {
+				error = "saveState: cannot write " + path;
+				throw std::runtime_error(error);
+			}
+		}
+
+		void FluidSimulation::loadState(const std::string& path)
+		{
+			uint32_t n = 0;
+			SphParams p;
+			std::vector<float> pos, vel;
+			if (!readSnapshotFileImpl(path, n, p, pos, vel)) {
+				error = "loadState: " + path + " is not a complete snapshot file";
+				throw std::runtime_error(error);
+			}
+			params = p;
+			pushParams();                                 // (an existing context is reused by InitializeData without a push)
+			InitializeData((int)n);                       // sizes the contexts and the mirrors for n particles (and spawns: overwritten next)
+			for (uint32_t i = 0; i < n; i++) positions[i] = vec3(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2]);
+			uploadState(n ? vel.data() : nullptr);
+			for (uint32_t i = 0; i < n; i++) OutPositions[i] = vec4(positions[i].x, positions[i].y, positions[i].z, 0.34f);
+		}
+
 		void FluidSimulation::downloadVelocities(std::vector<vec3>& out)
 		{
 			out.resize(numParticles);
@@ -303,4 +360,15 @@ namespace Physics
 		void FluidSimulation::setBound(const vec3& value) { params.bound[0] = value.x; params.bound[1] = value.y; params.bound[2] = value.z; pushParams(); }
 		FluidSimulation::vec3 FluidSimulation::getBounds() { return vec3(params.bound[0], params.bound[1], params.bound[2]); }
 	}
+}
+
+namespace sphb200 {
+bool writeSnapshotFile(const std::string& path, uint32_t n, const SphParams& p, const float* pos3, const float* vel3)
+{
+	return Physics::Fluid::writeSnapshotFileImpl(path, n, p, pos3, vel3);
+}
+bool readSnapshotFile(const std::string& path, uint32_t& n, SphParams& p, std::vector<float>& pos3, std::vector<float>& vel3)
+{
+	return Physics::Fluid::readSnapshotFileImpl(path, n, p, pos3, vel3);
+}
 }

@@ -19,7 +19,13 @@
 
 #include "sph_b200.h"
 
-namespace sphb200 { class SlabGroup; }
+namespace sphb200 {
+class SlabGroup;
+// the snapshot file of sph_save_state / FluidSimulation::saveState, host-side (no device): "SPHB2001", u32 n, SphParams,
+// n x pos3, n x vel3 (fp32, particle index order); false on I/O errors or a file that is not a complete snapshot
+bool writeSnapshotFile(const std::string& path, uint32_t n, const SphParams& params, const float* pos3, const float* vel3);
+bool readSnapshotFile(const std::string& path, uint32_t& n, SphParams& params, std::vector<float>& pos3, std::vector<float>& vel3);
+}
 
 #ifdef SPH_B200_USE_GLM
 namespace sphb200 { using vec3 = glm::vec3; using vec4 = glm::vec4; }
@@ -110,6 +116,12 @@ namespace Physics
 			void downloadVelocities(std::vector<vec3>& out);
 			void downloadDensities(std::vector<float>& rhoNearRhoPairs);
 			void downloadColors(std::vector<vec4>& out);   // FluidSimCPU::updateColors on the device
+			// State snapshots (the reference has none: Reset re-spawns).  The file is the C ABI's
+			// (sph_save_state: "SPHB2001", u32 n, SphParams, n x pos3, n x vel3, particle index order), written and
+			// read here on the host so it works the same on one GPU and on several -- a snapshot taken on one
+			// configuration resumes on the other.  loadState replaces parameters, particle count and state.
+			void saveState(const std::string& path);
+			void loadState(const std::string& path);
 			// Sub-stepping (the reference's README notes the pressure "going crazy" below
 			// 40 fps): Update(dt) with dt > maxDt runs ceil(dt / maxDt) equal steps.  0 (default) = one step,
 			// exactly the reference's behaviour.

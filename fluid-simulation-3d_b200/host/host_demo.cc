@@ -1,7 +1,7 @@
 // host/host_demo.cc -- headless driver of the host class, the way FluidSimCPU drives the reference
 // (fluidSimCPU.cc:9-46): InitializeData(n), then Update(dt) per frame.  Prints one line per run that
 // tests/test_variants_gpu.py / tests/test_host_gpu.py compare with the same scene run through the C ABI from Python.
-//   host_demo n steps table_mode [class | adapter | getters | substeps | multi ndev]
+//   host_demo n steps table_mode [class | adapter | getters | substeps | multi ndev | snapshot path [ndev] | snapshotio path | slabgroup ndev]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -190,6 +190,44 @@ int main(int argc, char** argv)
         if (!strcmp(what, "getters")) return run_getters(n, steps, mode);
         if (!strcmp(what, "substeps")) return run_substeps(n, steps, mode);
         if (!strcmp(what, "multi")) return run_multi(n, steps, argc > 5 ? atoi(argv[5]) : 2);
+        if (!strcmp(what, "snapshot")) {               // saveState / loadState through the class: resume == uninterrupted run
+            const char* path = argc > 5 ? argv[5] : "/tmp/sph_snapshot.bin";
+            const int ndev = argc > 6 ? atoi(argv[6]) : 1;
+            if (ndev > 1) { std::vector<int> devs; for (int d = 0; d < ndev; d++) devs.push_back(d); sim.setDevices(devs); }
+            sim.setTableMode(mode);
+            sim.setGravity(true);
+            sim.setViscosityStrength(0.6f);
+            sim.setHostMirrors(true, true);
+            sim.InitializeData(n);
+            for (int s = 0; s < steps; s++) sim.Update(0.016667f);
+            sim.saveState(path);
+            for (int s = 0; s < 2; s++) sim.Update(0.016667f);
+            const unsigned long long straight = fnv1a(sim.positions.data(), sim.positions.size() * 12);
+            sim.setViscosityStrength(0.1f);             // loadState must bring the parameters back too
+            sim.loadState(path);
+            const float mu = sim.getViscosityStrength();
+            for (int s = 0; s < 2; s++) sim.Update(0.016667f);
+            const unsigned long long resumed = fnv1a(sim.positions.data(), sim.positions.size() * 12);
+            printf("snapshot n=%d steps=%d ndev=%d straight_fnv=%016llx resumed_fnv=%016llx mu=%.2f\n", n, steps, ndev, straight, resumed, mu);
+            sim.shutdown();
+            return 0;
+        }
+        if (!strcmp(what, "snapshotio")) {             // the snapshot file format, host-side only: argv[5] = path
+            const char* path = argc > 5 ? argv[5] : "/tmp/sph_snapshot.bin";
+            SphParams p;
+            sph_default_params(&p);
+            p.gravity = 1; p.viscosity_strength = 0.75f; p.bound[2] = 7.5f;
+            std::vector<float> pos((size_t)n * 3), vel((size_t)n * 3);
+            for (size_t i = 0; i < pos.size(); i++) { pos[i] = 0.25f * (float)i - 3.0f; vel[i] = -0.5f * (float)i; }
+            if (!sphb200::writeSnapshotFile(path, (uint32_t)n, p, pos.data(), vel.data())) { printf("snapshotio write failed\n"); return 3; }
+            uint32_t n2 = 0; SphParams q; std::vector<float> pos2, vel2;
+            const bool ok = sphb200::readSnapshotFile(path, n2, q, pos2, vel2) && n2 == (uint32_t)n && pos2 == pos && vel2 == vel &&
+                            !memcmp(&p, &q, sizeof(p));
+            std::vector<float> dummy;
+            const bool rejects = !sphb200::readSnapshotFile(std::string(path) + ".missing", n2, q, dummy, dummy);
+            printf("snapshotio n=%d roundtrip=%d rejects_missing=%d\n", n, (int)ok, (int)rejects);
+            return ok && rejects ? 0 : 3;
+        }
         if (!strcmp(what, "slabgroup")) {              // the group on its own: construction (and its failure path), nothing else
             SphParams p;
             sph_default_params(&p);

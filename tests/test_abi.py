@@ -153,3 +153,24 @@ def test_every_entry_point_survives_null_arguments(pkg):
     for name, (call, want) in benign.items():
         assert call() == want, name
     assert L.sph_comm_id_bytes() >= 128 and isinstance(L.sph_last_error(None), bytes)
+
+
+def test_host_snapshot_file_is_the_documented_format(tmp_path):
+    """FluidSimulation::saveState / loadState go through sphb200::writeSnapshotFile / readSnapshotFile (pure host code):
+    the file is the C ABI's snapshot format (include/sph_b200.h: "SPHB2001", u32 n, SphParams, n x pos3, n x vel3)"""
+    import numpy as np
+    demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
+    path = str(tmp_path / "state.bin")
+    n = 777
+    r = subprocess.run([demo, str(n), "0", "0", "snapshotio", path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert r.returncode == 0 and "roundtrip=1 rejects_missing=1" in r.stdout, r.stdout
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"SPHB2001" and len(raw) == 8 + 4 + 44 + 24 * n
+    assert int(np.frombuffer(raw, np.uint32, 1, 8)[0]) == n
+    par = np.frombuffer(raw, np.float32, 11, 12)
+    assert abs(par[0] - 0.35) < 1e-7 and par[5] == np.float32(0.75) and np.frombuffer(raw, np.int32, 1, 12 + 28)[0] == 1
+    assert list(par[8:11]) == [20.0, 20.0, 7.5]
+    pos = np.frombuffer(raw, np.float32, 3 * n, 56)
+    vel = np.frombuffer(raw, np.float32, 3 * n, 56 + 12 * n)
+    i = np.arange(3 * n, dtype=np.float32)
+    assert np.array_equal(pos, np.float32(0.25) * i - np.float32(3.0)) and np.array_equal(vel, np.float32(-0.5) * i)
