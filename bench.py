@@ -145,21 +145,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def cpu_reference_run(scene_name, steps, warmup, budget_s=25.0):
+def reference_cpu_class(ob, parallel):
+    """(oracle class, kind, threads, description) of the reference CPU step to time: the unmodified reference built
+    against oracle/pstl_threads (its std::execution::par loops on every host thread) when `parallel` and present, else
+    the same TU on libstdc++'s serial PSTL backend (TBB is not installed), else the C restatement"""
+    if parallel and ob.have_ref_par():
+        t = ob.RefOracleParallel.set_threads(os.cpu_count() or 1)
+        return ob.RefOracleParallel, "reference", t, ("unmodified reference Update(), its std::execution::par loops on %d host "
+                                                       "threads (libstdc++ parallel backend over oracle/pstl_threads)" % t)
+    if ob.have_ref():
+        return ob.RefOracle, "reference", 1, "unmodified reference Update() (serial PSTL: TBB absent)"
+    return ob.PortOracle, "port", 1, "C restatement, 1 thread"
+
+
+def cpu_reference_run(scene_name, steps, warmup, budget_s=25.0, parallel=True):
     """Time the reference CPU Update() on a bounded sample of the workload.  Returns a dict."""
     ob = graft.load_oracle()
     pkg = graft.load_package()
     from fluid_simulation_3d_b200 import scenes
-    kind = "reference" if ob.have_ref() else "port"
-    # per-particle cost is flat in N (SURVEY 6.2: 0.13-0.16 M updates/s from 10 k to 1 M), so a sub-block
+    cls, kind, cores, what = reference_cpu_class(ob, parallel)
+    # per-particle cost is flat in N (SURVEY 6.2: 0.13-0.16 M updates/s per core from 10 k to 1 M), so a sub-block
     # of the same lattice / rule is a faithful sample; size it so (steps + warmup) fit the budget
-    rate_guess = 0.14e6
+    rate_guess = 0.14e6 * (1.0 if cores == 1 else 0.6 * min(cores, 32))
     total = max(1, steps + warmup)
     side = int(round((budget_s * rate_guess / total) ** (1.0 / 3.0)))
     full = scenes.CONFIGS[scene_name][0] if scene_name in scenes.CONFIGS else 100
     side = max(16, min(side, full))
     sc = scenes.small_dam_break(side, seed=scenes.CONFIGS.get(scene_name, (0, 0, 0, 7))[3])
-    orc = (ob.RefOracle if kind == "reference" else ob.PortOracle)(sc["n"], **sc["params"])
+    orc = cls(sc["n"], **sc["params"])
     orc.set_state(sc["pos"], sc["vel"])
     step = (lambda: orc.update(scenes.DT)) if kind == "reference" else (lambda: orc.step(scenes.DT, jacobi=True))
     for _ in range(warmup):
@@ -168,20 +181,18 @@ def cpu_reference_run(scene_name, steps, warmup, budget_s=25.0):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return dict(value=sc["n"] * steps / dt / 1e6, unit=METRIC, cores=1, kind=kind, ms_per_step=dt / steps * 1e3,
+    return dict(value=sc["n"] * steps / dt / 1e6, unit=METRIC, cores=cores, kind=kind, ms_per_step=dt / steps * 1e3,
                 sample="%d^3 = %d-particle corner block of the %s lattice (same spacing, jitter, bounds rule, dt), "
-                       "%d steps after %d warm-up, %s" % (side, sc["n"], scene_name, steps, warmup,
-                                                          "unmodified reference Update() (serial PSTL: TBB absent)"
-                                                          if kind == "reference" else "C restatement, 1 thread"),
+                       "%d steps after %d warm-up, %s" % (side, sc["n"], scene_name, steps, warmup, what),
                 n=sc["n"])
 
 
-def cpu_reference_c1(steps, warmup):
+def cpu_reference_c1(steps, warmup, parallel=True):
     """C1: the reference's default scene, whole (10 000 particles): InitializeData(10000), gravity on, Update(dt)."""
     ob = graft.load_oracle()
-    kind = "reference" if ob.have_ref() else "port"
+    cls, kind, cores, what = reference_cpu_class(ob, parallel)
     n = 10000
-    orc = ob.RefOracle(n, spawn=True, gravity=1) if kind == "reference" else ob.PortOracle(n, gravity=1)
+    orc = cls(n, spawn=True, gravity=1) if kind == "reference" else cls(n, gravity=1)
     if kind == "port":
         orc.spawn_grid()
     dt = float(np.float32(0.016667))
@@ -192,10 +203,9 @@ def cpu_reference_c1(steps, warmup):
     for _ in range(steps):
         step()
     t = time.perf_counter() - t0
-    return dict(value=n * steps / t / 1e6, unit=METRIC, cores=1, kind=kind, ms_per_step=t / steps * 1e3, n=n,
+    return dict(value=n * steps / t / 1e6, unit=METRIC, cores=cores, kind=kind, ms_per_step=t / steps * 1e3, n=n,
                 sample="the whole C1 scene (InitializeData(10000), default bounds, gravity on), %d steps after %d warm-up, %s"
-                       % (steps, warmup, "unmodified reference Update() (serial PSTL: TBB absent)" if kind == "reference"
-                          else "C restatement, 1 thread"))
+                       % (steps, warmup, what))
 
 
 def workload_text(name, n, bound, mu):
@@ -502,16 +512,27 @@ def bench_single(args, pkg, scenes, torch, dev):
         "clocks": clk,
     }
     sim.close()
+    def one_thread(fn, **kw):            # the same reference on libstdc++'s serial backend, beside the all-threads number
+        try:
+            q = fn(parallel=False, **kw)
+            return {"value": q["value"], "unit": "M updates/s", "cores": q["cores"], "kind": q["kind"], "sample": q["sample"]}
+        except Exception as e:
+            return {"error": str(e)}
+
     if not args.no_cpu_baseline and name == C1_NAME:
         r = cpu_reference_c1(steps=100, warmup=20)
         result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
                                   "sample": r["sample"], "host_cores": os.cpu_count()}
+        if r["cores"] > 1:
+            result["cpu_baseline"]["one_thread"] = one_thread(cpu_reference_c1, steps=50, warmup=10)
     elif not args.no_cpu_baseline:
-        r = cpu_reference_run(name if name in scenes.CONFIGS else "C2_dambreak_1M", steps=2, warmup=1, budget_s=20.0)
+        cfg = name if name in scenes.CONFIGS else "C2_dambreak_1M"
+        r = cpu_reference_run(cfg, steps=2, warmup=1, budget_s=15.0)
         result["cpu_baseline"] = {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
                                   "sample": r["sample"], "host_cores": os.cpu_count()}
-        # a second, clearly labelled line: the C restatement with OpenMP on every host core (the reference's
-        # own std::execution::par falls back to one thread here because TBB is not installed)
+        if r["cores"] > 1:
+            result["cpu_baseline"]["one_thread"] = one_thread(cpu_reference_run, scene_name=cfg, steps=2, warmup=1, budget_s=10.0)
+        # a further, clearly labelled line: the C restatement with OpenMP on every host core
         try:
             ob = graft.load_oracle()
             cores = os.cpu_count() or 1

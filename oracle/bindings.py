@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libsph_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsph_ref.so")
+REF_PAR_SO = os.path.join(HERE, "_ref", "libsph_ref_par.so")      # same TU, std::execution::par on every host thread
 
 DEFAULTS = dict(interaction_radius=0.35, sqr_radius=float(np.float32(0.35) * np.float32(0.35)),
                 target_density=99.7, pressure_multiplier=300.0, near_pressure_multiplier=20.0,
@@ -65,6 +66,10 @@ def have_port():
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def have_ref_par():
+    return os.path.exists(REF_PAR_SO)
 
 
 class PortOracle:
@@ -209,10 +214,12 @@ class RefOracle:
     _lib = None
     kind = "reference"
 
+    SO = REF_SO
+
     @classmethod
     def lib(cls):
         if cls._lib is None:
-            L = C.CDLL(REF_SO)
+            L = C.CDLL(cls.SO)
             L.ref_initialize_data.argtypes = [C.c_int]
             L.ref_allocate.argtypes = [C.c_int]
             L.ref_set_params.argtypes = [C.POINTER(RefParams)]
@@ -317,3 +324,34 @@ def fnv1a64(*arrays):
         for b in np.ascontiguousarray(a).tobytes():
             h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
     return "%016x" % h
+
+
+class RefOracleParallel(RefOracle):
+    """The same unmodified reference TU built against oracle/pstl_threads: its std::execution::par loops run on every
+    host thread (OpenMP).  For TIMING (bench.py --impl reference) and race-free stages; the in-place viscosity update
+    of Update() is a data race under a parallel backend, so values come from RefOracle."""
+    _lib = None
+    SO = REF_PAR_SO
+    kind = "reference"
+
+    @staticmethod
+    def _omp():
+        import ctypes.util
+        return C.CDLL(ctypes.util.find_library("gomp") or "libgomp.so.1")
+
+    @classmethod
+    def threads(cls):
+        try:
+            return int(cls._omp().omp_get_max_threads())
+        except OSError:
+            return os.cpu_count() or 1
+
+    @classmethod
+    def set_threads(cls, n):
+        """(torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and takes the box)"""
+        try:
+            cls._omp().omp_set_num_threads(int(max(1, n)))
+        except OSError:
+            pass
+        return cls.threads()
+

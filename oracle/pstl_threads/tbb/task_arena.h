@@ -1,0 +1,2 @@
+/* see tbb.h in this directory (test infrastructure) */
+#include "tbb.h"

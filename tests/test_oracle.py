@@ -243,6 +243,75 @@ def test_live_reference_vs_port_coincident_particles(ob):
         assert np.array_equal(bits(p.densities()), bits(r.densities()))
 
 
+needs_ref_par = pytest.mark.skipif(not g.load_oracle().have_ref_par(), reason="oracle/_ref/libsph_ref_par.so not built")
+
+
+@needs_ref
+@needs_ref_par
+def test_parallel_reference_build_equals_the_serial_one_where_it_is_race_free(ob):
+    """oracle/_ref/libsph_ref_par.so is the same unmodified TU with its std::execution::par loops really parallel
+    (oracle/pstl_threads).  With mu = 0 nothing in Update() races, so several whole steps are bit-identical to the serial
+    build; with viscosity on the in-place update is a data race (Q11) and only the stages before it are compared."""
+    g.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(20)
+    dt = scenes.DT
+    assert ob.RefOracleParallel.set_threads(4) == 4
+    p0 = dict(sc["params"], viscosity_strength=0.0)
+    a, b = ob.RefOracle(sc["n"], **p0), ob.RefOracleParallel(sc["n"], **p0)
+    for o in (a, b):
+        o.set_state(sc["pos"], sc["vel"])
+        for _ in range(3):
+            o.update(dt)
+    for f in ("positions", "velocities", "densities", "out_positions", "predicted"):
+        assert np.array_equal(bits(getattr(a, f)()), bits(getattr(b, f)())), f
+    assert np.array_equal(a.sorted_lookup()[2], b.sorted_lookup()[2]) and np.array_equal(a.start_indices(), b.start_indices())
+    for o in (a, b):                                   # viscosity on: everything up to the pressure stage still agrees
+        o.set_params(viscosity_strength=0.5)
+        o.set_state(sc["pos"], sc["vel"])
+        o.update(dt)
+    assert np.array_equal(bits(a.densities()), bits(b.densities()))
+    assert np.array_equal(a.neighbour_counts(), b.neighbour_counts())
+    # after the racy stage only sanity holds: Gauss-Seidel in index order (serial) against whatever interleaving the
+    # threads produced moves velocities by up to ~0.1 in one step of this scene (SURVEY App. A Q11)
+    assert np.all(np.isfinite(b.positions())) and np.abs(a.positions() - b.positions()).max() < 0.05
+
+
+def test_pstl_threads_stand_in_really_runs_par_loops_in_parallel(tmp_path):
+    """oracle/pstl_threads/tbb/tbb.h: libstdc++ picks its parallel PSTL backend when <tbb/tbb.h> is found; the stand-in's
+    parallel_for must spread a std::for_each(par) over the OpenMP threads and visit every element exactly once"""
+    import subprocess
+    root = os.path.dirname(HERE)
+    src = tmp_path / "probe.cc"
+    src.write_text(r'''
+#include <execution>
+#include <algorithm>
+#include <vector>
+#include <cstdio>
+#include <omp.h>
+int main() {
+    std::vector<unsigned> idx(300000);
+    for (unsigned i = 0; i < idx.size(); i++) idx[i] = i;
+    std::vector<int> tid(idx.size(), -1), hits(idx.size(), 0);
+    std::for_each(std::execution::par, idx.begin(), idx.end(), [&](unsigned i) { tid[i] = omp_get_thread_num(); hits[i]++; });
+    int mx = 0, bad = 0;
+    for (size_t i = 0; i < idx.size(); i++) { mx = tid[i] > mx ? tid[i] : mx; bad += hits[i] != 1; }
+    std::vector<unsigned> tiny(7, 1u);                       // below one chunk: runs inline
+    unsigned s = 0;
+    std::for_each(std::execution::par, tiny.begin(), tiny.end(), [&](unsigned v) { s += v; });
+    std::printf("threads=%d bad=%d tiny=%u\n", mx + 1, bad, s);
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-fopenmp", "-I", os.path.join(root, "oracle", "pstl_threads"), str(src), "-o", str(exe)],
+                   check=True, timeout=300)
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, env=env, timeout=60, check=True).stdout
+    assert "bad=0 tiny=7" in out
+    assert "threads=4" in out or (os.cpu_count() or 1) < 2, out
+
+
 @needs_ref
 def test_live_reference_getters_bounds(ob):
     r = ob.RefOracle(64, spawn=True)
