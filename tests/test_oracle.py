@@ -277,6 +277,38 @@ def test_parallel_reference_build_equals_the_serial_one_where_it_is_race_free(ob
     assert np.all(np.isfinite(b.positions())) and np.abs(a.positions() - b.positions()).max() < 0.05
 
 
+@needs_ref_par
+def test_restatement_pinned_at_125k_particles_against_the_parallel_reference(ob):
+    """the pin of the restatement at a size the serial reference makes slow: 50^3 particles, two whole steps of the
+    unmodified reference on every host thread (mu = 0: race-free, bit-identical to its serial build) against the
+    restatement given the reference's sorted tie order -- every buffer bit for bit.  At this size many cells share a
+    bucket of the `hash % N` table, the regime the 10 k scenes barely touch."""
+    g.load_package()
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(50, seed=0x51)
+    dt = scenes.DT
+    prm = dict(sc["params"], viscosity_strength=0.0)
+    ob.RefOracleParallel.set_threads(os.cpu_count() or 1)
+    r = ob.RefOracleParallel(sc["n"], **prm)
+    p = ob.PortOracle(sc["n"], threads=os.cpu_count() or 1, **prm)
+    r.set_state(sc["pos"], sc["vel"]); p.set_state(sc["pos"], sc["vel"])
+    try:
+        for _ in range(2):
+            r.update(dt)
+            idx, _, key = r.sorted_lookup()
+            p.stage_predict(dt); p.stage_spatial(forced_order=idx); p.stage_density(); p.stage_pressure(dt)
+            p.stage_viscosity(dt, jacobi=False); p.stage_integrate(dt)
+            assert np.array_equal(p.sorted_lookup()[2], key) and np.array_equal(p.start_indices(), r.start_indices())
+            assert np.array_equal(bits(p.positions()), bits(r.positions()))
+            assert np.array_equal(bits(p.velocities()), bits(r.velocities()))
+            assert np.array_equal(bits(p.densities()), bits(r.densities()))
+        h, k, cells = r.hash_key()
+        shared = len(np.unique(np.stack([k, h], 1), axis=0)) - len(np.unique(k))
+        assert shared > 100, "meant to exercise buckets shared by several cells (got %d)" % shared
+    finally:
+        ob.PortOracle.lib().oracle_set_threads(1)
+
+
 def test_pstl_threads_stand_in_really_runs_par_loops_in_parallel(tmp_path):
     """oracle/pstl_threads/tbb/tbb.h: libstdc++ picks its parallel PSTL backend when <tbb/tbb.h> is found; the stand-in's
     parallel_for must spread a std::for_each(par) over the OpenMP threads and visit every element exactly once"""
