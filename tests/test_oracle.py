@@ -278,14 +278,17 @@ def test_parallel_reference_build_equals_the_serial_one_where_it_is_race_free(ob
 
 
 @needs_ref_par
-def test_restatement_pinned_at_125k_particles_against_the_parallel_reference(ob):
-    """the pin of the restatement at a size the serial reference makes slow: 50^3 particles, two whole steps of the
+@pytest.mark.parametrize("side,seed,steps", [(50, 0x51, 2), (100, 0xC2, 1)], ids=["125k", "C2_full_1M"])
+def test_restatement_pinned_at_size_against_the_parallel_reference(ob, side, seed, steps):
+    """the pin of the restatement at sizes the serial reference makes slow -- 50^3 particles, and the WHOLE C2 workload
+    (100^3, seed 0xC2: the state bench.py and tests/test_fullsize_gpu.py use, which closes the chain CUDA step <->
+    restatement <-> unmodified reference at full size): whole steps of the
     unmodified reference on every host thread (mu = 0: race-free, bit-identical to its serial build) against the
     restatement given the reference's sorted tie order -- every buffer bit for bit.  At this size many cells share a
     bucket of the `hash % N` table, the regime the 10 k scenes barely touch."""
     g.load_package()
     from fluid_simulation_3d_b200 import scenes
-    sc = scenes.small_dam_break(50, seed=0x51)
+    sc = scenes.small_dam_break(side, seed=seed)
     dt = scenes.DT
     prm = dict(sc["params"], viscosity_strength=0.0)
     ob.RefOracleParallel.set_threads(os.cpu_count() or 1)
@@ -293,7 +296,7 @@ def test_restatement_pinned_at_125k_particles_against_the_parallel_reference(ob)
     p = ob.PortOracle(sc["n"], threads=os.cpu_count() or 1, **prm)
     r.set_state(sc["pos"], sc["vel"]); p.set_state(sc["pos"], sc["vel"])
     try:
-        for _ in range(2):
+        for _ in range(steps):
             r.update(dt)
             idx, _, key = r.sorted_lookup()
             p.stage_predict(dt); p.stage_spatial(forced_order=idx); p.stage_density(); p.stage_pressure(dt)
@@ -305,6 +308,17 @@ def test_restatement_pinned_at_125k_particles_against_the_parallel_reference(ob)
         h, k, cells = r.hash_key()
         shared = len(np.unique(np.stack([k, h], 1), axis=0)) - len(np.unique(k))
         assert shared > 100, "meant to exercise buckets shared by several cells (got %d)" % shared
+        if side == 100:
+            # and the viscous step the GPU is held against: snapshot (Jacobi) viscosity produced from the UNMODIFIED
+            # CalculateViscosityForce by call / record / restore (Q11), every stage buffer and the neighbour counts
+            r.set_params(viscosity_strength=0.5); p.set_params(viscosity_strength=0.5)
+            r.set_state(sc["pos"], sc["vel"]); p.set_state(sc["pos"], sc["vel"])
+            r.step(dt, jacobi=True)
+            p.stage_predict(dt); p.stage_spatial(forced_order=r.sorted_lookup()[0]); p.stage_density(); p.stage_pressure(dt)
+            p.stage_viscosity(dt, jacobi=True); p.stage_integrate(dt)
+            for f in ("densities", "vel_after_pressure", "vel_after_viscosity", "positions", "velocities", "out_positions"):
+                assert np.array_equal(bits(getattr(p, f)()), bits(getattr(r, f)())), f
+            assert np.array_equal(p.neighbour_counts(), r.neighbour_counts())
     finally:
         ob.PortOracle.lib().oracle_set_threads(1)
 
