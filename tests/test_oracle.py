@@ -243,6 +243,41 @@ def test_live_reference_vs_port_coincident_particles(ob):
         assert np.array_equal(bits(p.densities()), bits(r.densities()))
 
 
+@needs_ref
+def test_restatement_fuzzed_against_the_live_reference(ob):
+    """80 random problems -- particle count 1..1500, box, interaction radius (also != the cut-off, Q2), every solver
+    parameter, gravity on/off, dt, positions partly outside the box, fast particles, stacked duplicates -- one viscous
+    staged step each: the restatement (given the reference's sorted tie order) equals the unmodified reference bit for
+    bit on every buffer, and on hash, key, start table and neighbour counts"""
+    rng = np.random.default_rng(2026)
+    for case in range(80):
+        n = int(rng.integers(1, 1500))
+        bound = tuple(float(x) for x in rng.uniform(2.0, 12.0, 3))
+        r = float(rng.choice([0.35, 0.35, 0.25, 0.5, float(rng.uniform(0.2, 0.6))]))
+        prm = dict(interaction_radius=r, target_density=float(rng.uniform(20, 200)), pressure_multiplier=float(rng.uniform(10, 500)),
+                   near_pressure_multiplier=float(rng.uniform(1, 40)), viscosity_strength=float(rng.uniform(0, 1)),
+                   gravity_scale=float(rng.uniform(0, 20)), gravity=int(rng.integers(0, 2)), bound=bound)
+        half = np.array(bound, np.float32) / 2
+        pos = ((rng.random((n, 3)) - 0.5) * 2 * half * rng.choice([0.3, 0.9, 1.2])).astype(np.float32)
+        vel = ((rng.random((n, 3)) - 0.5) * rng.choice([0.0, 2.0, 16.0])).astype(np.float32)
+        if n > 4 and rng.random() < 0.5:
+            d = rng.integers(0, n, max(1, n // 10)); s_ = rng.integers(0, n, len(d))
+            pos[d] = pos[s_]; vel[d] = vel[s_]
+        dt = float(np.float32(rng.choice([0.016667, 0.005, 0.033])))
+        a, p = ob.RefOracle(n, **prm), ob.PortOracle(n, **prm)
+        a.set_state(pos, vel); p.set_state(pos, vel)
+        a.step(dt, jacobi=True)
+        p.stage_predict(dt); p.stage_spatial(forced_order=a.sorted_lookup()[0]); p.stage_density(); p.stage_pressure(dt)
+        p.stage_viscosity(dt, jacobi=True); p.stage_integrate(dt)
+        what = "case %d (n=%d, r=%g)" % (case, n, r)
+        for f in ("predicted", "densities", "vel_after_pressure", "vel_after_viscosity", "positions", "velocities", "out_positions"):
+            assert np.array_equal(bits(getattr(p, f)()), bits(getattr(a, f)())), what + ": " + f
+        for x, y in zip(p.hash_key(), a.hash_key()):
+            assert np.array_equal(x, y), what + ": hash / key / cell"
+        assert np.array_equal(p.start_indices(), a.start_indices()), what + ": start table"
+        assert np.array_equal(p.neighbour_counts(), a.neighbour_counts()), what + ": neighbour counts"
+
+
 needs_ref_par = pytest.mark.skipif(not g.load_oracle().have_ref_par(), reason="oracle/_ref/libsph_ref_par.so not built")
 
 
