@@ -733,6 +733,17 @@ int sph_slab_balance_layers(const uint32_t* hist, int32_t gz, int32_t nranks, co
                 while (cut > old && cum[cut] - cum[old] > row_budget) cut--;
                 while (cut < old && cum[old] - cum[cut] > row_budget) cut++;
             }
+            // hysteresis: a quantile that sits in the middle of a layer makes both of its boundaries equally good, and
+            // the plane would flip between them (a whole layer migrating each time) on the smallest change of the
+            // histogram.  A move must bring the plane nearer to its quantile by at least a quarter of the rows it moves.
+            while (cut != old) {
+                const unsigned __int128 c_old = (unsigned __int128)cum[old] * (unsigned)R, c_new = (unsigned __int128)cum[cut] * (unsigned)R;
+                const unsigned __int128 d_old = c_old > target ? c_old - target : target - c_old;
+                const unsigned __int128 d_new = c_new > target ? c_new - target : target - c_new;
+                const unsigned __int128 moved = (c_new > c_old ? c_new - c_old : c_old - c_new);
+                if (d_old > d_new && (d_old - d_new) * 4u >= moved) break;
+                cut += cut > old ? -1 : 1;           // not worth it: try the next nearer boundary, down to staying put
+            }
         }
         L[k] = cut;
     }

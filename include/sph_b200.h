@@ -247,8 +247,9 @@ int  sph_comm_rebalance(SphContext* ctx, uint32_t max_shift, int32_t* layers_out
 /* Pure host function (no device, no context): cut hist[0, gz) into nranks contiguous runs of layers with particle
  * counts as equal as layer granularity allows, every run at least three layers thick (the slab protocol's minimum).
  * With layers_old != NULL every plane stays within max_shift layers of its old place, never crosses its old
- * neighbours (migration is single-hop) and moves at most row_budget particles (0: unlimited); with layers_old ==
- * NULL the cut is unconstrained.  Deterministic: every rank derives the same planes from the same histogram. */
+ * neighbours (migration is single-hop), moves at most row_budget particles (0: unlimited) and moves only if that
+ * brings it nearer to its quantile by at least a quarter of the rows moved (hysteresis: no flipping between the two
+ * boundaries of a layer the quantile falls into); with layers_old == NULL the cut is unconstrained.  Deterministic: every rank derives the same planes from the same histogram. */
 int  sph_slab_balance_layers(const uint32_t* hist, int32_t gz, int32_t nranks, const int32_t* layers_old,
                              uint32_t max_shift, uint64_t row_budget, int32_t* layers_new);
 

@@ -143,13 +143,26 @@ def test_balance_layers_pure_function(pkg):
             cur = new
         assert sm.balance_layers(pkg, hist, R, cur, shift, budget) == cur       # a fixed point stays one
         if budget == 0 and cum[-1] > 0:
-            # without a row limit the walk ends where no plane can get nearer to its quantile
+            # without a row limit the walk ends where no single-layer move is worth making: it would bring the plane
+            # nearer to its quantile by less than a quarter of the rows it hands over (the hysteresis that keeps a plane
+            # from flipping between the two boundaries of the layer its quantile falls into)
             for k in range(1, R):
                 t = cum[-1] * k / R
                 for step in (-1, 1):
                     trial_L = list(cur); trial_L[k] += step
                     if all(b - a >= 3 for a, b in zip(trial_L, trial_L[1:])):
-                        assert abs(cum[cur[k]] - t) <= abs(cum[trial_L[k]] - t) + 1e-9, (cur, k, step)
+                        gain = abs(cum[cur[k]] - t) - abs(cum[trial_L[k]] - t)
+                        moved = abs(int(cum[trial_L[k]]) - int(cum[cur[k]]))
+                        assert gain < 0.25 * moved + 1e-6 or gain <= 0, (cur, k, step, gain, moved)
+    # the flip the hysteresis is there for: the quantile in the middle of a layer, the histogram wobbling around it
+    hist = np.array([100] * 10, np.uint32)                  # 2 ranks: quantile at 500 = the boundary 5 exactly
+    assert sm.balance_layers(pkg, hist, 2, [0, 5, 10], 1) == [0, 5, 10]
+    wob = np.array([100, 100, 100, 150, 110, 90, 90, 90, 90, 80], np.uint32)   # quantile 500 inside layer 4: boundary 4 at 450, 5 at 560
+    assert sm.balance_layers(pkg, wob, 2, None) == [0, 4, 10]                  # a free cut takes the nearer boundary,
+    assert sm.balance_layers(pkg, wob, 2, [0, 5, 10], 1) == [0, 5, 10]         # a plane already at 5 stays: 10 nearer for 110 rows moved
+    assert sm.balance_layers(pkg, wob, 2, [0, 4, 10], 1) == [0, 4, 10]         # and so does one at 4
+    far = hist.copy(); far[:3] = 400                        # a real imbalance moves it
+    assert sm.balance_layers(pkg, far, 2, [0, 5, 10], 1) == [0, 4, 10]
     # errors: too few layers, a broken old partition
     with pytest.raises(ValueError):
         sm.balance_layers(pkg, np.ones(5, np.uint32), 2)
