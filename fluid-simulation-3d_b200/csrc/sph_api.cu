@@ -716,7 +716,7 @@ int sph_load_state(SphContext* c, const char* path)
 int sph_host_register(void* ptr, size_t bytes)
 {
     if (!ptr || !bytes) return SPH_ERR_INVALID;
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable)   /* pinned for every device's context (multi-GPU hosts) */;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped)   /* pinned for every device's context and mapped into their address spaces (multi-GPU hosts, sph_download_owned_scatter) */;
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SPH_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
     return SPH_OK;
 }

@@ -860,7 +860,7 @@ static size_t owned_field_bytes(int field)
 }
 
 // export `field` of the owned rows, device order, into dev_out (enqueued on the solver's stream)
-static int owned_export(SphContext* c, int field, void* dev_out, uint32_t n)
+static int owned_export(SphContext* c, int field, void* dev_out, uint32_t n, bool by_id = false)
 {
     // per-step arrays live at sorted rows [o0, o1); the state arrays were compacted to [0, n)
     const uint32_t off = c->slab ? c->slab->o0 : 0;
@@ -881,8 +881,31 @@ static int owned_export(SphContext* c, int field, void* dev_out, uint32_t n)
     if (needs_step && !c->step_valid) return fail(c, SPH_ERR_INVALID, "field needs a step first");
     DevParams P;
     make_dev_params(c, n, &P);
-    launch_export(c->st, field, c->A_pos, src, nullptr, dev_out, n, P, false, &c->launches);
+    launch_export(c->st, field, c->A_pos, src, nullptr, dev_out, n, P, by_id, &c->launches);
     SPH_CUDA(c, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_download_owned_scatter(SphContext* c, int field, void* host_base, size_t host_elems, uint32_t* out_n)
+{
+    if (!c) return SPH_ERR_INVALID;
+    SPH_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n = c->n;
+    if (out_n) *out_n = n;
+    if (!owned_field_bytes(field)) return fail(c, SPH_ERR_INVALID, "unknown field");
+    if (!n) return SPH_OK;
+    if (!host_base || host_elems < n) return fail(c, SPH_ERR_INVALID, "sph_download_owned_scatter: host array missing or smaller than the owned count");
+    // the export kernel writes row s to host_base[id(s)] itself, over PCIe: the array must be page-locked and mapped
+    // into this device's address space (sph_host_register: portable + mapped under unified addressing)
+    void* dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dev, host_base, 0);
+    if (e != cudaSuccess || !dev) {
+        cudaGetLastError();
+        return fail(c, SPH_ERR_INVALID, "sph_download_owned_scatter: the host array is not page-locked / device-mapped (sph_host_register it)");
+    }
+    int rc = owned_export(c, field, dev, n, true);
+    if (rc != SPH_OK) return rc;
+    SPH_CUDA(c, cudaStreamSynchronize(c->st));
     return SPH_OK;
 }
 

@@ -148,6 +148,7 @@ namespace Physics
 				sph_destroy(ctx); ctx = nullptr; capacity = 0;
 				try {
 					group.reset(new sphb200::SlabGroup(devices, numParticles, params));
+					group->setDirectScatter(directMirrors);
 					group->upload(numParticles, bulkPos.data(), nullptr);
 				} catch (const std::exception& e) { group.reset(); error = e.what(); throw; }
 				bulkFresh.store(true, std::memory_order_release);

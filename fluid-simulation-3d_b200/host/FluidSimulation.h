@@ -100,6 +100,10 @@ namespace Physics
 			void setDevices(const std::vector<int>& cudaDevices);
 			// Multi-GPU: move the slab planes towards the particle-count quantiles every N Updates (0 = never)
 			void setRebalanceInterval(uint32 everyNUpdates) { rebalanceEvery = everyNUpdates; }
+			// Multi-GPU, opt-in (before InitializeData): the page-locked mirrors (`positions`, `OutPositions`) are written
+			// by the GPUs' export kernels directly, row by row at the particle's index, instead of copied per rank and
+			// scattered on the host
+			void setDirectMirrors(bool on) { directMirrors = on; }
 			std::vector<uint32> particlesPerDevice() const;
 			// Multi-GPU: host milliseconds since the last call, slowest slab per phase -- step, download (wait + export +
 			// copy), scatter into index order, re-balancing; zeros on one GPU
@@ -146,6 +150,7 @@ namespace Physics
 			std::vector<int> devices;                            // more than one entry: slab mode through `group`
 			std::unique_ptr<sphb200::SlabGroup> group;
 			uint32 rebalanceEvery = 0, updatesSinceRebalance = 0;
+			bool directMirrors = false;
 			bool multi() const { return group != nullptr; }
 			void fetch(int field, void* out, size_t bytes, const char* what);   // sph_download / SlabGroup::download
 			SphParams params = defaultParams();

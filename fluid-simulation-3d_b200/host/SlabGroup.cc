@@ -218,6 +218,21 @@ void SlabGroup::download(int field, void* out, size_t out_bytes)
     if (out_bytes < per * (size_t)n_) throw std::runtime_error("SlabGroup::download: output buffer too small");
     std::vector<uint32_t> got((size_t)ranks(), 0u);
     unsigned char* dst = static_cast<unsigned char*>(out);
+    if (direct_) {
+        // every rank's export kernel writes its rows to out[id] itself; any failure (the array is not device-mapped)
+        // sends this call down the staged path below, which overwrites whatever was written
+        std::vector<int> rc((size_t)ranks(), SPH_OK);
+        parallel([&](int k) {
+            Rank& rk = rank_[(size_t)k];
+            const double t0 = nowMs();
+            rc[(size_t)k] = sph_download_owned_scatter(rk.ctx, field, out, n_, &got[(size_t)k]);
+            rk.ms[1] += nowMs() - t0;
+        });
+        bool ok = true;
+        uint64_t total = 0;
+        for (int k = 0; k < ranks(); k++) { ok = ok && rc[(size_t)k] == SPH_OK; total += got[(size_t)k]; }
+        if (ok && total == n_) return;
+    }
     parallel([&](int k) {
         Rank& rk = rank_[(size_t)k];
         const uint32_t m = sph_num_particles(rk.ctx);

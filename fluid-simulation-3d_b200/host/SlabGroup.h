@@ -39,6 +39,10 @@ public:
     bool rebalance(uint32_t max_shift = 1);
     // gather a field into index order; `out` holds particles() elements of the field's size (sph_b200.h: SPH_FIELD_*)
     void download(int field, void* out, size_t out_bytes);
+    // Opt-in: downloads into page-locked, device-mapped arrays (sph_host_register) let every rank's export kernel write
+    // its rows straight to out[id] (sph_download_owned_scatter): no staging copy, no host scatter.  An array that is
+    // not mapped falls back to the staged path for that call.
+    void setDirectScatter(bool on) { direct_ = on; }
     void timings(double out6[6]);                                 // per stage: the slowest rank
     std::vector<int32_t> layers() const;
     std::vector<uint32_t> ownedCounts() const;
@@ -79,6 +83,7 @@ private:
     SphParams params_;
     uint32_t n_ = 0;
     uint32_t cap_ = 0;
+    bool direct_ = false;
 };
 
 }  // namespace sphb200

@@ -138,6 +138,7 @@ static int run_multi(int n, int steps, int ndev)
     std::vector<int> devs;
     for (int d = 0; d < ndev; d++) devs.push_back(d);
     sim.setDevices(devs);
+    sim.setDirectMirrors(getenv("SPH_DEMO_DIRECT_MIRRORS") != nullptr);     // A/B: GPUs write the mirrors themselves
     sim.setRebalanceInterval(2);
     sim.InitializeData(n);                               // the reset path: same lattice, now handed to the slabs
     const float rho_spawn_multi = sim.getDensity((uint32)n / 2u);      // valid before the first Update, like the reference

@@ -224,6 +224,12 @@ int  sph_comm_set_planes(SphContext* ctx, const float* planes);
 int  sph_upload_owned(SphContext* ctx, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3);
 /* Download this rank's owned particles (device order): ids + requested field. */
 int  sph_download_owned(SphContext* ctx, int field, uint32_t* global_id, void* host, size_t host_bytes, uint32_t* out_n);
+/* The same download WITHOUT the gather on the host: the export kernel writes every owned row straight to
+ * host_base[global id] (element = the field's size), so after all ranks have called it the caller's array is complete
+ * in particle index order -- no staging copy, no ids, no host-side scatter.  host_base (host_elems elements, at least
+ * the largest id + 1) must be page-locked and device-mapped: sph_host_register it first.  Returns when this rank's rows
+ * are in host memory.  Ranks write disjoint elements, so they may call it concurrently from their own threads. */
+int  sph_download_owned_scatter(SphContext* ctx, int field, void* host_base, size_t host_elems, uint32_t* out_n);
 /* Pipelined forms of the two calls above (same rules as sph_upload_state_begin / sph_download_begin; committed with
  * sph_upload_state_commit, completed with sph_download_wait).  out_n is this rank's owned count at the time of the call. */
 int  sph_upload_owned_begin(SphContext* ctx, uint32_t n, const uint32_t* global_id, const float* pos3, const float* vel3);

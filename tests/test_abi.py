@@ -136,6 +136,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
         "sph_download_owned": lambda: L.sph_download_owned(None, 0, None, None, 0, None),
         "sph_upload_owned_begin": lambda: L.sph_upload_owned_begin(None, 0, None, None, None),
         "sph_download_owned_begin": lambda: L.sph_download_owned_begin(None, 0, None, None, 0, None),
+        "sph_download_owned_scatter": lambda: L.sph_download_owned_scatter(None, 0, None, 0, None),
         "sph_comm_stats": lambda: L.sph_comm_stats(None, None), "sph_comm_get_layers": lambda: L.sph_comm_get_layers(None, None),
         "sph_comm_rebalance": lambda: L.sph_comm_rebalance(None, 1, None, None, 0, None),
         "sph_slab_balance_layers": lambda: L.sph_slab_balance_layers(None, 0, 0, None, 0, 0, None),
