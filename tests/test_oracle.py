@@ -394,6 +394,23 @@ int main() {
 
 
 @needs_ref
+def test_reference_build_reproduces_its_own_fingerprints(ob):
+    """The unmodified reference, built by oracle/Makefile, on its own default scene (InitializeData(10000), gravity on,
+    dt = 0.016667f): FNV-1a fingerprints of positions and of the sorted key sequence after 1 and 10 verbatim Update()
+    calls.  They pin the BUILD (compiler flags, the abs() and `vector>` accommodations, no -march=native): any change that
+    alters a single bit of the reference's output shows up here.  (SURVEY 8(c) quotes fingerprints of the same runs from
+    a throw-away probe whose byte convention was not recorded; these are re-derived with ob.fnv1a64 over the raw fp32 /
+    u32 arrays.)"""
+    dt = float(np.float32(0.016667))
+    r = ob.RefOracle(10000, spawn=True, gravity=1)
+    r.update(dt)
+    assert (ob.fnv1a64(r.positions()), ob.fnv1a64(r.sorted_lookup()[2])) == ("1c71b1884d4c581d", "76a76230a85562c0")
+    for _ in range(9):
+        r.update(dt)
+    assert (ob.fnv1a64(r.positions()), ob.fnv1a64(r.sorted_lookup()[2])) == ("2c3ef7a42996212b", "a561be42e741eb31")
+
+
+@needs_ref
 def test_live_reference_getters_bounds(ob):
     r = ob.RefOracle(64, spawn=True)
     assert np.all(r.getter_probe(64) == 0) and np.all(r.getter_probe(2 ** 31) == 0)      # OOB -> zeros
