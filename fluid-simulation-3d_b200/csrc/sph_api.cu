@@ -138,8 +138,18 @@ int ensure_list(SphContext* c, NbrList* L)
     if (!c->h_overflow) {
         SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, sizeof(uint32_t)));
         *c->h_overflow = 0;
-        SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, sizeof(uint32_t)));
-        SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, sizeof(uint32_t), c->st));
+        SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, 2 * sizeof(uint32_t)));
+        SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, 2 * sizeof(uint32_t), c->st));
+        SPH_CUDA(c, cudaMallocHost((void**)&c->h_tile_need, sizeof(uint32_t)));
+        *c->h_tile_need = 0;
+        c->d_tile_need = c->d_overflow + 1;
+        c->tile_capn = tile_default_capn();
+    }
+    // tile generation: a cell whose 27-cell neighbourhood did not fit the staging buffer was walked instead (exact,
+    // slower); grow the buffer for the next step, as far as four warps' worth of 32-byte records fit one SM
+    if (!c->capturing && *c->h_tile_need > c->tile_capn) {
+        const uint32_t want = (*c->h_tile_need * 9u / 8u + 127u) & ~127u;
+        c->tile_capn = want > 1664u ? 1664u : want;
     }
     // auto-grow: the value may lag the kernels by a step or two (read without synchronising); overflowing
     // particles are exact meanwhile (the later passes walk the table for them), only slower
@@ -163,6 +173,9 @@ int ensure_list(SphContext* c, NbrList* L)
     L->ncount = c->ncount;
     L->k = c->list_k;
     L->stride = c->cap;
+    L->keys = c->sorted_where ? c->key_b : c->key_a;
+    L->capn = c->tile_capn;
+    L->tile_need = c->d_tile_need;
     return SPH_OK;
 }
 
@@ -174,6 +187,7 @@ static void free_all(SphContext* c)
                     c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
+    if (c->h_tile_need) cudaFreeHost(c->h_tile_need);
     if (c->d_overflow) cudaFree(c->d_overflow);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
@@ -391,6 +405,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_tile_need, c->d_tile_need, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (advance) {
@@ -436,7 +451,7 @@ static SphContext::StepKey step_key(const SphContext* c, float dt)
 {
     SphContext::StepKey k;
     memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
-    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc;
+    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn;
     k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
     return k;
 }

@@ -32,6 +32,9 @@ struct SphContext {
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
     uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
     uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
+    uint32_t tile_capn = 0;          // tile generation: staged candidates per warp (0: not initialised yet)
+    uint32_t* d_tile_need = nullptr; // device word: largest single-cell neighbourhood that did not fit
+    uint32_t* h_tile_need = nullptr; // pinned mirror, refreshed with h_overflow
     uint32_t *tstart = nullptr, *tend = nullptr;
     size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
     uint32_t* scan_tmp = nullptr; // block sums of the table scan (counting sort)
@@ -55,7 +58,7 @@ struct SphContext {
     // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
     // plain step and re-captures
     struct StepKey {
-        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc; int nc_tap;
+        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap;
         const void *nlist, *tstart, *scan_tmp, *tend;
     };
     cudaGraph_t graph = nullptr;

@@ -992,7 +992,7 @@ static int gather_variant()
         const char* e = getenv("SPH_GATHER");
         if (e && e[0] == 'v' && e[1] == '1') return 1;
         if (e && e[0] == 'v' && e[1] == '2') return 2;
-        return 0;
+        return 0;                            // "list" (lane per particle + list) or "tile" (sph_tile.cu, the default)
     }();
     return v;
 }
@@ -1041,7 +1041,17 @@ static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const 
     if (gather_variant() == 0 && L.idx && L.k) { A.list_idx = L.idx; A.list_k = L.k; A.list_stride = L.stride; }
     A.list_cnt = L.cnt;
     A.list_overflow = L.overflow;
+    A.key_sorted = L.keys;
+    A.list16 = reinterpret_cast<uint16_t*>(L.idx);
+    A.list_w = L.w;
+    A.tile_need = L.tile_need;
     return A;
+}
+
+// the tile generation (sph_tile.cu) runs a pass when the GRID table, the list and the sorted keys are all there
+static bool use_tile(const NbrList& L, const DevParams& P)
+{
+    return tile_enabled() && P.mode == SPH_TABLE_GRID && L.idx && L.k && L.w && L.keys && L.capn;
 }
 
 void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
@@ -1050,6 +1060,8 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.predpk = pred_pk;
     A.dens_out = dens; A.ncount = L.ncount;
+    if (use_tile(L, P) && launch_tile(st, PASS_DENSITY, A, P, L.capn, 0.0f, launches) == 0) return;
+    A.list_w = nullptr;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_DENSITY>(st, A, P, 0.0f, launches);
     else if (A.list_idx && density_variant() == 3 && P.mode == SPH_TABLE_GRID) {       // SPH_DENSITY=2: pair2
         if (P.row1 <= P.row0) return;
@@ -1092,6 +1104,7 @@ void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, co
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.dens = dens; A.vel_s = vel_s; A.velp_out = vel_p;
+    if (use_tile(L, P) && launch_tile(st, PASS_PRESSURE, A, P, L.capn, dt, launches) == 0) return;
     if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_PRESSURE>(st, A, P, dt, launches);
     else launch_walk_or_list<PASS_PRESSURE>(st, A, P, dt, A.list_idx != nullptr, launches);
 }
@@ -1102,6 +1115,7 @@ void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.velp = vel_p; A.velv_out = vel_v;
+    if (use_tile(L, P) && launch_tile(st, PASS_VISCOSITY, A, P, L.capn, dt, launches) == 0) return;
     if (density_is_pk(L, P) && !getenv("SPH_VISC_NOW")) {        // weights recorded by k_density_pk
         if (P.row1 <= P.row0) return;
         A.list_w = L.w;

@@ -32,6 +32,10 @@ struct GatherArgs {
     float4* velp_out;          // pressure pass: v' (velocity after pressure)
     const float4* velp;        // viscosity pass: post-pressure snapshot
     float4* velv_out;          // viscosity pass
+    // tile generation (sph_tile.cu)
+    const uint32_t* key_sorted; // GRID keys of the sorted rows
+    uint16_t* list16;          // neighbour list as 16-bit indices into the warp's staged runs (same geometry as list_idx)
+    uint32_t* tile_need;       // device word: largest single-cell neighbourhood that did not fit the staging buffer
 };
 
 // ---- packed fp32x2 (sm_100a) -------------------------------------------------
@@ -155,9 +159,11 @@ __device__ __forceinline__ bool eval(const DevParams& P, const Self& s, const ui
         }
     } else if (PASS == PASS_PRESSURE) {
         if (j == s.i) return false;                        // :396
-        const bool zero = !(d2 > 0.0f);
-        const float inv = zero ? 0.0f : rsqrt_approx(d2);
-        const float d = d2 * inv;
+        // the reference's own distance (sqrtf is correctly rounded): r - d keeps no bit that an approximate root gets
+        // wrong when d is within ulps of r -- a lone neighbour at the rim of the kernel (tools/gpu_fuzz.py)
+        const float d = __fsqrt_rn(d2);
+        const bool zero = !(d > 0.0f);
+        const float inv = zero ? 0.0f : rcp_approx(d);
         if (d <= P.r) {                                    // kernels.h:51,63
             const float v = P.r - d;
             // (P_i + P_j)/rho_j = (P_i - k rho0)/rho_j + k ;  (nP_i + nP_j)/nrho_j = nP_i/nrho_j + kn

@@ -100,7 +100,15 @@ struct NbrList {
     uint32_t* overflow; // host-mapped: largest list length that did not fit (0 = none)
     uint32_t  k;        // entries per row before a row counts as overflowed
     uint32_t  stride;
+    // tile generation (sph_tile.cu): sorted GRID keys, staging capacity per warp, "did not fit" report
+    const uint32_t* keys;
+    uint32_t  capn;
+    uint32_t* tile_need;
 };
+struct GatherArgs;
+bool tile_enabled();
+uint32_t tile_default_capn();
+int launch_tile(cudaStream_t st, int pass, const GatherArgs& A, const DevParams& P, uint32_t capn, float dt, uint64_t* launches);
 void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
                     Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches);
 void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
