@@ -210,10 +210,15 @@ def cpu_reference_c1(steps, warmup, parallel=True):
 
 def workload_text(name, n, bound, mu):
     """the `config.workload` string of a single-GPU run; the reference arm names its workload with the same words"""
-    return (("%s: %d particles, the reference's InitializeData lattice (gap 0.215, centred), bounds %s, "
-             "r=0.35, gravity on, mu=%.2f, dt=0.016667" if name == C1_NAME else
-             "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, "
-             "r=0.35, gravity on, mu=%.2f, dt=0.016667") % (name, n, tuple(round(float(x), 3) for x in bound), mu))
+    if name == C1_NAME:
+        f = "%s: %d particles, the reference's InitializeData lattice (gap 0.215, centred), bounds %s, r=0.35, gravity on, mu=%.2f, dt=0.016667"
+    elif name == C5_NAME:
+        f = ("%s: %d particles, jittered lattice gap 0.1216 (~100 neighbours per particle), a 100 x 800 x 100 column centred on the "
+             "floor, velocities uniform in [-0.5, 0.5]^3, bounds %s, r=0.35, gravity on, mu=%.2f, dt=0.016667; the dense spawn "
+             "state is restored before every timed step (the column explodes within three steps, in the reference too)")
+    else:
+        f = "%s: %d particles, jittered lattice gap 0.215 in the -x/floor corner, bounds %s, r=0.35, gravity on, mu=%.2f, dt=0.016667"
+    return f % (name, n, tuple(round(float(x), 3) for x in bound), mu)
 
 
 def reference_arm_workload(name, gpus):
@@ -241,7 +246,7 @@ def run_reference_arm(args, rank):
     text, n_full = reference_arm_workload(name, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "M updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": text, "particles": n_full, "sample_particles": r["n"],
                        "note": "the reference CPU step on a bounded sample of this workload (see cpu_baseline.sample)"},
             "cpu_baseline": {"value": r["value"], "unit": "M updates/s", "cores": r["cores"], "kind": r["kind"],
@@ -261,8 +266,10 @@ def main():
     ap.add_argument("--table", default="grid", choices=["grid", "refhash"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--rebalance", type=int, default=0, metavar="K",
+    ap.add_argument("--rebalance", type=int, default=4, metavar="K",
                     help="multi-GPU: sph_comm_rebalance every K steps (inside the timed region); 0 = planes stay where the initial quantile cut put them")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the short C1 / C3 / C5 / C4 lines of the `configs` block")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU parity gate")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -292,7 +299,7 @@ def main():
     else:
         from fluid_simulation_3d_b200 import slab_driver
         result = slab_driver.bench_multi(args, pkg, scenes, torch, dist, rank, world, local_rank, METRIC, A_BYTES,
-                                         measured_peaks, ClockSampler)
+                                         measured_peaks, ClockSampler, short_line=short_line)
     if rank == 0 and result is not None:
         print(json.dumps(result), flush=True)
     if world > 1:
@@ -301,6 +308,7 @@ def main():
 
 
 C1_NAME = "C1_default_10k"      # BASELINE.json configs[0]: exactly InitializeData(10000), default bounds, gravity on
+C5_NAME = "C5_column_8M"        # configs[4]: the high-density column; every timed step starts from the dense spawn state
 
 
 def c1_scene(pkg, dev):
@@ -313,6 +321,63 @@ def c1_scene(pkg, dev):
     pos = sim.download("positions").copy()
     sim.close()
     return dict(pos=pos, vel=np.zeros_like(pos), bound=(20.0, 20.0, 20.0), n=n, params=params)
+
+
+def short_line(pkg, scenes, torch, dev, name, steps=5, warmup=3, flush=None):
+    """A short device-timed line of another BASELINE config (the `configs` block of the default run, and the same-workload
+    1-GPU anchor of the multi-GPU curve): the scene is spawned on the device (sph_spawn_grid / sph_spawn_block, bit-identical
+    to the host generators), `warmup` untimed steps, `steps` steps each inside its own CUDA-event pair on the solver's
+    stream, L2 flushed between them."""
+    peak, _ = measured_peaks()
+    dt = scenes.DT
+    if name == C1_NAME:
+        n, bound, mu = 10000, (20.0, 20.0, 20.0), 0.5
+        sim = pkg.FluidSimulation(n, device=dev, gravity=1)
+        respawn = lambda: sim.spawn_grid(n)
+    else:
+        meta = scenes.config_meta(name)
+        n, bound, mu = meta["n"], meta["bound"], meta["params"].get("viscosity_strength", 0.5)
+        sim = pkg.FluidSimulation(n, device=dev, **meta["params"])
+        respawn = lambda: sim.spawn_block(**meta["spawn"])
+    dense = name == C5_NAME
+    if dense:
+        sim.set_neighbour_list_capacity(192)
+    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=dev)
+    respawn()
+    for _ in range(warmup):
+        if dense:
+            respawn()
+        sim.step(dt)
+    sim.synchronize()
+    stage, total_ms = np.zeros(6), 0.0
+    for _ in range(steps):
+        if dense:
+            respawn()
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sim.step(dt)
+        b.record(stream)
+        stage += sim.timings()
+        sim.synchronize()
+        total_ms += a.elapsed_time(b)
+    stage /= steps
+    mean_nb = float(sim.download("neighbour_count").mean()) if n <= (1 << 24) else None
+    sim.close()
+    names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
+    gather = {"density": stage[2], "pressure": stage[3], "viscosity": stage[4]}
+    dom = max(gather, key=gather.get)
+    ach = A_BYTES[dom] * n / (gather[dom] * 1e-3) / 1e9
+    value = n * steps / (total_ms * 1e-3) / 1e6
+    return {"workload": workload_text(name, n, bound, mu), "particles": n, "value": value, "unit": "M updates/s",
+            "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+            "stage_ms": {k: float(v) for k, v in zip(names, stage)},
+            "mean_neighbours_last_step": mean_nb,
+            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(gather[dom]),
+                         "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak}}}
 
 
 def bench_single(args, pkg, scenes, torch, dev):
@@ -335,7 +400,16 @@ def bench_single(args, pkg, scenes, torch, dev):
             with torch.cuda.stream(stream):
                 flush.fill_(1)
 
+    dense = name == C5_NAME          # the column explodes within three steps: every step starts from the dense spawn state
+    if dense:
+        sim.set_neighbour_list_capacity(192)
+
+    def restore():
+        if dense:
+            sim.spawn_block(**sc["spawn"])         # device-side, bit-identical to the host arrays (tests/test_spawn_gpu.py)
+
     for _ in range(args.warmup):
+        restore()
         sim.step(dt)
     sim.synchronize()
     torch.cuda.synchronize()
@@ -347,6 +421,7 @@ def bench_single(args, pkg, scenes, torch, dev):
     stage = np.zeros(6)
     l0 = sim.launch_count()
     for a, b in ev:
+        restore()                       # outside the event pair
         l2_flush()
         a.record(stream)
         sim.step(dt)
@@ -354,7 +429,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         stage += sim.timings()          # waits for the step's last stage event
     sim.synchronize()
     torch.cuda.synchronize()
-    launches = sim.launch_count() - l0
+    launches = sim.launch_count() - l0 - (args.steps if dense else 0)      # the restoring spawn kernel is not part of the step
     ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(ms.sum())
     value = n * args.steps / (total_ms * 1e-3) / 1e6
@@ -364,7 +439,10 @@ def bench_single(args, pkg, scenes, torch, dev):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sim.set_stage_timing(False)
     steady_steps = max(args.steps, 200) if n <= 200000 else args.steps    # small scenes: enough steps to time
-    sim.step_n(dt, 4)                            # records the step's CUDA graph outside the timed region
+    if dense:
+        steady_steps = 2                         # back to back from the dense state: the second step is already a blow-up
+        restore()
+    sim.step_n(dt, 4 if not dense else 1)        # records the step's CUDA graph outside the timed region
     r0 = sim.graph_replays()
     a.record(stream)
     sim.step_n(dt, steady_steps)
@@ -478,7 +556,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         gather_kernels[key] = row
     result = {
         "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_text(name, n, sc["bound"], sc["params"].get("viscosity_strength", 0.5)),
                    "particles": n, "table": args.table,
@@ -486,7 +564,8 @@ def bench_single(args, pkg, scenes, torch, dev):
                          else "not flushed"},
         "steady_state": {"value": n / (steady_ms * 1e-3) / 1e6, "ms_per_step": steady_ms,
                          "steps": steady_steps, "graph_replays": int(steady_replays),
-                         "note": "sph_step_n: steps back to back (CUDA-graph replay), no L2 flush, stage timers off"},
+                         "note": ("sph_step_n: steps back to back (CUDA-graph replay), no L2 flush, stage timers off" if not dense else
+                                  "two steps back to back from the dense state: the second one is already the blow-up")},
         "stage_ms": {k: float(v) for k, v in zip(names, stage)},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -512,6 +591,20 @@ def bench_single(args, pkg, scenes, torch, dev):
         "clocks": clk,
     }
     sim.close()
+    if not args.config and not args.no_configs:
+        # the other BASELINE configs, short lines under the driver's eyes; C4 on ONE GPU is the same-workload anchor of the
+        # multi-GPU curve (the N > 1 lines run C4 slab-decomposed): efficiency(N) = strong_base.ms_per_step / (N * ms_per_step(N))
+        del h_pos, h_vel, h_out, h_out2
+        result["configs"] = {}
+        for cname in (C1_NAME, "C3_dambreak_8M", C5_NAME, "C4_dambreak_64M"):
+            try:
+                result["configs"][cname] = short_line(pkg, scenes, torch, dev, cname, flush=flush)
+            except Exception as ex:                         # a failing extra line must not cost the headline
+                result["configs"][cname] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        c4 = result["configs"].get("C4_dambreak_64M", {})
+        if "ms_per_step" in c4:
+            result["strong_base"] = {"workload": "C4_dambreak_64M on one GPU", "ms_per_step": c4["ms_per_step"], "value": c4["value"],
+                                     "unit": "M updates/s", "particles": c4["particles"]}
     def one_thread(fn, **kw):            # the same reference on libstdc++'s serial backend, beside the all-threads number
         try:
             q = fn(parallel=False, **kw)

@@ -72,6 +72,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
     P->row0 = 0; P->row1 = n; P->n_a = n;
+    P->rim_check = (double)p.sqr_radius > (double)r * (double)r * (1.0 + 4e-7) ? 1 : 0;
     P->slab = 0; P->zlo = 0; P->gz_global = c->gdim[2]; P->own_lo = 0; P->own_hi = c->gdim[2];
     return SPH_OK;
 }

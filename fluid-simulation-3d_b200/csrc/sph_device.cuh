@@ -97,6 +97,23 @@ __device__ __forceinline__ Win window_of(const float px, const float py, const f
     W.rows = rows;
     return W;
 }
+// Cells on the rim of the GRID table collect what lies beyond it (grid_cell clamps), so there the table cell is not the
+// reference's cell.  A particle whose table cell is within one cell of the rim can meet such outliers among its 27
+// table cells; for it the walk also compares TRUE cell coordinates: j is in one of the reference's 27 cells of i iff
+// they differ by at most one per axis (:331-337).  It matters when the cut-off exceeds the cell size (Q2): with
+// sqrt(sqrRadius) <= r the distance test alone excludes everything outside the 27 true cells.
+__device__ __forceinline__ bool near_table_rim(const int3 g, const DevParams& P)
+{
+    if (!P.rim_check) return false;
+    const int cx = g.x / P.xsub, ncx = P.gdim[0] / P.xsub, gzg = g.z + P.zlo;
+    return cx <= 1 || cx >= ncx - 2 || g.y <= 1 || g.y >= P.gdim[1] - 2 || gzg <= 1 || gzg >= P.gz_global - 2;
+}
+static __device__ __noinline__ bool within_27(const float4 q, const float4 p, const float r)
+{
+    const int3 a = cell_of(q.x, q.y, q.z, r), b = cell_of(p.x, p.y, p.z, r);
+    return abs(a.x - b.x) <= 1 && abs(a.y - b.y) <= 1 && abs(a.z - b.z) <= 1;
+}
+
 __device__ __forceinline__ uint32_t grid_key(int3 g, const DevParams& P)
 {
     return ((uint32_t)g.z * (uint32_t)P.gdim[1] + (uint32_t)g.y) * (uint32_t)P.gdim[0] + (uint32_t)g.x;

@@ -970,6 +970,48 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
     report_overflow(A, (valid && kbase > K) ? kbase : 0u);
 }
 
+
+// ---- rim fix-up (Q2 regime only: the cut-off exceeds the cell size) -----------------------------------------------
+// Cells on the rim of the GRID table hold clamped outliers, so for a particle within one cell of the rim the 27 table
+// cells are a superset of the reference's 27 cells; when the cut-off is larger than a cell the distance test no longer
+// removes the extras.  The main kernels stay as they are; this pass recomputes the few particles concerned with the
+// table walk plus a true-cell comparison (sph_device.cuh: within_27) and overwrites their results.  Launched only
+// when DevParams::rim_check is set (an interaction radius below sqrt(sqrRadius): a UI slider position).
+template <int PASS>
+__global__ void __launch_bounds__(kWalkThreads)
+k_rim_fix(const GatherArgs A, const DevParams P, const float dt)
+{
+    const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.row1) return;
+    const float4 p = A.pred[i];
+    if (!near_table_rim(grid_cell(p.x, p.y, p.z, P), P)) return;
+    const Self s = load_self<PASS>(A, P, i);
+    Acc acc = {0.0f, 0.0f, 0.0f, 0u};
+    for_each_candidate<SPH_TABLE_GRID, true>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) {
+        Fetched f;
+        f.q = q;
+        f.aux = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (PASS != PASS_DENSITY) {
+            float ox, oy, oz;
+            if (sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r) return;
+            f = fetch<PASS>(A, j);
+        }
+        (void)eval<PASS>(P, s, j, f, acc);
+    });
+    finish<PASS>(A, P, s, acc, dt);
+    // the list the main density kernel recorded holds the extras: mark it overflowed, the later passes walk the
+    // table for this particle and their own fix-up overwrites the result
+    if (PASS == PASS_DENSITY && A.list_cnt) A.list_cnt[i] = 0xFFFFFFFFu;
+}
+
+template <int PASS>
+static void launch_rim_fix(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
+{
+    if (!P.rim_check || P.mode != SPH_TABLE_GRID || P.row1 <= P.row0) return;
+    k_rim_fix<PASS><<<(P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, st>>>(A, P, dt);
+    ++*launches;
+}
+
 template <int PASS>
 void launch(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
 {
@@ -1054,8 +1096,8 @@ static bool use_tile(const NbrList& L, const DevParams& P)
     return tile_enabled() && P.mode == SPH_TABLE_GRID && L.idx && L.k && L.w && L.keys && L.capn;
 }
 
-void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
-                    Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
+static void launch_density_main(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
+                                Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.predpk = pred_pk;
@@ -1098,9 +1140,9 @@ void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk
     } else launch_walk_or_list<PASS_DENSITY>(st, A, P, 0.0f, false, launches);           // SPH_DENSITY=walk / no list
 }
 
-void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
-                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
-                     float dt, uint64_t* launches)
+static void launch_pressure_main(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
+                                 const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+                                 float dt, uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.dens = dens; A.vel_s = vel_s; A.velp_out = vel_p;
@@ -1109,9 +1151,9 @@ void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, co
     else launch_walk_or_list<PASS_PRESSURE>(st, A, P, dt, A.list_idx != nullptr, launches);
 }
 
-void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
-                      const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
-                      uint64_t* launches)
+static void launch_viscosity_main(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+                                  const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
+                                  uint64_t* launches)
 {
     GatherArgs A = base_args(pred_s, tstart, tend, L);
     A.velp = vel_p; A.velv_out = vel_v;
@@ -1123,6 +1165,40 @@ void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p
         ++*launches;
     } else if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_VISCOSITY>(st, A, P, dt, launches);
     else launch_walk_or_list<PASS_VISCOSITY>(st, A, P, dt, A.list_idx != nullptr, launches);
+}
+
+// the public launchers: the pass itself, then (Q2 regime only, never for the tile generation, which compares true cells
+// itself) the fix-up of the particles next to the table's rim
+void launch_density(cudaStream_t st, const float4* pred_s, const float4* pred_pk, const uint32_t* tstart, const uint32_t* tend,
+                    Rec8* dens, const NbrList& L, const DevParams& P, uint64_t* launches)
+{
+    launch_density_main(st, pred_s, pred_pk, tstart, tend, dens, L, P, launches);
+    if (!P.rim_check || use_tile(L, P)) return;
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.dens_out = dens; A.ncount = L.ncount;
+    launch_rim_fix<PASS_DENSITY>(st, A, P, 0.0f, launches);
+}
+
+void launch_pressure(cudaStream_t st, const float4* pred_s, const Rec8* dens, const float4* vel_s,
+                     const uint32_t* tstart, const uint32_t* tend, float4* vel_p, const NbrList& L, const DevParams& P,
+                     float dt, uint64_t* launches)
+{
+    launch_pressure_main(st, pred_s, dens, vel_s, tstart, tend, vel_p, L, P, dt, launches);
+    if (!P.rim_check || use_tile(L, P)) return;
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.dens = dens; A.vel_s = vel_s; A.velp_out = vel_p;
+    launch_rim_fix<PASS_PRESSURE>(st, A, P, dt, launches);
+}
+
+void launch_viscosity(cudaStream_t st, const float4* pred_s, const float4* vel_p, const uint32_t* tstart,
+                      const uint32_t* tend, float4* vel_v, const NbrList& L, const DevParams& P, float dt,
+                      uint64_t* launches)
+{
+    launch_viscosity_main(st, pred_s, vel_p, tstart, tend, vel_v, L, P, dt, launches);
+    if (!P.rim_check || use_tile(L, P)) return;
+    GatherArgs A = base_args(pred_s, tstart, tend, L);
+    A.velp = vel_p; A.velv_out = vel_v;
+    launch_rim_fix<PASS_VISCOSITY>(st, A, P, dt, launches);
 }
 
 }  // namespace sphb200

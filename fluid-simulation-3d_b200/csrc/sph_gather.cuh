@@ -161,9 +161,11 @@ __device__ __forceinline__ bool eval(const DevParams& P, const Self& s, const ui
         if (j == s.i) return false;                        // :396
         // the reference's own distance (sqrtf is correctly rounded): r - d keeps no bit that an approximate root gets
         // wrong when d is within ulps of r -- a lone neighbour at the rim of the kernel (tools/gpu_fuzz.py)
-        const float d = __fsqrt_rn(d2);
-        const bool zero = !(d > 0.0f);
-        const float inv = zero ? 0.0f : rcp_approx(d);
+        const float rs = rsqrt_approx(d2);
+        const bool zero = !(d2 > 0.0f);
+        const float d0 = d2 * rs;
+        const float d = zero ? 0.0f : fmaf(fmaf(-d0, d0, d2), 0.5f * rs, d0);     // one Newton step: sqrtf's value
+        const float inv = zero ? 0.0f : rs;
         if (d <= P.r) {                                    // kernels.h:51,63
             const float v = P.r - d;
             // (P_i + P_j)/rho_j = (P_i - k rho0)/rho_j + k ;  (nP_i + nP_j)/nrho_j = nP_i/nrho_j + kn
@@ -216,7 +218,7 @@ __device__ __forceinline__ void finish(const GatherArgs& A, const DevParams& P, 
 
 // ---- neighbour walk ---------------------------------------------------------
 // Calls f(j, pred_j) for every candidate row the reference's walk would reach for a particle at pi.
-template <int MODE, class F>
+template <int MODE, bool RIM = false, class F>
 __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pred_s,
                                                    const uint32_t* __restrict__ tstart,
                                                    const uint32_t* __restrict__ tend,
@@ -243,6 +245,7 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pr
         const Win W = window_of(pi.x, pi.y, pi.z, P);
         const int3 g = W.g;
         const int x0 = W.x0, x1 = W.x1;
+        const bool rim = RIM && near_table_rim(g, P);
         #pragma unroll 1
         for (int dz = -1; dz <= 1; dz++) {
             const int z = g.z + dz;
@@ -254,7 +257,11 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pr
                 const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
                 const uint32_t b = __ldg(&tstart[row + x0]);
                 const uint32_t e = __ldg(&tstart[row + x1 + 1]);
-                for (uint32_t j = b; j < e; j++) f(j, __ldg(&pred_s[j]));
+                for (uint32_t j = b; j < e; j++) {
+                    const float4 q = __ldg(&pred_s[j]);
+                    if (RIM && rim && !within_27(q, pi, P.r)) continue;      // clamped outliers in the rim cells (Q2)
+                    f(j, q);
+                }
             }
         }
     }

@@ -41,6 +41,7 @@ struct DevParams {
     int      zlo, gz_global, own_lo, own_hi;
     int      has_lo, has_hi;   // a neighbour rank exists below / above
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
+    int      rim_check;        // the cut-off exceeds the cell size (Q2): particles next to the table's rim compare true cells (sph_device.cuh)
 };
 
 // 32-byte per-particle record read with ONE 256-bit load (LDG.E.256 on sm_100a) by the pressure pass:

@@ -97,14 +97,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan16(uint32_t v, const int lane)
     return v;
 }
 
-// true-cell test for targets next to the table border (cells there hold clamped outliers): j is one of the
-// reference's 27 cells of i iff the true cell coordinates differ by at most one per axis (:331-337)
-__device__ __forceinline__ bool within_27(const float4 q, const float4 p, const float r)
-{
-    const int3 a = cell_of(q.x, q.y, q.z, r), b = cell_of(p.x, p.y, p.z, r);
-    return abs(a.x - b.x) <= 1 && abs(a.y - b.y) <= 1 && abs(a.z - b.z) <= 1;
-}
-
 // S4 term with the reference's own distance: sqrtf is correctly rounded there, and (r - d) loses every bit that an
 // approximate root gets wrong when d is within ulps of r (a lone neighbour at the rim of the kernel)
 __device__ __forceinline__ void pressure_term(const DevParams& P, const float4 p, const float c0, const float c1s,
@@ -113,10 +105,13 @@ __device__ __forceinline__ void pressure_term(const DevParams& P, const float4 p
     float ox, oy, oz;
     const float d2 = sqr_dist(qlo, p, ox, oy, oz);
     if (d2 > P.sqr_r) return;                              // :402
-    const float d = __fsqrt_rn(d2);
+    const float rs = rsqrt_approx(d2);
+    const bool zero = !(d2 > 0.0f);
+    const float d0 = d2 * rs;
+    const float dn = fmaf(fmaf(-d0, d0, d2), 0.5f * rs, d0);   // one Newton step on the approximate root: sqrtf's value
+    const float d = zero ? 0.0f : dn;
     if (d <= P.r) {                                        // kernels.h:51,63
-        const bool zero = !(d > 0.0f);
-        const float inv = zero ? 0.0f : rcp_approx(d);
+        const float inv = zero ? 0.0f : rs;
         const float v = P.r - d;
         const float c1 = fmaf(c0, qhi.y, P.k);             // (P_i + P_j)/rho_j = (P_i - k rho0)/rho_j + k
         const float c2 = fmaf(c1s, qhi.z, P.kn);           // (nP_i + nP_j)/nrho_j = nP_i/nrho_j + kn
@@ -136,10 +131,9 @@ __device__ __noinline__ void walk_target(const GatherArgs& A, const DevParams& P
 {
     const Self s = load_self<PASS>(A, P, t);
     Acc acc = {0.0f, 0.0f, 0.0f, 0u};
-    for_each_candidate<SPH_TABLE_GRID>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) {
+    for_each_candidate<SPH_TABLE_GRID, true>(A.pred, A.table, A.tend, s.p, P, [&](const uint32_t j, const float4 q) {
         float ox, oy, oz;
         if (sqr_dist(q, s.p, ox, oy, oz) > P.sqr_r) return;
-        if (border && !within_27(q, s.p, P.r)) return;
         if (PASS == PASS_PRESSURE) {
             if (j == t) return;
             const Rec8 r = ld256(&A.dens[j]);
@@ -186,7 +180,7 @@ k_tile(const __grid_constant__ GatherArgs A, const __grid_constant__ DevParams P
     const int cx = (int)((key - R * gx) >> xs);
     const int gyy = (int)(R % gyd), gzz = (int)(R / gyd);
     const int gzg = gzz + P.zlo;                           // global z layer (slab mode: the table is a window of it)
-    const bool border = cx <= 1 || cx >= ncx - 2 || gyy <= 1 || gyy >= (int)gyd - 2 || gzg <= 1 || gzg >= P.gz_global - 2;
+    const bool border = P.rim_check && (cx <= 1 || cx >= ncx - 2 || gyy <= 1 || gyy >= (int)gyd - 2 || gzg <= 1 || gzg >= P.gz_global - 2);   // near_table_rim
     const uint32_t K = A.list_k;
     const size_t stride = A.list_stride;
 

@@ -89,6 +89,22 @@ CONFIGS = {
 }
 
 
+def config_meta(name):
+    """dict(bound, params, n, dims, spawn) of a named BASELINE config WITHOUT generating the particles: `spawn` are the
+    sph_spawn_block arguments that make the same set, bit for bit, on the device"""
+    if name in CONFIGS:
+        nx, ny, nz, seed = CONFIGS[name]
+        bound = (3 * nx * GAP0, 1.5 * ny * GAP0, nz * GAP0 + GAP0)
+        return dict(bound=bound, n=nx * ny * nz, dims=(nx, ny, nz), params=dict(gravity=1, viscosity_strength=0.5, bound=bound),
+                    spawn=device_spawn_args(nx, ny, nz, GAP0, bound, seed, anchor="corner"))
+    if name == "C5_column_8M":
+        nx, ny, nz, gap = 100, 800, 100, 0.1216
+        bound = (36.5, 146.0, 36.5)
+        return dict(bound=bound, n=nx * ny * nz, dims=(nx, ny, nz), params=dict(gravity=1, viscosity_strength=1.0, bound=bound),
+                    spawn=device_spawn_args(nx, ny, nz, gap, bound, 0xC5, anchor="floor_center", vel_amp=0.5))
+    raise KeyError(name)
+
+
 def config(name, ids=None):
     """Returns dict(pos, vel, bound, params, n) for a named BASELINE config."""
     if name in CONFIGS:

@@ -158,6 +158,93 @@ def broadcast_id(pkg, dist, torch, rank, device):
     return obj[0]
 
 
+def gather_by_id(dist, n_total, ids, arr):
+    """every rank's (ids, rows) assembled into index order on every rank; ownership must be a partition"""
+    objs = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, (ids, arr))
+    out = np.zeros((n_total,) + arr.shape[1:], arr.dtype)
+    seen = np.zeros(n_total, np.int32)
+    for i, a in objs:
+        out[i] = a
+        seen[i] += 1
+    if not np.all(seen == 1):
+        raise AssertionError("ownership is not a partition: %d missing, %d duplicated" % ((seen == 0).sum(), (seen > 1).sum()))
+    return out
+
+
+PARITY_FIELDS = ("neighbour_count", "hash", "densities", "vel_after_pressure", "vel_after_viscosity", "positions", "velocities")
+
+
+def parity_gate(pkg, scenes, dist, torch, rank, world, dev, n_side=100, seed=0xC2, steps=2):
+    """The slab-decomposed step against the single-GPU step on the same state (n_side^3 <= 2^24 particles of the
+    dam-break rule; n_side = 100, seed 0xC2 is BASELINE configs[1]): every rank steps its slab, rank 0 steps the whole
+    set on its own GPU, rows are matched by particle id.  Hashes and neighbour counts bit-exact; floats within
+    1e-5 * (step + 1) of max(|ref|, max|ref| of the field) -- summation order is the only difference between the two.
+    Returns the dict bench.py prints as "parity"; raises AssertionError on a mismatch (on every rank)."""
+    sc = scenes.small_dam_break(n_side, seed=seed)
+    n, dt = sc["n"], scenes.DT
+    idb = broadcast_id(pkg, dist, torch, rank, dev)
+    slab = SlabSimulation(pkg, int(n / world * 1.5) + 65536, rank, world, dev, idb, **sc["params"])
+    gmin_z, gz = int(slab.origin[2]), int(slab.dims[2])
+    layers = choose_layers(sc["pos"][:, 2], world, slab.r, gmin_z, gz)
+    slab.set_layers(layers)
+    own = owner_of(sc["pos"][:, 2], layers, slab.r, gmin_z, gz) == rank
+    slab.sim.set_neighbour_count_tap(True)
+    slab.upload_owned(np.nonzero(own)[0].astype(np.uint32), sc["pos"][own], sc["vel"][own])
+    single = None
+    if rank == 0:
+        single = pkg.FluidSimulation(n, device=dev, **sc["params"])
+        single.set_neighbour_count_tap(True)
+        single.upload_state(sc["pos"], sc["vel"])
+    worst, migrated, err = {}, 0, None
+    for s in range(steps):
+        slab.step(dt)
+        st = slab.stats()
+        migrated += st["migrated_lo"] + st["migrated_hi"]
+        fields = {}
+        for f in PARITY_FIELDS:
+            i, a = slab.download_owned(f)
+            fields[f] = gather_by_id(dist, n, i, a)
+        if rank == 0:
+            single.step(dt)
+            try:
+                assert np.array_equal(fields["hash"], single.download("hash")), "step %d: cell hashes differ" % s
+                nc = single.download("neighbour_count")
+                assert np.array_equal(fields["neighbour_count"], nc), "step %d: %d neighbour counts differ" % (
+                    s, int((fields["neighbour_count"] != nc).sum()))
+                for f in PARITY_FIELDS[2:]:
+                    ref = single.download(f).astype(np.float64)
+                    got = fields[f].astype(np.float64)
+                    floor = 0.0 if f == "densities" else np.abs(ref).max()
+                    scale = np.maximum(np.abs(ref), floor + 1e-30)
+                    rel = np.abs(got - ref) / scale
+                    worst[f] = max(worst.get(f, 0.0), float(rel.max()))
+                    assert rel.max() <= 1e-5 * (s + 1), "step %d: %s off by %.3g of its scale" % (s, f, rel.max())
+            except AssertionError as e:
+                err = str(e)
+        flag = torch.tensor([1 if err else 0], device="cuda:%d" % dev)
+        dist.all_reduce(flag)
+        if int(flag.item()):
+            break
+    tot = torch.tensor([migrated], device="cuda:%d" % dev)
+    dist.all_reduce(tot)
+    if single is not None:
+        single.close()
+    slab.close()
+    dist.barrier()
+    res = {"ok": err is None, "against": "single-GPU step of the same state on rank 0's GPU, rows matched by particle id",
+           "particles": n, "state": "dam-break rule %d^3, seed 0x%X" % (n_side, seed), "steps": steps, "ranks": world,
+           "layers": layers, "migrations": int(tot.item()),
+           "integers": "cell hash and neighbour count bit-exact",
+           "floats_worst_rel": worst, "float_tolerance": "1e-5 * (step + 1) of max(|ref|, max|ref| of the field); densities: of |ref|"}
+    if int(flag.item()):
+        if rank == 0:
+            res["error"] = err
+            print(json.dumps({"parity": res}), flush=True)
+        raise AssertionError("multi-GPU parity gate failed" + (": " + err if err else " (see rank 0)"))
+    return res
+
+
 def lattice_ids_for_rank(nx, ny, nz, iz_lo, iz_hi):
     """Global ids of the lattice sites with iz in [iz_lo, iz_hi): id = (iy*nx + ix)*nz + iz."""
     iz = np.arange(max(iz_lo, 0), min(iz_hi, nz), dtype=np.uint64)
@@ -181,8 +268,25 @@ def generate_rank_particles(scenes, name, layers, rank, r, gmin_z, gz):
     return ids[own].astype(np.uint32), pos[own], vel[own], bound
 
 
-def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler):
+def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler, short_line=None):
     name = args.config or "C4_dambreak_64M"
+    # (0) parity gate: the slab-decomposed step must equal the single-GPU step before anything is timed
+    parity = None
+    if not getattr(args, "no_parity", False):
+        parity = parity_gate(pkg, scenes, dist, torch, rank, world, dev)       # raises (exit code != 0) on a mismatch
+    # (0b) the same workload on ONE GPU (rank 0's), the anchor of the strong-scaling curve
+    strong_base = None
+    if short_line is not None and not getattr(args, "no_configs", False):
+        if rank == 0:
+            try:
+                q = short_line(pkg, scenes, torch, dev, name, steps=5, warmup=3,
+                               flush=None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % dev))
+                strong_base = {"workload": name + " on one GPU (rank 0, before the multi-GPU run)", "ms_per_step": q["ms_per_step"],
+                               "value": q["value"], "unit": "M updates/s", "stage_ms": q["stage_ms"]}
+            except Exception as ex:
+                strong_base = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            torch.cuda.empty_cache()
+        dist.barrier()
     nx, ny, nz, seed = scenes.CONFIGS[name]
     n_total = nx * ny * nz
     bound = (3 * nx * scenes.GAP0, 1.5 * ny * scenes.GAP0, nz * scenes.GAP0 + scenes.GAP0)
@@ -254,7 +358,7 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
     tp = torch.from_numpy(pos_h).pin_memory(); tv = torch.from_numpy(vel_h).pin_memory(); ti = torch.from_numpy(ids_h.astype(np.int32)).pin_memory()
     out_h = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
     L = slab.sim.L
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(20, args.steps)
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -320,7 +424,15 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
     dom = max(gather, key=gather.get)
     achieved = A_BYTES[dom] * (n_total / world) / (gather[dom] * 1e-3) / 1e9
     names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
+    extra = {}
+    if parity is not None:
+        extra["parity"] = parity
+    if strong_base is not None:
+        extra["strong_base"] = strong_base
+        if "ms_per_step" in strong_base:
+            extra["efficiency_vs_strong_base"] = strong_base["ms_per_step"] / (world * (total_ms / args.steps))
     return {
+        **extra,
         "metric": METRIC, "value": value, "unit": "M updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -186,3 +186,39 @@ def compare_to_golden(get, gold, reference_table):
     out["out_positions"] = assert_close("out_positions", o4[:, :3], gold["out1"][:, :3], speed * dt + (ps + vs)[:, None] * dt)
     assert np.all(o4[:, 3] == np.float32(0.34)) and np.all(gold["out1"][:, 3] == np.float32(0.34))
     return out
+
+
+def check_step_port(pkg, ob, scene, dt, list_capacity=None, label=""):
+    """One GPU step against the OpenMP restatement on every host core, for sizes the serial reference build cannot step
+    in test time (8 M particles).  The restatement is pinned bit for bit to the unmodified reference by tests/test_oracle.py.
+    Integers bit-exact, floats within 1e-5 of the stage scale.  Returns the mean neighbour count."""
+    import os
+    n = scene["n"]
+    threads = max(1, os.cpu_count() or 1)
+    o = ob.PortOracle(n, threads=threads, **scene["params"])
+    o.set_state(scene["pos"], scene["vel"])
+    o.step(dt, jacobi=True)
+    ps, vs = o.force_scales(dt)
+    ob.PortOracle.lib().oracle_set_threads(1)
+    sim = pkg.FluidSimulation(n, **scene["params"])
+    try:
+        if list_capacity:
+            sim.set_neighbour_list_capacity(list_capacity)
+        sim.set_neighbour_count_tap(True)
+        sim.upload_state(scene["pos"], scene["vel"])
+        sim.step(dt)
+        h, k, _ = o.hash_key()
+        assert np.array_equal(sim.download("predicted").view(np.uint32), o.predicted().view(np.uint32)), label + ": predicted"
+        assert np.array_equal(sim.download("hash"), h) and np.array_equal(sim.download("key"), k), label + ": hash / key"
+        nc, nc_ref = sim.download("neighbour_count"), o.neighbour_counts()
+        assert np.array_equal(nc, nc_ref), "%s: %d neighbour counts differ" % (label, int((nc != nc_ref).sum()))
+        assert_close(label + " density", sim.download("densities"), o.densities(), 0.0)
+        assert_close(label + " vel_after_pressure", sim.download("vel_after_pressure"), o.vel_after_pressure(), ps[:, None])
+        assert_close(label + " vel_after_viscosity", sim.download("vel_after_viscosity"), o.vel_after_viscosity(), (ps + vs)[:, None])
+        speed = np.abs(o.vel_after_viscosity()).max(axis=1, keepdims=True)
+        assert_close(label + " positions", sim.download("positions"), o.positions(), speed * dt + (ps + vs)[:, None] * dt)
+        assert_close(label + " velocities", sim.download("velocities"), o.velocities(), (ps + vs)[:, None])
+        return float(nc.mean())
+    finally:
+        sim.close()
+        o.close()

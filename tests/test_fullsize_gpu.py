@@ -88,3 +88,39 @@ def test_c3_8m_properties(pkg):
     assert np.allclose(dens_b, dens_a, rtol=2e-5, atol=0)
     assert np.abs(pos_b - pos_a).max() < 2e-5
     b.close()
+
+
+def test_c3_8m_one_step_against_oracle(pkg, ob):
+    """BASELINE configs[2] whole (8 M particles): one step against the restatement on every host core."""
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.config("C3_dambreak_8M")
+    mean = helpers.check_step_port(pkg, ob, sc, scenes.DT, label="C3")
+    assert 15 < mean < 25, mean
+
+
+def test_c5_8m_dense_column_one_step_against_oracle(pkg, ob):
+    """BASELINE configs[4] whole (8 M-particle column at gap 0.1216, mu = 1, random velocities): the dense step the
+    bench times, against the restatement.  ~100 neighbours per particle in the interior of the column."""
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.config("C5_column_8M")
+    mean = helpers.check_step_port(pkg, ob, sc, scenes.DT, list_capacity=192, label="C5")
+    assert mean > 80, mean
+
+
+def test_c2_evolved_state_against_oracle(pkg, ob):
+    """A state the solver made itself: 200 steps of C2 on the GPU (the block has collapsed: particles piled against the
+    walls and the floor, |v| of several units per second, clamped positions exactly on the walls), then one more step
+    on the GPU against the restatement from that very state."""
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.config("C2_dambreak_1M")
+    sim = pkg.FluidSimulation(sc["n"], **sc["params"])
+    sim.upload_state(sc["pos"], sc["vel"])
+    sim.step_n(scenes.DT, 200)
+    pos, vel = sim.download("positions"), sim.download("velocities")
+    sim.close()
+    assert np.all(np.isfinite(pos)) and np.all(np.isfinite(vel))
+    half = np.array(sc["bound"], np.float32) / 2
+    on_wall = int((np.abs(pos) == half).any(axis=1).sum())
+    assert on_wall > 1000 and np.abs(vel).max() > 1.0, (on_wall, float(np.abs(vel).max()))
+    ev = dict(pos=np.ascontiguousarray(pos), vel=np.ascontiguousarray(vel), n=sc["n"], params=sc["params"])
+    helpers.check_step_port(pkg, ob, ev, scenes.DT, label="C2 after 200 steps")
