@@ -72,6 +72,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
     P->row0 = 0; P->row1 = n; P->n_a = n;
+    P->seg_off = (uint32_t)table_layout(c->ncell).cells_pad;
     P->rim_check = (double)p.sqr_radius > (double)r * (double)r * (1.0 + 4e-7) ? 1 : 0;
     P->slab = 0; P->zlo = 0; P->gz_global = c->gdim[2]; P->own_lo = 0; P->own_hi = c->gdim[2];
     return SPH_OK;
@@ -102,17 +103,18 @@ static int update_grid_geometry(SphContext* c)
 
 int ensure_tables(SphContext* c, const DevParams& P)
 {
-    // GRID: prefix table over ncell (+1 departed bucket in slab mode) + end, zero-padded for the in-place scan
-    const size_t need = (P.mode == SPH_TABLE_GRID) ? scan_pad((size_t)P.ncell + 3) : (size_t)c->cap + 1;
+    // GRID: two-level prefix table over ncell (+1 departed bucket in slab mode) + end: cells, segment bases, dirty flags
+    const size_t need = (P.mode == SPH_TABLE_GRID) ? table_layout(P.ncell).total : (size_t)c->cap + 1;
     if (need > c->table_cap) {
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
         if (c->tstart) cudaFree(c->tstart);
         c->tstart = nullptr; c->table_cap = 0;
         SPH_CUDA(c, cudaMalloc(&c->tstart, need * sizeof(uint32_t)));
         c->table_cap = need;
+        c->table_two_level = false;
     }
     if (P.mode == SPH_TABLE_GRID) {
-        const size_t sneed = scan_temp_entries(need);
+        const size_t sneed = scan_temp_entries(table_layout(P.ncell).nseg_pad);
         if (sneed > c->scan_cap) {
             SPH_CUDA(c, cudaStreamSynchronize(c->st));
             if (c->scan_tmp) cudaFree(c->scan_tmp);
@@ -379,12 +381,18 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     if (P.mode == SPH_TABLE_GRID && counting_sort_enabled()) {
         // counting sort over the table (a one-pass radix sort whose digit is the whole key): tickets in the cell
         // counters, in-place scan -> prefix table, placement; the reorder restores the canonical (stable) order
-        const size_t padded = scan_pad((size_t)P.ncell + 3);
-        SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, padded * sizeof(uint32_t), st));
+        const TableLayout T = table_layout(P.ncell);
+        if (c->table_ncell != P.ncell) { c->table_two_level = false; c->table_ncell = P.ncell; }
+        c->table_seg_off = P.seg_off;
+        if (!c->table_two_level) {                 // first build, or the allocation last held a flat / reference table
+            SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, T.total * sizeof(uint32_t), st));
+            if (!c->capturing) c->table_two_level = true;
+        } else launch_table_clear(st, c->tstart, T, &c->launches);
         launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, c->tstart, c->perm_b, &c->launches);
         if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
-        exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
-        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, &c->launches);
+        exclusive_scan_u32(st, c->tstart + T.cells_pad, T.nseg_pad, c->scan_tmp, &c->launches);
+        launch_inseg_scan(st, c->tstart, T, &c->launches);
+        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, P, &c->launches);
         launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred,
                        c->predpk, P, dt, &c->launches);
         c->sorted_where = 1;
@@ -397,6 +405,8 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         const uint32_t* keys = c->sorted_where ? c->key_b : c->key_a;
         const uint32_t* perm = c->sorted_where ? c->perm_b : c->perm_a;
         launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, P, &c->launches);
+        c->table_two_level = false;
+        c->table_seg_off = P.seg_off;
         launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt,
                        &c->launches);
     }
@@ -452,7 +462,7 @@ static SphContext::StepKey step_key(const SphContext* c, float dt)
 {
     SphContext::StepKey k;
     memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
-    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn;
+    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0;
     k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
     return k;
 }
@@ -661,6 +671,25 @@ int sph_download_table(SphContext* c, int table, void* host, size_t host_bytes, 
     case SPH_TABLE_START_INDICES:
         src = c->tstart;
         len = (c->mode == SPH_TABLE_GRID) ? (size_t)c->ncell + 1 : (size_t)c->n;
+        if (c->mode == SPH_TABLE_GRID && host) {            // the flat prefix table, from its two levels
+            if (host_bytes < len * 4) return fail(c, SPH_ERR_INVALID, "sph_download_table: host buffer too small");
+            DevParams P;
+            int rc = make_dev_params(c, c->n, &P);
+            if (rc != SPH_OK) return rc;
+            if (len * 4 > (size_t)c->cap * 32) {            // larger than the staging buffer: a temporary
+                uint32_t* tmp = nullptr;
+                SPH_CUDA(c, cudaMalloc(&tmp, len * 4));
+                launch_table_flatten(c->st, c->tstart, P, tmp, (uint32_t)len, &c->launches);
+                cudaError_t e = cudaMemcpyAsync(host, tmp, len * 4, cudaMemcpyDeviceToHost, c->st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+                cudaFree(tmp);
+                if (e != cudaSuccess) return cuda_fail(c, e, "sph_download_table");
+                if (out_len) *out_len = len;
+                return SPH_OK;
+            }
+            launch_table_flatten(c->st, c->tstart, P, (uint32_t*)c->stage, (uint32_t)len, &c->launches);
+            src = c->stage;
+        }
         break;
     default: return fail(c, SPH_ERR_INVALID, "unknown table");
     }

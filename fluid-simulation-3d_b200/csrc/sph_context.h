@@ -37,6 +37,10 @@ struct SphContext {
     uint32_t* h_tile_need = nullptr; // pinned mirror, refreshed with h_overflow
     uint32_t *tstart = nullptr, *tend = nullptr;
     size_t table_cap = 0;        // entries allocated for tstart (tend has cap entries, hash mode only)
+    uint32_t table_ncell = 0;     // cells the table in tstart was laid out for
+    uint32_t table_seg_off = 0;   // ... and the word offset of its segment bases (tbl_at)
+    bool table_two_level = false; // tstart holds a consistent two-level GRID table (cells of clean segments are zero): the next
+                                  // counting-sort build clears only what the last one touched
     uint32_t* scan_tmp = nullptr; // block sums of the table scan (counting sort)
     size_t scan_cap = 0;
     uint32_t* gap_list = nullptr;
@@ -58,7 +62,7 @@ struct SphContext {
     // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
     // plain step and re-captures
     struct StepKey {
-        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap;
+        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level;
         const void *nlist, *tstart, *scan_tmp, *tend;
     };
     cudaGraph_t graph = nullptr;
@@ -83,7 +87,7 @@ struct SphContext {
     int gmin[3] = {0, 0, 0};
     int gdim[3] = {1, 1, 1};
     uint32_t ncell = 1;
-    int xsub = 4;                // x subdivision of the GRID table cells (power of two)
+    int xsub = 8;                // x subdivision of the GRID table cells (power of two; SPH_XSUB overrides)
 
     // slab-decomposed multi-GPU (sph_multi.cu)
     ncclComm* comm = nullptr;

@@ -37,6 +37,16 @@ __device__ __forceinline__ uint32_t key_of_hash(uint32_t h, const DevParams& P)
     const uint64_t low = P.modM * (uint64_t)h;
     return (uint32_t)__umul64hi(low, (uint64_t)P.n);
 }
+// GRID prefix table entry c = number of rows with key < c, from its two levels (sph_internal.h: kSegShift).  A table
+// built flat (radix path) has an all-zero segment array.
+__device__ __forceinline__ uint32_t tbl_at(const uint32_t* __restrict__ t, const uint32_t seg_off, const uint32_t c)
+{
+    return __ldg(&t[c]) + __ldg(&t[seg_off + (c >> kSegShift)]);
+}
+__device__ __forceinline__ uint32_t tbl(const uint32_t* __restrict__ t, const DevParams& P, const uint32_t c)
+{
+    return tbl_at(t, P.seg_off, c);
+}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // GRID table cell of a predicted position: (fine x, y, z).  y and z are the reference's cells

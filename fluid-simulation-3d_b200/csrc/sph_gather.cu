@@ -134,8 +134,8 @@ __device__ __forceinline__ void row_bounds(const GatherArgs& A, const DevParams&
         const int z = g.z + r / 3 - 1, y = g.y + r % 3 - 1;
         if (!((rows >> r) & 1u) || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
         const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
-        b = __ldg(&A.table[row + x0]);
-        e = __ldg(&A.table[row + x1 + 1]);
+        b = tbl(A.table, P, row + x0);
+        e = tbl(A.table, P, row + x1 + 1);
     } else {                                               // 27 buckets, offsets[27] order (physicsWorld.h:131-143)
         const uint32_t h = hash_cell(c.x + r / 9 - 1, c.y + (r / 3) % 3 - 1, c.z + r % 3 - 1);
         const uint32_t key = key_of_hash(h, P);
@@ -332,8 +332,8 @@ __device__ __forceinline__ void row_range(const uint32_t* __restrict__ table, co
     b = e = 0;
     if (r9 >= 9 || !((rows >> r9) & 1u) || z < 0 || z >= P.gdim[2] || y < 0 || y >= P.gdim[1]) return;
     const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
-    b = __ldg(&table[row + xa]);
-    e = __ldg(&table[row + xb + 1]);
+    b = tbl(table, P, row + xa);
+    e = tbl(table, P, row + xb + 1);
 }
 
 template <int PASS>
@@ -867,16 +867,16 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
         if ((uint32_t)(W.g.z + a3 - 1) >= (uint32_t)P.gdim[2]) vm &= ~(0x7u << (3 * a3));
     }
     const uint32_t gd0 = (uint32_t)P.gdim[0];
-    const int64_t zstep = (int64_t)P.gdim[1] * gd0 - 3 * (int64_t)gd0;
-    const uint32_t* const tp0 = A.table + ((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0;
-    const uint32_t* tp = tp0;
+    const uint32_t zstep = (uint32_t)P.gdim[1] * gd0 - 3u * gd0;
+    const uint32_t tc0 = (uint32_t)(((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0);   // only read where the row exists
+    uint32_t tc = tc0;
     const uint32_t xspan = (uint32_t)(W.x1 - W.x0) + 1u;
     int dyc = 0;
     auto bounds = [&](const int r9, uint32_t& b, uint32_t& e) {
         b = e = 0;
-        if ((vm >> r9) & 1u) { b = __ldg(tp); e = __ldg(tp + xspan); }
-        tp += gd0;
-        if (++dyc == 3) { dyc = 0; tp += zstep; }
+        if ((vm >> r9) & 1u) { b = tbl(A.table, P, tc); e = tbl(A.table, P, tc + xspan); }
+        tc += gd0;
+        if (++dyc == 3) { dyc = 0; tc += zstep; }
     };
 
     // STAGED: union of the block's windows per row -> shared memory
@@ -894,7 +894,7 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
             const uint32_t hi = __reduce_max_sync(0xffffffffu, e > b ? ((e + 1u) >> 1) : 0u);
             if ((tid & 31) == 0 && hi > lo) { atomicMin(&s_lo[r9], lo); atomicMax(&s_hi[r9], hi); }
         }
-        tp = tp0; dyc = 0;
+        tc = tc0; dyc = 0;
         __syncthreads();
         if (tid == 0) {
             uint32_t off = 0;

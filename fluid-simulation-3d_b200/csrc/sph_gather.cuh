@@ -255,8 +255,8 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ pr
                 const int y = g.y + dy;
                 if (y < 0 || y >= P.gdim[1] || !((W.rows >> ((dz + 1) * 3 + dy + 1)) & 1u)) continue;
                 const uint32_t row = ((uint32_t)z * (uint32_t)P.gdim[1] + (uint32_t)y) * (uint32_t)P.gdim[0];
-                const uint32_t b = __ldg(&tstart[row + x0]);
-                const uint32_t e = __ldg(&tstart[row + x1 + 1]);
+                const uint32_t b = tbl(tstart, P, row + x0);
+                const uint32_t e = tbl(tstart, P, row + x1 + 1);
                 for (uint32_t j = b; j < e; j++) {
                     const float4 q = __ldg(&pred_s[j]);
                     if (RIM && rim && !within_27(q, pi, P.r)) continue;      // clamped outliers in the rim cells (Q2)

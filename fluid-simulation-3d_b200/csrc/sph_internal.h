@@ -41,6 +41,7 @@ struct DevParams {
     int      zlo, gz_global, own_lo, own_hi;
     int      has_lo, has_hi;   // a neighbour rank exists below / above
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
+    uint32_t seg_off;          // GRID table: word offset of the per-segment base array behind the per-cell array (tbl(), sph_device.cuh)
     int      rim_check;        // the cut-off exceeds the cell size (Q2): particles next to the table's rim compare true cells (sph_device.cuh)
 };
 
@@ -52,6 +53,10 @@ struct __align__(32) Rec8 { float4 lo, hi; };
 // pair records of padding behind `predpk`: a density-pass warp may read this far past the last row's pair without
 // clamping its addresses (the slots are outside every window, so whatever they hold is rejected)
 constexpr uint32_t kPairPad = 2048;
+// GRID table, two levels: cells are grouped in segments of 64; t(c) = in-segment prefix[c] + segment base[c >> 6].
+// Building it costs O(particles + occupied segments), not O(cells): the air above the fluid is never touched.
+constexpr int kSegShift = 6;
+constexpr uint32_t kSegCells = 1u << kSegShift;
 
 // Pair-interleaved predicted positions (`predpk`): rows 2m and 2m+1 share one 32-byte record
 //   lo = (x0, x1, y0, y1)   hi = (z0, z1, w0, w1)
@@ -81,7 +86,13 @@ void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, u
 void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
                       uint32_t* count, uint32_t* rank, uint64_t* launches);
 void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,
-                  uint32_t n, uint64_t* launches);
+                  uint32_t n, const DevParams& P, uint64_t* launches);
+// two-level GRID table (counting sort): clear what the last step touched, in-segment prefixes, flat copy for the taps
+struct TableLayout { size_t cells_pad, nseg, nseg_pad, total; };   // [cells][segment bases][dirty flags], in words
+TableLayout table_layout(uint32_t ncell);
+void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
+void launch_inseg_scan(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
+void launch_table_flatten(cudaStream_t st, const uint32_t* table, const DevParams& P, uint32_t* flat, uint32_t entries, uint64_t* launches);
 // sph_sort.cu: in-place exclusive scan of a zero-padded array (multiple of 4096 entries)
 size_t scan_pad(size_t entries);
 size_t scan_temp_entries(size_t entries);

@@ -25,6 +25,13 @@ namespace sphb200 {
 namespace {
 
 
+__device__ __forceinline__ void count_segment(uint32_t* __restrict__ count, const DevParams& P, const uint32_t k)
+{
+    const uint32_t sg = k >> kSegShift;
+    const uint32_t peers = __match_any_sync(__activemask(), sg);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[P.seg_off + sg], (uint32_t)__popc(peers));
+}
+
 __global__ void __launch_bounds__(256)
 k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
               uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt,
@@ -32,7 +39,8 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
 {
     // counting sort (GRID table): the row takes a ticket in its cell's counter; the tickets are made
     // canonical (ascending source row) later, in k_reorder_binned
-    #define SPH_EMIT_KEY(K) do { const uint32_t k__ = (K); key[s] = k__; if (count) rank[s] = atomicAdd(&count[k__], 1u); } while (0)
+    // ... and is counted in its segment (one atomic per distinct segment of the warp: rows arrive nearly sorted)
+    #define SPH_EMIT_KEY(K) do { const uint32_t k__ = (K); key[s] = k__; if (count) { rank[s] = atomicAdd(&count[k__], 1u); count_segment(count, P, k__); } } while (0)
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= rows) return;
     const float4 p = pos[s];
@@ -85,16 +93,68 @@ k_ghost_key(const float4* __restrict__ ghost_pred, uint32_t* __restrict__ key, c
     const float4 q = ghost_pred[s];
     const uint32_t k = grid_key(grid_cell(q.x, q.y, q.z, P), P);
     key[s] = k;
-    if (count) rank[s] = atomicAdd(&count[k], 1u);
+    if (count) { rank[s] = atomicAdd(&count[k], 1u); count_segment(count, P, k); }
 }
 
 // counting sort, placement: slot of row s = first slot of its cell + its ticket
 __global__ void __launch_bounds__(256)
 k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ table,
-        uint32_t* __restrict__ slot_row, const uint32_t n)
+        uint32_t* __restrict__ slot_row, const uint32_t n, const DevParams P)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) slot_row[table[key[s]] + rank[s]] = s;
+    if (s < n) slot_row[tbl(table, P, key[s]) + rank[s]] = s;
+}
+
+// ---- two-level GRID table (counting sort) -----------------------------------------------------------------------
+// Layout of the allocation: [cells: ncell + 3, padded][segment bases, padded for the scan][dirty flag per segment].
+// One warp per segment throughout.
+__global__ void __launch_bounds__(256)
+k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg)
+{   // zero the cell counters of the segments the LAST step touched, and every segment counter.  One THREAD looks at
+    // one segment's flag (coalesced); the warp then zeroes its dirty segments together, 64 cells at a time.
+    const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool in = sg < nseg;
+    const bool dirty = in && table[dirty_off + sg] != 0u;
+    if (in) table[seg_off + sg] = 0u;
+    if (dirty) table[dirty_off + sg] = 0u;
+    uint32_t todo = __ballot_sync(0xffffffffu, dirty);
+    const uint32_t sg0 = sg - lane;
+    while (todo) {
+        const uint32_t k = (uint32_t)__ffs(todo) - 1u;
+        todo &= todo - 1u;
+        reinterpret_cast<uint2*>(table + ((size_t)(sg0 + k) << kSegShift))[lane] = make_uint2(0u, 0u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_inseg_scan(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg)
+{   // occupied segments: cell counters -> exclusive prefix inside the segment (the base comes from the segment scan).
+    // One thread decides for one segment; the warp then scans its occupied segments together.
+    const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool occ = sg < nseg && table[seg_off + sg + 1] != table[seg_off + sg];   // empty: its cells are, and stay, zero
+    if (occ) table[dirty_off + sg] = 1u;
+    uint32_t todo = __ballot_sync(0xffffffffu, occ);
+    const uint32_t sg0 = sg - lane;
+    while (todo) {
+        const uint32_t k = (uint32_t)__ffs(todo) - 1u;
+        todo &= todo - 1u;
+        uint2* cells = reinterpret_cast<uint2*>(table + ((size_t)(sg0 + k) << kSegShift));
+        const uint2 v = cells[lane];
+        uint32_t inc = v.x + v.y;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += u; }
+        const uint32_t ex = inc - (v.x + v.y);
+        cells[lane] = make_uint2(ex, ex + v.x);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_table_flatten(const uint32_t* __restrict__ table, uint32_t* __restrict__ flat, const uint32_t entries, const DevParams P)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < entries) flat[c] = tbl(table, P, c);
 }
 
 // ---- S2 tables -------------------------------------------------------------
@@ -184,8 +244,9 @@ constexpr uint32_t kMaxCanonical = 1024;
 
 __device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
                                                const uint32_t* __restrict__ table, const uint32_t s, uint32_t* key_sorted,
-                                               const uint32_t ncell)
+                                               const DevParams& P)
 {
+    const uint32_t ncell = P.ncell;
     const uint32_t s0 = perm[s];
     if (!key) return s0;
     const uint32_t k = key[s0];
@@ -193,7 +254,7 @@ __device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm
     // slab mode: key == ncell collects the rows that leave this rank; they are dropped after the step, their order
     // is irrelevant -- and there can be hundreds of them, which the O(m^2)-per-thread ranking below must never see
     if (k >= ncell) return s0;
-    const uint32_t b = table[k], m = table[k + 1] - b;
+    const uint32_t b = tbl(table, P, k), m = tbl(table, P, k + 1u) - b;
     if (m == 1u || m > kMaxCanonical) return s0;
     const uint32_t r = s - b;
     for (uint32_t t = 0; t < m; t++) {                       // the entry with exactly r smaller entries
@@ -215,7 +276,7 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
     const bool valid = s < P.n;                    // no early return: the pair-interleaved copy is written with shuffles
     float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (valid) {
-        const uint32_t src = source_row(perm, key, table, s, key_sorted, P.ncell);
+        const uint32_t src = source_row(perm, key, table, s, key_sorted, P);
         if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
             const float4 gq = ghost_pred[src - P.n_a];
             const int3 c = cell_of(gq.x, gq.y, gq.z, P.r);
@@ -431,6 +492,8 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
         if (P.n) { k_build_table_hash<<<blocks_for(P.n, 256), 256, 0, st>>>(key_sorted, tstart, tend, P.n); ++*launches; }
     } else {
         cudaMemsetAsync(gap_list, 0, sizeof(uint32_t), st);
+        const TableLayout T = table_layout(P.ncell);     // a flat table: every segment base is zero (tbl(), sph_device.cuh)
+        cudaMemsetAsync(tstart + P.seg_off, 0, T.nseg_pad * sizeof(uint32_t), st);
         k_build_table_grid<<<blocks_for(P.n + 1, 256), 256, 0, st>>>(key_sorted, tstart, gap_list, P.n, P.ncell);
         k_fill_gaps<<<148 * 4, 256, 0, st>>>(tstart, gap_list);
         *launches += 2;
@@ -438,10 +501,39 @@ void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* t
 }
 
 void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,
-                  uint32_t n, uint64_t* launches)
+                  uint32_t n, const DevParams& P, uint64_t* launches)
 {
     if (n == 0) return;
-    k_place<<<blocks_for(n, 256), 256, 0, st>>>(key, rank, table, slot_row, n);
+    k_place<<<blocks_for(n, 256), 256, 0, st>>>(key, rank, table, slot_row, n, P);
+    ++*launches;
+}
+
+TableLayout table_layout(const uint32_t ncell)
+{
+    TableLayout T;
+    T.cells_pad = scan_pad((size_t)ncell + 3);            // a multiple of 4096, hence of the segment size
+    T.nseg = T.cells_pad >> kSegShift;
+    T.nseg_pad = scan_pad(T.nseg + 1);                    // the exclusive scan runs in place over zero-padded entries
+    T.total = T.cells_pad + 2 * T.nseg_pad;
+    return T;
+}
+
+void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
+{
+    k_table_clear<<<blocks_for((uint32_t)T.nseg, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg);
+    ++*launches;
+}
+
+void launch_inseg_scan(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
+{
+    k_inseg_scan<<<blocks_for((uint32_t)T.nseg, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg);
+    ++*launches;
+}
+
+void launch_table_flatten(cudaStream_t st, const uint32_t* table, const DevParams& P, uint32_t* flat, uint32_t entries, uint64_t* launches)
+{
+    if (entries == 0) return;
+    k_table_flatten<<<blocks_for(entries, 256), 256, 0, st>>>(table, flat, entries, P);
     ++*launches;
 }
 

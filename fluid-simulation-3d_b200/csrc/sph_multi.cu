@@ -28,6 +28,7 @@
 #include <string>
 
 #include "sph_context.h"
+#include "sph_device.cuh"
 
 using namespace sphb200;
 
@@ -282,13 +283,14 @@ k_slab_pack(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, con
 }
 
 __global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __restrict__ out, uint32_t i0, uint32_t i1,
-                            uint32_t i2, uint32_t i3, uint32_t i4)
+                            uint32_t i2, uint32_t i3, uint32_t i4, const DevParams P)
 {
     if (threadIdx.x == 0) {
-        out[0] = table[i0]; out[1] = table[i1]; out[2] = table[i2]; out[3] = table[i3]; out[4] = table[i4];
+        const uint32_t t0 = tbl(table, P, i0), t1 = tbl(table, P, i1), t2 = tbl(table, P, i2), t3 = tbl(table, P, i3);
+        out[0] = t0; out[1] = t1; out[2] = t2; out[3] = t3; out[4] = tbl(table, P, i4);
         // boundary-layer lengths this rank will SEND in the later halos: lo, hi
-        out[5] = table[i1] - table[i0];
-        out[6] = table[i3] - table[i2];
+        out[5] = t1 - t0;
+        out[6] = t3 - t2;
     }
 }
 
@@ -298,12 +300,12 @@ int ceil_log2_u64(uint64_t v) { int b = 0; while ((1ull << b) < v && b < 63) b++
 // spans the entries [l * plane, (l + 1) * plane)); the other layers of the global histogram stay zero on this rank
 __global__ void __launch_bounds__(256)
 k_layer_hist(const uint32_t* __restrict__ table, uint32_t* __restrict__ hist, const uint32_t plane, const int zlo,
-             const int own_lo, const int own_hi)
+             const int own_lo, const int own_hi, const uint32_t seg_off)
 {
     const int g = own_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (g >= own_hi) return;
-    const size_t l = (size_t)(g - zlo);
-    hist[g] = table[(l + 1) * plane] - table[l * plane];
+    const uint32_t l = (uint32_t)(g - zlo);
+    hist[g] = tbl_at(table, seg_off, (l + 1u) * plane) - tbl_at(table, seg_off, l * plane);
 }
 
 }  // namespace
@@ -360,6 +362,7 @@ static int slab_params(SphContext* c, DevParams* P, uint32_t n_rows)
     P->gdim[2] = zhi - zlo;
     P->ncell = (uint32_t)((uint64_t)P->gdim[0] * P->gdim[1] * P->gdim[2]);
     P->mode = SPH_TABLE_GRID;
+    P->seg_off = (uint32_t)table_layout(P->ncell).cells_pad;      // the slab's own table, not the whole grid's
     return SPH_OK;
 }
 
@@ -385,7 +388,13 @@ int multi_step(SphContext* c, float dt)
     // (1) predict + classify + key of the resident rows
     const bool binned = counting_sort_enabled();
     const size_t padded = scan_pad((size_t)P.ncell + 3);
-    if (binned) SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, padded * sizeof(uint32_t), st));
+    const TableLayout TL = table_layout(P.ncell);
+    if (c->table_ncell != P.ncell) { c->table_two_level = false; c->table_ncell = P.ncell; }   // the planes moved: another layout
+    c->table_seg_off = P.seg_off;
+    if (binned) {
+        if (!c->table_two_level) { SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, TL.total * sizeof(uint32_t), st)); c->table_two_level = true; }
+        else launch_table_clear(st, c->tstart, TL, &c->launches);
+    }
     launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, binned ? c->tstart : nullptr, c->perm_b,
                        &c->launches);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
@@ -482,8 +491,9 @@ int multi_step(SphContext* c, float dt)
     launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, binned ? c->tstart : nullptr, c->perm_b + n_a, &c->launches);
     if (binned) {
         // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
-        exclusive_scan_u32(st, c->tstart, padded, c->scan_tmp, &c->launches);
-        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, n_all, &c->launches);
+        exclusive_scan_u32(st, c->tstart + TL.cells_pad, TL.nseg_pad, c->scan_tmp, &c->launches);
+        launch_inseg_scan(st, c->tstart, TL, &c->launches);
+        launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, n_all, P, &c->launches);
         SLAB_MARK(4);
         launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt, &c->launches);
         c->sorted_where = 1;
@@ -496,6 +506,7 @@ int multi_step(SphContext* c, float dt)
         DevParams PT = P;
         PT.ncell = P.ncell + 1;
         launch_build_table(st, keys, c->tstart, c->tend, c->gap_list, PT, &c->launches);
+        c->table_two_level = false;
         launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, s->ghost_pred, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt,
                        &c->launches);
     }
@@ -504,7 +515,7 @@ int multi_step(SphContext* c, float dt)
     const uint32_t plane = (uint32_t)P.gdim[0] * (uint32_t)P.gdim[1];
     const uint32_t l_own_lo = (uint32_t)(P.own_lo - P.zlo), l_own_hi = (uint32_t)(P.own_hi - P.zlo);
     k_slab_pick<<<1, 32, 0, st>>>(c->tstart, picks, l_own_lo * plane, (l_own_lo + 1) * plane, (l_own_hi - 1) * plane,
-                                  l_own_hi * plane, P.ncell);
+                                  l_own_hi * plane, P.ncell, P);
     ++c->launches;
     // Row ranges of the sorted arrays.  With at least three owned layers they follow from the exchanged counts --
     //   ghost-lo layer  = ghosts received from lo + my migrants to lo that I keep mirroring
@@ -795,7 +806,7 @@ int sph_comm_rebalance(SphContext* c, uint32_t max_shift, int32_t* layers_out, u
     const int own = t_own_hi - t_own_lo;
     const uint32_t plane = (uint32_t)c->gdim[0] * (uint32_t)c->gdim[1];
     if (own > 0) {
-        k_layer_hist<<<(own + 255) / 256, 256, 0, st>>>(c->tstart, s->hist_dev, plane, t_zlo, t_own_lo, t_own_hi);
+        k_layer_hist<<<(own + 255) / 256, 256, 0, st>>>(c->tstart, s->hist_dev, plane, t_zlo, t_own_lo, t_own_hi, c->table_seg_off);
         ++c->launches;
     }
     SPH_CUDA(c, cudaMemcpyAsync(s->hist_dev + GZ, &s->xcap, sizeof(uint32_t), cudaMemcpyHostToDevice, st));

@@ -221,8 +221,8 @@ k_tile(const __grid_constant__ GatherArgs A, const __grid_constant__ DevParams P
             int c1 = cB;
             for (;;) {
                 const uint32_t xlo = (uint32_t)max(c0 - 1, 0) << xs, xhi = (uint32_t)min(c1 + 2, ncx) << xs;
-                Rd.runb = Rd.rv ? __ldg(&A.table[Rd.rb + xlo]) : 0u;
-                const uint32_t rune = Rd.rv ? __ldg(&A.table[Rd.rb + xhi]) : 0u;
+                Rd.runb = Rd.rv ? tbl(A.table, P, Rd.rb + xlo) : 0u;
+                const uint32_t rune = Rd.rv ? tbl(A.table, P, Rd.rb + xhi) : 0u;
                 Rd.len = rune - Rd.runb;
                 const uint32_t inc = warp_incl_scan16(Rd.len, lane);
                 Rd.total = __shfl_sync(FULL, inc, 8);
@@ -274,8 +274,8 @@ k_tile(const __grid_constant__ GatherArgs A, const __grid_constant__ DevParams P
                     const uint32_t cl = __ballot_sync(FULL, mine && cx == c);               // this cell's targets (lanes)
                     cpend &= ~cl;
                     const uint32_t plo = (uint32_t)max(c - 1, 0) << xs, phi = (uint32_t)min(c + 2, ncx) << xs;
-                    const uint32_t cb = Rd.rv ? __ldg(&A.table[Rd.rb + plo]) : 0u;
-                    const uint32_t ce = Rd.rv ? __ldg(&A.table[Rd.rb + phi]) : 0u;
+                    const uint32_t cb = Rd.rv ? tbl(A.table, P, Rd.rb + plo) : 0u;
+                    const uint32_t ce = Rd.rv ? tbl(A.table, P, Rd.rb + phi) : 0u;
                     const uint32_t plen = ce - cb;
                     const uint32_t pinc = warp_incl_scan16(plen, lane);
                     const uint32_t L = __shfl_sync(FULL, pinc, 8);
