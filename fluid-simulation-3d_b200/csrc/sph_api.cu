@@ -51,7 +51,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
 {
     const SphParams& p = c->params;
     memset(P, 0, sizeof(*P));
-    P->n = n; P->n_owned = n; P->mode = c->mode; P->gravity = p.gravity ? 1 : 0;
+    P->n = n; P->n_owned = n; P->mode = c->grid_too_large ? (int)SPH_TABLE_REFERENCE_HASH : c->mode; P->gravity = p.gravity ? 1 : 0;
     P->r = p.interaction_radius; P->sqr_r = p.sqr_radius; P->rho0 = p.target_density;
     P->k = p.pressure_multiplier; P->kn = p.near_pressure_multiplier; P->mu = p.viscosity_strength;
     P->g = p.gravity_scale;
@@ -84,19 +84,40 @@ static int update_grid_geometry(SphContext* c)
 {
     const SphParams& p = c->params;
     if (!(p.interaction_radius > 0.0f)) return fail(c, SPH_ERR_INVALID, "interaction_radius must be > 0");
-    uint64_t cells = 1;
+    // The UI's radius slider goes down to 0.01 (gameApp.cc:371) and the reference's setters cannot fail: a grid that
+    // would get too large is first coarsened in x (the subdivision only trims candidate windows), and if even the
+    // unsubdivided grid exceeds the limit the context steps on the reference's own table, whose size is the particle
+    // count, instead of refusing the parameter.
+    const uint64_t kMaxCells = 1ull << 30;          // 4 GB of cell counters (C4, 64 M particles in a 258 x 129 x 86 box: 0.56 G cells)
+    int dims[3], los[3];
+    uint64_t base_cells = 1;
     for (int a = 0; a < 3; a++) {
         const float half = p.bound[a] * 0.5f;
         if (!(half >= 0.0f) || !std::isfinite(half)) return fail(c, SPH_ERR_INVALID, "bound must be finite and >= 0");
-        const double q = std::floor((double)half / (double)p.interaction_radius);
-        if (q > 1e8) return fail(c, SPH_ERR_INVALID, "bound / interaction_radius too large for the grid table");
+        double q = std::floor((double)half / (double)p.interaction_radius);
+        if (q > 1e6) q = 1e6;                       // far beyond any table: falls through to grid_too_large
         const int hi = (int)q + 2, lo = -(int)q - 3;
-        c->gmin[a] = lo;
-        c->gdim[a] = (hi - lo + 1) * (a == 0 ? c->xsub : 1);          // x is subdivided (sph_device.cuh: grid_cell)
+        los[a] = lo;
+        dims[a] = hi - lo + 1;
+        base_cells *= (uint64_t)dims[a];
+    }
+    c->grid_too_large = base_cells > kMaxCells;
+    int xs = c->xsub_pref;
+    while (xs > 1 && base_cells * (uint64_t)xs > kMaxCells) xs >>= 1;
+    if (c->grid_too_large) {                        // a token grid: nothing is built on it while the flag is set
+        if (c->nranks > 1) return fail(c, SPH_ERR_INVALID, "grid table too large for slab mode (radius too small for this box)");
+        for (int a = 0; a < 3; a++) { c->gmin[a] = 0; c->gdim[a] = 1; }
+        c->xsub = 1;
+        c->ncell = 1;
+        return SPH_OK;
+    }
+    c->xsub = xs;
+    uint64_t cells = 1;
+    for (int a = 0; a < 3; a++) {
+        c->gmin[a] = los[a];
+        c->gdim[a] = dims[a] * (a == 0 ? c->xsub : 1);          // x is subdivided (sph_device.cuh: grid_cell)
         cells *= (uint64_t)c->gdim[a];
     }
-    if (cells > (1ull << 31))
-        return fail(c, SPH_ERR_INVALID, "grid table would exceed 2^31 cells; use SPH_TABLE_REFERENCE_HASH");
     c->ncell = (uint32_t)cells;
     return SPH_OK;
 }
@@ -242,7 +263,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
 
     SphContext* c = new SphContext();
-    if (const char* xs = getenv("SPH_XSUB")) { const int v = atoi(xs); if (v == 1 || v == 2 || v == 4 || v == 8) c->xsub = v; }
+    if (const char* xs = getenv("SPH_XSUB")) { const int v = atoi(xs); if (v == 1 || v == 2 || v == 4 || v == 8) c->xsub_pref = c->xsub = v; }
     c->device = device;
     c->cap = capacity;
     sph_default_params(&c->params);
@@ -670,8 +691,8 @@ int sph_download_table(SphContext* c, int table, void* host, size_t host_bytes, 
         src = c->stage; } break;
     case SPH_TABLE_START_INDICES:
         src = c->tstart;
-        len = (c->mode == SPH_TABLE_GRID) ? (size_t)c->ncell + 1 : (size_t)c->n;
-        if (c->mode == SPH_TABLE_GRID && host) {            // the flat prefix table, from its two levels
+        len = (c->mode == SPH_TABLE_GRID && !c->grid_too_large) ? (size_t)c->ncell + 1 : (size_t)c->n;
+        if (c->mode == SPH_TABLE_GRID && !c->grid_too_large && host) {            // the flat prefix table, from its two levels
             if (host_bytes < len * 4) return fail(c, SPH_ERR_INVALID, "sph_download_table: host buffer too small");
             DevParams P;
             int rc = make_dev_params(c, c->n, &P);
@@ -726,9 +747,10 @@ int sph_save_state(SphContext* c, const char* path)
     if (rc != SPH_OK) return rc;
     FILE* f = fopen(path, "wb");
     if (!f) return fail(c, SPH_ERR_INVALID, std::string("sph_save_state: cannot open ") + path);
-    const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '1'};
-    const uint32_t n = c->n;
-    bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&c->params, sizeof(SphParams), 1, f) == 1;
+    const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '2'};      // "...1" had no sizeof(SphParams) word
+    const uint32_t n = c->n, psize = (uint32_t)sizeof(SphParams);
+    bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&psize, 4, 1, f) == 1 &&
+              fwrite(&c->params, sizeof(SphParams), 1, f) == 1;
     ok = ok && (n == 0 || (fwrite(pos.data(), 12, n, f) == n && fwrite(vel.data(), 12, n, f) == n));
     ok = (fclose(f) == 0) && ok;
     return ok ? SPH_OK : fail(c, SPH_ERR_INVALID, "sph_save_state: short write");
@@ -743,9 +765,13 @@ int sph_load_state(SphContext* c, const char* path)
     char magic[8];
     uint32_t n = 0;
     SphParams p;
-    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "SPHB2001", 8) == 0 && fread(&n, 4, 1, f) == 1 &&
-              fread(&p, sizeof(SphParams), 1, f) == 1;
-    if (!ok) { fclose(f); return fail(c, SPH_ERR_INVALID, "sph_load_state: not a snapshot file"); }
+    bool ok = fread(magic, 1, 8, f) == 8 && fread(&n, 4, 1, f) == 1;
+    const bool v2 = ok && memcmp(magic, "SPHB2002", 8) == 0;
+    ok = ok && (v2 || memcmp(magic, "SPHB2001", 8) == 0);
+    uint32_t psize = (uint32_t)sizeof(SphParams);
+    if (ok && v2) ok = fread(&psize, 4, 1, f) == 1 && psize == (uint32_t)sizeof(SphParams);
+    ok = ok && fread(&p, sizeof(SphParams), 1, f) == 1;
+    if (!ok) { fclose(f); return fail(c, SPH_ERR_INVALID, "sph_load_state: not a snapshot file (or one of another ABI version)"); }
     if (n > c->cap) { fclose(f); return fail(c, SPH_ERR_CAPACITY, "sph_load_state: snapshot exceeds capacity"); }
     std::vector<float> pos((size_t)n * 3), vel((size_t)n * 3);
     ok = n == 0 || (fread(pos.data(), 12, n, f) == n && fread(vel.data(), 12, n, f) == n);

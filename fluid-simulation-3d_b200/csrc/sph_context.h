@@ -87,7 +87,10 @@ struct SphContext {
     int gmin[3] = {0, 0, 0};
     int gdim[3] = {1, 1, 1};
     uint32_t ncell = 1;
-    int xsub = 8;                // x subdivision of the GRID table cells (power of two; SPH_XSUB overrides)
+    int xsub = 8;                // x subdivision of the GRID table cells in force (power of two)
+    int xsub_pref = 8;           // ... the preferred one (SPH_XSUB overrides); coarsened when the grid would get too large
+    bool grid_too_large = false; // even the unsubdivided grid exceeds the table limit: single-GPU steps run on the
+                                 // REFERENCE_HASH table (whose size is the particle count) until the geometry fits again
 
     // slab-decomposed multi-GPU (sph_multi.cu)
     ncclComm* comm = nullptr;

@@ -93,7 +93,7 @@ struct SlabState {
     float4* ghost_pred = nullptr;                 // [gcap] recv_lo | keep_lo | recv_hi | keep_hi
     uint32_t* block_counts = nullptr;             // [6][nblocks]
     uint8_t* block_any = nullptr;                 // [nblocks] block has at least one row in some list
-    uint32_t* dev_small = nullptr;                // 64 u32: totals[6], recv counts[4], picks[8], peer counts[4]
+    uint32_t* dev_small = nullptr;                // 64 u32: totals[6], picks[8] at 16, peer lengths[2] at 24, count messages out (lo, hi: 8 words each) at 32, in at 48
     uint32_t* host_small = nullptr;               // pinned mirror
     uint32_t nblocks_cap = 0;
     std::vector<int> layers;                      // nranks + 1 global layer indices
@@ -102,6 +102,13 @@ struct SlabState {
     bool verify_pending = false;
     uint32_t stats[5] = {0, 0, 0, 0, 0};
     bool have_planes = false;
+    // A capacity or consistency error of one rank must not leave its neighbours blocked in a matched exchange: every rank
+    // keeps the communication pattern of the step, links whose two ends cannot both go ahead are skipped BY BOTH ENDS
+    // (the verdict is computed from the same eight words on either side), the error is returned when the step has been
+    // enqueued, and it is sticky: a failed rank says so in its next count message, so the failure spreads one hop per
+    // step until every rank has returned it.  sph_upload_owned clears it.
+    bool failed = false;
+    std::string failure;
     cudaStream_t halo_stream = nullptr;           // halos 2 and 3 travel here, overlapped with interior compute
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
     // SPH_SLAB_TIMING=1: finer timers of the spatial stage (events on the stream + host clock around the syncs)
@@ -282,6 +289,24 @@ k_slab_pack(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, con
     }
 }
 
+// The count message of a side: (migrants, ghosts, kept migrants) towards that neighbour, then what the neighbour needs to
+// reach the same verdict about the link as this rank: status (0 = fine), rows an exchange buffer holds, free rows and free
+// ghost rows this rank can take FROM that side (half of what is left once its own kept migrants are in).
+__global__ void k_slab_msg(const uint32_t* __restrict__ totals, uint32_t* __restrict__ msg, const uint32_t status, const uint32_t xcap,
+                           const uint32_t cap, const uint32_t gcap, const uint32_t n_old)
+{
+    if (threadIdx.x >= 2) return;
+    const int side = threadIdx.x;                            // 0: to lo, 1: to hi
+    const uint32_t keep = totals[L_KEEP_LO] + totals[L_KEEP_HI];
+    const uint32_t used = n_old + keep;
+    uint32_t* m = msg + 8 * side;
+    m[0] = totals[3 * side]; m[1] = totals[3 * side + 1]; m[2] = totals[3 * side + 2];
+    m[3] = status; m[4] = xcap;
+    m[5] = cap > used ? (cap - used) / 2u : 0u;
+    m[6] = gcap > keep ? (gcap - keep) / 2u : 0u;
+    m[7] = 0u;
+}
+
 __global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __restrict__ out, uint32_t i0, uint32_t i1,
                             uint32_t i2, uint32_t i3, uint32_t i4, const DevParams P)
 {
@@ -291,6 +316,11 @@ __global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __rest
         // boundary-layer lengths this rank will SEND in the later halos: lo, hi
         out[5] = t1 - t0;
         out[6] = t3 - t2;
+        // (boundary layer I send, ghost layer I expect) per side, at words 8..11 of the small buffer: the pair that
+        // crosses a link in the synchronous cross-check
+        uint32_t* pair = out - 8;
+        pair[0] = t1 - t0; pair[1] = t0;
+        pair[2] = t3 - t2; pair[3] = out[4] - t3;
     }
 }
 
@@ -314,7 +344,7 @@ namespace sphb200 {
 
 void multi_adopt_upload(SphContext* c, uint32_t n)
 {
-    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; }
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; c->slab->failed = false; c->slab->failure.clear(); c->slab->verify_pending = false; }
 }
 
 int multi_params_changed(SphContext* c)
@@ -418,42 +448,85 @@ int multi_step(SphContext* c, float dt)
         c->launches += 3;
     }
     SLAB_MARK(1);
-    // (3a) counts to / from the neighbours
+    // (3a) count messages to / from the neighbours (k_slab_msg)
+    uint32_t* msg_out = s->dev_small + 32;
+    uint32_t* msg_in = s->dev_small + 48;
+    k_slab_msg<<<1, 32, 0, st>>>(totals, msg_out, s->failed ? 1u : 0u, s->xcap, c->cap, s->gcap, n_old);
+    ++c->launches;
     SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) { SPH_NCCL(c, ncclSend(totals + L_MIG_LO, 3, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 0, 3, ncclUint32, lo, comm, st)); }
-    if (has_hi) { SPH_NCCL(c, ncclSend(totals + L_MIG_HI, 3, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(rcounts + 3, 3, ncclUint32, hi, comm, st)); }
+    if (has_lo) { SPH_NCCL(c, ncclSend(msg_out, 8, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(msg_in, 8, ncclUint32, lo, comm, st)); }
+    if (has_hi) { SPH_NCCL(c, ncclSend(msg_out + 8, 8, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(msg_in + 8, 8, ncclUint32, hi, comm, st)); }
     SPH_NCCL(c, ncclGroupEnd());
-    SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // (words 16..31 of the pinned mirror still hold the previous step's table picks: they are compared below)
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 32, s->dev_small + 32, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SLAB_MARK(2);
     const double h0 = host_now();
     SPH_CUDA(c, cudaStreamSynchronize(st));
     const double h1 = host_now();
-    const uint32_t* T = s->host_small;
-    const uint32_t* R = s->host_small + 8;
-    for (int l = 0; l < NLISTS; l++)
-        if (T[l] > s->xcap) return fail(c, SPH_ERR_CAPACITY, "slab mode: exchange buffer too small (raise capacity)");
+    // The verdict about a link, from the two messages that crossed it: identical on both of its ends.
+    auto link_ok = [](const uint32_t* a, const uint32_t* b) {        // a -> b and b -> a are the same test with the roles swapped
+        auto one_way = [](const uint32_t* from, const uint32_t* to) {
+            return from[0] <= from[4] && from[1] <= from[4] && from[2] <= from[4] &&      // the sender's lists fit its exchange buffers
+                   (uint64_t)from[0] + from[1] <= to[5] && from[1] <= to[6];              // ... and the receiver has the room
+        };
+        return a[3] == 0u && b[3] == 0u && one_way(a, b) && one_way(b, a);
+    };
+    const uint32_t* MO = s->host_small + 32;
+    const uint32_t* MI = s->host_small + 48;
+    const bool was_failed = s->failed;
+    const bool link_lo = has_lo && link_ok(MO, MI), link_hi = has_hi && link_ok(MO + 8, MI + 8);
+    if ((has_lo && !link_lo) || (has_hi && !link_hi)) {
+        if (!s->failed) {
+            auto why = [&](const uint32_t* mo, const uint32_t* mi, const char* side) -> std::string {
+                if (mi[3]) return std::string("the ") + side + " neighbour reported a failure";
+                if (mo[0] > mo[4] || mo[1] > mo[4] || mo[2] > mo[4]) return std::string("exchange buffer towards the ") + side + " neighbour too small (raise capacity)";
+                if (mi[0] > mi[4] || mi[1] > mi[4] || mi[2] > mi[4]) return std::string("the ") + side + " neighbour's exchange buffer is too small";
+                if ((uint64_t)mi[0] + mi[1] > mo[5] || mi[1] > mo[6]) return std::string("capacity too small for the arrivals + ghosts from the ") + side + " neighbour";
+                return std::string("the ") + side + " neighbour has no room for this rank's migrants + ghosts";
+            };
+            s->failure = "slab mode: " + ((has_lo && !link_lo) ? why(MO, MI, "lower") : why(MO + 8, MI + 8, "upper"));
+        }
+        s->failed = true;
+    }
+    // a link that does not go ahead carries nothing this step, in either direction
+    uint32_t Teff[NLISTS], Reff[NLISTS];
+    for (int l = 0; l < 3; l++) {
+        Teff[l] = link_lo ? MO[l] : 0u;       Reff[l] = link_lo ? MI[l] : 0u;
+        Teff[3 + l] = link_hi ? MO[8 + l] : 0u; Reff[3 + l] = link_hi ? MI[8 + l] : 0u;
+    }
+    // kept migrants are this rank's own rows (ghost copies for its own boundary layers): they do not depend on the link
+    Teff[L_KEEP_LO] = s->host_small[L_KEEP_LO] <= s->xcap ? s->host_small[L_KEEP_LO] : 0u;
+    Teff[L_KEEP_HI] = s->host_small[L_KEEP_HI] <= s->xcap ? s->host_small[L_KEEP_HI] : 0u;
+    if (!link_lo) Teff[L_KEEP_LO] = 0u;
+    if (!link_hi) Teff[L_KEEP_HI] = 0u;
+    const uint32_t* T = Teff;
+    const uint32_t* R = Reff;
+    const bool has_lo_x = link_lo, has_hi_x = link_hi;               // the links that exchange payloads and halos this step
     const uint32_t mig_in_lo = R[0], ghost_in_lo = R[1], mig_in_hi = R[3], ghost_in_hi = R[4];
     const uint32_t kept_by_lo = R[2], kept_by_hi = R[5];   // arrivals the neighbour still mirrors: they lie in my boundary layers
     // deferred check of the previous step's row ranges (computed on the host, see below) against the table
     if (s->verify_pending) {
         s->verify_pending = false;
         const uint32_t* V = s->host_small + 16;
-        for (int q = 0; q < 5; q++)
-            if (V[q] != s->expect[q] && !(q == 1 && !has_lo) && !(q == 2 && !has_hi))      // no neighbour: no boundary layer on that side
-                return fail(c, SPH_ERR_INVALID, "slab mode: row ranges derived from the exchanged counts disagree with the table (range " +
-                                                    std::to_string(q) + ": " + std::to_string(s->expect[q]) + " vs " + std::to_string(V[q]) + ")");
+        for (int q = 0; q < 5 && !s->failed; q++)
+            if (V[q] != s->expect[q] && !(q == 1 && !has_lo) && !(q == 2 && !has_hi)) {    // no neighbour: no boundary layer on that side
+                s->failed = true;
+                s->failure = "slab mode: row ranges derived from the exchanged counts disagree with the table (range " +
+                             std::to_string(q) + ": " + std::to_string(s->expect[q]) + " vs " + std::to_string(V[q]) + ")";
+            }
     }
     const uint32_t n_a = n_old + mig_in_lo + mig_in_hi;                 // resident + arrived (departed rows still inside)
     const uint32_t n_ghost = ghost_in_lo + T[L_KEEP_LO] + ghost_in_hi + T[L_KEEP_HI];
-    if ((uint64_t)n_a + n_ghost > c->cap || n_ghost > s->gcap)
-        return fail(c, SPH_ERR_CAPACITY, "slab mode: capacity too small for arrivals + ghosts");
+    if ((uint64_t)n_a + n_ghost > c->cap || n_ghost > s->gcap)          // cannot happen for links that passed the verdict
+        return fail(c, SPH_ERR_CAPACITY, "slab mode: internal error: accepted links exceed the capacity");
     // (3b) payloads: migrants land straight behind the resident rows, ghosts in the ghost buffer
     float4* g_recv_lo = s->ghost_pred;
     float4* g_keep_lo = g_recv_lo + ghost_in_lo;
     float4* g_recv_hi = g_keep_lo + T[L_KEEP_LO];
     float4* g_keep_hi = g_recv_hi + ghost_in_hi;
     SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) {
+    if (has_lo_x) {
         if (T[L_MIG_LO]) {
             SPH_NCCL(c, ncclSend(s->mig_send[0], (size_t)T[L_MIG_LO] * 4, ncclFloat, lo, comm, st));
             SPH_NCCL(c, ncclSend(s->mig_send[0] + s->xcap, (size_t)T[L_MIG_LO] * 4, ncclFloat, lo, comm, st));
@@ -465,7 +538,7 @@ int multi_step(SphContext* c, float dt)
         }
         if (ghost_in_lo) SPH_NCCL(c, ncclRecv(g_recv_lo, (size_t)ghost_in_lo * 4, ncclFloat, lo, comm, st));
     }
-    if (has_hi) {
+    if (has_hi_x) {
         if (T[L_MIG_HI]) {
             SPH_NCCL(c, ncclSend(s->mig_send[1], (size_t)T[L_MIG_HI] * 4, ncclFloat, hi, comm, st));
             SPH_NCCL(c, ncclSend(s->mig_send[1] + s->xcap, (size_t)T[L_MIG_HI] * 4, ncclFloat, hi, comm, st));
@@ -526,10 +599,11 @@ int multi_step(SphContext* c, float dt)
     // SPH_SLAB_CHECK=1 read the table now and cross-check the layer lengths with the neighbours, as before.
     static const bool force_check = [] { const char* e = getenv("SPH_SLAB_CHECK"); return e && e[0] == '1'; }();
     uint32_t o0, b_lo_end, b_hi_begin, o1, live_end;
+    bool halo_lo = has_lo_x, halo_hi = has_hi_x;          // the links whose boundary / ghost layers travel in the gather stage
     const double h2 = host_now();
     if (!force_check && P.own_hi - P.own_lo >= 3) {
         o0 = ghost_in_lo + T[L_KEEP_LO];
-        live_end = n_all - (T[L_MIG_LO] + T[L_MIG_HI]);
+        live_end = n_all - (s->host_small[L_MIG_LO] + s->host_small[L_MIG_HI]);     // every row classified as a migrant sorted behind the table
         o1 = live_end - (ghost_in_hi + T[L_KEEP_HI]);
         b_lo_end = o0 + T[L_GHOST_LO] + kept_by_lo;
         b_hi_begin = o1 - (T[L_GHOST_HI] + kept_by_hi);
@@ -538,21 +612,32 @@ int multi_step(SphContext* c, float dt)
         s->verify_pending = true;
         SLAB_MARK(6);
     } else {
-        // cross-check: the neighbour's boundary layer must be exactly as long as my ghost layer
+        // cross-check: the neighbour's boundary layer must be exactly as long as my ghost layer, and the other way
+        // round; both numbers cross the link, so its two ends reach the same verdict
+        uint32_t* pair_out = s->dev_small + 8;      // written by k_slab_pick: (my boundary, my ghost layer) lo, then hi
+        uint32_t* pair_in = s->dev_small + 12;
         SPH_NCCL(c, ncclGroupStart());
-        if (has_lo) { SPH_NCCL(c, ncclSend(picks + 5, 1, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(peer + 0, 1, ncclUint32, lo, comm, st)); }
-        if (has_hi) { SPH_NCCL(c, ncclSend(picks + 6, 1, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(peer + 1, 1, ncclUint32, hi, comm, st)); }
+        if (has_lo_x) { SPH_NCCL(c, ncclSend(pair_out, 2, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(pair_in, 2, ncclUint32, lo, comm, st)); }
+        if (has_hi_x) { SPH_NCCL(c, ncclSend(pair_out + 2, 2, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(pair_in + 2, 2, ncclUint32, hi, comm, st)); }
         SPH_NCCL(c, ncclGroupEnd());
-        SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 16, s->dev_small + 16, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 8, s->dev_small + 8, 24 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SLAB_MARK(6);
         SPH_CUDA(c, cudaStreamSynchronize(st));
         const uint32_t* K = s->host_small + 16;
         o0 = K[0]; b_lo_end = K[1]; b_hi_begin = K[2]; o1 = K[3]; live_end = K[4];
-        const uint32_t peer_lo = s->host_small[24], peer_hi = s->host_small[25];
-        if ((has_lo && peer_lo != o0) || (has_hi && peer_hi != live_end - o1))
-            return fail(c, SPH_ERR_INVALID, "slab mode: ghost layer and neighbour boundary layer disagree (" +
-                                                std::to_string(o0) + " vs " + std::to_string(peer_lo) + ", " +
-                                                std::to_string(live_end - o1) + " vs " + std::to_string(peer_hi) + ")");
+        const uint32_t* PO = s->host_small + 8;
+        const uint32_t* PI = s->host_small + 12;
+        const bool agree_lo = !has_lo_x || (PI[0] == PO[1] && PI[1] == PO[0]);
+        const bool agree_hi = !has_hi_x || (PI[2] == PO[3] && PI[3] == PO[2]);
+        if (!agree_lo || !agree_hi) {
+            // that link carries no halo this step -- on either end -- the step is completed and the error returned at its end
+            if (!s->failed)
+                s->failure = "slab mode: ghost layer and neighbour boundary layer disagree (" + std::to_string(PO[1]) + " vs " +
+                             std::to_string(PI[0]) + ", " + std::to_string(PO[3]) + " vs " + std::to_string(PI[2]) + ")";
+            s->failed = true;
+            if (!agree_lo) halo_lo = false;
+            if (!agree_hi) halo_hi = false;
+        }
     }
     const double h3 = host_now();
     if (s->prof && ++s->pseen > 3) {
@@ -580,11 +665,11 @@ int multi_step(SphContext* c, float dt)
         SPH_CUDA(c, cudaEventRecord(s->ev_boundary, st));
         SPH_CUDA(c, cudaStreamWaitEvent(hs, s->ev_boundary, 0));
         SPH_NCCL(c, ncclGroupStart());
-        if (has_lo) {
+        if (halo_lo) {
             if (b_lo_end > o0) SPH_NCCL(c, ncclSend(rows + o0 * fpr, (size_t)(b_lo_end - o0) * fpr, ncclFloat, lo, comm, hs));
             if (o0) SPH_NCCL(c, ncclRecv(rows, (size_t)o0 * fpr, ncclFloat, lo, comm, hs));
         }
-        if (has_hi) {
+        if (halo_hi) {
             if (o1 > b_hi_begin) SPH_NCCL(c, ncclSend(rows + b_hi_begin * fpr, (size_t)(o1 - b_hi_begin) * fpr, ncclFloat, hi, comm, hs));
             if (live_end > o1) SPH_NCCL(c, ncclRecv(rows + o1 * fpr, (size_t)(live_end - o1) * fpr, ncclFloat, hi, comm, hs));
         }
@@ -623,6 +708,10 @@ int multi_step(SphContext* c, float dt)
     c->step_valid = true;
     s->stats[0] = c->n; s->stats[1] = o0; s->stats[2] = live_end - o1; s->stats[3] = T[L_MIG_LO]; s->stats[4] = T[L_MIG_HI];
     s->t_zlo = P.zlo; s->t_own_lo = P.own_lo; s->t_own_hi = P.own_hi; s->table_valid = true;
+    if (s->failed) {                      // the step was enqueued in full (no neighbour is left waiting); its result is not valid
+        (void)was_failed;
+        return fail(c, SPH_ERR_CAPACITY, s->failure.empty() ? std::string("slab mode: a neighbour rank failed") : s->failure);
+    }
     return SPH_OK;
 }
 
@@ -785,7 +874,7 @@ int sph_comm_rebalance(SphContext* c, uint32_t max_shift, int32_t* layers_out, u
     // the layers the last step's table was built for (a single-rank context steps through the plain path: whole grid)
     bool table_valid = s->table_valid;
     int t_zlo = s->t_zlo, t_own_lo = s->t_own_lo, t_own_hi = s->t_own_hi;
-    if (c->nranks == 1) { table_valid = c->step_valid && c->mode == SPH_TABLE_GRID; t_zlo = 0; t_own_lo = 0; t_own_hi = GZ; }
+    if (c->nranks == 1) { table_valid = c->step_valid && c->mode == SPH_TABLE_GRID && !c->grid_too_large; t_zlo = 0; t_own_lo = 0; t_own_hi = GZ; }
     if (!table_valid) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: needs a completed sph_step (the histogram is read off its table)");
     if (hist_out && hist_entries < (size_t)GZ) return fail(c, SPH_ERR_INVALID, "sph_comm_rebalance: hist_out too small");
     SPH_CUDA(c, cudaSetDevice(c->device));
@@ -855,7 +944,7 @@ int sph_upload_owned(SphContext* c, uint32_t n, const uint32_t* global_id, const
     c->n = n;
     c->step_valid = false;
     c->ncount_valid = false;
-    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; }
+    if (c->slab) { c->slab->o0 = 0; c->slab->o1 = n; c->slab->table_valid = false; c->slab->failed = false; c->slab->failure.clear(); c->slab->verify_pending = false; }
     return SPH_OK;
 }
 

@@ -61,6 +61,29 @@ namespace Physics
 			pushParams();
 		}
 
+		// The reference's setters cannot fail (physicsWorld.cc:246-297) and are driven by UI sliders: a value the device
+		// side rejects is NOT committed -- the host copy, the context and every slab keep the parameters in force -- and the
+		// reason is kept in lastError() instead of an exception.
+		bool FluidSimulation::commitParams(const SphParams& cand)
+		{
+			const SphParams old = params;
+			if (ctx && sph_set_params(ctx, &cand) != SPH_OK) {       // the context restores its old state itself
+				const char* msg = sph_last_error(ctx);
+				error = std::string("sph_set_params: ") + (msg ? msg : "unknown error");
+				return false;
+			}
+			if (group) {
+				try { group->setParams(cand); }                       // all ranks or none
+				catch (const std::exception& e) {
+					error = e.what();
+					if (ctx) sph_set_params(ctx, &old);
+					return false;
+				}
+			}
+			params = cand;
+			return true;
+		}
+
 		void FluidSimulation::pushParams()
 		{
 			if (ctx) check(sph_set_params(ctx, &params), "sph_set_params");
@@ -212,12 +235,15 @@ namespace Physics
 		}
 
 		// ---- snapshots: the C ABI's file format (sph_api.cu: sph_save_state), host-side so it serves every device layout
+		// header: "SPHB2002", u32 particle count, u32 sizeof(SphParams), SphParams, then pos3[n], vel3[n] ("SPHB2001", the
+		// first version, has no size word and is still read)
 		static bool writeSnapshotFileImpl(const std::string& path, uint32_t n, const SphParams& p, const float* pos3, const float* vel3)
 		{
 			FILE* f = fopen(path.c_str(), "wb");
 			if (!f) return false;
-			const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '1'};
-			bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&p, sizeof(SphParams), 1, f) == 1;
+			const char magic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', '2'};
+			const uint32_t psize = (uint32_t)sizeof(SphParams);
+			bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&psize, 4, 1, f) == 1 && fwrite(&p, sizeof(SphParams), 1, f) == 1;
 			ok = ok && (n == 0 || (fwrite(pos3, 12, n, f) == n && fwrite(vel3, 12, n, f) == n));
 			return (fclose(f) == 0) && ok;
 		}
@@ -226,8 +252,19 @@ namespace Physics
 			FILE* f = fopen(path.c_str(), "rb");
 			if (!f) return false;
 			char magic[8];
-			bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "SPHB2001", 8) == 0 && fread(&n, 4, 1, f) == 1 &&
-			          fread(&p, sizeof(SphParams), 1, f) == 1;
+			bool ok = fread(magic, 1, 8, f) == 8 && fread(&n, 4, 1, f) == 1;
+			const bool v2 = ok && memcmp(magic, "SPHB2002", 8) == 0;
+			ok = ok && (v2 || memcmp(magic, "SPHB2001", 8) == 0);
+			uint32_t psize = (uint32_t)sizeof(SphParams);
+			if (ok && v2) ok = fread(&psize, 4, 1, f) == 1 && psize == (uint32_t)sizeof(SphParams);   // another ABI's parameter block
+			ok = ok && fread(&p, sizeof(SphParams), 1, f) == 1;
+			if (ok) {
+				// the count comes from the file: it must fit the rest of the file and the reference's int particle count
+				const long here = ftell(f);
+				ok = here >= 0 && fseek(f, 0, SEEK_END) == 0;
+				const long end = ok ? ftell(f) : -1;
+				ok = ok && end >= here && n <= 0x7FFFFFFFu && (uint64_t)(end - here) >= (uint64_t)n * 24u && fseek(f, here, SEEK_SET) == 0;
+			}
 			if (ok) {
 				pos3.resize((size_t)n * 3); vel3.resize((size_t)n * 3);
 				ok = n == 0 || (fread(pos3.data(), 12, n, f) == n && fread(vel3.data(), 12, n, f) == n);
@@ -344,21 +381,21 @@ namespace Physics
 		// setters only store a scalar; they take effect on the next Update (:214-302)
 		void FluidSimulation::setSimulationTime(float time) { simTime = time; }
 		float FluidSimulation::getSimulationTime() { return simTime; }
-		void FluidSimulation::setGravity(bool status) { params.gravity = status ? 1 : 0; pushParams(); }
+		void FluidSimulation::setGravity(bool status) { SphParams p = params; p.gravity = status ? 1 : 0; commitParams(p); }
 		bool FluidSimulation::getGravityStatus() { return params.gravity != 0; }
-		void FluidSimulation::setInteractionRadius(float value) { params.interaction_radius = value; pushParams(); }   // sqr_radius untouched (Q2)
+		void FluidSimulation::setInteractionRadius(float value) { SphParams p = params; p.interaction_radius = value; commitParams(p); }   // sqr_radius untouched (Q2)
 		float FluidSimulation::getInteractionRadius() { return params.interaction_radius; }
-		void FluidSimulation::setDensityTarget(float value) { params.target_density = value; pushParams(); }
+		void FluidSimulation::setDensityTarget(float value) { SphParams p = params; p.target_density = value; commitParams(p); }
 		float FluidSimulation::getDensityTarget() { return params.target_density; }
-		void FluidSimulation::setPressureMultiplier(float value) { params.pressure_multiplier = value; pushParams(); }
+		void FluidSimulation::setPressureMultiplier(float value) { SphParams p = params; p.pressure_multiplier = value; commitParams(p); }
 		float FluidSimulation::getPressureMultiplier() { return params.pressure_multiplier; }
-		void FluidSimulation::setNearPressureMultiplier(float value) { params.near_pressure_multiplier = value; pushParams(); }
+		void FluidSimulation::setNearPressureMultiplier(float value) { SphParams p = params; p.near_pressure_multiplier = value; commitParams(p); }
 		float FluidSimulation::getNearPressureMultiplier() { return params.near_pressure_multiplier; }
-		void FluidSimulation::setViscosityStrength(float value) { params.viscosity_strength = value; pushParams(); }
+		void FluidSimulation::setViscosityStrength(float value) { SphParams p = params; p.viscosity_strength = value; commitParams(p); }
 		float FluidSimulation::getViscosityStrength() { return params.viscosity_strength; }
-		void FluidSimulation::setGravityScale(float value) { params.gravity_scale = value; pushParams(); }
+		void FluidSimulation::setGravityScale(float value) { SphParams p = params; p.gravity_scale = value; commitParams(p); }
 		float FluidSimulation::getGravityScale() { return params.gravity_scale; }
-		void FluidSimulation::setBound(const vec3& value) { params.bound[0] = value.x; params.bound[1] = value.y; params.bound[2] = value.z; pushParams(); }
+		void FluidSimulation::setBound(const vec3& value) { SphParams p = params; p.bound[0] = value.x; p.bound[1] = value.y; p.bound[2] = value.z; commitParams(p); }
 		FluidSimulation::vec3 FluidSimulation::getBounds() { return vec3(params.bound[0], params.bound[1], params.bound[2]); }
 	}
 }

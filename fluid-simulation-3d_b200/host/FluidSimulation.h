@@ -142,6 +142,7 @@ namespace Physics
 
 			void ensureContext(uint32_t capacity);
 			void pushParams();
+			bool commitParams(const SphParams& candidate);   // setters: apply everywhere or nowhere; failure -> lastError(), no throw
 			void check(int rc, const char* what);
 			void refreshTimings();
 			void readParticle(uint32 index, float out10[10]);

@@ -133,9 +133,16 @@ SlabGroup::~SlabGroup()
 }
 
 void SlabGroup::setParams(const SphParams& p)
-{
+{   // all ranks or none: ranks that disagree on the grid geometry would disagree on the ghost layers of the next step
+    const SphParams old = params_;
+    for (size_t k = 0; k < rank_.size(); k++) {
+        if (sph_set_params(rank_[k].ctx, &p) == SPH_OK) continue;
+        const char* msg = sph_last_error(rank_[k].ctx);
+        const std::string why = std::string("sph_set_params (rank ") + std::to_string(k) + "): " + (msg ? msg : "unknown error");
+        for (size_t j = 0; j < k; j++) sph_set_params(rank_[j].ctx, &old);      // the failing rank restored itself
+        throw std::runtime_error(why);
+    }
     params_ = p;
-    for (auto& r : rank_) check(r.ctx, sph_set_params(r.ctx, &params_), "sph_set_params");
 }
 
 void SlabGroup::upload(uint32_t n, const float* pos3, const float* vel3)

@@ -1,7 +1,7 @@
 // host/host_demo.cc -- headless driver of the host class, the way FluidSimCPU drives the reference
 // (fluidSimCPU.cc:9-46): InitializeData(n), then Update(dt) per frame.  Prints one line per run that
 // tests/test_variants_gpu.py / tests/test_host_gpu.py compare with the same scene run through the C ABI from Python.
-//   host_demo n steps table_mode [class | adapter | getters | substeps | multi ndev | snapshot path [ndev] | snapshotio path | slabgroup ndev]
+//   host_demo n steps table_mode [class | adapter | getters | substeps | multi ndev | snapshot path [ndev] | snapshotio path | snapshotread path | slabgroup ndev | setters]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -228,6 +228,35 @@ int main(int argc, char** argv)
             const bool rejects = !sphb200::readSnapshotFile(std::string(path) + ".missing", n2, q, dummy, dummy);
             printf("snapshotio n=%d roundtrip=%d rejects_missing=%d\n", n, (int)ok, (int)rejects);
             return ok && rejects ? 0 : 3;
+        }
+        if (!strcmp(what, "setters")) {                // UI sliders: setters never throw, a rejected value is not committed
+            sim.setTableMode(mode);
+            sim.setGravity(true);
+            sim.setHostMirrors(true, true);
+            sim.InitializeData(n);
+            sim.Update(0.016667f);
+            sim.setInteractionRadius(0.01f);            // gameApp.cc:371 slider minimum: 2000^3 cells -- the context falls back
+            const float r_small = sim.getInteractionRadius();      // to the reference's own table instead of refusing
+            sim.Update(0.016667f);
+            const float rho_small = sim.getDensity(0);
+            sim.setInteractionRadius(0.0f);             // nonsense: refused, recorded, not committed
+            const float r_after_bad = sim.getInteractionRadius();
+            const bool recorded = !sim.lastError().empty();
+            sim.setBound(sphb200::vec3(30.0f, 30.0f, 30.0f));           // slider maximum (gameApp.cc:408)
+            sim.setInteractionRadius(0.35f);
+            sim.Update(0.016667f);
+            bool finite = true;
+            for (const auto& q : sim.positions) finite = finite && std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z);
+            printf("setters r_small=%.3f rho_small=%.4f r_after_bad=%.3f recorded=%d r_final=%.3f bound=%.1f finite=%d\n", r_small, rho_small,
+                   r_after_bad, (int)recorded, sim.getInteractionRadius(), sim.getBounds().x, (int)finite);
+            sim.shutdown();
+            return 0;
+        }
+        if (!strcmp(what, "snapshotread")) {           // read only: a malformed header must be refused (argv[5] = path)
+            uint32_t n2 = 0; SphParams q; std::vector<float> pos2, vel2;
+            const bool ok = sphb200::readSnapshotFile(argc > 5 ? argv[5] : "", n2, q, pos2, vel2);
+            printf("snapshotread read=%d n=%u\n", (int)ok, ok ? n2 : 0u);
+            return 0;
         }
         if (!strcmp(what, "slabgroup")) {              // the group on its own: construction (and its failure path), nothing else
             SphParams p;

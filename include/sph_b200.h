@@ -177,7 +177,8 @@ int  sph_get_grid(const SphContext* ctx, int32_t* dims3, int32_t* origin3);
 int  sph_grid_x_subdivision(const SphContext* ctx);
 
 /* -- state snapshots (the reference has none: Reset re-spawns, physicsWorld.cc:112) ---- */
-/* Little-endian file: "SPHB2001", u32 n, SphParams, then n x (pos3, vel3) fp32 in particle index order.
+/* Little-endian file: "SPHB2002", u32 n, u32 sizeof(SphParams), SphParams, then n x pos3, n x vel3 (fp32, particle index
+ * order); "SPHB2001" files (no size word) are still read.  n is checked against the file size before anything is allocated.
  * Loading replaces parameters and state (n must fit the capacity). */
 int  sph_save_state(SphContext* ctx, const char* path);
 int  sph_load_state(SphContext* ctx, const char* path);

@@ -179,6 +179,34 @@ def main():
     dist.barrier()
     if rank == 0:
         print("pipelined_owned_transfers: 3 frames bit-identical to the blocking calls", flush=True)
+    # (6) a capacity error comes back as an error on EVERY rank, never as a hang: the slabs hold their own rows but have
+    # no room for the ghost layers, so both ends of the link refuse it (the verdict is computed from the same count
+    # messages on either side), complete the step's communication pattern and return the error; it is sticky until the
+    # next upload
+    sc = scenes.small_dam_break(24)
+    idb = slab_driver.broadcast_id(pkg, dist, torch, rank, dev)
+    probe = slab_driver.SlabSimulation(pkg, sc["n"], rank, world, dev, idb, **sc["params"])
+    gmin_z, gz = int(probe.origin[2]), int(probe.dims[2])
+    layers = slab_driver.choose_layers(sc["pos"][:, 2], world, probe.r, gmin_z, gz)
+    own = slab_driver.owner_of(sc["pos"][:, 2], layers, probe.r, gmin_z, gz) == rank
+    probe.close()
+    dist.barrier()
+    idb = slab_driver.broadcast_id(pkg, dist, torch, rank, dev)
+    slab = slab_driver.SlabSimulation(pkg, int(own.sum()) + 64, rank, world, dev, idb, **sc["params"])
+    slab.set_layers(layers)
+    slab.upload_owned(np.nonzero(own)[0].astype(np.uint32), sc["pos"][own], sc["vel"][own])
+    errors = 0
+    for _ in range(3):
+        try:
+            slab.step(scenes.DT)
+        except pkg.SphError as e:
+            errors += 1
+            assert "capacity" in str(e) or "room" in str(e) or "neighbour" in str(e), str(e)
+    assert errors == 3, "rank %d: %d of 3 steps reported the capacity error" % (rank, errors)
+    slab.close()
+    dist.barrier()
+    if rank == 0:
+        print("capacity_error: returned by every rank on every step, no rank left waiting", flush=True)
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_CHECK_OK")

@@ -158,7 +158,8 @@ def test_every_entry_point_survives_null_arguments(pkg):
 
 def test_host_snapshot_file_is_the_documented_format(tmp_path):
     """FluidSimulation::saveState / loadState go through sphb200::writeSnapshotFile / readSnapshotFile (pure host code):
-    the file is the C ABI's snapshot format (include/sph_b200.h: "SPHB2001", u32 n, SphParams, n x pos3, n x vel3)"""
+    the file is the C ABI's snapshot format (include/sph_b200.h: "SPHB2002", u32 n, u32 sizeof(SphParams), SphParams,
+    n x pos3, n x vel3); a count that does not fit the file is rejected before anything is allocated"""
     import numpy as np
     demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
     path = str(tmp_path / "state.bin")
@@ -166,12 +167,18 @@ def test_host_snapshot_file_is_the_documented_format(tmp_path):
     r = subprocess.run([demo, str(n), "0", "0", "snapshotio", path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert r.returncode == 0 and "roundtrip=1 rejects_missing=1" in r.stdout, r.stdout
     raw = open(path, "rb").read()
-    assert raw[:8] == b"SPHB2001" and len(raw) == 8 + 4 + 44 + 24 * n
-    assert int(np.frombuffer(raw, np.uint32, 1, 8)[0]) == n
-    par = np.frombuffer(raw, np.float32, 11, 12)
-    assert abs(par[0] - 0.35) < 1e-7 and par[5] == np.float32(0.75) and np.frombuffer(raw, np.int32, 1, 12 + 28)[0] == 1
+    assert raw[:8] == b"SPHB2002" and len(raw) == 8 + 4 + 4 + 44 + 24 * n
+    assert int(np.frombuffer(raw, np.uint32, 1, 8)[0]) == n and int(np.frombuffer(raw, np.uint32, 1, 12)[0]) == 44
+    par = np.frombuffer(raw, np.float32, 11, 16)
+    assert abs(par[0] - 0.35) < 1e-7 and par[5] == np.float32(0.75) and np.frombuffer(raw, np.int32, 1, 16 + 28)[0] == 1
     assert list(par[8:11]) == [20.0, 20.0, 7.5]
-    pos = np.frombuffer(raw, np.float32, 3 * n, 56)
-    vel = np.frombuffer(raw, np.float32, 3 * n, 56 + 12 * n)
+    pos = np.frombuffer(raw, np.float32, 3 * n, 60)
+    vel = np.frombuffer(raw, np.float32, 3 * n, 60 + 12 * n)
     i = np.arange(3 * n, dtype=np.float32)
     assert np.array_equal(pos, np.float32(0.25) * i - np.float32(3.0)) and np.array_equal(vel, np.float32(-0.5) * i)
+    # a header that claims more particles than the file holds (or more than an int) must be refused, not allocated
+    bad = str(tmp_path / "bad.bin")
+    for claim in (n + 1, 0x7FFFFFFF, 0xFFFFFFFF):
+        open(bad, "wb").write(raw[:8] + np.uint32(claim).tobytes() + raw[12:])
+        r = subprocess.run([demo, "0", "0", "0", "snapshotread", bad], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+        assert r.returncode == 0 and "read=0" in r.stdout, (claim, r.stdout)

@@ -57,6 +57,20 @@ def test_getters_single_reads_and_parallel_bulk_mirror(pkg):
     sim.close()
 
 
+def test_setters_never_throw_and_never_commit_a_rejected_value():
+    """The reference's setters cannot fail and are driven by UI sliders (gameApp.cc:371-408).  Radius 0.01 in the default
+    20-unit box is 2000^3 grid cells: the context steps on the reference's own table instead of refusing it; a radius of
+    0 is refused, recorded in lastError(), and neither the host copy nor the device see it; the largest box of the
+    slider (30 units) and the default radius again give a finite step."""
+    r = subprocess.run([DEMO, "4000", "1", "0", "setters"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("setters ")][0]
+    got = dict(kv.split("=") for kv in line.split()[1:])
+    assert got["r_small"] == "0.010" and float(got["rho_small"]) > 0.0
+    assert got["r_after_bad"] == "0.010" and got["recorded"] == "1"
+    assert got["r_final"] == "0.350" and got["bound"] == "30.0" and got["finite"] == "1"
+
+
 def test_substepping_equals_explicit_smaller_steps(pkg):
     ob = g.load_oracle()
     n, steps = 4096, 2
