@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_spawn_block", "sph_upload_state",
-    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_synchronize", "sph_refresh_densities",
+    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_noncanonical_cells", "sph_set_extras", "sph_get_extras", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
@@ -49,6 +49,11 @@ class SphParams(C.Structure):
                 ("target_density", C.c_float), ("pressure_multiplier", C.c_float),
                 ("near_pressure_multiplier", C.c_float), ("viscosity_strength", C.c_float),
                 ("gravity_scale", C.c_float), ("gravity", C.c_int32), ("bound", C.c_float * 3)]
+
+
+class SphExtras(C.Structure):
+    """Mirror of ``struct SphExtras`` (rotatable bound, wall stickiness: off by default)."""
+    _fields_ = [("bound_rotation", C.c_float * 4), ("stick_strength", C.c_float), ("stick_distance", C.c_float)]
 
 
 class SphBlockSpawn(C.Structure):
@@ -129,6 +134,10 @@ def load_library():
     L.sph_launch_count.restype = C.c_uint64
     L.sph_graph_replays.argtypes = [vp]
     L.sph_graph_replays.restype = C.c_uint64
+    L.sph_set_extras.argtypes = [vp, C.POINTER(SphExtras)]
+    L.sph_get_extras.argtypes = [vp, C.POINTER(SphExtras)]
+    L.sph_noncanonical_cells.argtypes = [vp]
+    L.sph_noncanonical_cells.restype = C.c_uint64
     L.sph_stream.argtypes = [vp]
     L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
@@ -231,6 +240,17 @@ class FluidSimulation:
         p = _update_params(self.get_params(), kw)
         self._check(self.L.sph_set_params(self.h, C.byref(p)))
 
+    def set_extras(self, bound_rotation=(0.0, 0.0, 0.0, 1.0), stick_strength=0.0, stick_distance=0.0):
+        e = SphExtras()
+        e.bound_rotation[:] = [float(x) for x in bound_rotation]
+        e.stick_strength, e.stick_distance = float(stick_strength), float(stick_distance)
+        self._check(self.L.sph_set_extras(self.h, C.byref(e)))
+
+    def get_extras(self):
+        e = SphExtras()
+        self._check(self.L.sph_get_extras(self.h, C.byref(e)))
+        return dict(bound_rotation=tuple(e.bound_rotation), stick_strength=e.stick_strength, stick_distance=e.stick_distance)
+
     def set_table_mode(self, mode):
         self._check(self.L.sph_set_table_mode(self.h, int(mode)))
 
@@ -331,6 +351,9 @@ class FluidSimulation:
 
     def launch_count(self):
         return int(self.L.sph_launch_count(self.h))
+
+    def noncanonical_cells(self):
+        return int(self.L.sph_noncanonical_cells(self.h))
 
     def graph_replays(self):
         return int(self.L.sph_graph_replays(self.h))

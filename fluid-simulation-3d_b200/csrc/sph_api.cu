@@ -73,6 +73,10 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
     P->row0 = 0; P->row1 = n; P->n_a = n;
     P->seg_off = (uint32_t)table_layout(c->ncell).cells_pad;
+    P->noncanonical = c->d_noncanonical;
+    P->extras = c->extras_on ? 1 : 0;
+    for (int i = 0; i < 9; i++) P->rot[i] = c->rot[i];
+    P->stick_k = c->extras.stick_strength; P->stick_d = c->extras.stick_distance;
     P->rim_check = (double)p.sqr_radius > (double)r * (double)r * (1.0 + 4e-7) ? 1 : 0;
     P->slab = 0; P->zlo = 0; P->gz_global = c->gdim[2]; P->own_lo = 0; P->own_hi = c->gdim[2];
     return SPH_OK;
@@ -92,8 +96,11 @@ static int update_grid_geometry(SphContext* c)
     int dims[3], los[3];
     uint64_t base_cells = 1;
     for (int a = 0; a < 3; a++) {
-        const float half = p.bound[a] * 0.5f;
-        if (!(half >= 0.0f) || !std::isfinite(half)) return fail(c, SPH_ERR_INVALID, "bound must be finite and >= 0");
+        const float half0 = p.bound[a] * 0.5f;
+        if (!(half0 >= 0.0f) || !std::isfinite(half0)) return fail(c, SPH_ERR_INVALID, "bound must be finite and >= 0");
+        // a rotated box (SphExtras): the table covers its bounding box, |R| * half
+        double half = half0;
+        if (c->extras_on) { half = 0.0; for (int b = 0; b < 3; b++) half += std::fabs((double)c->rot[3 * a + b]) * (double)(p.bound[b] * 0.5f); }
         double q = std::floor((double)half / (double)p.interaction_radius);
         if (q > 1e6) q = 1e6;                       // far beyond any table: falls through to grid_too_large
         const int hi = (int)q + 2, lo = -(int)q - 3;
@@ -208,7 +215,7 @@ int ensure_list(SphContext* c, NbrList* L)
 static void free_all(SphContext* c)
 {
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->predpk, c->velp, c->dens, c->key_a, c->key_b,
-                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->d_noncanonical, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     if (c->h_tile_need) cudaFreeHost(c->h_tile_need);
@@ -285,6 +292,8 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     ALLOC(c->ncount, cap * 4);
     ALLOC(c->lcount, cap * 4);
     ALLOC(c->stage, cap * 32);
+    ALLOC(c->d_noncanonical, 4);
+    cudaMemset(c->d_noncanonical, 0, 4);
     c->counts_cap = radix_sort_temp_entries(capacity);
     ALLOC(c->counts, c->counts_cap * 4);
 #undef ALLOC
@@ -323,6 +332,49 @@ int sph_set_params(SphContext* c, const SphParams* p)
     return SPH_OK;
 }
 
+int sph_set_extras(SphContext* c, const SphExtras* e)
+{
+    if (!c || !e) return SPH_ERR_INVALID;
+    const float* q = e->bound_rotation;
+    const double n2 = (double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2] + (double)q[3] * q[3];
+    if (!(n2 > 1e-12) || !std::isfinite(n2)) return fail(c, SPH_ERR_INVALID, "sph_set_extras: the rotation quaternion is zero or not finite");
+    if (!(e->stick_strength >= 0.0f) || !std::isfinite(e->stick_strength)) return fail(c, SPH_ERR_INVALID, "sph_set_extras: stick_strength must be >= 0");
+    if (e->stick_strength > 0.0f && !(e->stick_distance > 0.0f && std::isfinite(e->stick_distance)))
+        return fail(c, SPH_ERR_INVALID, "sph_set_extras: stick_distance must be > 0 when stick_strength is");
+    const SphExtras old = c->extras;
+    float oldrot[9];
+    memcpy(oldrot, c->rot, sizeof(oldrot));
+    const bool old_on = c->extras_on;
+    const double inv = 1.0 / std::sqrt(n2);
+    const double x = q[0] * inv, y = q[1] * inv, z = q[2] * inv, w = q[3] * inv;
+    c->extras = *e;
+    c->extras.bound_rotation[0] = (float)x; c->extras.bound_rotation[1] = (float)y; c->extras.bound_rotation[2] = (float)z; c->extras.bound_rotation[3] = (float)w;
+    const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+    for (int i = 0; i < 9; i++) c->rot[i] = (float)R[i];
+    const bool rotated = std::fabs(w) < 1.0 - 1e-12 || x != 0.0 || y != 0.0 || z != 0.0;
+    c->extras_on = rotated || e->stick_strength > 0.0f;
+    if (!rotated) { const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(c->rot, I, sizeof(I)); }
+    int rc = update_grid_geometry(c);
+    if (rc == SPH_OK) rc = multi_params_changed(c);
+    if (rc != SPH_OK) {
+        const std::string m = c->err;
+        c->extras = old; memcpy(c->rot, oldrot, sizeof(oldrot)); c->extras_on = old_on;
+        update_grid_geometry(c); multi_params_changed(c);
+        c->err = m;
+        return rc;
+    }
+    return SPH_OK;
+}
+
+int sph_get_extras(const SphContext* c, SphExtras* e)
+{
+    if (!c || !e) return SPH_ERR_INVALID;
+    *e = c->extras;
+    return SPH_OK;
+}
+
 int sph_get_params(const SphContext* c, SphParams* p)
 {
     if (!c || !p) return SPH_ERR_INVALID;
@@ -354,6 +406,14 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
 uint64_t sph_graph_replays(const SphContext* c) { return c ? c->graph_replays : 0; }
+uint64_t sph_noncanonical_cells(SphContext* c)
+{   // cells (summed over all steps so far) too crowded for the counting sort's canonical-order ranking; synchronises
+    if (!c || !c->d_noncanonical) return 0;
+    uint32_t v = 0;
+    cudaSetDevice(c->device);
+    if (cudaStreamSynchronize(c->st) != cudaSuccess || cudaMemcpy(&v, c->d_noncanonical, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return v;
+}
 void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
 
 int sph_grid_x_subdivision(const SphContext* c) { return c ? c->xsub : 0; }
@@ -483,7 +543,7 @@ static SphContext::StepKey step_key(const SphContext* c, float dt)
 {
     SphContext::StepKey k;
     memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
-    k.n = c->n; k.dt = dt; k.params = c->params; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0;
+    k.n = c->n; k.dt = dt; k.params = c->params; k.extras = c->extras; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0;
     k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
     return k;
 }

@@ -11,6 +11,9 @@ struct SphContext {
     uint32_t cap = 0;            // row capacity of every per-particle array
     uint32_t n = 0;              // rows in use (single GPU: particles; slab mode: owned particles)
     SphParams params;
+    SphExtras extras = {{0.0f, 0.0f, 0.0f, 1.0f}, 0.0f, 0.0f};
+    float rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // rotation matrix of extras.bound_rotation (world = R * local)
+    bool extras_on = false;
     int mode = SPH_TABLE_GRID;
     bool timing = true;
     bool nc_tap = false;
@@ -32,6 +35,7 @@ struct SphContext {
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
     uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
     uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
+    uint32_t* d_noncanonical = nullptr;   // device counter, see DevParams::noncanonical
     uint32_t tile_capn = 0;          // tile generation: staged candidates per warp (0: not initialised yet)
     uint32_t* d_tile_need = nullptr; // device word: largest single-cell neighbourhood that did not fit
     uint32_t* h_tile_need = nullptr; // pinned mirror, refreshed with h_overflow
@@ -62,7 +66,7 @@ struct SphContext {
     // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
     // plain step and re-captures
     struct StepKey {
-        uint32_t n; float dt; SphParams params; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level;
+        uint32_t n; float dt; SphParams params; SphExtras extras; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level;
         const void *nlist, *tstart, *scan_tmp, *tend;
     };
     cudaGraph_t graph = nullptr;

@@ -42,6 +42,11 @@ struct DevParams {
     int      has_lo, has_hi;   // a neighbour rank exists below / above
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
     uint32_t seg_off;          // GRID table: word offset of the per-segment base array behind the per-cell array (tbl(), sph_device.cuh)
+    uint32_t* noncanonical;    // device counter: cells too crowded for the canonical-order ranking of the counting sort (sph_kernels.cu)
+    // optional features (SphExtras): box rotation (rows of R: world = R * local) and wall stickiness
+    int      extras;           // 0: S6 is the reference's, bit for bit
+    float    rot[9];
+    float    stick_k, stick_d;
     int      rim_check;        // the cut-off exceeds the cell size (Q2): particles next to the table's rim compare true cells (sph_device.cuh)
 };
 

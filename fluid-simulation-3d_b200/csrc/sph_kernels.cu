@@ -240,11 +240,18 @@ k_fill_gaps(uint32_t* __restrict__ table, const uint32_t* __restrict__ gap_list)
 // atomicAdd put a cell's rows into its slots in arbitrary order; the canonical (= stable sort) order is ascending
 // source row, so slot number r of the cell takes the r-th smallest source row of the cell's slots.  Cells hold a
 // handful of rows; a cell with more than kMaxCanonical rows (clamped border cells in a blow-up) keeps ticket order.
-constexpr uint32_t kMaxCanonical = 1024;
+constexpr uint32_t kSmallCell = 32;         // up to here: rank every entry (m^2 compares per slot, m ~ 4)
+constexpr uint32_t kMaxCanonical = 16384;   // up to here: bisection on the value (32 m compares per slot); beyond: ticket order
 
+// Slot number r of a cell takes the r-th smallest source row of the cell's slots (the stable sort's order).  Cells hold a
+// handful of rows, where ranking every entry is cheapest; crowded cells (a dense column, rows piled into a clamped rim
+// cell) bisect on the value instead: the r-th smallest of m distinct values is the smallest x with #{v <= x} = r + 1.
+// A cell above kMaxCanonical rows -- a blow-up that clamps a large part of the scene into one rim cell -- keeps its
+// ticket order; each such cell is counted in *noncanonical (sph_noncanonical_cells): its neighbour sets are unaffected
+// (the cull is by distance), only the summation order of floats, and with it the last bits, stop being reproducible.
 __device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key,
                                                const uint32_t* __restrict__ table, const uint32_t s, uint32_t* key_sorted,
-                                               const DevParams& P)
+                                               const DevParams& P, uint32_t* __restrict__ noncanonical)
 {
     const uint32_t ncell = P.ncell;
     const uint32_t s0 = perm[s];
@@ -252,18 +259,32 @@ __device__ __forceinline__ uint32_t source_row(const uint32_t* __restrict__ perm
     const uint32_t k = key[s0];
     if (key_sorted) key_sorted[s] = k;
     // slab mode: key == ncell collects the rows that leave this rank; they are dropped after the step, their order
-    // is irrelevant -- and there can be hundreds of them, which the O(m^2)-per-thread ranking below must never see
+    // is irrelevant -- and there can be hundreds of them
     if (k >= ncell) return s0;
     const uint32_t b = tbl(table, P, k), m = tbl(table, P, k + 1u) - b;
-    if (m == 1u || m > kMaxCanonical) return s0;
+    if (m == 1u) return s0;
     const uint32_t r = s - b;
-    for (uint32_t t = 0; t < m; t++) {                       // the entry with exactly r smaller entries
-        const uint32_t v = perm[b + t];
-        uint32_t less = 0;
-        for (uint32_t u = 0; u < m; u++) less += perm[b + u] < v;
-        if (less == r) return v;
+    if (m > kMaxCanonical) {
+        if (r == 0u && noncanonical) atomicAdd(noncanonical, 1u);
+        return s0;
     }
-    return s0;
+    if (m <= kSmallCell) {
+        for (uint32_t t = 0; t < m; t++) {                   // the entry with exactly r smaller entries
+            const uint32_t v = perm[b + t];
+            uint32_t less = 0;
+            for (uint32_t u = 0; u < m; u++) less += perm[b + u] < v;
+            if (less == r) return v;
+        }
+        return s0;
+    }
+    uint32_t lo = 0u, hi = 0xFFFFFFFFu;                      // smallest x with #{v <= x} >= r + 1
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t le = 0;
+        for (uint32_t u = 0; u < m; u++) le += perm[b + u] <= mid;
+        if (le >= r + 1u) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
 }
 
 __global__ void __launch_bounds__(256)
@@ -276,7 +297,7 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
     const bool valid = s < P.n;                    // no early return: the pair-interleaved copy is written with shuffles
     float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (valid) {
-        const uint32_t src = source_row(perm, key, table, s, key_sorted, P);
+        const uint32_t src = source_row(perm, key, table, s, key_sorted, P, P.noncanonical);
         if (src >= P.n_a) {                 // slab mode ghost row: only its predicted position exists here
             const float4 gq = ghost_pred[src - P.n_a];
             const int3 c = cell_of(gq.x, gq.y, gq.z, P.r);
@@ -305,15 +326,53 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
         pred_pk[s] = (s & 1u) ? make_float4(az, q.z, aw, q.w) : make_float4(q.x, ax, q.y, ay);
 }
 
+// S6 with the optional features of SphExtras: everything happens in the box's own axes (local = R^T * world).
+//  1. stickiness: a particle within stick_d of a wall is pulled towards it, v -= dt * k * d * (1 - d / stick_d) * n
+//     (n the wall's inward normal, d the distance to the wall);
+//  2. the reference's move, clamp and -0.95 reflection (:84-107) on the local coordinates;
+//  3. back to world axes.
+__device__ __noinline__ void integrate_extras(float4& p, float4& v, const DevParams& P, const float dt)
+{
+    const float* R = P.rot;
+    float l[3] = {R[0] * p.x + R[3] * p.y + R[6] * p.z, R[1] * p.x + R[4] * p.y + R[7] * p.z, R[2] * p.x + R[5] * p.y + R[8] * p.z};
+    float u[3] = {R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z};
+    if (P.stick_k > 0.0f) {
+        #pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float dlo = l[a] + P.half[a], dhi = P.half[a] - l[a];          // distances to the two walls of this axis
+            if (dlo >= 0.0f && dlo < P.stick_d) u[a] -= dt * P.stick_k * dlo * (1.0f - dlo / P.stick_d);     // inward normal +a
+            if (dhi >= 0.0f && dhi < P.stick_d) u[a] += dt * P.stick_k * dhi * (1.0f - dhi / P.stick_d);     // inward normal -a
+        }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        l[a] = __fadd_rn(l[a], __fmul_rn(u[a], dt));
+        if (__fsub_rn(P.half[a], fabsf(l[a])) <= 0.0f) {
+            const float sg = (l[a] > 0.0f) ? 1.0f : ((l[a] < 0.0f) ? -1.0f : 0.0f);
+            l[a] = __fmul_rn(P.half[a], sg);
+            u[a] = __fmul_rn(u[a], -0.95f);
+        }
+    }
+    p.x = R[0] * l[0] + R[1] * l[1] + R[2] * l[2]; p.y = R[3] * l[0] + R[4] * l[1] + R[5] * l[2]; p.z = R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+    v.x = R[0] * u[0] + R[1] * u[1] + R[2] * u[2]; v.y = R[3] * u[0] + R[4] * u[1] + R[5] * u[2]; v.z = R[6] * u[0] + R[7] * u[1] + R[8] * u[2];
+}
+
 // S6 (:84-107)
 __global__ void __launch_bounds__(256)
 k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
-            float4* __restrict__ vel_out, const DevParams P, const float dt)
+            float4* __restrict__ vel_out, const __grid_constant__ DevParams P, const float dt)
 {
     const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.row1) return;
     float4 p = pos_s[s];
     float4 v = vel_v[s];
+    if (P.extras) {                                  // optional features (SphExtras): off in the reference's configuration
+        integrate_extras(p, v, P, dt);
+        v.w = 0.0f;
+        pos_out[s - P.row0] = p;
+        vel_out[s - P.row0] = v;
+        return;
+    }
     p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
     p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
     p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
@@ -389,11 +448,13 @@ __device__ __forceinline__ float4 speed_color(float t)
     const float4 c3 = make_float4(1.0f, 1.0f, 0.0f, 1.0f), c4 = make_float4(1.0f, 0.0f, 0.0f, 1.0f);
     const float b1 = 0.33f, b2 = 0.66f;
     float a; float4 lo, hi;
-    if (t <= b1) { a = t / b1; lo = c1; hi = c2; }
-    else if (t <= b2) { a = (t - b1) / (b2 - b1); lo = c2; hi = c3; }
-    else { a = (t - b2) / (1.0f - b2); lo = c3; hi = c4; }
-    const float ia = 1.0f - a;
-    return make_float4(ia * lo.x + a * hi.x, ia * lo.y + a * hi.y, ia * lo.z + a * hi.z, ia * lo.w + a * hi.w);
+    // the reference's operations one by one, unfused (oracle/colors.py restates them in numpy; bit-exact against it)
+    if (t <= b1) { a = __fdiv_rn(t, b1); lo = c1; hi = c2; }
+    else if (t <= b2) { a = __fdiv_rn(__fsub_rn(t, b1), __fsub_rn(b2, b1)); lo = c2; hi = c3; }
+    else { a = __fdiv_rn(__fsub_rn(t, b2), __fsub_rn(1.0f, b2)); lo = c3; hi = c4; }
+    const float ia = __fsub_rn(1.0f, a);
+    return make_float4(__fadd_rn(__fmul_rn(ia, lo.x), __fmul_rn(a, hi.x)), __fadd_rn(__fmul_rn(ia, lo.y), __fmul_rn(a, hi.y)),
+                       __fadd_rn(__fmul_rn(ia, lo.z), __fmul_rn(a, hi.z)), __fadd_rn(__fmul_rn(ia, lo.w), __fmul_rn(a, hi.w)));
 }
 
 // out[dst] = field of device row s, dst = particle id (by_id) or s.
@@ -429,8 +490,9 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
         break;
     case SPH_FIELD_SPEED_NORMALIZED: case SPH_FIELD_COLORS: {
         const float4 a = ((const float4*)src)[s];
-        const float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-        const float t = fminf(fmaxf(len, 0.0f), 1.5f) / 1.5f;              // :181
+        // glm::length = sqrt(dot): (x*x + y*y) + z*z, unfused; clamp; / 1.5f                       (:181)
+        const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)), __fmul_rn(a.z, a.z)));
+        const float t = __fdiv_rn(fminf(fmaxf(len, 0.0f), 1.5f), 1.5f);
         if (field == SPH_FIELD_SPEED_NORMALIZED) ((float*)out)[dst] = t;
         else ((float4*)out)[dst] = speed_color(t);
     } break;

@@ -84,9 +84,37 @@ namespace Physics
 			return true;
 		}
 
+		bool FluidSimulation::commitExtras(const SphExtras& cand)
+		{
+			if (ctx && sph_set_extras(ctx, &cand) != SPH_OK) {
+				const char* msg = sph_last_error(ctx);
+				error = std::string("sph_set_extras: ") + (msg ? msg : "unknown error");
+				return false;
+			}
+			if (group) {
+				try { group->setExtras(cand); }
+				catch (const std::exception& e) { error = e.what(); if (ctx) sph_set_extras(ctx, &extras); return false; }
+			}
+			extras = cand;
+			return true;
+		}
+		bool FluidSimulation::setBoundRotation(float qx, float qy, float qz, float qw)
+		{
+			SphExtras e = extras;
+			e.bound_rotation[0] = qx; e.bound_rotation[1] = qy; e.bound_rotation[2] = qz; e.bound_rotation[3] = qw;
+			return commitExtras(e);
+		}
+		bool FluidSimulation::setStickiness(float strength, float distance)
+		{
+			SphExtras e = extras;
+			e.stick_strength = strength; e.stick_distance = distance;
+			return commitExtras(e);
+		}
+
 		void FluidSimulation::pushParams()
 		{
 			if (ctx) check(sph_set_params(ctx, &params), "sph_set_params");
+			if (ctx) check(sph_set_extras(ctx, &extras), "sph_set_extras");
 			if (group) {
 				try { group->setParams(params); }
 				catch (const std::exception& e) { error = e.what(); throw; }

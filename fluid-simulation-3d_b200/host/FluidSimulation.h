@@ -85,6 +85,10 @@ namespace Physics
 			void setGravityScale(float value);
 			float getGravityScale();
 			void setBound(const vec3& value);
+			// beyond the reference (its TODO list, README.md:38,43; physicsWorld.h:146-147): both off by default
+			bool setBoundRotation(float qx, float qy, float qz, float qw);      // unit quaternion; (0,0,0,1) = axis-aligned
+			bool setStickiness(float strength, float distance);                  // wall adhesion; strength 0 = off
+			const SphExtras& getExtras() const { return extras; }
 			vec3 getBounds();
 
 			std::vector<vec3> positions;                                         // physicsWorld.h:79
@@ -142,7 +146,9 @@ namespace Physics
 
 			void ensureContext(uint32_t capacity);
 			void pushParams();
-			bool commitParams(const SphParams& candidate);   // setters: apply everywhere or nowhere; failure -> lastError(), no throw
+			bool commitParams(const SphParams& candidate);
+			bool commitExtras(const SphExtras& candidate);
+			SphExtras extras = {{0.0f, 0.0f, 0.0f, 1.0f}, 0.0f, 0.0f};   // setters: apply everywhere or nowhere; failure -> lastError(), no throw
 			void check(int rc, const char* what);
 			void refreshTimings();
 			void readParticle(uint32 index, float out10[10]);

@@ -145,6 +145,19 @@ void SlabGroup::setParams(const SphParams& p)
     params_ = p;
 }
 
+void SlabGroup::setExtras(const SphExtras& e)
+{
+    std::vector<SphExtras> old(rank_.size());
+    for (size_t k = 0; k < rank_.size(); k++) {
+        sph_get_extras(rank_[k].ctx, &old[k]);
+        if (sph_set_extras(rank_[k].ctx, &e) == SPH_OK) continue;
+        const char* msg = sph_last_error(rank_[k].ctx);
+        const std::string why = std::string("sph_set_extras (rank ") + std::to_string(k) + "): " + (msg ? msg : "unknown error");
+        for (size_t j = 0; j < k; j++) sph_set_extras(rank_[j].ctx, &old[j]);
+        throw std::runtime_error(why);
+    }
+}
+
 void SlabGroup::upload(uint32_t n, const float* pos3, const float* vel3)
 {
     const int R = ranks();

@@ -31,6 +31,7 @@ public:
     int ranks() const { return (int)rank_.size(); }
     uint32_t particles() const { return n_; }
     void setParams(const SphParams& p);
+    void setExtras(const SphExtras& e);          // all ranks or none, like setParams
     // Replace the whole state (index order, velocities may be null = zero).  Cuts the slabs at the particle-count
     // quantiles of the z cell layers (sph_slab_balance_layers) and hands every rank its particles.
     void upload(uint32_t n, const float* pos3, const float* vel3);

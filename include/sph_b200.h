@@ -56,6 +56,22 @@ typedef struct SphParams {
     float   bound[3];                  /* BoundScale         (20,20,20): full box extents, centred on 0 */
 } SphParams;
 
+/* Solver features from the reference's TODO list (README.md:38,43) that it has not implemented: SURVEY 8(f) rank 4.
+ * Both are OFF by default (identity rotation, zero strength) and then S6 is the reference's, bit for bit.
+ *  - rotatable bound: the unused members boundRotation / boundTransform (physicsWorld.h:146-147).  The box BoundScale is
+ *    rotated about the origin by the unit quaternion (x, y, z, w); S6's clamp and -0.95 reflection (physicsWorld.cc:88-106)
+ *    run on the position / velocity expressed in the box's own axes.  Gravity stays along world -y.  The GRID table
+ *    covers the rotated box's bounding box.
+ *  - stickiness ("Apply stickyness to the particles to mimic water better"): the wall adhesion impulse of the double-density
+ *    relaxation scheme the reference follows (README.md:64): a particle closer than stick_distance to a wall of the box
+ *    gets  v -= dt * stick_strength * d * (1 - d / stick_distance) * n  with d its distance to that wall and n the wall's
+ *    inward normal, before S6 moves it. */
+typedef struct SphExtras {
+    float bound_rotation[4];           /* unit quaternion (x, y, z, w); (0,0,0,1) = the reference's axis-aligned box */
+    float stick_strength;              /* 0 = off */
+    float stick_distance;              /* > 0 when stick_strength != 0 */
+} SphExtras;
+
 /* Which neighbour table the step builds and walks.
  *  SPH_TABLE_GRID            B200 layout (default): cell key = linear index of the reference's
  *                            integer cell floor(pred/r) inside the bounding box, x fastest, so the
@@ -105,6 +121,10 @@ int  sph_abi_version(void);
 /* -- parameters (setters/getters .cc:214-302) ------------------------------ */
 void sph_default_params(SphParams* p);
 int  sph_set_params(SphContext* ctx, const SphParams* p);
+/* the optional features above; rejected (state unchanged) for a zero quaternion, a negative strength or a distance <= 0 with a
+ * non-zero strength.  The quaternion is normalised. */
+int  sph_set_extras(SphContext* ctx, const SphExtras* e);
+int  sph_get_extras(const SphContext* ctx, SphExtras* e);
 int  sph_get_params(const SphContext* ctx, SphParams* p);
 int  sph_set_table_mode(SphContext* ctx, int mode);
 int  sph_get_table_mode(const SphContext* ctx);
@@ -155,6 +175,10 @@ int  sph_step(SphContext* ctx, float dt);
 int  sph_step_n(SphContext* ctx, float dt, uint32_t nsteps);
 /* steps executed by graph replay since creation (diagnostic) */
 uint64_t sph_graph_replays(const SphContext* ctx);
+/* GRID table, counting sort: cells that held more than 16384 rows (a blow-up clamping much of the scene into one rim cell) keep
+ * the arrival order of their rows instead of the canonical ascending-index order: neighbour sets are unaffected, float sums lose
+ * run-to-run reproducibility in the last bits.  Number of such cells over all steps so far (0 in any sane scene); synchronises. */
+uint64_t sph_noncanonical_cells(SphContext* ctx);
 int  sph_synchronize(SphContext* ctx);
 /* rebuild lookup + densities for the current positions without advancing (InitializeData's tail, .cc:144-145) */
 int  sph_refresh_densities(SphContext* ctx);

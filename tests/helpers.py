@@ -115,6 +115,7 @@ def check_step(pkg, scene, mode, dt, report=None):
             dims, origin = sim.grid()
             gk = grid_keys(pred, cells, dims, origin, sim.grid_x_subdivision(), float(sim.get_params().interaction_radius))
             assert np.array_equal(s_key, gk[s_idx]), "grid key of sorted rows"
+            assert np.array_equal(canonical_order(s_idx, s_key), s_idx), "rows of a cell are not in ascending particle index order"
             ncell = int(dims[0]) * int(dims[1]) * int(dims[2])
             assert table.size == ncell + 1 and table[0] == 0 and table[-1] == n
             assert np.array_equal(table, np.searchsorted(s_key, np.arange(ncell + 1, dtype=np.uint64)).astype(np.uint32)), "prefix table"

@@ -116,6 +116,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
     status = {          # must report an error
         "sph_create": lambda: L.sph_create(None, 0, 10),
         "sph_set_params": lambda: L.sph_set_params(None, C.byref(P)), "sph_get_params": lambda: L.sph_get_params(None, C.byref(P)),
+        "sph_set_extras": lambda: L.sph_set_extras(None, None), "sph_get_extras": lambda: L.sph_get_extras(None, None),
         "sph_set_table_mode": lambda: L.sph_set_table_mode(None, 0), "sph_set_stage_timing": lambda: L.sph_set_stage_timing(None, 1),
         "sph_set_neighbour_count_tap": lambda: L.sph_set_neighbour_count_tap(None, 1),
         "sph_set_neighbour_list_capacity": lambda: L.sph_set_neighbour_list_capacity(None, 8),
@@ -146,6 +147,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
         "sph_num_particles": (lambda: L.sph_num_particles(None), 0), "sph_graph_replays": (lambda: L.sph_graph_replays(None), 0),
         "sph_launch_count": (lambda: L.sph_launch_count(None), 0), "sph_stream": (lambda: L.sph_stream(None), None),
         "sph_grid_x_subdivision": (lambda: L.sph_grid_x_subdivision(None), 0),
+        "sph_noncanonical_cells": (lambda: L.sph_noncanonical_cells(None), 0),
     }
     other = {"sph_default_params", "sph_last_error", "sph_abi_version", "sph_comm_id_bytes"}     # take no handle / checked elsewhere
     assert set(status) | set(benign) | other == set(pkg.ABI_SYMBOLS)

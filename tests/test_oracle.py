@@ -431,3 +431,25 @@ def test_openmp_port_is_thread_count_invariant(ob):
     ob.PortOracle.lib().oracle_set_threads(1)
     for x, y in zip(*res):
         assert np.array_equal(bits(x), bits(y))
+
+
+def test_colour_restatement_known_answers():
+    """oracle/colors.py (getSpeedNormalzied + FluidSimCPU::updateColors) on values worked out by hand from
+    fluidSimCPU.cc:100-125 and the gradient stops of fluidSimCPU.h:26-29."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import colors
+    f = np.float32
+    v = np.array([[0, 0, 0], [0.3, 0.4, 0], [0.495, 0, 0], [0.99, 0, 0], [1.5, 0, 0], [3, 4, 0]], f)
+    t = colors.speed_normalized(v)
+    assert t[0] == 0 and t[1] == f(0.5) / f(1.5) and t[2] == f(0.33) and t[3] == f(0.66) and t[4] == 1 and t[5] == 1   # clamp at 1.5
+    c = colors.speed_colors(v)
+    assert np.array_equal(c[0], [0.0, 0.75, 1.0, 1.0])                    # at rest: Color1
+    assert np.array_equal(c[2], [0.0, 1.0, 0.0, 1.0])                     # first breakpoint (inclusive, :113): Color2
+    assert np.array_equal(c[3], [1.0, 1.0, 0.0, 1.0])                     # second breakpoint (:116): Color3
+    assert np.array_equal(c[4], [1.0, 0.0, 0.0, 1.0]) and np.array_equal(c[5], c[4])   # clamped: Color4
+    a = (t[1] - f(0.33)) / (f(0.66) - f(0.33))                            # second segment: Color2 -> Color3
+    assert np.array_equal(c[1], np.array([a, (f(1) - a) + a, 0.0, (f(1) - a) + a], f))
+    w = colors.speed_colors(np.array([[0.25, 0, 0]], f))[0]               # first segment: only green moves, 0.75 -> 1
+    a0 = (f(0.25) / f(1.5)) / f(0.33)
+    assert np.array_equal(w, np.array([0.0, (f(1) - a0) * f(0.75) + a0, (f(1) - a0), (f(1) - a0) + a0], f))

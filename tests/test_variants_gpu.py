@@ -159,6 +159,34 @@ def test_getters_timers_and_colors(pkg, ob):
     sim.close()
 
 
+def test_speed_gradient_colours_match_the_reference_restatement(pkg):
+    """SPH_FIELD_COLORS / SPH_FIELD_SPEED_NORMALIZED against oracle/colors.py, the numpy restatement of
+    getSpeedNormalzied (physicsWorld.cc:178-182) and FluidSimCPU::updateColors (fluidSimCPU.cc:100-125): bit for bit, on
+    velocities that cover all three gradient segments, the breakpoints themselves, rest and far beyond the clamp."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import colors
+    rng = np.random.default_rng(3)
+    n = 20000
+    vel = (rng.standard_normal((n, 3)) * rng.choice([0.05, 0.4, 1.0, 4.0], (n, 1))).astype(np.float32)
+    vel[0] = 0.0
+    vel[1] = (np.float32(0.495), 0.0, 0.0)          # |v| / 1.5 == 0.33f exactly
+    vel[2] = (0.0, np.float32(0.99), 0.0)           # ... == 0.66f
+    vel[3] = (1.5, 0.0, 0.0)
+    vel[4] = (30.0, -40.0, 5.0)
+    pos = ((rng.random((n, 3)) - 0.5) * 8).astype(np.float32)
+    sim = pkg.FluidSimulation(n)
+    sim.upload_state(pos, vel)                      # the getters read the state as uploaded (no step)
+    t = sim.download("speed_normalized")
+    assert np.array_equal(t.view(np.uint32), colors.speed_normalized(vel).view(np.uint32))
+    col = sim.download("colors")
+    ref = colors.speed_colors(vel)
+    assert np.array_equal(col.view(np.uint32), ref.view(np.uint32)), int((col != ref).any(axis=1).sum())
+    segs = [int((t <= colors.B1).sum()), int(((t > colors.B1) & (t <= colors.B2)).sum()), int((t > colors.B2).sum())]
+    assert min(segs) > 1000, segs
+    sim.close()
+
+
 def test_empty_and_tiny_inputs(pkg):
     sim = pkg.FluidSimulation(8)
     sim.upload_state(np.zeros((0, 3), np.float32))
@@ -212,3 +240,89 @@ def test_snapshot_roundtrip_resumes_bit_exactly(pkg, tmp_path):
     with pytest.raises(pkg.SphError):
         b.load_state(str(tmp_path / "missing.sphb"))
     a.close(); b.close()
+
+
+def _quat(axis, angle):
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    return tuple(float(x) for x in (*(a * np.sin(angle / 2)), np.cos(angle / 2)))
+
+
+def _rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def test_extras_off_is_the_reference_step_and_rotated_bound_contains_the_fluid(pkg):
+    """SphExtras (the reference's TODO list): with the identity rotation and zero stickiness the step
+    is bit-identical to a context that never heard of them; with the box rotated 30 degrees about z every particle stays
+    inside the ROTATED box, S6 equals a numpy restatement of move + clamp + reflection in the box's own axes, and the
+    neighbour search (table over the rotated box's bounding box) still agrees with itself in both table modes."""
+    from fluid_simulation_3d_b200 import scenes
+    sc = scenes.small_dam_break(16)
+    dt = scenes.DT
+    a = pkg.FluidSimulation(sc["n"], **sc["params"])
+    b = pkg.FluidSimulation(sc["n"], **sc["params"])
+    b.set_extras()                                           # defaults: off
+    assert b.get_extras()["bound_rotation"] == (0.0, 0.0, 0.0, 1.0)
+    for s in (a, b):
+        s.upload_state(sc["pos"], sc["vel"])
+        s.step_n(dt, 5)
+    for f in ("positions", "velocities", "densities"):
+        assert np.array_equal(a.download(f).view(np.uint32), b.download(f).view(np.uint32)), f
+    a.close(); b.close()
+    with pytest.raises(pkg.SphError):
+        pkg.FluidSimulation(8).set_extras(bound_rotation=(0, 0, 0, 0))
+    with pytest.raises(pkg.SphError):
+        pkg.FluidSimulation(8).set_extras(stick_strength=1.0, stick_distance=0.0)
+
+    q = _quat((0, 0, 1), np.pi / 6)
+    R = _rot(q)
+    half = np.array(sc["bound"], np.float64) / 2
+    rng = np.random.default_rng(11)
+    n = 20000
+    local = (rng.random((n, 3)) - 0.5) * 2 * half * 0.999
+    pos = (local @ R.T).astype(np.float32)                   # inside the rotated box, up to its walls
+    vel = ((rng.random((n, 3)) - 0.5) * 40).astype(np.float32)
+    prm = dict(sc["params"], gravity=0, viscosity_strength=0.0, pressure_multiplier=0.0, near_pressure_multiplier=0.0)
+    outs = []
+    for mode in (pkg.TABLE_GRID, pkg.TABLE_REFERENCE_HASH):
+        sim = pkg.FluidSimulation(n, table_mode=mode, **prm)
+        sim.set_extras(bound_rotation=q)
+        sim.set_neighbour_count_tap(True)
+        sim.upload_state(pos, vel)
+        sim.step(dt)
+        p1, v1 = sim.download("positions").astype(np.float64), sim.download("velocities").astype(np.float64)
+        outs.append((sim.download("neighbour_count"), p1))
+        # no forces (k = kn = mu = 0, no gravity): the step is S6 alone -- move, clamp, reflect in the box's axes
+        l = pos.astype(np.float64) @ R + (vel.astype(np.float64) @ R) * dt
+        u = vel.astype(np.float64) @ R
+        hit = half[None, :] - np.abs(l) <= 0
+        l = np.where(hit, half[None, :] * np.sign(l), l)
+        u = np.where(hit, u * -0.95, u)
+        assert hit.any() and np.abs(p1 - l @ R.T).max() < 2e-5 and np.abs(v1 - u @ R.T).max() < 2e-4
+        assert np.all(np.abs(p1 @ R) <= half[None, :] * (1 + 1e-6) + 1e-5)
+        sim.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_stickiness_pulls_towards_a_near_wall_only(pkg):
+    """stick_strength k, stick_distance d0: a particle at distance d < d0 from a wall gets the impulse
+    dt * k * d * (1 - d / d0) towards that wall before S6 moves it; farther particles are untouched."""
+    bound = (4.0, 4.0, 4.0)
+    prm = dict(bound=bound, gravity=0, viscosity_strength=0.0, pressure_multiplier=0.0, near_pressure_multiplier=0.0)
+    pos = np.array([[-1.9, 0.0, 0.0], [0.0, 1.7, 0.0], [0.0, 0.0, 0.0], [1.95, -1.95, 0.3]], np.float32)   # far apart: no neighbours
+    dt, k, d0 = 0.01, 50.0, 0.4
+    sim = pkg.FluidSimulation(4, **prm)
+    sim.set_extras(stick_strength=k, stick_distance=d0)
+    sim.upload_state(pos, np.zeros_like(pos))
+    sim.step(dt)
+    v = sim.download("velocities").astype(np.float64)
+    imp = lambda d: dt * k * d * (1 - d / d0)
+    assert abs(v[0, 0] + imp(0.1)) < 1e-5 and abs(v[0, 1]) < 1e-7 and abs(v[0, 2]) < 1e-7       # towards the -x wall
+    assert abs(v[1, 1] - imp(0.3)) < 1e-5                                                        # towards the +y wall
+    assert np.all(v[2] == 0)                                                                     # mid-box: nothing
+    assert abs(v[3, 0] - imp(0.05)) < 1e-5 and abs(v[3, 1] + imp(0.05)) < 1e-5 and abs(v[3, 2]) < 1e-7   # a corner: both walls
+    sim.close()
