@@ -323,6 +323,42 @@ def c1_scene(pkg, dev):
     return dict(pos=pos, vel=np.zeros_like(pos), bound=(20.0, 20.0, 20.0), n=n, params=params)
 
 
+def write_snapshot(path, pos, vel, params_struct):
+    """the snapshot file format of sph_save_state / FluidSimulation::saveState (include/sph_b200.h): "SPHB2002", u32 n,
+    u32 sizeof(SphParams), SphParams, n x pos3, n x vel3"""
+    import ctypes
+    raw = bytes(ctypes.string_at(ctypes.addressof(params_struct), ctypes.sizeof(params_struct)))
+    with open(path, "wb") as f:
+        f.write(b"SPHB2002")
+        f.write(np.uint32(len(pos)).tobytes())
+        f.write(np.uint32(len(raw)).tobytes())
+        f.write(raw)
+        f.write(np.ascontiguousarray(pos, np.float32).tobytes())
+        f.write(np.ascontiguousarray(vel, np.float32).tobytes())
+
+
+def class_update_e2e(pkg, sc, sim_params, frames, ndev=1, direct=False):
+    """The drop-in class timed the way the application drives it: host_demo (C++, fluid-simulation-3d_b200/host) loads the
+    scene through FluidSimulation::loadState and calls FluidSimulation::Update(dt) per frame, each call returning with
+    the OutPositions mirror refreshed in host memory (fluidSimCPU.cc:35-40,58)."""
+    import tempfile
+    demo = os.path.join(ROOT, "fluid-simulation-3d_b200", "host", "host_demo")
+    if not os.path.exists(demo):
+        return {"error": "host_demo is not built"}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "state.bin")
+        write_snapshot(path, sc["pos"], sc["vel"], sim_params)
+        cmd = [demo, "0", str(frames), "0", "classbench", path, str(ndev), "1" if direct else "0"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("classbench ")]
+    if r.returncode != 0 or not line:
+        return {"error": "host_demo classbench failed: " + r.stdout[-300:]}
+    kv = dict(x.split("=", 1) for x in line[0].split()[1:])
+    return {"value": float(kv["updates_per_s"]) / 1e6, "unit": "M updates/s", "ms_per_step": float(kv["update_ms"]), "frames": frames,
+            "devices": ndev, "path": "FluidSimulation::Update(dt) per frame, OutPositions mirror refreshed by every call (blocking D2H of "
+            "16 B/particle inside Update); state resident on the device between frames, like the reference's"}
+
+
 def short_line(pkg, scenes, torch, dev, name, steps=5, warmup=3, flush=None):
     """A short device-timed line of another BASELINE config (the `configs` block of the default run, and the same-workload
     1-GPU anchor of the multi-GPU curve): the scene is spawned on the device (sph_spawn_grid / sph_spawn_block, bit-identical
@@ -493,6 +529,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         e2e_path = "sph_upload_state -> sph_step -> sph_download(OUT_POSITIONS), serial (pipelined calls failed: %s)" % ex
     e2e = n * args.steps / e2e_s / 1e6
     clk = clocks.stop()          # sampled across the timed, steady-state and end-to-end loops (all under load)
+    params_now = sim.get_params()
 
     peak, peak_src = measured_peaks()
     names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]
@@ -591,6 +628,12 @@ def bench_single(args, pkg, scenes, torch, dev):
         "clocks": clk,
     }
     sim.close()
+    # the same frames through the C++ drop-in class (what a caller of the reference actually uses)
+    try:
+        if not dense:                                         # (the C5 column would blow up across consecutive frames)
+            result["e2e"]["class_update"] = class_update_e2e(pkg, sc, params_now, max(args.steps, 20))
+    except Exception as ex:
+        result["e2e"]["class_update"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     if not args.config and not args.no_configs:
         # the other BASELINE configs, short lines under the driver's eyes; C4 on ONE GPU is the same-workload anchor of the
         # multi-GPU curve (the N > 1 lines run C4 slab-decomposed): efficiency(N) = strong_base.ms_per_step / (N * ms_per_step(N))

@@ -331,7 +331,7 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
 //     (n the wall's inward normal, d the distance to the wall);
 //  2. the reference's move, clamp and -0.95 reflection (:84-107) on the local coordinates;
 //  3. back to world axes.
-__device__ __noinline__ void integrate_extras(float4& p, float4& v, const DevParams& P, const float dt)
+__device__ __forceinline__ void integrate_extras(float4& p, float4& v, const DevParams& P, const float dt)
 {
     const float* R = P.rot;
     float l[3] = {R[0] * p.x + R[3] * p.y + R[6] * p.z, R[1] * p.x + R[4] * p.y + R[7] * p.z, R[2] * p.x + R[5] * p.y + R[8] * p.z};
@@ -360,19 +360,12 @@ __device__ __noinline__ void integrate_extras(float4& p, float4& v, const DevPar
 // S6 (:84-107)
 __global__ void __launch_bounds__(256)
 k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
-            float4* __restrict__ vel_out, const __grid_constant__ DevParams P, const float dt)
+            float4* __restrict__ vel_out, const DevParams P, const float dt)
 {
     const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.row1) return;
     float4 p = pos_s[s];
     float4 v = vel_v[s];
-    if (P.extras) {                                  // optional features (SphExtras): off in the reference's configuration
-        integrate_extras(p, v, P, dt);
-        v.w = 0.0f;
-        pos_out[s - P.row0] = p;
-        vel_out[s - P.row0] = v;
-        return;
-    }
     p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
     p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
     p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
@@ -389,6 +382,21 @@ k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, 
     #undef SPH_COLLIDE
     v.w = 0.0f;
     pos_out[s - P.row0] = p;      // .w still carries the particle id; owned rows compact to [0, row1-row0)
+    vel_out[s - P.row0] = v;
+}
+
+// S6 with SphExtras on (launched instead of k_integrate, so the reference's configuration pays nothing for them)
+__global__ void __launch_bounds__(256)
+k_integrate_extras(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
+                   float4* __restrict__ vel_out, const DevParams P, const float dt)
+{
+    const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.row1) return;
+    float4 p = pos_s[s];
+    float4 v = vel_v[s];
+    integrate_extras(p, v, P, dt);
+    v.w = 0.0f;
+    pos_out[s - P.row0] = p;
     vel_out[s - P.row0] = v;
 }
 
@@ -612,7 +620,8 @@ void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v,
                       const DevParams& P, float dt, uint64_t* launches)
 {
     if (P.row1 <= P.row0) return;
-    k_integrate<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    if (P.extras) k_integrate_extras<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    else k_integrate<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
     ++*launches;
 }
 

@@ -229,6 +229,34 @@ int main(int argc, char** argv)
             printf("snapshotio n=%d roundtrip=%d rejects_missing=%d\n", n, (int)ok, (int)rejects);
             return ok && rejects ? 0 : 3;
         }
+        if (!strcmp(what, "classbench")) {
+            // the drop-in path timed the way the application drives it (fluidSimCPU.cc:35-40,58): per frame ONE
+            // FluidSimulation::Update(dt) that returns with the OutPositions mirror refreshed in host memory.
+            //   host_demo 0 frames 0 classbench state.bin [ndev [direct]]      (state.bin: a snapshot file, saveState's format)
+            const char* path = argc > 5 ? argv[5] : "/tmp/sph_snapshot.bin";
+            const int ndev = argc > 6 ? atoi(argv[6]) : 1;
+            const bool direct = argc > 7 && atoi(argv[7]) != 0;
+            if (ndev > 1) { std::vector<int> devs; for (int d = 0; d < ndev; d++) devs.push_back(d); sim.setDevices(devs); sim.setDirectMirrors(direct); sim.setRebalanceInterval(4); }
+            sim.setHostMirrors(true, false);
+            sim.loadState(path);
+            const int count = (int)sim.positions.size();
+            auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const int warm = 5;
+            for (int s = 0; s < warm; s++) sim.Update(0.016667f);
+            double phase[4] = {0, 0, 0, 0};
+            if (ndev > 1) sim.multiGpuBreakdown(phase);
+            const double a = now();
+            for (int s = 0; s < steps; s++) sim.Update(0.016667f);
+            const double ms = (now() - a) / (steps > 0 ? steps : 1);
+            if (ndev > 1) sim.multiGpuBreakdown(phase);
+            bool finite = true;
+            for (int i = 0; i < count; i += 997) finite = finite && std::isfinite(sim.OutPositions[(size_t)i].x) && sim.OutPositions[(size_t)i].w == 0.34f;
+            printf("classbench n=%d ndev=%d direct=%d frames=%d update_ms=%.4f updates_per_s=%.1f finite=%d phase_ms=step:%.3f,download:%.3f,scatter:%.3f,rebalance:%.3f\n",
+                   count, ndev, (int)direct, steps, ms, count / (ms * 1e-3), (int)finite,
+                   steps ? phase[0] / steps : 0.0, steps ? phase[1] / steps : 0.0, steps ? phase[2] / steps : 0.0, steps ? phase[3] / steps : 0.0);
+            sim.shutdown();
+            return finite ? 0 : 3;
+        }
         if (!strcmp(what, "setters")) {                // UI sliders: setters never throw, a rejected value is not committed
             sim.setTableMode(mode);
             sim.setGravity(true);
