@@ -72,6 +72,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->ncell = c->ncell;
     P->modM = n ? (UINT64_MAX / n + 1) : 0;
     P->row0 = 0; P->row1 = n; P->n_a = n;
+    P->pair_cap = (c->cap + 8u) / 2u + kPairPad;
     P->seg_off = (uint32_t)table_layout(c->ncell).cells_pad;
     P->noncanonical = c->d_noncanonical;
     P->extras = c->extras_on ? 1 : 0;
@@ -270,7 +271,7 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
 
     SphContext* c = new SphContext();
-    if (const char* xs = getenv("SPH_XSUB")) { const int v = atoi(xs); if (v == 1 || v == 2 || v == 4 || v == 8) c->xsub_pref = c->xsub = v; }
+    if (const char* xs = getenv("SPH_XSUB")) { const int v = atoi(xs); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->xsub_pref = c->xsub = v; }
     c->device = device;
     c->cap = capacity;
     sph_default_params(&c->params);

@@ -740,15 +740,12 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 constexpr int PKS = SPH_PKS;    // stack entries per thread: sparse scenes (one or two flushes per particle)
 constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
 
-// STAGED (SPH_DENSITY=staged, an A/B variant): the block first copies the union of its threads' row windows into
-// shared memory and the walk reads its candidates from there.  It answers "would staging the neighbourhood in
-// shared memory lift the L1 roof?" with a measurement: no -- shared memory is served by the same data pipe.
-template <bool STAGED>
+// ncu: bound by the L1 data pipe; candidates are read as a 16-byte (x0, x1, y0, y1) and an 8-byte (z0, z1) load per pair:
+// 24 bytes per pair instead of the former 32-byte record with its two dead w words (-26 % of the cull's wavefronts).
 __global__ void __launch_bounds__(kWalkThreads)
-k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, const uint32_t stage_pairs)
+k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
 {
     extern __shared__ uint2 stk_raw[];             // [stack_rows][kWalkThreads] survivors: (row, bits of the FMA-fused d^2)
-                                                   // STAGED: followed by stage_pairs 32-byte pair records
     uint2 (*stk)[kWalkThreads] = reinterpret_cast<uint2 (*)[kWalkThreads]>(stk_raw);
     const uint32_t full_mark = (stack_rows - 4u) * (kWalkThreads * 8u);
     constexpr uint32_t kRow = kWalkThreads * 8;    // bytes between two stack rows of a thread
@@ -809,15 +806,17 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
     };
 
     const Win W = window_of(s.p.x, s.p.y, s.p.z, P);
-    const Rec8* __restrict__ pairs = reinterpret_cast<const Rec8*>(A.predpk);
+    // candidates: pair m = rows (2m, 2m+1) as (x0, x1, y0, y1) in one array and (z0, z1) in another (sph_internal.h)
+    const float4* __restrict__ pxy = A.predpk;
+    const float2* __restrict__ pzz = reinterpret_cast<const float2*>(A.predpk + P.pair_cap);
     const uint32_t last_pair = (P.n - 1u) >> 1;
     const uint64_t px = pk(s.p.x, s.p.x), py = pk(s.p.y, s.p.y), pz = pk(s.p.z, s.p.z);
     const float cull_hi = P.cull_hi;
 
     // cull one pair: rows (cj, cj + 1), the first at position t of a window of `len` rows (t = -1 when the window
     // starts on an odd row).  Row cj is inside iff 0 <= t < len (one unsigned compare), row cj + 1 iff t < len - 1.
-    auto cull = [&](const Rec8& c, const int t, const int len, const uint32_t cj) {
-        const uint64_t ox = sub2(pk(c.lo.x, c.lo.y), px), oy = sub2(pk(c.lo.z, c.lo.w), py), oz = sub2(pk(c.hi.x, c.hi.y), pz);
+    auto cull = [&](const float4 cxy, const float2 cz, const int t, const int len, const int len1, const uint32_t cj) {
+        const uint64_t ox = sub2(pk(cxy.x, cxy.y), px), oy = sub2(pk(cxy.z, cxy.w), py), oz = sub2(pk(cz.x, cz.y), pz);
         const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
         float d0, d1;
         upk(d2, d0, d1);
@@ -831,32 +830,19 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
                      " @q st.shared.v2.b32 [%0], {%8, %4};\n"
                      " @q add.u32 %0, %0, %9; }"
                      : "+r"(sa)
-                     : "r"(t), "r"(len), "f"(d0), "f"(d1), "f"(cull_hi), "r"(len - 1), "r"(cj), "r"(cj + 1u), "n"(kRow)
+                     : "r"(t), "r"(len), "f"(d0), "f"(d1), "f"(cull_hi), "r"(len1), "r"(cj), "r"(cj + 1u), "n"(kRow)
                      SPH_PK_CLOBBER);
     };
-
-#if SPH_PK_NOCLAMP
-    const uint32_t full_mark_r = full_mark;
-    const float cull_hi_r = cull_hi;
-    auto cull_fast = [&](const Rec8& c, const int t, const int len, const int len1, const uint32_t cj) {
-        const uint64_t ox = sub2(pk(c.lo.x, c.lo.y), px), oy = sub2(pk(c.lo.z, c.lo.w), py), oz = sub2(pk(c.hi.x, c.hi.y), pz);
-        const uint64_t d2 = fma2(oz, oz, fma2(oy, oy, mul2(ox, ox)));
-        float d0, d1;
-        upk(d2, d0, d1);
-        asm volatile("{ .reg .pred p, q;\n"
-                     " setp.gt.f32 p, %3, %5;\n"
-                     " setp.lt.and.u32 q, %1, %2, !p;\n"
-                     " @q st.shared.v2.b32 [%0], {%7, %3};\n"
-                     " @q add.u32 %0, %0, %9;\n"
-                     " setp.gt.f32 p, %4, %5;\n"
-                     " setp.lt.and.s32 q, %1, %6, !p;\n"
-                     " @q st.shared.v2.b32 [%0], {%8, %4};\n"
-                     " @q add.u32 %0, %0, %9; }"
-                     : "+r"(sa)
-                     : "r"(t), "r"(len), "f"(d0), "f"(d1), "f"(cull_hi_r), "r"(len1), "r"(cj), "r"(cj + 1u), "n"(kRow)
-                     SPH_PK_CLOBBER);
+    auto ldxy = [](const float4* p) {
+        float4 r;
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+        return r;
     };
-#endif
+    auto ldz = [](const float2* p) {
+        float2 r;
+        asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+        return r;
+    };
 
     // 9 row windows; the bounds of the next row are requested while this one is culled.  Rows and 2-pair chunks
     // are warp-uniform loop levels.
@@ -868,8 +854,7 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
     }
     const uint32_t gd0 = (uint32_t)P.gdim[0];
     const uint32_t zstep = (uint32_t)P.gdim[1] * gd0 - 3u * gd0;
-    const uint32_t tc0 = (uint32_t)(((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0);   // only read where the row exists
-    uint32_t tc = tc0;
+    uint32_t tc = (uint32_t)(((int64_t)(W.g.z - 1) * P.gdim[1] + (W.g.y - 1)) * (int64_t)gd0 + W.x0);   // only read where the row exists
     const uint32_t xspan = (uint32_t)(W.x1 - W.x0) + 1u;
     int dyc = 0;
     auto bounds = [&](const int r9, uint32_t& b, uint32_t& e) {
@@ -878,43 +863,6 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
         tc += gd0;
         if (++dyc == 3) { dyc = 0; tc += zstep; }
     };
-
-    // STAGED: union of the block's windows per row -> shared memory
-    __shared__ uint32_t s_lo[9], s_hi[9], s_off[10];
-    const float4* stage = reinterpret_cast<const float4*>(stk_raw + (size_t)stack_rows * kWalkThreads);
-    bool staged = false;
-    if (STAGED) {
-        if (tid < 9) { s_lo[tid] = 0xFFFFFFFFu; s_hi[tid] = 0u; }
-        __syncthreads();
-        #pragma unroll 1
-        for (int r9 = 0; r9 < 9; r9++) {
-            uint32_t b, e;
-            bounds(r9, b, e);
-            const uint32_t lo = __reduce_min_sync(0xffffffffu, e > b ? (b >> 1) : 0xFFFFFFFFu);
-            const uint32_t hi = __reduce_max_sync(0xffffffffu, e > b ? ((e + 1u) >> 1) : 0u);
-            if ((tid & 31) == 0 && hi > lo) { atomicMin(&s_lo[r9], lo); atomicMax(&s_hi[r9], hi); }
-        }
-        tc = tc0; dyc = 0;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t off = 0;
-            for (int r9 = 0; r9 < 9; r9++) { s_off[r9] = off; off += s_hi[r9] > s_lo[r9] ? s_hi[r9] - s_lo[r9] : 0u; }
-            s_off[9] = off;
-        }
-        __syncthreads();
-        staged = s_off[9] <= stage_pairs;          // a block whose union does not fit reads global memory as usual
-        if (staged) {
-            float4* dst = const_cast<float4*>(stage);
-            const float4* src = A.predpk;
-            #pragma unroll 1
-            for (int r9 = 0; r9 < 9; r9++) {
-                const uint32_t lo = s_lo[r9], hi = s_hi[r9], off = s_off[r9];
-                if (hi <= lo) continue;
-                for (uint32_t q = 2u * lo + tid; q < 2u * hi; q += kWalkThreads) dst[2u * off + (q - 2u * lo)] = __ldg(&src[q]);
-            }
-        }
-        __syncthreads();
-    }
 
     uint32_t bn, en;
     bounds(0, bn, en);
@@ -927,37 +875,29 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
         const uint32_t np = len ? ((e + 1u) >> 1) - p0 : 0u;
         const uint32_t iters = __reduce_max_sync(0xffffffffu, np);
         int t = -(int)(b & 1u);
-        const uint32_t slo = STAGED ? s_lo[r9] : 0u, shi = STAGED ? s_hi[r9] : 0u;
-        const float4* srow = stage + 2u * (STAGED ? s_off[r9] : 0u);
-#if SPH_PK_NOCLAMP
-        if (!STAGED && iters <= kPairPad) {        // every lane's reads end inside the padded allocation
-            const Rec8* pp = pairs + p0;
+        const int len1 = len - 1;
+        if (iters <= kPairPad) {                   // every lane's reads end inside the padded allocation: running pointers
+            const float4* qxy = pxy + p0;
+            const float2* qz = pzz + p0;
             uint32_t cj = 2u * p0;
-            const int len1 = len - 1;
             #pragma unroll 1
-            for (uint32_t it = 0; it < iters; it += 2, t += 4, pp += 2, cj += 4u) {
-                if (__any_sync(0xffffffffu, sa - sa0 > full_mark_r)) flush(false);
-                const Rec8 c0 = ld256(pp), c1 = ld256(pp + 1);
-                cull_fast(c0, t, len, len1, cj);
-                cull_fast(c1, t + 2, len, len1, cj + 2u);
+            for (uint32_t it = 0; it < iters; it += 2, t += 4, qxy += 2, qz += 2, cj += 4u) {
+                if (__any_sync(0xffffffffu, sa - sa0 > full_mark)) flush(false);
+                const float4 a0 = ldxy(qxy), a1 = ldxy(qxy + 1);
+                const float2 z0 = ldz(qz), z1 = ldz(qz + 1);
+                cull(a0, z0, t, len, len1, cj);
+                cull(a1, z1, t + 2, len, len1, cj + 2u);
             }
             continue;
         }
-#endif
         #pragma unroll 1
         for (uint32_t it = 0; it < iters; it += 2, t += 4) {
             if (__any_sync(0xffffffffu, sa - sa0 > full_mark)) flush(false);
-            Rec8 c0, c1;
-            if (STAGED && staged) {                // lanes past their own window re-read the staged run's last pair
-                const uint32_t q0 = min(max(p0 + it, slo), shi - 1u) - slo, q1 = min(max(p0 + it + 1u, slo), shi - 1u) - slo;
-                c0.lo = srow[2u * q0]; c0.hi = srow[2u * q0 + 1u];
-                c1.lo = srow[2u * q1]; c1.hi = srow[2u * q1 + 1u];
-            } else {
-                const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
-                c0 = ld256(pairs + q0); c1 = ld256(pairs + q1);
-            }
-            cull(c0, t, len, 2u * (p0 + it));
-            cull(c1, t + 2, len, 2u * (p0 + it) + 2u);
+            const uint32_t q0 = min(p0 + it, last_pair), q1 = min(p0 + it + 1u, last_pair);
+            const float4 a0 = ldxy(pxy + q0), a1 = ldxy(pxy + q1);
+            const float2 z0 = ldz(pzz + q0), z1 = ldz(pzz + q1);
+            cull(a0, z0, t, len, len1, 2u * (p0 + it));
+            cull(a1, z1, t + 2, len, len1, 2u * (p0 + it) + 2u);
         }
     }
     flush(true);
@@ -970,13 +910,6 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows, c
     report_overflow(A, (valid && kbase > K) ? kbase : 0u);
 }
 
-
-// ---- rim fix-up (Q2 regime only: the cut-off exceeds the cell size) -----------------------------------------------
-// Cells on the rim of the GRID table hold clamped outliers, so for a particle within one cell of the rim the 27 table
-// cells are a superset of the reference's 27 cells; when the cut-off is larger than a cell the distance test no longer
-// removes the extras.  The main kernels stay as they are; this pass recomputes the few particles concerned with the
-// table walk plus a true-cell comparison (sph_device.cuh: within_27) and overwrites their results.  Launched only
-// when DevParams::rim_check is set (an interaction radius below sqrt(sqrRadius): a UI slider position).
 template <int PASS>
 __global__ void __launch_bounds__(kWalkThreads)
 k_rim_fix(const GatherArgs A, const DevParams P, const float dt)
@@ -1123,16 +1056,10 @@ static void launch_density_main(cudaStream_t st, const float4* pred_s, const flo
             // the deep stack needs the opt-in above 48 KB; the attribute is per device, so it is (re)set whenever used
             uint32_t rows = PKS;
             if (A.list_k > 64) {
-                if (cudaFuncSetAttribute(k_density_pk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
+                if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
                 else cudaGetLastError();
             }
-            static const int stage_pairs = [] { const char* e = getenv("SPH_STAGE_PAIRS"); return e ? atoi(e) : 0; }();
-            if (stage_pairs > 0 && rows == PKS) {  // SPH_STAGE_PAIRS=n: the shared-memory staged variant, n pair records per block
-                const size_t bytes = (size_t)rows * kWalkThreads * 8 + (size_t)stage_pairs * 32;
-                cudaFuncSetAttribute(k_density_pk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                k_density_pk<true><<<blocks, kWalkThreads, bytes, st>>>(A, P, rows, (uint32_t)stage_pairs);
-            } else
-                k_density_pk<false><<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows, 0u);
+            k_density_pk<<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows);
         }
         else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
         else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);

@@ -41,6 +41,7 @@ struct DevParams {
     int      zlo, gz_global, own_lo, own_hi;
     int      has_lo, has_hi;   // a neighbour rank exists below / above
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
+    uint32_t pair_cap;         // candidate pairs: float4 entries of the (x0,x1,y0,y1) array; the (z0,z1) array starts right behind it
     uint32_t seg_off;          // GRID table: word offset of the per-segment base array behind the per-cell array (tbl(), sph_device.cuh)
     uint32_t* noncanonical;    // device counter: cells too crowded for the canonical-order ranking of the counting sort (sph_kernels.cu)
     // optional features (SphExtras): box rotation (rows of R: world = R * local) and wall stickiness
@@ -63,10 +64,12 @@ constexpr uint32_t kPairPad = 2048;
 constexpr int kSegShift = 6;
 constexpr uint32_t kSegCells = 1u << kSegShift;
 
-// Pair-interleaved predicted positions (`predpk`): rows 2m and 2m+1 share one 32-byte record
-//   lo = (x0, x1, y0, y1)   hi = (z0, z1, w0, w1)
-// so that ONE 256-bit load hands the density pass two candidates as three aligned register pairs, ready for the
-// packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2).  Written by k_reorder next to the plain `pred` rows.
+// Pair-interleaved predicted positions (`predpk`), the density pass's candidate stream: rows 2m and 2m+1 form pair m,
+//   xy[m] = (x0, x1, y0, y1)   at predpk[m]                          (16 bytes)
+//   z[m]  = (z0, z1)           at ((float2*)(predpk + pair_cap))[m]   (8 bytes)
+// so that a 128-bit and a 64-bit load hand the density pass two candidates as three aligned register pairs, ready for the
+// packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2) -- 24 bytes per pair through the L1, not 32.  Written by k_reorder
+// next to the plain `pred` rows.
 
 // slab mode: classification of an owned row by the z layer of its predicted position
 enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8 };

@@ -317,13 +317,15 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
         }
         pred_s[s] = q;
     }
-    // PredPair record of rows (2m, 2m+1): the even row's thread writes lo = (x0, x1, y0, y1), the odd row's thread
-    // hi = (z0, z1, w0, w1) -- thread s writes float4 number s of the array, fully coalesced.  The partner of the
-    // last row of an odd-sized array contributes zeros (that slot is past every window, so it is never accepted).
+    // candidate pair m = rows (2m, 2m+1): the even row's thread writes xy[m] = (x0, x1, y0, y1), the odd row's thread
+    // z[m] = (z0, z1) (sph_internal.h).  The partner of the last row of an odd-sized array contributes zeros (that slot
+    // is past every window, so it is never accepted).
     const float ax = __shfl_xor_sync(0xffffffffu, q.x, 1), ay = __shfl_xor_sync(0xffffffffu, q.y, 1);
-    const float az = __shfl_xor_sync(0xffffffffu, q.z, 1), aw = __shfl_xor_sync(0xffffffffu, q.w, 1);
-    if (pred_pk && s < ((P.n + 1u) & ~1u))
-        pred_pk[s] = (s & 1u) ? make_float4(az, q.z, aw, q.w) : make_float4(q.x, ax, q.y, ay);
+    const float az = __shfl_xor_sync(0xffffffffu, q.z, 1);
+    if (pred_pk && s < ((P.n + 1u) & ~1u)) {
+        if (s & 1u) reinterpret_cast<float2*>(pred_pk + P.pair_cap)[s >> 1] = make_float2(az, q.z);
+        else pred_pk[s >> 1] = make_float4(q.x, ax, q.y, ay);
+    }
 }
 
 // S6 with the optional features of SphExtras: everything happens in the box's own axes (local = R^T * world).

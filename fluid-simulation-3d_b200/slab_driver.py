@@ -268,8 +268,31 @@ def generate_rank_particles(scenes, name, layers, rank, r, gmin_z, gz):
     return ids[own].astype(np.uint32), pos[own], vel[own], bound
 
 
+def bind_to_gpu_numa(torch, dev):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (before any page-locked buffer is allocated: the
+    pages are then local to the GPU's root complex).  Returns a short description for the bench line."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "GPU %s reports no NUMA node: not bound" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "NUMA node %d of GPU %s has no CPU this process may use: not bound" % (node, bdf)
+        os.sched_setaffinity(0, cpus)
+        return "bound to the %d CPUs of NUMA node %d (GPU %s)" % (len(cpus), node, bdf)
+    except Exception as ex:
+        return "not bound (%s: %s)" % (type(ex).__name__, ex)
+
+
 def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler, short_line=None):
     name = args.config or "C4_dambreak_64M"
+    numa = bind_to_gpu_numa(torch, dev)
     # (0) parity gate: the slab-decomposed step must equal the single-GPU step before anything is timed
     parity = None
     if not getattr(args, "no_parity", False):
@@ -357,6 +380,7 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
     n_own = ids_h.size
     tp = torch.from_numpy(pos_h).pin_memory(); tv = torch.from_numpy(vel_h).pin_memory(); ti = torch.from_numpy(ids_h.astype(np.int32)).pin_memory()
     out_h = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+    ids_out = [torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory()]   # row k of a download is OutPositions[ids[k]]
     L = slab.sim.L
     e2e_steps = max(20, args.steps)
     dist.barrier()
@@ -365,7 +389,7 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
         slab.sim._check(L.sph_upload_owned(slab.sim.h, n_own, C.c_void_p(ti.data_ptr()), C.c_void_p(tp.data_ptr()), C.c_void_p(tv.data_ptr())))
         slab.step(dt)
         cnt = C.c_uint32(0)
-        slab.sim._check(L.sph_download_owned(slab.sim.h, pkg.FIELDS["out_positions"], None, C.c_void_p(out_h.data_ptr()),
+        slab.sim._check(L.sph_download_owned(slab.sim.h, pkg.FIELDS["out_positions"], C.c_void_p(ids_out[0].data_ptr()), C.c_void_p(out_h.data_ptr()),
                                              cap * 16, C.byref(cnt)))
     e2e_blocking_s = time.perf_counter() - t0
     t = torch.tensor([e2e_blocking_s], dtype=torch.float64, device="cuda:%d" % dev)
@@ -390,8 +414,8 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
             if k:
                 slab.sim._check(L.sph_download_wait(h))
             c2 = C.c_uint32(0)
-            slab.sim._check(L.sph_download_owned_begin(h, pkg.FIELDS["out_positions"], None, C.c_void_p(out_h2[k & 1].data_ptr()),
-                                                       cap * 16, C.byref(c2)))
+            slab.sim._check(L.sph_download_owned_begin(h, pkg.FIELDS["out_positions"], C.c_void_p(ids_out[k & 1].data_ptr()),
+                                                       C.c_void_p(out_h2[k & 1].data_ptr()), cap * 16, C.byref(c2)))
         slab.sim._check(L.sph_download_wait(h))
         slab.sim.synchronize()
 
@@ -449,7 +473,8 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(gather[dom]),
                      "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9 / world,
                               "frac": A_BYTES["step"] * value * 1e6 / 1e9 / world / peak}},
-        "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": int(n_total) * 28, "d2h_bytes_per_step": int(n_total) * 16,
+        "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": int(n_total) * 28, "d2h_bytes_per_step": int(n_total) * 20,
+                "result": "per rank (global id, OutPositions row) of every owned particle: row k is OutPositions[ids[k]]", "numa": numa,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                 "path": e2e_path,
                 "blocking": {"value": n_total * e2e_steps / e2e_blocking_s / 1e6, "ms_per_step": e2e_blocking_s / e2e_steps * 1e3,

@@ -27,10 +27,10 @@ print("VARIANT_OK")
 
 
 @pytest.mark.parametrize("env", [{"SPH_GATHER": "v1"}, {"SPH_GATHER": "v2"}, {"SPH_DENSITY": "walk"}, {"SPH_DENSITY": "pair"}, {"SPH_DENSITY": "2"}, {"SPH_SORT": "radix"},
-                                 {"SPH_DENSITY": "list"}, {"SPH_VISC_NOW": "1"}, {"SPH_STAGE_PAIRS": "1024"},
+                                 {"SPH_DENSITY": "list"}, {"SPH_VISC_NOW": "1"},
                                  {"SPH_GATHER": "tile"}, {"SPH_GATHER": "tile", "SPH_TILE_CAPN": "128"}, {"SPH_GATHER": "tile", "SPH_XSUB": "1"}, {"SPH_XSUB": "4"}],
                          ids=["walk_every_pass", "packed_two_phase", "list_with_walk_density", "list_with_pair_density", "list_with_pair2_density", "radix_sort_grid",
-                              "scalar_list_density_on_grid", "packed_density_viscosity_without_weights", "packed_density_staged_in_shared_memory",
+                              "scalar_list_density_on_grid", "packed_density_viscosity_without_weights",
                               "tile_generation_tma_staged", "tile_smallest_staging_buffer", "tile_whole_cells_xsub1", "xsub4"])
 def test_enumeration_variants_match_oracle(env):
     e = dict(os.environ, **env)
