@@ -450,14 +450,38 @@ def bench_single(args, pkg, scenes, torch, dev):
     sim.synchronize()
     torch.cuda.synchronize()
 
-    # ---- device-resident timing: one CUDA-event pair per step on the solver's stream, L2 flushed between
+    # ---- device-resident timing: one CUDA-event pair per step on the solver's stream, L2 flushed between.  The step is
+    # launched the way a frame loop launches it: sph_step_n(dt, 1) replays the recorded CUDA graph of the step (one
+    # cudaGraphLaunch instead of a dozen kernel launches); the same steps through plain launches with the six stage
+    # timers on follow, and give stage_ms.
     clocks = ClockSampler(dev)
     clocks.start()
+    sim.set_stage_timing(False)
+    restore()
+    sim.step_n(dt, 4)                        # records the graph (outside the timed region)
+    sim.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage = np.zeros(6)
     l0 = sim.launch_count()
+    r0 = sim.graph_replays()
     for a, b in ev:
         restore()                       # outside the event pair
+        l2_flush()
+        a.record(stream)
+        sim.step_n(dt, 1)
+        b.record(stream)
+    sim.synchronize()
+    torch.cuda.synchronize()
+    launches = sim.launch_count() - l0 - (args.steps if dense else 0)      # the restoring spawn kernel is not part of the step
+    timed_replays = sim.graph_replays() - r0
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(ms.sum())
+    value = n * args.steps / (total_ms * 1e-3) / 1e6
+    # the same steps, plain launches, stage timers on
+    sim.set_stage_timing(True)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage = np.zeros(6)
+    for a, b in ev2:
+        restore()
         l2_flush()
         a.record(stream)
         sim.step(dt)
@@ -465,10 +489,7 @@ def bench_single(args, pkg, scenes, torch, dev):
         stage += sim.timings()          # waits for the step's last stage event
     sim.synchronize()
     torch.cuda.synchronize()
-    launches = sim.launch_count() - l0 - (args.steps if dense else 0)      # the restoring spawn kernel is not part of the step
-    ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(ms.sum())
-    value = n * args.steps / (total_ms * 1e-3) / 1e6
+    plain_ms = float(np.array([a.elapsed_time(b) for a, b in ev2]).sum()) / args.steps
     stage /= args.steps
 
     # ---- steady state: K steps back to back, no flush (what a simulation loop sees)
@@ -604,6 +625,10 @@ def bench_single(args, pkg, scenes, torch, dev):
                          "note": ("sph_step_n: steps back to back (CUDA-graph replay), no L2 flush, stage timers off" if not dense else
                                   "two steps back to back from the dense state: the second one is already the blow-up")},
         "stage_ms": {k: float(v) for k, v in zip(names, stage)},
+        "launch": {"timed_steps": "sph_step_n(dt, 1): CUDA-graph replay of the step" if timed_replays == args.steps else
+                                  "sph_step_n(dt, 1): %d of %d steps replayed the graph" % (timed_replays, args.steps),
+                   "ms_per_step_plain_launches": plain_ms,
+                   "note": "stage_ms are CUDA-event timers between the stages of the plain-launch steps"},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),

@@ -591,12 +591,15 @@ static bool record_step(SphContext* c, float dt)
 int sph_step_n(SphContext* c, float dt, uint32_t nsteps)
 {
     if (!c) return SPH_ERR_INVALID;
-    const bool replay = graphs_enabled() && !c->graph_disabled && c->nranks == 1 && nsteps >= 3 && c->n > 0;
+    // with the stage timers off nothing needs a plain last step, and a recording that is already there is replayed
+    // even for a single step (bench.py times sph_step_n(dt, 1) per frame that way)
+    const bool replay = graphs_enabled() && !c->graph_disabled && c->nranks == 1 && c->n > 0 && (nsteps >= 3 || (!c->timing && c->graph_valid));
     for (uint32_t i = 0; i < nsteps; i++) {
         const bool last = i + 1 == nsteps;
-        if (replay && !last && !c->graph_disabled) {
-            // a list that has to grow, or any change of configuration: plain step (it reallocates), record afterwards
-            const bool grow = c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k;
+        if (replay && (!last || !c->timing) && !c->graph_disabled) {
+            // a list or staging buffer that has to grow, or any change of configuration: plain step (it reallocates), record afterwards
+            const bool grow = (c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k) ||
+                              (c->h_tile_need && *c->h_tile_need > c->tile_capn);
             const SphContext::StepKey k = step_key(c, dt);
             const bool match = c->graph_valid && memcmp(&k, &c->graph_key, sizeof(k)) == 0;
             if (!grow && (match || (c->step_valid && i > 0 && record_step(c, dt)))) {

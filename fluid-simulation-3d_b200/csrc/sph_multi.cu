@@ -110,7 +110,7 @@ struct SlabState {
     bool failed = false;
     std::string failure;
     cudaStream_t halo_stream = nullptr;           // halos 2 and 3 travel here, overlapped with interior compute
-    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr, ev_counts = nullptr, ev_msg = nullptr;
     // SPH_SLAB_TIMING=1: finer timers of the spatial stage (events on the stream + host clock around the syncs)
     bool prof = false;
     cudaEvent_t pe[8] = {};
@@ -375,6 +375,8 @@ void multi_teardown(SphContext* c)
     if (s->halo_stream) { cudaStreamSynchronize(s->halo_stream); cudaStreamDestroy(s->halo_stream); }
     if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+    if (s->ev_counts) cudaEventDestroy(s->ev_counts);
+    if (s->ev_msg) cudaEventDestroy(s->ev_msg);
     delete s;
     c->slab = nullptr;
 }
@@ -435,34 +437,43 @@ int multi_step(SphContext* c, float dt)
     // (2) order-preserving pack of the six lists
     const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
     uint32_t* totals = s->dev_small;            // [6]
-    uint32_t* rcounts = s->dev_small + 8;       // [6] from lo: its (mig, ghost, keep) towards me, then the same from hi
     uint32_t* picks = s->dev_small + 16;        // [8]
     uint32_t* peer = s->dev_small + 24;         // [2] boundary lengths of the neighbours' layers
     SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
+    uint32_t* msg_out = s->dev_small + 32;
+    uint32_t* msg_in = s->dev_small + 48;
     if (n_old) {
         k_slab_count<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, n_old, nblocks, P, dt);
         k_slab_scan<<<NLISTS, kPackThreads, 0, st>>>(s->block_counts, totals, nblocks);
+        c->launches += 2;
+    }
+    // (3a) count messages to / from the neighbours (k_slab_msg).  They travel on the halo stream, with the copy of the
+    // counts to the host behind them, WHILE the solver's stream packs the six lists: the host's round trip (the one
+    // synchronisation of the step) is hidden behind the pack kernel instead of leaving the GPU idle.
+    k_slab_msg<<<1, 32, 0, st>>>(totals, msg_out, s->failed ? 1u : 0u, s->xcap, c->cap, s->gcap, n_old);
+    ++c->launches;
+    cudaStream_t cs = s->halo_stream;
+    SPH_CUDA(c, cudaEventRecord(s->ev_counts, st));
+    SPH_CUDA(c, cudaStreamWaitEvent(cs, s->ev_counts, 0));
+    SPH_NCCL(c, ncclGroupStart());
+    if (has_lo) { SPH_NCCL(c, ncclSend(msg_out, 8, ncclUint32, lo, comm, cs)); SPH_NCCL(c, ncclRecv(msg_in, 8, ncclUint32, lo, comm, cs)); }
+    if (has_hi) { SPH_NCCL(c, ncclSend(msg_out + 8, 8, ncclUint32, hi, comm, cs)); SPH_NCCL(c, ncclRecv(msg_in + 8, 8, ncclUint32, hi, comm, cs)); }
+    SPH_NCCL(c, ncclGroupEnd());
+    // (words 16..31 of the pinned mirror still hold the previous step's table picks: they are compared below)
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 32, s->dev_small + 32, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    SPH_CUDA(c, cudaEventRecord(s->ev_msg, cs));
+    // (2) order-preserving pack of the six lists
+    if (n_old) {
         k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, s->mig_send[0],
                                                       s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0],
                                                       s->keep[1], n_old, nblocks, s->xcap, P, dt);
-        c->launches += 3;
+        ++c->launches;
     }
     SLAB_MARK(1);
-    // (3a) count messages to / from the neighbours (k_slab_msg)
-    uint32_t* msg_out = s->dev_small + 32;
-    uint32_t* msg_in = s->dev_small + 48;
-    k_slab_msg<<<1, 32, 0, st>>>(totals, msg_out, s->failed ? 1u : 0u, s->xcap, c->cap, s->gcap, n_old);
-    ++c->launches;
-    SPH_NCCL(c, ncclGroupStart());
-    if (has_lo) { SPH_NCCL(c, ncclSend(msg_out, 8, ncclUint32, lo, comm, st)); SPH_NCCL(c, ncclRecv(msg_in, 8, ncclUint32, lo, comm, st)); }
-    if (has_hi) { SPH_NCCL(c, ncclSend(msg_out + 8, 8, ncclUint32, hi, comm, st)); SPH_NCCL(c, ncclRecv(msg_in + 8, 8, ncclUint32, hi, comm, st)); }
-    SPH_NCCL(c, ncclGroupEnd());
-    // (words 16..31 of the pinned mirror still hold the previous step's table picks: they are compared below)
-    SPH_CUDA(c, cudaMemcpyAsync(s->host_small, s->dev_small, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SPH_CUDA(c, cudaMemcpyAsync(s->host_small + 32, s->dev_small + 32, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SLAB_MARK(2);
     const double h0 = host_now();
-    SPH_CUDA(c, cudaStreamSynchronize(st));
+    SPH_CUDA(c, cudaEventSynchronize(s->ev_msg));
     const double h1 = host_now();
     // The verdict about a link, from the two messages that crossed it: identical on both of its ends.
     auto link_ok = [](const uint32_t* a, const uint32_t* b) {        // a -> b and b -> a are the same test with the roles swapped
@@ -768,6 +779,8 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
     }
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+    SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming));
+    SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_msg, cudaEventDisableTiming));
     if (const char* e = getenv("SPH_SLAB_TIMING")) {
         s->prof = e[0] == '1';
         if (s->prof) for (auto& ev : s->pe) SPH_CUDA(c, cudaEventCreate(&ev));
