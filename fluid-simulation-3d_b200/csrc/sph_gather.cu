@@ -738,7 +738,7 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 #define SPH_PK_NOCLAMP 1
 #endif
 constexpr int PKS = SPH_PKS;    // stack entries per thread: sparse scenes (one or two flushes per particle)
-constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 64): fewer, fuller flushes
+constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 128): fewer, fuller flushes
 
 // ncu: bound by the L1 data pipe; candidates are read as a 16-byte (x0, x1, y0, y1) and an 8-byte (z0, z1) load per pair:
 // 24 bytes per pair instead of the former 32-byte record with its two dead w words (-26 % of the cull's wavefronts).
@@ -1055,7 +1055,9 @@ static void launch_density_main(cudaStream_t st, const float4* pred_s, const flo
             A.list_w = L.w;
             // the deep stack needs the opt-in above 48 KB; the attribute is per device, so it is (re)set whenever used
             uint32_t rows = PKS;
-            if (A.list_k > 64) {
+            // (a capacity that auto-grew a little past 64 because ONE pile-up in a corner needed it must not cost every block
+            // three quarters of its occupancy: the deep stack is for scenes whose lists are long throughout, like C5)
+            if (A.list_k > 128) {
                 if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
                 else cudaGetLastError();
             }
