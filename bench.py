@@ -450,47 +450,44 @@ def bench_single(args, pkg, scenes, torch, dev):
     sim.synchronize()
     torch.cuda.synchronize()
 
-    # ---- device-resident timing: one CUDA-event pair per step on the solver's stream, L2 flushed between.  The step is
-    # launched the way a frame loop launches it: sph_step_n(dt, 1) replays the recorded CUDA graph of the step (one
-    # cudaGraphLaunch instead of a dozen kernel launches); the same steps through plain launches with the six stage
-    # timers on follow, and give stage_ms.
+    # ---- device-resident timing: one CUDA-event pair per step on the solver's stream, L2 flushed between.  sph_step
+    # replays the recorded CUDA graph of the step from the second step of an unchanged configuration on (one
+    # cudaGraphLaunch instead of a dozen kernel launches; include/sph_b200.h: sph_set_graph_replay).  Loop A times `value`
+    # that way, stage timers off; loop B runs the same number of steps through plain launches with the six stage timers on
+    # and gives stage_ms (the recording carries no timers: seven event nodes cost more than the replay saves).
     clocks = ClockSampler(dev)
     clocks.start()
+
+    def timed_loop(steps, timers):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        acc = []
+        for a, b in ev:
+            restore()                       # outside the event pair
+            l2_flush()
+            a.record(stream)
+            sim.step(dt)
+            b.record(stream)
+            if timers:
+                acc.append(sim.timings())   # waits for the step's last stage event
+        sim.synchronize()
+        torch.cuda.synchronize()
+        return np.array([a.elapsed_time(b) for a, b in ev]), (np.median(np.array(acc), axis=0) if acc else None)
+
     sim.set_stage_timing(False)
     restore()
-    sim.step_n(dt, 4)                        # records the graph (outside the timed region)
+    sim.step_n(dt, 3)                        # plain step, recording, first replay: outside the timed region
     sim.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = sim.launch_count()
-    r0 = sim.graph_replays()
-    for a, b in ev:
-        restore()                       # outside the event pair
-        l2_flush()
-        a.record(stream)
-        sim.step_n(dt, 1)
-        b.record(stream)
-    sim.synchronize()
-    torch.cuda.synchronize()
+    l0, r0 = sim.launch_count(), sim.graph_replays()
+    ms, _ = timed_loop(args.steps, False)
     launches = sim.launch_count() - l0 - (args.steps if dense else 0)      # the restoring spawn kernel is not part of the step
     timed_replays = sim.graph_replays() - r0
-    ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(ms.sum())
     value = n * args.steps / (total_ms * 1e-3) / 1e6
-    # the same steps, plain launches, stage timers on
     sim.set_stage_timing(True)
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage = np.zeros(6)
-    for a, b in ev2:
-        restore()
-        l2_flush()
-        a.record(stream)
-        sim.step(dt)
-        b.record(stream)
-        stage += sim.timings()          # waits for the step's last stage event
-    sim.synchronize()
-    torch.cuda.synchronize()
-    plain_ms = float(np.array([a.elapsed_time(b) for a, b in ev2]).sum()) / args.steps
-    stage /= args.steps
+    sim.set_graph_replay(False)
+    ms_b, stage = timed_loop(args.steps, True)           # medians: a list that has to grow reallocates inside one of these steps
+    plain_ms = float(np.median(ms_b))
+    sim.set_graph_replay(True)
 
     # ---- steady state: K steps back to back, no flush (what a simulation loop sees).  The scene is restarted first:
     # the block keeps collapsing (more neighbours per particle every step), and this loop should see the same stretch
@@ -504,7 +501,7 @@ def bench_single(args, pkg, scenes, torch, dev):
     if dense:
         steady_steps = 2                         # back to back from the dense state: the second step is already a blow-up
         restore()
-    sim.step_n(dt, 4 if not dense else 1)        # records the step's CUDA graph outside the timed region
+    sim.step_n(dt, 4 if not dense else 1)        # plain step + recording outside the timed region
     r0 = sim.graph_replays()
     a.record(stream)
     sim.step_n(dt, steady_steps)
@@ -630,10 +627,10 @@ def bench_single(args, pkg, scenes, torch, dev):
                          "note": ("sph_step_n: steps back to back (CUDA-graph replay), no L2 flush, stage timers off" if not dense else
                                   "two steps back to back from the dense state: the second one is already the blow-up")},
         "stage_ms": {k: float(v) for k, v in zip(names, stage)},
-        "launch": {"timed_steps": "sph_step_n(dt, 1): CUDA-graph replay of the step" if timed_replays == args.steps else
-                                  "sph_step_n(dt, 1): %d of %d steps replayed the graph" % (timed_replays, args.steps),
+        "launch": {"timed_steps": "sph_step: %d of %d steps replayed the step's CUDA graph" % (timed_replays, args.steps),
                    "ms_per_step_plain_launches": plain_ms,
-                   "note": "stage_ms are CUDA-event timers between the stages of the plain-launch steps"},
+                   "note": "stage_ms (medians) and ms_per_step_plain_launches (median) come from a second loop over as many steps through "
+                           "plain launches with the six stage timers on (sph_set_graph_replay(ctx, 0))"},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_spawn_block", "sph_upload_state",
-    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_noncanonical_cells", "sph_set_extras", "sph_get_extras", "sph_synchronize", "sph_refresh_densities",
+    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_set_graph_replay", "sph_noncanonical_cells", "sph_set_extras", "sph_get_extras", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
@@ -136,6 +136,7 @@ def load_library():
     L.sph_graph_replays.restype = C.c_uint64
     L.sph_set_extras.argtypes = [vp, C.POINTER(SphExtras)]
     L.sph_get_extras.argtypes = [vp, C.POINTER(SphExtras)]
+    L.sph_set_graph_replay.argtypes = [vp, C.c_int]
     L.sph_noncanonical_cells.argtypes = [vp]
     L.sph_noncanonical_cells.restype = C.c_uint64
     L.sph_stream.argtypes = [vp]
@@ -351,6 +352,9 @@ class FluidSimulation:
 
     def launch_count(self):
         return int(self.L.sph_launch_count(self.h))
+
+    def set_graph_replay(self, on):
+        self._check(self.L.sph_set_graph_replay(self.h, 1 if on else 0))
 
     def noncanonical_cells(self):
         return int(self.L.sph_noncanonical_cells(self.h))

@@ -407,6 +407,12 @@ int sph_set_neighbour_list_capacity(SphContext* c, uint32_t entries)
 uint32_t sph_num_particles(const SphContext* c) { return c ? c->n : 0; }
 uint64_t sph_launch_count(const SphContext* c) { return c ? c->launches : 0; }
 uint64_t sph_graph_replays(const SphContext* c) { return c ? c->graph_replays : 0; }
+int sph_set_graph_replay(SphContext* c, int enabled)
+{
+    if (!c) return SPH_ERR_INVALID;
+    c->graph_user_off = enabled == 0;
+    return SPH_OK;
+}
 uint64_t sph_noncanonical_cells(SphContext* c)
 {   // cells (summed over all steps so far) too crowded for the counting sort's canonical-order ranking; synchronises
     if (!c || !c->d_noncanonical) return 0;
@@ -447,6 +453,14 @@ int sph_upload_state(SphContext* c, uint32_t n, const float* pos3, const float* 
     return SPH_OK;
 }
 
+// Stage timer i.  (Recording them INTO the graph as external event-record nodes was measured: seven such nodes cost a
+// 1 M-particle step 0.066 ms, more than the replay saves; the recording therefore carries no timers, and a context with
+// the timers on takes every 16th step through plain launches to refresh them -- step_once.)
+static cudaError_t stage_event(SphContext* c, int i)
+{
+    return cudaEventRecord(c->ev[i], c->st);
+}
+
 // the whole step; dt == 0 with `advance == false` is InitializeData's tail (lookup + densities only)
 static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = true)
 {
@@ -459,7 +473,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     if (rc != SPH_OK) return rc;
     const bool timing = c->timing && advance && allow_timing;
     cudaStream_t st = c->st;
-    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[0], st));
+    if (timing) SPH_CUDA(c, stage_event(c, 0));
     if (P.mode == SPH_TABLE_GRID && counting_sort_enabled()) {
         // counting sort over the table (a one-pass radix sort whose digit is the whole key): tickets in the cell
         // counters, in-place scan -> prefix table, placement; the reorder restores the canonical (stable) order
@@ -471,7 +485,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
             if (!c->capturing) c->table_two_level = true;
         } else launch_table_clear(st, c->tstart, T, &c->launches);
         launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, c->tstart, c->perm_b, &c->launches);
-        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+        if (timing) SPH_CUDA(c, stage_event(c, 1));
         exclusive_scan_u32(st, c->tstart + T.cells_pad, T.nseg_pad, c->scan_tmp, &c->launches);
         launch_inseg_scan(st, c->tstart, T, &c->launches);
         launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, P, &c->launches);
@@ -480,7 +494,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         c->sorted_where = 1;
     } else {
         launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, nullptr, nullptr, &c->launches);
-        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
+        if (timing) SPH_CUDA(c, stage_event(c, 1));
         const int bits = ceil_log2(P.mode == SPH_TABLE_GRID ? (uint64_t)P.ncell : (uint64_t)P.n);
         c->sorted_where = radix_sort_pairs(st, c->key_a, c->key_b, c->perm_a, c->perm_b, true, P.n, bits, c->counts,
                                            &c->launches);
@@ -492,7 +506,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         launch_reorder(st, perm, nullptr, nullptr, nullptr, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred, c->predpk, P, dt,
                        &c->launches);
     }
-    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[2], st));
+    if (timing) SPH_CUDA(c, stage_event(c, 2));
     NbrList L;
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
@@ -500,16 +514,16 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_tile_need, c->d_tile_need, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
-    if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
+    if (timing) SPH_CUDA(c, stage_event(c, 3));
     if (advance) {
         launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
-        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
+        if (timing) SPH_CUDA(c, stage_event(c, 4));
         // v'' goes into S_vel: dead after the pressure pass read it, and never read by the viscosity pass
         launch_viscosity(st, c->pred, c->velp, c->tstart, c->tend, c->S_vel, L, P, dt, &c->launches);
-        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[5], st));
+        if (timing) SPH_CUDA(c, stage_event(c, 5));
         launch_integrate(st, c->S_pos, c->S_vel, c->A_pos, c->A_vel, P, dt, &c->launches);
-        if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[6], st));
-        c->ev_recorded = timing;
+        if (timing) SPH_CUDA(c, stage_event(c, 6));
+        if (!c->capturing) c->ev_recorded = timing;       // (a recording runs nothing: the last plain step's events stay valid)
     } else {
         // keep "every per-particle array shares the device order": adopt the sorted order
         SPH_CUDA(c, cudaMemcpyAsync(c->A_pos, c->S_pos, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
@@ -518,13 +532,6 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     SPH_CUDA(c, cudaGetLastError());
     c->step_valid = true;
     return SPH_OK;
-}
-
-int sph_step(SphContext* c, float dt)
-{
-    if (!c) return SPH_ERR_INVALID;
-    if (c->nranks > 1) return multi_step(c, dt);
-    return run_step(c, dt, true);
 }
 
 // ---- CUDA-graph replay inside sph_step_n ------------------------------------------------------------------------
@@ -544,7 +551,7 @@ static SphContext::StepKey step_key(const SphContext* c, float dt)
 {
     SphContext::StepKey k;
     memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
-    k.n = c->n; k.dt = dt; k.params = c->params; k.extras = c->extras; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0;
+    k.n = c->n; k.dt = dt; k.params = c->params; k.extras = c->extras; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0; k.timing = 0;
     k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
     return k;
 }
@@ -563,7 +570,7 @@ static bool record_step(SphContext* c, float dt)
     if (cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_disabled = true; return false; }
     const uint64_t l0 = c->launches;
     c->capturing = true;
-    const int rc = run_step(c, dt, true, false);
+    const int rc = run_step(c, dt, true, false);      // no stage timers inside the recording (stage_event)
     c->capturing = false;
     const uint64_t per_step = c->launches - l0;
     c->launches = l0;                               // nothing ran yet
@@ -588,32 +595,51 @@ static bool record_step(SphContext* c, float dt)
     return true;
 }
 
+// One step: replayed as a CUDA graph when a recording for exactly this configuration exists, recorded when the
+// configuration has just been stepped plainly with the same key (so a frame loop replays from its third frame on),
+// plain otherwise -- a list or staging buffer that has to grow, or any change of configuration, takes the plain step,
+// which also does the reallocation.
+static int step_once(SphContext* c, float dt)
+{
+    if (c->nranks > 1) return multi_step(c, dt);
+    const bool can = graphs_enabled() && !c->graph_disabled && !c->graph_user_off && c->n > 0;
+    if (can) {
+        const bool grow = (c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k) ||
+                          (c->h_tile_need && *c->h_tile_need > c->tile_capn);
+        const SphContext::StepKey k = step_key(c, dt);
+        bool match = c->graph_valid && memcmp(&k, &c->graph_key, sizeof(k)) == 0;
+        if (!grow && !match && c->step_valid && c->have_last_key && memcmp(&k, &c->last_key, sizeof(k)) == 0) match = record_step(c, dt);
+        // the six stage timers (getElapsedTime*) are refreshed by a plain step every 16 steps while replays run
+        const bool refresh = c->timing && c->replays_since_timed >= 15;
+        if (!grow && match && !refresh) {
+            SPH_CUDA(c, cudaSetDevice(c->device));
+            SPH_CUDA(c, cudaGraphLaunch(c->graph_exec, c->st));
+            c->launches += c->graph_launches;
+            c->graph_replays++;
+            c->replays_since_timed++;
+            c->ncount_valid = true;
+            c->step_valid = true;
+            // (the stage events of the last plain step stay recorded: sph_get_timings keeps reporting that step)
+            return SPH_OK;
+        }
+    }
+    const int rc = run_step(c, dt, true);
+    c->replays_since_timed = 0;
+    if (can && rc == SPH_OK) { c->last_key = step_key(c, dt); c->have_last_key = true; }
+    return rc;
+}
+
+int sph_step(SphContext* c, float dt)
+{
+    if (!c) return SPH_ERR_INVALID;
+    return step_once(c, dt);
+}
+
 int sph_step_n(SphContext* c, float dt, uint32_t nsteps)
 {
     if (!c) return SPH_ERR_INVALID;
-    // with the stage timers off nothing needs a plain last step, and a recording that is already there is replayed
-    // even for a single step (bench.py times sph_step_n(dt, 1) per frame that way)
-    const bool replay = graphs_enabled() && !c->graph_disabled && c->nranks == 1 && c->n > 0 && (nsteps >= 3 || (!c->timing && c->graph_valid));
     for (uint32_t i = 0; i < nsteps; i++) {
-        const bool last = i + 1 == nsteps;
-        if (replay && (!last || !c->timing) && !c->graph_disabled) {
-            // a list or staging buffer that has to grow, or any change of configuration: plain step (it reallocates), record afterwards
-            const bool grow = (c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k) ||
-                              (c->h_tile_need && *c->h_tile_need > c->tile_capn);
-            const SphContext::StepKey k = step_key(c, dt);
-            const bool match = c->graph_valid && memcmp(&k, &c->graph_key, sizeof(k)) == 0;
-            if (!grow && (match || (c->step_valid && i > 0 && record_step(c, dt)))) {
-                SPH_CUDA(c, cudaSetDevice(c->device));
-                SPH_CUDA(c, cudaGraphLaunch(c->graph_exec, c->st));
-                c->launches += c->graph_launches;
-                c->graph_replays++;
-                c->ncount_valid = true;
-                c->step_valid = true;
-                c->ev_recorded = false;
-                continue;
-            }
-        }
-        int rc = c->nranks > 1 ? multi_step(c, dt) : run_step(c, dt, true);
+        const int rc = step_once(c, dt);
         if (rc != SPH_OK) return rc;
     }
     return SPH_OK;

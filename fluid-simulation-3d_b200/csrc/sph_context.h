@@ -66,17 +66,21 @@ struct SphContext {
     // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
     // plain step and re-captures
     struct StepKey {
-        uint32_t n; float dt; SphParams params; SphExtras extras; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level;
+        uint32_t n; float dt; SphParams params; SphExtras extras; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level, timing;
         const void *nlist, *tstart, *scan_tmp, *tend;
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     StepKey graph_key = {};
+    StepKey last_key = {};           // configuration of the last plain step: the same key again records the graph
+    bool have_last_key = false;
     bool graph_valid = false;
+    bool graph_user_off = false;     // sph_set_graph_replay(ctx, 0)
     bool graph_disabled = false;     // SPH_GRAPH=0, or a capture failed once on this context
     bool capturing = false;          // run_step is being recorded: no allocation, no list growth
     uint64_t graph_launches = 0;     // kernels per replay
     uint64_t graph_replays = 0;
+    uint32_t replays_since_timed = 0; // replays since the last plain step (which refreshes the stage timers)
     int sorted_where = 0;        // 0: sorted keys in key_a, 1: key_b
     bool step_valid = false;     // per-step arrays describe the current device order
     bool ncount_valid = false;

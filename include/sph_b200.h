@@ -175,6 +175,11 @@ int  sph_step(SphContext* ctx, float dt);
 int  sph_step_n(SphContext* ctx, float dt, uint32_t nsteps);
 /* steps executed by graph replay since creation (diagnostic) */
 uint64_t sph_graph_replays(const SphContext* ctx);
+/* sph_step / sph_step_n replay the step as a CUDA graph from the second consecutive step of an unchanged configuration on
+ * (one cudaGraphLaunch instead of a dozen kernel launches).  The recording carries no stage timers: while the timers are on
+ * (sph_set_stage_timing, the default) every 16th step runs through plain launches and refreshes them, and sph_get_timings
+ * reports the last such step.  On by default; enabled = 0 makes every step a sequence of plain launches. */
+int  sph_set_graph_replay(SphContext* ctx, int enabled);
 /* GRID table, counting sort: cells that held more than 16384 rows (a blow-up clamping much of the scene into one rim cell) keep
  * the arrival order of their rows instead of the canonical ascending-index order: neighbour sets are unaffected, float sums lose
  * run-to-run reproducibility in the last bits.  Number of such cells over all steps so far (0 in any sane scene); synchronises. */

@@ -116,6 +116,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
     status = {          # must report an error
         "sph_create": lambda: L.sph_create(None, 0, 10),
         "sph_set_params": lambda: L.sph_set_params(None, C.byref(P)), "sph_get_params": lambda: L.sph_get_params(None, C.byref(P)),
+        "sph_set_graph_replay": lambda: L.sph_set_graph_replay(None, 1),
         "sph_set_extras": lambda: L.sph_set_extras(None, None), "sph_get_extras": lambda: L.sph_get_extras(None, None),
         "sph_set_table_mode": lambda: L.sph_set_table_mode(None, 0), "sph_set_stage_timing": lambda: L.sph_set_stage_timing(None, 1),
         "sph_set_neighbour_count_tap": lambda: L.sph_set_neighbour_count_tap(None, 1),

@@ -1,5 +1,6 @@
-"""-m gpu: sph_step_n replays the step as a CUDA graph; the results are bit-identical to plain sph_step calls, and a
-change of configuration between (or during) calls falls back to plain steps and records again."""
+"""-m gpu: sph_step / sph_step_n replay the step as a CUDA graph from the second consecutive step of an unchanged
+configuration on; the results are bit-identical to plain launches (sph_set_graph_replay(ctx, 0)), the stage timers are
+refreshed by a plain step every 16 steps, and a change of configuration falls back to a plain step and records again."""
 import numpy as np
 import pytest
 
@@ -16,30 +17,37 @@ def test_step_n_graph_replay_equals_plain_steps(pkg, mode):
     sc = scenes.small_dam_break(18)
     a = pkg.FluidSimulation(sc["n"], table_mode=mode, **sc["params"])
     b = pkg.FluidSimulation(sc["n"], table_mode=mode, **sc["params"])
+    b.set_graph_replay(False)                       # b: plain launches throughout
     for s in (a, b):
         s.upload_state(sc["pos"], sc["vel"])
     a.step_n(scenes.DT, 12)
     for _ in range(12):
         b.step(scenes.DT)
-    assert a.graph_replays() == 10                  # step 0 and the last step run plainly
+    assert a.graph_replays() == 11 and b.graph_replays() == 0      # step 0 runs plainly, step 1 records and replays
     assert a.launch_count() == b.launch_count()
     for f in ("positions", "velocities", "densities", "predicted"):
         assert np.array_equal(_bits(a.download(f)), _bits(b.download(f))), f
-    # the timers describe the last (plain) step
-    assert a.timings().sum() > 0.0
+    # the six stage timers describe the last plain step (step 0 here; every 16th step is a plain one)
+    ta, tb = a.timings(), b.timings()
+    assert np.all(ta > 0.0) and np.all(tb > 0.0), (ta, tb)
+    a.step_n(scenes.DT, 20)
+    for _ in range(20):
+        b.step(scenes.DT)
+    assert a.graph_replays() == 11 + 19             # one of the twenty refreshed the timers through plain launches
+    assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
     # a parameter change invalidates the recording: plain step, new recording, same answers as plain stepping
     for s in (a, b):
         s.set_params(viscosity_strength=0.1, gravity_scale=4.0)
     a.step_n(scenes.DT, 6)
     for _ in range(6):
         b.step(scenes.DT)
-    assert a.graph_replays() == 14
+    assert a.graph_replays() == 35                  # one plain step, then five replays of the new recording
     assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
-    # a different dt as well; short calls (< 3 steps) never record
-    a.step_n(0.004, 2)
+    # a different dt as well, through sph_step this time: plain, then recorded and replayed
     for _ in range(2):
+        a.step(0.004)
         b.step(0.004)
-    assert a.graph_replays() == 14
+    assert a.graph_replays() == 36
     assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
     a.close(); b.close()
 
@@ -57,6 +65,7 @@ def test_step_n_replay_with_growing_neighbour_lists(pkg):
     for s in (a, b):
         s.set_neighbour_count_tap(True)
         s.upload_state(sc["pos"], sc["vel"])
+    b.set_graph_replay(False)
     a.step_n(scenes.DT, 8)
     for _ in range(8):
         b.step(scenes.DT)
