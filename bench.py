@@ -634,9 +634,10 @@ def bench_single(args, pkg, scenes, torch, dev):
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(dom_ms),
-                     "binding_roof": "L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M), not HBM: every lane streams "
-                                     "its own 16-byte candidates and the gather re-reads neighbours from L1/L2 by design "
-                                     "(ncu: profiles/r01_gather_final_C2.txt, r01_gather_final_C3.txt; DESIGN.md section 5)",
+                     "binding_roof": "instruction issue (76 % at 1 M, 79 % at 8 M) together with the SM's L1 data pipe "
+                                     "(l1tex__data_pipe_lsu_wavefronts 71 % / 78 %), not HBM: every lane streams its own 12-byte candidates "
+                                     "and the gather re-reads neighbours from L1/L2 by design (ncu: profiles/r02_gather_final_C2.txt, "
+                                     "r02_gather_final_C3.txt; DESIGN.md section 5)",
                      "stages": {k: {"algorithmic_bytes_per_particle": a, "ms": float(t), "achieved": a * n / (float(t) * 1e-3) / 1e9,
                                     "frac": a * n / (float(t) * 1e-3) / 1e9 / peak}
                                 for k, a, t in zip(names, (A_BYTES["predict_key"], A_BYTES["sort"] + A_BYTES["table"] + A_BYTES["reorder"],
