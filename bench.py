@@ -36,6 +36,16 @@ METRIC = "M particle-updates/s"
 # algorithmic (compulsory) bytes per particle-update, SURVEY.md 8(d) / DESIGN.md
 A_BYTES = dict(predict_key=72, sort=52, table=12, reorder=68, density=32, pressure=64, viscosity=56,
                integrate=84, step=440)
+# The timed step does not write OutPositions (16 of K8's 84 bytes): the export kernel runs with the download, inside the
+# e2e loops.  The whole-step roofline therefore counts 424 bytes per update; the contract's 440 is printed beside it.
+A_STEP_TIMED = A_BYTES["step"] - 16
+
+
+def step_roofline(value_m, peak, gpus=1):
+    ach = A_STEP_TIMED * value_m * 1e6 / 1e9 / gpus
+    return {"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_particle": A_STEP_TIMED,
+            "note": "SURVEY 8(d) A_step = 440 B minus the 16 B OutPositions write, which this implementation does at download time",
+            "frac_with_contract_440": A_BYTES["step"] * value_m * 1e6 / 1e9 / gpus / peak}
 
 
 def measured_peaks():
@@ -299,7 +309,7 @@ def main():
     else:
         from fluid_simulation_3d_b200 import slab_driver
         result = slab_driver.bench_multi(args, pkg, scenes, torch, dist, rank, world, local_rank, METRIC, A_BYTES,
-                                         measured_peaks, ClockSampler, short_line=short_line)
+                                         measured_peaks, ClockSampler, short_line=short_line, step_roofline=step_roofline)
     if rank == 0 and result is not None:
         print(json.dumps(result), flush=True)
     if world > 1:
@@ -413,7 +423,7 @@ def short_line(pkg, scenes, torch, dev, name, steps=5, warmup=3, flush=None):
             "mean_neighbours_last_step": mean_nb,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(gather[dom]),
-                         "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak}}}
+                         "step": step_roofline(value, peak)}}
 
 
 def bench_single(args, pkg, scenes, torch, dev):
@@ -645,8 +655,7 @@ def bench_single(args, pkg, scenes, torch, dev):
                                                            A_BYTES["integrate"]), stage)},
                      "gather_kernels": gather_kernels,
                      "streaming_kernels": streaming,
-                     "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / peak,
-                              "algorithmic_bytes_per_particle": A_BYTES["step"]}},
+                     "step": step_roofline(value, peak)},
         "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16,
                 "ms_per_step": e2e_s / args.steps * 1e3,
                 "path": e2e_path,

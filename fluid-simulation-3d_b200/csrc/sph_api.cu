@@ -216,7 +216,7 @@ int ensure_list(SphContext* c, NbrList* L)
 static void free_all(SphContext* c)
 {
     void* ptrs[] = {c->A_pos, c->A_vel, c->S_pos, c->S_vel, c->pred, c->predpk, c->velp, c->dens, c->key_a, c->key_b,
-                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->d_noncanonical, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
+                    c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->d_noncanonical, c->row_of, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     if (c->h_tile_need) cudaFreeHost(c->h_tile_need);
@@ -820,7 +820,10 @@ int sph_get_particle(SphContext* c, uint32_t index, float* out10)
     SPH_CUDA(c, cudaSetDevice(c->device));
     float* d = (float*)c->stage;
     SPH_CUDA(c, cudaMemsetAsync(d, 0, 10 * sizeof(float), c->st));
-    launch_find_particle(c->st, c->A_pos, c->A_vel, c->step_valid ? c->dens : nullptr, c->n, index, d, &c->launches);
+    if (!c->row_of) SPH_CUDA(c, cudaMalloc(&c->row_of, (size_t)c->cap * sizeof(uint32_t)));
+    const bool rebuild = c->row_of_stamp != c->launches;
+    launch_find_particle(c->st, c->A_pos, c->A_vel, c->step_valid ? c->dens : nullptr, c->n, index, d, c->row_of, rebuild, &c->launches);
+    c->row_of_stamp = c->launches;
     SPH_CUDA(c, cudaMemcpyAsync(out10, d, 10 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     SPH_CUDA(c, cudaStreamSynchronize(c->st));
     return SPH_OK;

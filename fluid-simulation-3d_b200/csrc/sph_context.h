@@ -35,6 +35,8 @@ struct SphContext {
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
     uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
     uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
+    uint32_t* row_of = nullptr;           // id -> row of the device order, built on demand by sph_get_particle
+    uint64_t row_of_stamp = ~0ull;        // c->launches when it was built: any kernel since then may have changed the order
     uint32_t* d_noncanonical = nullptr;   // device counter, see DevParams::noncanonical
     uint32_t tile_capn = 0;          // tile generation: staged candidates per warp (0: not initialised yet)
     uint32_t* d_tile_need = nullptr; // device word: largest single-cell neighbourhood that did not fit

@@ -148,7 +148,7 @@ void launch_spawn_block(cudaStream_t st, float4* pos, float4* vel, uint32_t nx, 
 void launch_export(cudaStream_t st, int field, const float4* id_src, const void* src, const void* src2, void* out,
                    uint32_t n, const DevParams& P, bool by_id, uint64_t* launches);
 void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const Rec8* dens, uint32_t n,
-                          uint32_t id, float* out10, uint64_t* launches);
+                          uint32_t id, float* out10, uint32_t* row_of, bool rebuild, uint64_t* launches);
 void launch_export_ids(cudaStream_t st, const float4* id_src, uint32_t* out, uint32_t n, uint64_t* launches);
 
 }  // namespace sphb200

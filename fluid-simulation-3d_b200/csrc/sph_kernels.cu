@@ -109,14 +109,15 @@ k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, con
 // Layout of the allocation: [cells: ncell + 3, padded][segment bases, padded for the scan][dirty flag per segment].
 // One warp per segment throughout.
 __global__ void __launch_bounds__(256)
-k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg)
+k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg,
+              const uint32_t nseg_pad)
 {   // zero the cell counters of the segments the LAST step touched, and every segment counter.  One THREAD looks at
     // one segment's flag (coalesced); the warp then zeroes its dirty segments together, 64 cells at a time.
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool in = sg < nseg;
     const bool dirty = in && table[dirty_off + sg] != 0u;
-    if (in) table[seg_off + sg] = 0u;
+    if (sg < nseg_pad) table[seg_off + sg] = 0u;          // the scan's padding too (it holds last step's totals)
     if (dirty) table[dirty_off + sg] = 0u;
     uint32_t todo = __ballot_sync(0xffffffffu, dirty);
     const uint32_t sg0 = sg - lane;
@@ -512,13 +513,19 @@ k_export(const int field, const float4* __restrict__ id_src, const void* __restr
 
 // getPosition/getVelocity/getDensity/getNearDensity/getSpeed/getSpeedNormalzied (:149-182) for one id
 __global__ void __launch_bounds__(256)
-k_find_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const Rec8* __restrict__ dens,
-                const uint32_t n, const uint32_t id, float* __restrict__ out10)
-{
+k_row_of_id(const float4* __restrict__ pos, uint32_t* __restrict__ row_of, const uint32_t n)
+{   // inverse of the device order: row_of[id] = row (ids are 0..n-1 on a single-GPU context)
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    const uint32_t id = __float_as_uint(pos[s].w);
+    if (id < n) row_of[id] = s;
+}
+
+__global__ void k_read_particle(const float4* __restrict__ pos, const float4* __restrict__ vel, const Rec8* __restrict__ dens,
+                                const uint32_t* __restrict__ row_of, const uint32_t id, float* __restrict__ out10)
+{
+    const uint32_t s = row_of[id];
     const float4 p = pos[s];
-    if (__float_as_uint(p.w) != id) return;
     const float4 v = vel[s];
     const float len = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
     out10[0] = p.x; out10[1] = p.y; out10[2] = p.z; out10[3] = v.x; out10[4] = v.y; out10[5] = v.z;
@@ -592,7 +599,8 @@ TableLayout table_layout(const uint32_t ncell)
 
 void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
 {
-    k_table_clear<<<blocks_for((uint32_t)T.nseg, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg);
+    k_table_clear<<<blocks_for((uint32_t)T.nseg_pad, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg,
+                                                                        (uint32_t)T.nseg_pad);
     ++*launches;
 }
 
@@ -652,10 +660,11 @@ void launch_export(cudaStream_t st, int field, const float4* id_src, const void*
 }
 
 void launch_find_particle(cudaStream_t st, const float4* pos, const float4* vel, const Rec8* dens, uint32_t n,
-                          uint32_t id, float* out10, uint64_t* launches)
-{
+                          uint32_t id, float* out10, uint32_t* row_of, bool rebuild, uint64_t* launches)
+{   // one particle by id: the id -> row map is rebuilt once per device order (a step, an upload), then a read is O(1)
     if (n == 0) return;
-    k_find_particle<<<blocks_for(n, 256), 256, 0, st>>>(pos, vel, dens, n, id, out10);
+    if (rebuild) { k_row_of_id<<<blocks_for(n, 256), 256, 0, st>>>(pos, row_of, n); ++*launches; }
+    k_read_particle<<<1, 1, 0, st>>>(pos, vel, dens, row_of, id, out10);
     ++*launches;
 }
 

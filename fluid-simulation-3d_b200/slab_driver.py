@@ -290,7 +290,7 @@ def bind_to_gpu_numa(torch, dev):
         return "not bound (%s: %s)" % (type(ex).__name__, ex)
 
 
-def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler, short_line=None):
+def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTES, measured_peaks, ClockSampler, short_line=None, step_roofline=None):
     name = args.config or "C4_dambreak_64M"
     numa = bind_to_gpu_numa(torch, dev)
     # (0) parity gate: the slab-decomposed step must equal the single-GPU step before anything is timed
@@ -471,8 +471,8 @@ def bench_multi(args, pkg, scenes, torch, dist, rank, world, dev, METRIC, A_BYTE
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "per": "rank (max over ranks)",
                      "algorithmic_bytes_per_particle": A_BYTES[dom], "kernel_ms": float(gather[dom]),
-                     "step": {"achieved": A_BYTES["step"] * value * 1e6 / 1e9 / world,
-                              "frac": A_BYTES["step"] * value * 1e6 / 1e9 / world / peak}},
+                     "step": (step_roofline(value, peak, world) if step_roofline else
+                              {"achieved": A_BYTES["step"] * value * 1e6 / 1e9 / world, "frac": A_BYTES["step"] * value * 1e6 / 1e9 / world / peak})},
         "e2e": {"value": e2e, "unit": "M updates/s", "h2d_bytes_per_step": int(n_total) * 28, "d2h_bytes_per_step": int(n_total) * 20,
                 "result": "per rank (global id, OutPositions row) of every owned particle: row k is OutPositions[ids[k]]", "numa": numa,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
