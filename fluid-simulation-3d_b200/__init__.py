@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
     "sph_comm_id_bytes", "sph_comm_get_id", "sph_comm_init", "sph_comm_set_planes",
     "sph_upload_owned", "sph_download_owned", "sph_upload_owned_begin", "sph_download_owned_begin", "sph_comm_stats",
-    "sph_comm_get_layers", "sph_comm_rebalance", "sph_slab_balance_layers", "sph_download_owned_scatter",
+    "sph_comm_get_layers", "sph_comm_rebalance", "sph_slab_balance_layers", "sph_slab_link_ok", "sph_download_owned_scatter",
 ]
 
 
@@ -163,6 +163,7 @@ def load_library():
     L.sph_download_owned_scatter.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(u32)]
     L.sph_comm_get_layers.argtypes = [vp, vp]
     L.sph_comm_rebalance.argtypes = [vp, u32, vp, vp, C.c_size_t, C.POINTER(C.c_int)]
+    L.sph_slab_link_ok.argtypes = [vp, vp]
     L.sph_slab_balance_layers.argtypes = [vp, C.c_int32, C.c_int32, vp, u32, C.c_uint64, vp]
     _lib = L
     return L

@@ -475,14 +475,8 @@ int multi_step(SphContext* c, float dt)
     const double h0 = host_now();
     SPH_CUDA(c, cudaEventSynchronize(s->ev_msg));
     const double h1 = host_now();
-    // The verdict about a link, from the two messages that crossed it: identical on both of its ends.
-    auto link_ok = [](const uint32_t* a, const uint32_t* b) {        // a -> b and b -> a are the same test with the roles swapped
-        auto one_way = [](const uint32_t* from, const uint32_t* to) {
-            return from[0] <= from[4] && from[1] <= from[4] && from[2] <= from[4] &&      // the sender's lists fit its exchange buffers
-                   (uint64_t)from[0] + from[1] <= to[5] && from[1] <= to[6];              // ... and the receiver has the room
-        };
-        return a[3] == 0u && b[3] == 0u && one_way(a, b) && one_way(b, a);
-    };
+    // The verdict about a link, from the two messages that crossed it: identical on both of its ends (sph_slab_link_ok).
+    auto link_ok = [](const uint32_t* a, const uint32_t* b) { return sph_slab_link_ok(a, b) == 1; };
     const uint32_t* MO = s->host_small + 32;
     const uint32_t* MI = s->host_small + 48;
     const bool was_failed = s->failed;
@@ -729,6 +723,20 @@ int multi_step(SphContext* c, float dt)
 }  // namespace sphb200
 
 extern "C" {
+
+// Pure host function (no device, no communicator): may the link between two slab neighbours carry its payloads this
+// step?  `mine` is the 8-word count message this rank sent over the link, `theirs` the one it received (k_slab_msg:
+// migrants, ghosts, kept migrants, status, exchange-buffer rows, free rows, free ghost rows, 0).  The expression is
+// symmetric -- sph_slab_link_ok(a, b) == sph_slab_link_ok(b, a) -- so both ends decide alike without another exchange.
+int sph_slab_link_ok(const uint32_t* mine, const uint32_t* theirs)
+{
+    if (!mine || !theirs) return -1;
+    auto one_way = [](const uint32_t* from, const uint32_t* to) {
+        return from[0] <= from[4] && from[1] <= from[4] && from[2] <= from[4] &&      // the sender's lists fit its exchange buffers
+               (uint64_t)from[0] + from[1] <= to[5] && from[1] <= to[6];              // ... and the receiver has the room
+    };
+    return (mine[3] == 0u && theirs[3] == 0u && one_way(mine, theirs) && one_way(theirs, mine)) ? 1 : 0;
+}
 
 size_t sph_comm_id_bytes(void) { return sizeof(ncclUniqueId); }
 

@@ -286,6 +286,11 @@ int  sph_comm_rebalance(SphContext* ctx, uint32_t max_shift, int32_t* layers_out
  * neighbours (migration is single-hop), moves at most row_budget particles (0: unlimited) and moves only if that
  * brings it nearer to its quantile by at least a quarter of the rows moved (hysteresis: no flipping between the two
  * boundaries of a layer the quantile falls into); with layers_old == NULL the cut is unconstrained.  Deterministic: every rank derives the same planes from the same histogram. */
+/* Pure host function: the verdict both ends of a slab link reach about it from the two 8-word count messages that crossed it
+ * (migrants, ghosts, kept migrants, status, exchange-buffer rows, free rows, free ghost rows, 0): 1 = the link carries its
+ * payloads and halos this step, 0 = both ends skip it and return a capacity error after the step, -1 = NULL argument.
+ * Symmetric in its arguments. */
+int  sph_slab_link_ok(const uint32_t* mine8, const uint32_t* theirs8);
 int  sph_slab_balance_layers(const uint32_t* hist, int32_t gz, int32_t nranks, const int32_t* layers_old,
                              uint32_t max_shift, uint64_t row_budget, int32_t* layers_new);
 

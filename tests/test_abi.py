@@ -142,6 +142,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
         "sph_comm_stats": lambda: L.sph_comm_stats(None, None), "sph_comm_get_layers": lambda: L.sph_comm_get_layers(None, None),
         "sph_comm_rebalance": lambda: L.sph_comm_rebalance(None, 1, None, None, 0, None),
         "sph_slab_balance_layers": lambda: L.sph_slab_balance_layers(None, 0, 0, None, 0, 0, None),
+        "sph_slab_link_ok": lambda: L.sph_slab_link_ok(None, None),
     }
     benign = {          # pure queries: a neutral answer
         "sph_destroy": (lambda: L.sph_destroy(None), 0), "sph_get_table_mode": (lambda: L.sph_get_table_mode(None), -1),
@@ -185,3 +186,31 @@ def test_host_snapshot_file_is_the_documented_format(tmp_path):
         open(bad, "wb").write(raw[:8] + np.uint32(claim).tobytes() + raw[12:])
         r = subprocess.run([demo, "0", "0", "0", "snapshotread", bad], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
         assert r.returncode == 0 and "read=0" in r.stdout, (claim, r.stdout)
+
+
+def test_slab_link_verdict_is_symmetric_and_catches_every_overflow(pkg):
+    """sph_slab_link_ok (pure host): the two ends of a slab link evaluate it with the messages swapped and must agree, or
+    one of them posts a receive the other never matches.  Checked on random messages, plus the four ways a link fails:
+    a failed rank, a list longer than the sender's exchange buffers, arrivals beyond the receiver's free rows, ghosts
+    beyond its free ghost rows."""
+    import numpy as np
+    L = pkg.load_library()
+    ok = lambda a, b: L.sph_slab_link_ok(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data))
+    rng = np.random.default_rng(5)
+    seen = set()
+    for _ in range(4000):
+        a = rng.integers(0, 12, 8).astype(np.uint32); b = rng.integers(0, 12, 8).astype(np.uint32)
+        a[3] = rng.integers(0, 8) == 0; b[3] = rng.integers(0, 8) == 0
+        va, vb = ok(a, b), ok(b, a)
+        assert va == vb and va in (0, 1)
+        seen.add(va)
+    assert seen == {0, 1}
+    good = np.array([5, 7, 2, 0, 100, 50, 40, 0], np.uint32)
+    assert ok(good, good) == 1
+    for word, value in ((3, 1), (0, 101), (1, 101), (2, 101)):                 # status, lists beyond the exchange buffer
+        bad = good.copy(); bad[word] = value
+        assert ok(bad, good) == 0 and ok(good, bad) == 0
+    tight = good.copy(); tight[5] = 11                                         # 5 + 7 arrivals > 11 free rows
+    assert ok(good, tight) == 0 and ok(tight, good) == 0
+    tight = good.copy(); tight[6] = 6                                          # 7 ghosts > 6 free ghost rows
+    assert ok(good, tight) == 0 and ok(tight, good) == 0
