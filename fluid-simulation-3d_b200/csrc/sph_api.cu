@@ -168,12 +168,11 @@ int ensure_tables(SphContext* c, const DevParams& P)
 int ensure_list(SphContext* c, NbrList* L)
 {
     if (!c->h_overflow) {
-        SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, sizeof(uint32_t)));
-        *c->h_overflow = 0;
+        SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, 2 * sizeof(uint32_t)));      // (list overflow, staging need): ONE copy per step
+        c->h_overflow[0] = c->h_overflow[1] = 0;
         SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, 2 * sizeof(uint32_t)));
         SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, 2 * sizeof(uint32_t), c->st));
-        SPH_CUDA(c, cudaMallocHost((void**)&c->h_tile_need, sizeof(uint32_t)));
-        *c->h_tile_need = 0;
+        c->h_tile_need = c->h_overflow + 1;
         c->d_tile_need = c->d_overflow + 1;
         c->tile_capn = tile_default_capn();
     }
@@ -219,7 +218,6 @@ static void free_all(SphContext* c)
                     c->perm_a, c->perm_b, c->ncount, c->lcount, c->nlist, c->d_noncanonical, c->row_of, c->scan_tmp, c->tstart, c->tend, c->gap_list, c->counts, c->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
-    if (c->h_tile_need) cudaFreeHost(c->h_tile_need);
     if (c->d_overflow) cudaFree(c->d_overflow);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
@@ -511,8 +509,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
-    if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_tile_need, c->d_tile_need, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, stage_event(c, 3));
     if (advance) {

@@ -688,8 +688,7 @@ int multi_step(SphContext* c, float dt)
         launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, Q, &c->launches);
         if (g == 1) { rc = halo(c->dens, 8); if (rc != SPH_OK) return rc; }
     }
-    if (c->list_auto && L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_tile_need, c->d_tile_need, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
 
