@@ -111,6 +111,8 @@ struct SlabState {
     std::string failure;
     cudaStream_t halo_stream = nullptr;           // halos 2 and 3 travel here, overlapped with interior compute
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr, ev_counts = nullptr, ev_msg = nullptr;
+    cudaStream_t bnd_stream = nullptr;            // the boundary layers of a gather pass run here, concurrently with the interior
+    cudaEvent_t ev_sorted = nullptr, ev_b[2] = {nullptr, nullptr}, ev_i[2] = {nullptr, nullptr};
     // SPH_SLAB_TIMING=1: finer timers of the spatial stage (events on the stream + host clock around the syncs)
     bool prof = false;
     cudaEvent_t pe[8] = {};
@@ -376,6 +378,8 @@ void multi_teardown(SphContext* c)
     if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
     if (s->ev_counts) cudaEventDestroy(s->ev_counts);
+    for (cudaEvent_t e : {s->ev_sorted, s->ev_b[0], s->ev_b[1], s->ev_i[0], s->ev_i[1]}) if (e) cudaEventDestroy(e);
+    if (s->bnd_stream) { cudaStreamSynchronize(s->bnd_stream); cudaStreamDestroy(s->bnd_stream); }
     if (s->ev_msg) cudaEventDestroy(s->ev_msg);
     delete s;
     c->slab = nullptr;
@@ -665,10 +669,9 @@ int multi_step(SphContext* c, float dt)
     const uint32_t hi_begin = b_hi_begin > b_lo_end ? b_hi_begin : b_lo_end;      // thin slab: the layers may coincide
     const uint32_t seg[3][2] = {{o0, b_lo_end}, {hi_begin, o1}, {b_lo_end, hi_begin}};   // lo layer, hi layer, interior
     cudaStream_t hs = s->halo_stream;
-    auto halo = [&](void* base, const size_t fpr) -> int {   // boundary layers out, ghost layers in (contiguous ranges of rows of `fpr` floats)
+    auto halo = [&](void* base, const size_t fpr, cudaEvent_t boundary_done) -> int {   // boundary layers out, ghost layers in (contiguous ranges of rows of `fpr` floats)
         float* rows = static_cast<float*>(base);
-        SPH_CUDA(c, cudaEventRecord(s->ev_boundary, st));
-        SPH_CUDA(c, cudaStreamWaitEvent(hs, s->ev_boundary, 0));
+        SPH_CUDA(c, cudaStreamWaitEvent(hs, boundary_done, 0));
         SPH_NCCL(c, ncclGroupStart());
         if (halo_lo) {
             if (b_lo_end > o0) SPH_NCCL(c, ncclSend(rows + o0 * fpr, (size_t)(b_lo_end - o0) * fpr, ncclFloat, lo, comm, hs));
@@ -682,23 +685,41 @@ int multi_step(SphContext* c, float dt)
         SPH_CUDA(c, cudaEventRecord(s->ev_halo, hs));
         return SPH_OK;
     };
+    // Boundary layers and interior of a pass are independent of each other, so they run CONCURRENTLY: the two boundary
+    // launches on a high-priority stream of their own (their blocks get the SMs first, their results leave on the halo
+    // stream as soon as they exist), the interior launch on the solver's stream, filling the machine around them --
+    // no tail of a small launch is waited for.  What a pass needs from the previous one crosses streams by events:
+    //   boundary rows of pass k+1  <-  ghost rows (halo of pass k) + interior rows of pass k (their inward neighbours)
+    //   interior rows of pass k+1  <-  boundary rows of pass k (their outward neighbours)
+    cudaStream_t bs = s->bnd_stream;
     DevParams Q = P;
-    for (int g = 0; g < 3; g++) {
-        Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
-        launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, Q, &c->launches);
-        if (g == 1) { rc = halo(c->dens, 8); if (rc != SPH_OK) return rc; }
-    }
+    auto boundary = [&](auto&& launch_rows) {
+        for (int g = 0; g < 2; g++) { Q.row0 = seg[g][0]; Q.row1 = seg[g][1]; launch_rows(bs); }
+    };
+    auto interior = [&](auto&& launch_rows) { Q.row0 = seg[2][0]; Q.row1 = seg[2][1]; launch_rows(st); };
+    SPH_CUDA(c, cudaEventRecord(s->ev_sorted, st));
+    SPH_CUDA(c, cudaStreamWaitEvent(bs, s->ev_sorted, 0));
+    // density
+    auto dens_rows = [&](cudaStream_t q) { launch_density(q, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, Q, &c->launches); };
+    boundary(dens_rows);
+    SPH_CUDA(c, cudaEventRecord(s->ev_b[0], bs));
+    rc = halo(c->dens, 8, s->ev_b[0]); if (rc != SPH_OK) return rc;
+    interior(dens_rows);
+    SPH_CUDA(c, cudaEventRecord(s->ev_i[0], st));
+    SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_b[0], 0));            // the solver's stream has every owned density from here on
     if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
 
     // pressure: the boundary layers need the ghost densities that were travelling during the interior density work
-    SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_halo, 0));
-    for (int g = 0; g < 3; g++) {
-        Q.row0 = seg[g][0]; Q.row1 = seg[g][1];
-        launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, Q, dt, &c->launches);
-        if (g == 1) { rc = halo(c->velp, 4); if (rc != SPH_OK) return rc; }
-    }
+    auto pres_rows = [&](cudaStream_t q) { launch_pressure(q, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, Q, dt, &c->launches); };
+    SPH_CUDA(c, cudaStreamWaitEvent(bs, s->ev_halo, 0));
+    SPH_CUDA(c, cudaStreamWaitEvent(bs, s->ev_i[0], 0));
+    boundary(pres_rows);
+    SPH_CUDA(c, cudaEventRecord(s->ev_b[1], bs));
+    rc = halo(c->velp, 4, s->ev_b[1]); if (rc != SPH_OK) return rc;
+    interior(pres_rows);
+    SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_b[1], 0));
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[4], st));
 
     SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_halo, 0));    // ghost post-pressure velocities are in
@@ -783,10 +804,13 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
         SPH_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
         const char* e = getenv("SPH_HALO_PRIO");
         SPH_CUDA(c, cudaStreamCreateWithPriority(&s->halo_stream, cudaStreamNonBlocking, (e && e[0] == '0') ? lo_p : hi_p));
+        // the boundary layers of a pass: ahead of the interior blocks too (their results are what the neighbours wait for)
+        SPH_CUDA(c, cudaStreamCreateWithPriority(&s->bnd_stream, cudaStreamNonBlocking, hi_p));
     }
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_counts, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&s->ev_sorted, &s->ev_b[0], &s->ev_b[1], &s->ev_i[0], &s->ev_i[1]}) SPH_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     SPH_CUDA(c, cudaEventCreateWithFlags(&s->ev_msg, cudaEventDisableTiming));
     if (const char* e = getenv("SPH_SLAB_TIMING")) {
         s->prof = e[0] == '1';
