@@ -389,27 +389,37 @@ def short_line(pkg, scenes, torch, dev, name, steps=5, warmup=3, flush=None):
     if dense:
         sim.set_neighbour_list_capacity(192)
     stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=dev)
+
+    def loop(k, timers):
+        acc, total = [], 0.0
+        for _ in range(k):
+            if dense:
+                respawn()
+            if flush is not None:
+                with torch.cuda.stream(stream):
+                    flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sim.step(dt)
+            b.record(stream)
+            if timers:
+                acc.append(sim.timings())
+            sim.synchronize()
+            total += a.elapsed_time(b)
+        return total, (np.median(np.array(acc), axis=0) if acc else None)
+
     respawn()
-    for _ in range(warmup):
+    sim.set_stage_timing(False)
+    for _ in range(warmup):                  # the first step is a plain one, the second records the step's graph
         if dense:
             respawn()
         sim.step(dt)
     sim.synchronize()
-    stage, total_ms = np.zeros(6), 0.0
-    for _ in range(steps):
-        if dense:
-            respawn()
-        if flush is not None:
-            with torch.cuda.stream(stream):
-                flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        sim.step(dt)
-        b.record(stream)
-        stage += sim.timings()
-        sim.synchronize()
-        total_ms += a.elapsed_time(b)
-    stage /= steps
+    total_ms, _ = loop(steps, False)         # value: replayed steps, as in the headline loop
+    sim.set_stage_timing(True)
+    sim.set_graph_replay(False)
+    _, stage = loop(steps, True)             # stage_ms: plain launches with the six stage timers on (medians)
+    sim.set_graph_replay(True)
     mean_nb = float(sim.download("neighbour_count").mean()) if n <= (1 << 24) else None
     sim.close()
     names = ["predict_key", "spatial", "density", "pressure", "viscosity", "integrate"]

@@ -138,16 +138,30 @@ k_inseg_scan(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_
     if (occ) table[dirty_off + sg] = 1u;
     uint32_t todo = __ballot_sync(0xffffffffu, occ);
     const uint32_t sg0 = sg - lane;
+    // four occupied segments per round: their loads are issued together (one round trip to the L2 for all four)
     while (todo) {
-        const uint32_t k = (uint32_t)__ffs(todo) - 1u;
-        todo &= todo - 1u;
-        uint2* cells = reinterpret_cast<uint2*>(table + ((size_t)(sg0 + k) << kSegShift));
-        const uint2 v = cells[lane];
-        uint32_t inc = v.x + v.y;
+        uint2* cells[4];
+        uint2 v[4];
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += u; }
-        const uint32_t ex = inc - (v.x + v.y);
-        cells[lane] = make_uint2(ex, ex + v.x);
+        for (int u = 0; u < 4; u++) {
+            cells[u] = nullptr;
+            if (todo) {
+                const uint32_t k = (uint32_t)__ffs(todo) - 1u;
+                todo &= todo - 1u;
+                cells[u] = reinterpret_cast<uint2*>(table + ((size_t)(sg0 + k) << kSegShift));
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = cells[u] ? cells[u][lane] : make_uint2(0u, 0u);
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!cells[u]) continue;                                     // warp-uniform
+            uint32_t inc = v[u].x + v[u].y;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t w = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += w; }
+            const uint32_t ex = inc - (v[u].x + v[u].y);
+            cells[u][lane] = make_uint2(ex, ex + v[u].x);
+        }
     }
 }
 

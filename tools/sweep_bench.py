@@ -20,6 +20,7 @@ from fluid_simulation_3d_b200 import scenes
 name, steps = sys.argv[1], int(sys.argv[2])
 sc = scenes.config(name)
 sim = pkg.FluidSimulation(sc["n"], **sc["params"])
+sim.set_graph_replay(False)          # plain launches: the six stage timers describe every step
 sim.upload_state(sc["pos"], sc["vel"])
 for _ in range(6):
     sim.step(scenes.DT)
