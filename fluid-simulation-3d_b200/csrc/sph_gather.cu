@@ -7,7 +7,7 @@
 // the kernels here differ only in how they enumerate candidates.  What runs by default:
 //
 //   k_density_pk     GRID table: two-phase density over packed candidate pairs (see the kernel): phase A culls two
-//                    candidates per 256-bit load with FFMA2 math and pushes survivors (row, d^2) on a small
+//                    candidates per pair record (a 128-bit + a 64-bit load) with FFMA2 math and pushes survivors (row, d^2) on a small
 //                    shared-memory stack; phase B pops them converged, sums the kernels, writes the NEIGHBOUR LIST
 //                    rows and the viscosity weight of every entry.
 //   k_density_list   REFERENCE_HASH table (27 bucket walks, hash filter): the same two phases with scalar exact math.
@@ -702,7 +702,7 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 // ---- density pass, packed candidate pairs (default for the GRID table) ---------------------------------------
 // One thread per particle, as k_density_list, but
 //  * the candidates come from the PAIR-INTERLEAVED copy of the predicted positions (PredPair, sph_internal.h): one
-//    256-bit load brings two candidates as three aligned register pairs, and their d^2 costs 6 packed instructions
+//    128-bit + one 64-bit load bring two candidates as three aligned register pairs, and their d^2 costs 6 packed instructions
 //    (3 FADD2, FMUL2, 2 FFMA2) instead of 16 scalar ones.  The FMA-fused d^2 decides everything outside a 2e-6 wide
 //    band around sqrRadius; inside the band the reference's exact predicate is evaluated on the plain rows
 //    (phase B, ~1e-6 of the candidates);
@@ -712,9 +712,9 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 //    also leaves the viscosity kernel value of every entry next to the index (k_viscosity_w);
 //  * phase B writes list row k for the whole warp at once (lanes that run short pad with their own index, which
 //    the pressure / viscosity passes skip), so list writes stay coalesced and list lengths are warp-uniform.
-// ncu: bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at 8 M particles): a 256-bit
-// load is served in 8 passes of 4 lanes, >= 1 wavefront each, i.e. >= 4 wavefronts per warp-candidate (measured
-// 5.25) -- the 16 bytes per lane per candidate are the cost, however they are loaded.
+// ncu (round 1, one 32-byte record per pair): bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 85 % at 1 M, 94 % at
+// 8 M particles): a 256-bit load is served in 8 passes of 4 lanes, >= 1 wavefront each, i.e. >= 4 wavefronts per
+// warp-candidate (measured 5.25).  Round 2 (24 bytes per pair): issue 76-79 %, L1 data pipe 71-78 %.
 #ifndef SPH_PKS
 #define SPH_PKS 24
 #endif
@@ -729,13 +729,6 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 #else
 #define SPH_PK_CLOBBER : "memory"
 #define SPH_PK_FENCE() do {} while (0)
-#endif
-// SPH_PK_NOCLAMP=1 (default): rows whose warp-wide window is at most kPairPad pair records long read their candidates
-// through a running pointer, without clamping the address to the end of the array (the allocation carries that much
-// padding, sph_internal.h).  54 instead of 61 instructions per 4-candidate iteration -- and the pass gets 0.5 % (1 M) /
-// 1.3 % (8 M) faster: one more measurement that says the L1 data pipe, not instruction issue, is its roof.
-#ifndef SPH_PK_NOCLAMP
-#define SPH_PK_NOCLAMP 1
 #endif
 constexpr int PKS = SPH_PKS;    // stack entries per thread: sparse scenes (one or two flushes per particle)
 constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 128): fewer, fuller flushes
