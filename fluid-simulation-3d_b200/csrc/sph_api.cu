@@ -168,10 +168,11 @@ int ensure_tables(SphContext* c, const DevParams& P)
 int ensure_list(SphContext* c, NbrList* L)
 {
     if (!c->h_overflow) {
-        SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, 2 * sizeof(uint32_t)));      // (list overflow, staging need): ONE copy per step
-        c->h_overflow[0] = c->h_overflow[1] = 0;
-        SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, 2 * sizeof(uint32_t)));
-        SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, 2 * sizeof(uint32_t), c->st));
+        // (list overflow, staging need, list rows written so far, warps that wrote them): ONE copy per step
+        SPH_CUDA(c, cudaMallocHost((void**)&c->h_overflow, 4 * sizeof(uint32_t)));
+        memset(c->h_overflow, 0, 4 * sizeof(uint32_t));
+        SPH_CUDA(c, cudaMalloc((void**)&c->d_overflow, 4 * sizeof(uint32_t)));
+        SPH_CUDA(c, cudaMemsetAsync(c->d_overflow, 0, 4 * sizeof(uint32_t), c->st));
         c->h_tile_need = c->h_overflow + 1;
         c->d_tile_need = c->d_overflow + 1;
         c->tile_capn = tile_default_capn();
@@ -200,6 +201,21 @@ int ensure_list(SphContext* c, NbrList* L)
     L->idx = c->list_k ? c->nlist : nullptr;
     L->w = c->list_k ? reinterpret_cast<float*>(c->nlist + (size_t)c->list_k_alloc * c->cap) : nullptr;
     L->cnt = c->lcount;
+    // Depth of the density pass's survivor stack, from the list length the last steps actually produced (the running sums
+    // of list rows and of the warps that wrote them, read back with the overflow word): the deep stack -- a quarter of the
+    // occupancy -- pays only when lists are long THROUGHOUT (C5: ~110 rows per warp), not because one pile-up once pushed
+    // the CAPACITY up (an evolved C2 run sat at 280 instead of 125 us per density pass that way).  Hysteresis 40 / 56 rows.
+    if (!c->capturing) {
+        const uint32_t rows = c->h_overflow[2] - c->rows_seen, warps = c->h_overflow[3] - c->warps_seen;
+        if (warps) {
+            const double mean = (double)rows / (double)warps;
+            if (mean > 56.0) c->deep_stack = true;
+            else if (mean < 40.0) c->deep_stack = false;
+            c->rows_seen = c->h_overflow[2]; c->warps_seen = c->h_overflow[3];
+        }
+    }
+    L->deep = c->deep_stack;
+    L->rows_sum = c->d_overflow + 2;
     L->overflow = c->d_overflow;
     L->ncount = c->ncount;
     L->k = c->list_k;
@@ -509,7 +525,7 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, stage_event(c, 3));
     if (advance) {
@@ -548,7 +564,7 @@ static SphContext::StepKey step_key(const SphContext* c, float dt)
 {
     SphContext::StepKey k;
     memset(&k, 0, sizeof(k));                       // padding too: keys are compared with memcmp
-    k.n = c->n; k.dt = dt; k.params = c->params; k.extras = c->extras; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0; k.timing = 0;
+    k.n = c->n; k.dt = dt; k.params = c->params; k.extras = c->extras; k.mode = c->mode; k.list_k = c->list_k; k.list_k_alloc = c->list_k_alloc; k.tile_capn = c->tile_capn; k.two_level = c->table_two_level ? 1 : 0; k.timing = c->deep_stack ? 1 : 0;
     k.nc_tap = c->nc_tap ? 1 : 0; k.nlist = c->nlist; k.tstart = c->tstart; k.scan_tmp = c->scan_tmp; k.tend = c->tend;
     return k;
 }

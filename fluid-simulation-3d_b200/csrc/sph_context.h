@@ -34,7 +34,9 @@ struct SphContext {
     uint32_t list_k_alloc = 0;
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
     uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
-    uint32_t* h_overflow = nullptr;  // pinned mirror, refreshed asynchronously after every density pass
+    uint32_t* h_overflow = nullptr;  // pinned mirror (4 words, see ensure_list), refreshed asynchronously after every density pass
+    uint32_t rows_seen = 0, warps_seen = 0;   // running sums of list rows / warps already accounted for
+    bool deep_stack = false;         // density pass: deep survivor stack (lists are long throughout)
     uint32_t* row_of = nullptr;           // id -> row of the device order, built on demand by sph_get_particle
     uint64_t row_of_stamp = ~0ull;        // c->launches when it was built: any kernel since then may have changed the order
     uint32_t* d_noncanonical = nullptr;   // device counter, see DevParams::noncanonical
@@ -68,7 +70,7 @@ struct SphContext {
     // launch sequence is valid for exactly one configuration (StepKey); anything that changes it falls back to a
     // plain step and re-captures
     struct StepKey {
-        uint32_t n; float dt; SphParams params; SphExtras extras; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level, timing;
+        uint32_t n; float dt; SphParams params; SphExtras extras; int mode; uint32_t list_k, list_k_alloc, tile_capn; int nc_tap, two_level, timing;   /* `timing` carries the deep-stack flag (the recording holds no timers) */
         const void *nlist, *tstart, *scan_tmp, *tend;
     };
     cudaGraph_t graph = nullptr;

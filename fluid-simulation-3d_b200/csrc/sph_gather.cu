@@ -901,6 +901,7 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
         A.list_cnt[i] = kbase;
     }
     report_overflow(A, (valid && kbase > K) ? kbase : 0u);
+    if ((tid & 31) == 0 && A.rows_sum) { atomicAdd(&A.rows_sum[0], kbase); atomicAdd(&A.rows_sum[1], 1u); }   // kbase is warp-uniform
 }
 
 template <int PASS>
@@ -1013,6 +1014,7 @@ static GatherArgs base_args(const float4* pred_s, const uint32_t* tstart, const 
     A.list16 = reinterpret_cast<uint16_t*>(L.idx);
     A.list_w = L.w;
     A.tile_need = L.tile_need;
+    A.rows_sum = L.rows_sum;
     return A;
 }
 
@@ -1050,7 +1052,7 @@ static void launch_density_main(cudaStream_t st, const float4* pred_s, const flo
             uint32_t rows = PKS;
             // (a capacity that auto-grew a little past 64 because ONE pile-up in a corner needed it must not cost every block
             // three quarters of its occupancy: the deep stack is for scenes whose lists are long throughout, like C5)
-            if (A.list_k > 128) {
+            if (L.deep) {
                 if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
                 else cudaGetLastError();
             }

@@ -36,6 +36,7 @@ struct GatherArgs {
     const uint32_t* key_sorted; // GRID keys of the sorted rows
     uint16_t* list16;          // neighbour list as 16-bit indices into the warp's staged runs (same geometry as list_idx)
     uint32_t* tile_need;       // device word: largest single-cell neighbourhood that did not fit the staging buffer
+    uint32_t* rows_sum;        // [2] running sums of list rows / warps (k_density_pk): the host picks the stack depth from their mean
 };
 
 // ---- packed fp32x2 (sm_100a) -------------------------------------------------

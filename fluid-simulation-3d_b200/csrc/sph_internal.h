@@ -118,6 +118,8 @@ struct NbrList {
     uint32_t* cnt;      // [rows] list length (may exceed k: overflowed; may include <= 1e-6 borderline extras)
     uint32_t* ncount;   // [rows] exact neighbour count incl. self (always written by the density pass)
     uint32_t* overflow; // host-mapped: largest list length that did not fit (0 = none)
+    uint32_t* rows_sum; // [2] running sums: list rows written by the density pass, warps that wrote them
+    bool      deep;     // density pass: deep survivor stack
     uint32_t  k;        // entries per row before a row counts as overflowed
     uint32_t  stride;
     // tile generation (sph_tile.cu): sorted GRID keys, staging capacity per warp, "did not fit" report
