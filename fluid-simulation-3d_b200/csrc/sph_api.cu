@@ -41,6 +41,13 @@ static int ceil_log2(uint64_t v)
 }
 
 // SPH_SORT=radix keeps the LSD radix sort + table build for the GRID table (the REFERENCE_HASH table always uses it)
+// SPH_PDL=0: the chain's kernels are launched ordinarily (launch_chained, sph_internal.h)
+bool chained_launches_enabled()
+{
+    static const bool on = [] { const char* e = getenv("SPH_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 bool counting_sort_enabled()
 {
     static const bool on = [] { const char* e = getenv("SPH_SORT"); return !(e && e[0] == 'r'); }();
@@ -525,7 +532,6 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     rc = ensure_list(c, &L);
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, stage_event(c, 3));
     if (advance) {
@@ -542,6 +548,9 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         SPH_CUDA(c, cudaMemcpyAsync(c->A_pos, c->S_pos, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
         SPH_CUDA(c, cudaMemcpyAsync(c->A_vel, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
     }
+    // list overflow / staging need / list-length sums of this step's density pass: one copy, at the END of the step (between
+    // the density and pressure passes it would cut the chain of dependent launches in two)
+    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SPH_CUDA(c, cudaGetLastError());
     c->step_valid = true;
     return SPH_OK;

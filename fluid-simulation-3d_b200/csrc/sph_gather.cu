@@ -232,6 +232,7 @@ template <int MODE, int PASS>
 __global__ void __launch_bounds__(kWalkThreads)
 k_gather_list(const GatherArgs A, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.row1) return;
     const Self s = load_self<PASS>(A, P, i);
@@ -275,6 +276,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kWalkThreads)
 k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.row1) return;
     const uint32_t cnt = A.list_cnt[i];
@@ -738,6 +740,7 @@ constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity ab
 __global__ void __launch_bounds__(kWalkThreads)
 k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
 {
+    chain_prologue();
     extern __shared__ uint2 stk_raw[];             // [stack_rows][kWalkThreads] survivors: (row, bits of the FMA-fused d^2)
     uint2 (*stk)[kWalkThreads] = reinterpret_cast<uint2 (*)[kWalkThreads]>(stk_raw);
     const uint32_t full_mark = (stack_rows - 4u) * (kWalkThreads * 8u);
@@ -908,6 +911,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kWalkThreads)
 k_rim_fix(const GatherArgs A, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t i = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.row1) return;
     const float4 p = A.pred[i];
@@ -935,7 +939,7 @@ template <int PASS>
 static void launch_rim_fix(cudaStream_t st, const GatherArgs& A, const DevParams& P, float dt, uint64_t* launches)
 {
     if (!P.rim_check || P.mode != SPH_TABLE_GRID || P.row1 <= P.row0) return;
-    k_rim_fix<PASS><<<(P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, st>>>(A, P, dt);
+    launch_chained(k_rim_fix<PASS>, dim3((P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads), dim3(kWalkThreads), 0, st, A, P, dt);
     ++*launches;
 }
 
@@ -991,8 +995,8 @@ static void launch_walk_or_list(cudaStream_t st, GatherArgs A, const DevParams& 
         if (P.mode == SPH_TABLE_REFERENCE_HASH) k_gather_walk<SPH_TABLE_REFERENCE_HASH, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
         else k_gather_walk<SPH_TABLE_GRID, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
     } else {
-        if (P.mode == SPH_TABLE_REFERENCE_HASH) k_gather_list<SPH_TABLE_REFERENCE_HASH, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
-        else k_gather_list<SPH_TABLE_GRID, PASS><<<blocks, kWalkThreads, 0, st>>>(A, P, dt);
+        if (P.mode == SPH_TABLE_REFERENCE_HASH) launch_chained(k_gather_list<SPH_TABLE_REFERENCE_HASH, PASS>, dim3(blocks), dim3(kWalkThreads), 0, st, A, P, dt);
+        else launch_chained(k_gather_list<SPH_TABLE_GRID, PASS>, dim3(blocks), dim3(kWalkThreads), 0, st, A, P, dt);
     }
     ++*launches;
 }
@@ -1056,7 +1060,7 @@ static void launch_density_main(cudaStream_t st, const float4* pred_s, const flo
                 if (cudaFuncSetAttribute(k_density_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, PKS_DENSE * kWalkThreads * 8) == cudaSuccess) rows = PKS_DENSE;
                 else cudaGetLastError();
             }
-            k_density_pk<<<blocks, kWalkThreads, rows * kWalkThreads * 8, st>>>(A, P, rows);
+            launch_chained(k_density_pk, dim3(blocks), dim3(kWalkThreads), (size_t)rows * kWalkThreads * 8, st, A, P, rows);
         }
         else if (P.mode == SPH_TABLE_REFERENCE_HASH) k_density_list<SPH_TABLE_REFERENCE_HASH><<<blocks, kWalkThreads, 0, st>>>(A, P);
         else k_density_list<SPH_TABLE_GRID><<<blocks, kWalkThreads, 0, st>>>(A, P);
@@ -1085,7 +1089,7 @@ static void launch_viscosity_main(cudaStream_t st, const float4* pred_s, const f
     if (density_is_pk(L, P) && !getenv("SPH_VISC_NOW")) {        // weights recorded by k_density_pk
         if (P.row1 <= P.row0) return;
         A.list_w = L.w;
-        k_viscosity_w<SPH_TABLE_GRID><<<(P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads, kWalkThreads, 0, st>>>(A, P, dt);
+        launch_chained(k_viscosity_w<SPH_TABLE_GRID>, dim3((P.row1 - P.row0 + kWalkThreads - 1) / kWalkThreads), dim3(kWalkThreads), 0, st, A, P, dt);
         ++*launches;
     } else if (gather_variant() == 2 && P.mode == SPH_TABLE_GRID) launch<PASS_VISCOSITY>(st, A, P, dt, launches);
     else launch_walk_or_list<PASS_VISCOSITY>(st, A, P, dt, A.list_idx != nullptr, launches);

@@ -127,6 +127,22 @@ struct NbrList {
     uint32_t  capn;
     uint32_t* tile_need;
 };
+// Launch of a kernel of the step's chain: programmatic stream serialisation (PDL), so the kernel may be scheduled while
+// its predecessor's last wave drains; the kernel itself orders its memory accesses with chain_prologue() (sph_device.cuh).
+// Stream capture records the edge as a programmatic dependency.  SPH_PDL=0 launches them ordinarily.
+bool chained_launches_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = chained_launches_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct GatherArgs;
 bool tile_enabled();
 uint32_t tile_default_capn();

@@ -37,6 +37,7 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
               uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt,
               uint32_t* __restrict__ count, uint32_t* __restrict__ rank)
 {
+    chain_prologue();
     // counting sort (GRID table): the row takes a ticket in its cell's counter; the tickets are made
     // canonical (ascending source row) later, in k_reorder_binned
     // ... and is counted in its segment (one atomic per distinct segment of the warp: rows arrive nearly sorted)
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256)
 k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ table,
         uint32_t* __restrict__ slot_row, const uint32_t n, const DevParams P)
 {
+    chain_prologue();
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) slot_row[tbl(table, P, key[s]) + rank[s]] = s;
 }
@@ -113,6 +115,7 @@ k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32
               const uint32_t nseg_pad)
 {   // zero the cell counters of the segments the LAST step touched, and every segment counter.  One THREAD looks at
     // one segment's flag (coalesced); the warp then zeroes its dirty segments together, 64 cells at a time.
+    chain_prologue();
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool in = sg < nseg;
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(256)
 k_inseg_scan(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg)
 {   // occupied segments: cell counters -> exclusive prefix inside the segment (the base comes from the segment scan).
     // One thread decides for one segment; the warp then scans its occupied segments together.
+    chain_prologue();
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool occ = sg < nseg && table[seg_off + sg + 1] != table[seg_off + sg];   // empty: its cells are, and stay, zero
@@ -308,6 +312,7 @@ k_reorder(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ key, c
           const float4* __restrict__ ghost_pred, float4* __restrict__ pos_s, float4* __restrict__ vel_s,
           float4* __restrict__ pred_s, float4* __restrict__ pred_pk, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s < P.n;                    // no early return: the pair-interleaved copy is written with shuffles
     float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -379,6 +384,7 @@ __global__ void __launch_bounds__(256)
 k_integrate(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
             float4* __restrict__ vel_out, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.row1) return;
     float4 p = pos_s[s];
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(256)
 k_integrate_extras(const float4* __restrict__ pos_s, const float4* __restrict__ vel_v, float4* __restrict__ pos_out,
                    float4* __restrict__ vel_out, const DevParams P, const float dt)
 {
+    chain_prologue();
     const uint32_t s = P.row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.row1) return;
     float4 p = pos_s[s];
@@ -565,7 +572,7 @@ void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, u
                         uint64_t* launches)
 {
     if (rows == 0) return;
-    k_predict_key<<<blocks_for(rows, 256), 256, 0, st>>>(pos, vel, key, cls, rows, may_migrate, P, dt, count, rank);
+    launch_chained(k_predict_key, dim3(blocks_for(rows, 256)), dim3(256), 0, st, pos, vel, key, cls, rows, may_migrate, P, dt, count, rank);
     ++*launches;
 }
 
@@ -597,7 +604,7 @@ void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, co
                   uint32_t n, const DevParams& P, uint64_t* launches)
 {
     if (n == 0) return;
-    k_place<<<blocks_for(n, 256), 256, 0, st>>>(key, rank, table, slot_row, n, P);
+    launch_chained(k_place, dim3(blocks_for(n, 256)), dim3(256), 0, st, key, rank, table, slot_row, n, P);
     ++*launches;
 }
 
@@ -613,14 +620,14 @@ TableLayout table_layout(const uint32_t ncell)
 
 void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
 {
-    k_table_clear<<<blocks_for((uint32_t)T.nseg_pad, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg,
-                                                                        (uint32_t)T.nseg_pad);
+    launch_chained(k_table_clear, dim3(blocks_for((uint32_t)T.nseg_pad, 256)), dim3(256), 0, st, table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg,
+                   (uint32_t)T.nseg_pad);
     ++*launches;
 }
 
 void launch_inseg_scan(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
 {
-    k_inseg_scan<<<blocks_for((uint32_t)T.nseg, 256), 256, 0, st>>>(table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg);
+    launch_chained(k_inseg_scan, dim3(blocks_for((uint32_t)T.nseg, 256)), dim3(256), 0, st, table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg);
     ++*launches;
 }
 
@@ -636,7 +643,7 @@ void launch_reorder(cudaStream_t st, const uint32_t* perm, const uint32_t* key, 
                     float4* pred_s, float4* pred_pk, const DevParams& P, float dt, uint64_t* launches)
 {
     if (P.n == 0) return;
-    k_reorder<<<blocks_for(P.n, 256), 256, 0, st>>>(perm, key, table, key_sorted, pos, vel, ghost_pred, pos_s, vel_s, pred_s, pred_pk, P, dt);
+    launch_chained(k_reorder, dim3(blocks_for(P.n, 256)), dim3(256), 0, st, perm, key, table, key_sorted, pos, vel, ghost_pred, pos_s, vel_s, pred_s, pred_pk, P, dt);
     ++*launches;
 }
 
@@ -644,8 +651,8 @@ void launch_integrate(cudaStream_t st, const float4* pos_s, const float4* vel_v,
                       const DevParams& P, float dt, uint64_t* launches)
 {
     if (P.row1 <= P.row0) return;
-    if (P.extras) k_integrate_extras<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
-    else k_integrate<<<blocks_for(P.row1 - P.row0, 256), 256, 0, st>>>(pos_s, vel_v, pos_out, vel_out, P, dt);
+    if (P.extras) launch_chained(k_integrate_extras, dim3(blocks_for(P.row1 - P.row0, 256)), dim3(256), 0, st, pos_s, vel_v, pos_out, vel_out, P, dt);
+    else launch_chained(k_integrate, dim3(blocks_for(P.row1 - P.row0, 256)), dim3(256), 0, st, pos_s, vel_v, pos_out, vel_out, P, dt);
     ++*launches;
 }
 

@@ -11,7 +11,7 @@
 // (<= 256 x 1184 entries) at any N.  HBM traffic per pass: keys read twice, pairs written once
 // = 20 B/pair (algorithmic 16 B/pair).
 #include <cstdlib>
-#include "sph_internal.h"
+#include "sph_device.cuh"
 
 namespace sphb200 {
 
@@ -239,6 +239,7 @@ constexpr int kScanBlock = kScanThreads * kScanPer;          // 4096
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_reduce(const uint4* __restrict__ data, uint32_t* __restrict__ blocksums)
 {
+    chain_prologue();
     __shared__ uint32_t wsum[kScanThreads / 32];
     const uint4* p = data + (size_t)blockIdx.x * (kScanBlock / 4);
     uint32_t s = 0;
@@ -258,6 +259,7 @@ k_scan_reduce(const uint4* __restrict__ data, uint32_t* __restrict__ blocksums)
 __global__ void __launch_bounds__(1024)
 k_scan_top(uint32_t* __restrict__ blocksums, const uint32_t nb)
 {
+    chain_prologue();
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,6 +290,7 @@ template <bool FOLD>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_apply(uint4* __restrict__ data, const uint32_t* __restrict__ blocksums)
 {
+    chain_prologue();
     __shared__ uint32_t wsum[kScanThreads / 32];
     __shared__ uint32_t fsum[kScanThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -335,14 +338,14 @@ void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, 
     const uint32_t nb = (uint32_t)(padded_entries / kScanBlock);
     if (nb == 0) return;
     static const bool fold_ok = [] { const char* e = getenv("SPH_SCAN_FOLD"); return !(e && e[0] == '0'); }();
-    k_scan_reduce<<<nb, kScanThreads, 0, st>>>((const uint4*)data, blocksums);
+    launch_chained(k_scan_reduce, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)data, blocksums);
     if (fold_ok && nb <= kFoldBlocks) {
-        k_scan_apply<true><<<nb, kScanThreads, 0, st>>>((uint4*)data, blocksums);
+        launch_chained(k_scan_apply<true>, dim3(nb), dim3(kScanThreads), 0, st, (uint4*)data, blocksums);
         if (launches) *launches += 2;
         return;
     }
-    k_scan_top<<<1, 1024, 0, st>>>(blocksums, nb);
-    k_scan_apply<false><<<nb, kScanThreads, 0, st>>>((uint4*)data, blocksums);
+    launch_chained(k_scan_top, dim3(1), dim3(1024), 0, st, blocksums, nb);
+    launch_chained(k_scan_apply<false>, dim3(nb), dim3(kScanThreads), 0, st, (uint4*)data, blocksums);
     if (launches) *launches += 3;
 }
 }  // namespace sphb200
