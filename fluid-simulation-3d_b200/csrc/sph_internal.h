@@ -72,7 +72,13 @@ constexpr uint32_t kSegCells = 1u << kSegShift;
 // next to the plain `pred` rows.
 
 // slab mode: classification of an owned row by the z layer of its predicted position
-enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8 };
+// (CLS_KEEP: a migrant that lands in the layer right across the plane -- it stays visible to this rank as a ghost)
+enum : uint8_t { CLS_STAY = 0, CLS_MIG_LO = 1, CLS_MIG_HI = 2, CLS_GHOST_LO = 4, CLS_GHOST_HI = 8, CLS_KEEP = 16 };
+// the six lists a slab rank packs for its neighbours; a pack block covers kPackSpan consecutive rows
+enum { L_MIG_LO = 0, L_GHOST_LO = 1, L_KEEP_LO = 2, L_MIG_HI = 3, L_GHOST_HI = 4, L_KEEP_HI = 5, NLISTS = 6 };
+constexpr int kPackThreads = 256;
+constexpr int kPackIters = 16;
+constexpr uint32_t kPackSpan = kPackIters * kPackThreads;
 
 struct SortTemp {
     uint32_t* counts;       // [256][nblocks] digit counts -> exclusive offsets
@@ -90,7 +96,7 @@ int radix_sort_pairs(cudaStream_t st, uint32_t* keys_a, uint32_t* keys_b, uint32
 // count / rank non-null: counting sort of the GRID table (the row takes a ticket in its cell's counter)
 void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
                         uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint32_t* count, uint32_t* rank,
-                        uint64_t* launches);
+                        uint64_t* launches, uint32_t* pack_counts = nullptr, uint32_t pack_blocks = 0);
 void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, uint32_t rows, const DevParams& P,
                       uint32_t* count, uint32_t* rank, uint64_t* launches);
 void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,

@@ -30,12 +30,16 @@ __device__ __forceinline__ void count_segment(uint32_t* __restrict__ count, cons
     const uint32_t sg = k >> kSegShift;
     const uint32_t peers = __match_any_sync(__activemask(), sg);
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[P.seg_off + sg], (uint32_t)__popc(peers));
+    // (Keeping the sums of the scan's 4096-segment tiles here as well, to save the scan its reduce launch, was measured:
+    // one more atomic per warp on a handful of addresses serialises -- k_predict_key 19 -> 46 us at 1 M rows, 0.11 -> 0.55 ms
+    // at 8 M.  The reduce launch costs 3 us.)
 }
 
 __global__ void __launch_bounds__(256)
 k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, uint32_t* __restrict__ key,
               uint8_t* __restrict__ cls, const uint32_t rows, const bool may_migrate, const DevParams P, const float dt,
-              uint32_t* __restrict__ count, uint32_t* __restrict__ rank)
+              uint32_t* __restrict__ count, uint32_t* __restrict__ rank, uint32_t* __restrict__ pack_counts,
+              const uint32_t pack_blocks)
 {
     chain_prologue();
     // counting sort (GRID table): the row takes a ticket in its cell's counter; the tickets are made
@@ -65,7 +69,22 @@ k_predict_key(const float4* __restrict__ pos, const float4* __restrict__ vel, ui
                 if (gz == P.own_lo && P.has_lo) k |= CLS_GHOST_LO;
                 if (gz == P.own_hi - 1 && P.has_hi) k |= CLS_GHOST_HI;
             }
+            if ((k & (CLS_MIG_LO | CLS_MIG_HI)) && (gz == P.own_lo - 1 || gz == P.own_hi)) k |= CLS_KEEP;
             cls[s] = k;
+            // rows of this warp in each of the six pack lists, added to the counters of its pack block (sph_multi.cu:
+            // the order-preserving pack needs them per block; only warps at a slab boundary have any)
+            const uint32_t act = __activemask();
+            if (pack_counts && __any_sync(act, k != 0)) {
+                const bool keep = k & CLS_KEEP;
+                const uint32_t b[NLISTS] = {__ballot_sync(act, k & CLS_MIG_LO), __ballot_sync(act, k & CLS_GHOST_LO),
+                                            __ballot_sync(act, (k & CLS_MIG_LO) && keep), __ballot_sync(act, k & CLS_MIG_HI),
+                                            __ballot_sync(act, k & CLS_GHOST_HI), __ballot_sync(act, (k & CLS_MIG_HI) && keep)};
+                if ((int)(threadIdx.x & 31) == __ffs(act) - 1) {
+                    #pragma unroll
+                    for (int l = 0; l < NLISTS; l++)
+                        if (b[l]) atomicAdd(&pack_counts[(size_t)l * pack_blocks + s / kPackSpan], (uint32_t)__popc(b[l]));
+                }
+            }
         }
         if (k & (CLS_MIG_LO | CLS_MIG_HI)) { SPH_EMIT_KEY(P.ncell); return; }  // leaves this rank: sorts past the table
         int3 g = grid_cell(pr.x, pr.y, pr.z, P);
@@ -569,10 +588,11 @@ inline uint32_t blocks_for(uint32_t n, int threads) { return (n + threads - 1) /
 // ---- launchers ---------------------------------------------------------------
 void launch_predict_key(cudaStream_t st, const float4* pos, const float4* vel, uint32_t* key, uint8_t* cls,
                         uint32_t rows, bool may_migrate, const DevParams& P, float dt, uint32_t* count, uint32_t* rank,
-                        uint64_t* launches)
+                        uint64_t* launches, uint32_t* pack_counts, uint32_t pack_blocks)
 {
     if (rows == 0) return;
-    launch_chained(k_predict_key, dim3(blocks_for(rows, 256)), dim3(256), 0, st, pos, vel, key, cls, rows, may_migrate, P, dt, count, rank);
+    launch_chained(k_predict_key, dim3(blocks_for(rows, 256)), dim3(256), 0, st, pos, vel, key, cls, rows, may_migrate, P, dt, count, rank,
+                   pack_counts, pack_blocks);
     ++*launches;
 }
 

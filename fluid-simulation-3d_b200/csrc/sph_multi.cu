@@ -91,8 +91,7 @@ struct SlabState {
     float4* ghost_send[2] = {nullptr, nullptr};   // [xcap] predicted positions, lo / hi
     float4* keep[2] = {nullptr, nullptr};         // [xcap] migrants that stay visible as ghosts, lo / hi
     float4* ghost_pred = nullptr;                 // [gcap] recv_lo | keep_lo | recv_hi | keep_hi
-    uint32_t* block_counts = nullptr;             // [6][nblocks]
-    uint8_t* block_any = nullptr;                 // [nblocks] block has at least one row in some list
+    uint32_t* block_counts = nullptr;             // [6][nblocks_cap] counts (k_predict_key), then [6][nblocks_cap] offsets (k_slab_scan)
     uint32_t* dev_small = nullptr;                // 64 u32: totals[6], picks[8] at 16, peer lengths[2] at 24, count messages out (lo, hi: 8 words each) at 32, in at 48
     uint32_t* host_small = nullptr;               // pinned mirror
     uint32_t nblocks_cap = 0;
@@ -128,9 +127,8 @@ struct SlabState {
 
 namespace {
 
-// the three lists of a side are contiguous, so a side's counts travel as one message
-enum { L_MIG_LO = 0, L_GHOST_LO = 1, L_KEEP_LO = 2, L_MIG_HI = 3, L_GHOST_HI = 4, L_KEEP_HI = 5, NLISTS = 6 };
-constexpr int kPackThreads = 256;
+// (the six lists -- L_MIG_LO ... -- and the pack block geometry live in sph_internal.h: k_predict_key counts into them;
+// the three lists of a side are contiguous, so a side's counts travel as one message)
 
 #define SPH_NCCL(c, call)                                                                   \
     do {                                                                                    \
@@ -139,79 +137,42 @@ constexpr int kPackThreads = 256;
             return fail((c), SPH_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__)); \
     } while (0)
 
-__device__ __forceinline__ bool in_list(uint8_t k, int list, bool keep)
+__device__ __forceinline__ bool in_list(uint8_t k, int list)
 {
     switch (list) {
     case L_MIG_LO: return k & CLS_MIG_LO;
     case L_MIG_HI: return k & CLS_MIG_HI;
     case L_GHOST_LO: return k & CLS_GHOST_LO;
     case L_GHOST_HI: return k & CLS_GHOST_HI;
-    case L_KEEP_LO: return (k & CLS_MIG_LO) && keep;
-    default: return (k & CLS_MIG_HI) && keep;
+    case L_KEEP_LO: return (k & CLS_MIG_LO) && (k & CLS_KEEP);
+    default: return (k & CLS_MIG_HI) && (k & CLS_KEEP);
     }
 }
 
-// a migrant stays visible as a ghost when it lands in the layer right across the plane
-__device__ __forceinline__ bool lands_adjacent(const float4 p, const float4 v0, const DevParams& P, float dt, float4* pred_out)
+// the predicted position a ghost row carries: the owner's own expression (predict, sph_device.cuh)
+__device__ __forceinline__ float4 ghost_pred_of(const float4 p, const float4 v0, const DevParams& P, float dt)
 {
     float4 v = v0;
-    const float gy = P.gravity ? -P.g : 0.0f;
-    v.x = __fadd_rn(v.x, __fmul_rn(0.0f, dt));
-    v.y = __fadd_rn(v.y, __fmul_rn(gy, dt));
-    v.z = __fadd_rn(v.z, __fmul_rn(0.0f, dt));
-    const float look = 1.0f / 120.0f;
-    const float px = __fadd_rn(p.x, __fmul_rn(v.x, look));
-    const float py = __fadd_rn(p.y, __fmul_rn(v.y, look));
-    const float pz = __fadd_rn(p.z, __fmul_rn(v.z, look));
-    *pred_out = make_float4(px, py, pz, 0.0f);
-    int gz = __float2int_rz(floorf(__fdiv_rn(pz, P.r))) - P.gmin[2];
-    gz = gz < 0 ? 0 : (gz > P.gz_global - 1 ? P.gz_global - 1 : gz);
-    return gz == P.own_lo - 1 || gz == P.own_hi;
+    float3 pr;
+    predict(p, v, pr, P, dt);
+    return make_float4(pr.x, pr.y, pr.z, 0.0f);
 }
 
-constexpr int kPackIters = 16;                       // a block packs kPackIters * kPackThreads consecutive rows
-constexpr uint32_t kPackSpan = kPackIters * kPackThreads;
-
-// per block: how many of its rows go into each of the six lists (+ a flag "anything at all")
+// The per-block list counts come from k_predict_key (it classifies the rows anyway).  One block per list: exclusive scan
+// of its row of block counts into `offsets`, total to totals[list]; the block that finishes last writes the two count
+// messages of the step.
+// The count message of a side: (migrants, ghosts, kept migrants) towards that neighbour, then what the neighbour needs to
+// reach the same verdict about the link as this rank: status (0 = fine), rows an exchange buffer holds, free rows and free
+// ghost rows this rank can take FROM that side (half of what is left once its own kept migrants are in).
 __global__ void __launch_bounds__(kPackThreads)
-k_slab_count(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
-             uint32_t* __restrict__ block_counts, uint8_t* __restrict__ block_any, const uint32_t rows,
-             const uint32_t nblocks, const DevParams P, const float dt)
-{
-    __shared__ uint32_t cnt[NLISTS];
-    if (threadIdx.x < NLISTS) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (int it = 0; it < kPackIters; it++) {
-        const uint32_t s = blockIdx.x * kPackSpan + it * kPackThreads + threadIdx.x;
-        uint8_t k = 0;
-        bool keep = false;
-        if (s < rows) {
-            k = cls[s];
-            if (k & (CLS_MIG_LO | CLS_MIG_HI)) { float4 pr; keep = lands_adjacent(pos[s], vel[s], P, dt, &pr); }
-        }
-        if (!__any_sync(0xffffffffu, k != 0)) continue;
-        #pragma unroll
-        for (int l = 0; l < NLISTS; l++) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, in_list(k, l, keep));
-            if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&cnt[l], __popc(bal));
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < NLISTS) block_counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
-    if (threadIdx.x == 0) {
-        uint32_t any = 0;
-        for (int l = 0; l < NLISTS; l++) any |= cnt[l];
-        block_any[blockIdx.x] = any ? 1 : 0;
-    }
-}
-
-// one block per list: exclusive scan of its row of block counts, total to totals[list]
-__global__ void __launch_bounds__(kPackThreads)
-k_slab_scan(uint32_t* __restrict__ block_counts, uint32_t* __restrict__ totals, const uint32_t nblocks)
+k_slab_scan(const uint32_t* __restrict__ block_counts, uint32_t* __restrict__ offsets, uint32_t* __restrict__ totals,
+            const uint32_t nblocks, uint32_t* __restrict__ done, uint32_t* __restrict__ msg, const uint32_t status,
+            const uint32_t xcap, const uint32_t cap, const uint32_t gcap, const uint32_t n_old)
 {
     __shared__ uint32_t wsum[kPackThreads / 32];
     __shared__ uint32_t carry_s;
-    uint32_t* row = block_counts + (size_t)blockIdx.x * nblocks;
+    const uint32_t* row = block_counts + (size_t)blockIdx.x * nblocks;
+    uint32_t* out = offsets + (size_t)blockIdx.x * nblocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -226,87 +187,103 @@ k_slab_scan(uint32_t* __restrict__ block_counts, uint32_t* __restrict__ totals, 
         uint32_t wbase = 0;
         for (int w = 0; w < warp; w++) wbase += wsum[w];
         const uint32_t carry = carry_s;
-        if (i < nblocks) row[i] = carry + wbase + inc - v;
+        if (i < nblocks) out[i] = carry + wbase + inc - v;
         __syncthreads();
         if (threadIdx.x == kPackThreads - 1) carry_s = carry + wbase + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+    if (threadIdx.x != 0) return;
+    totals[blockIdx.x] = carry_s;
+    __threadfence();
+    if (atomicAdd(done, 1u) != NLISTS - 1) return;
+    __threadfence();
+    volatile const uint32_t* T = totals;
+    const uint32_t keep = T[L_KEEP_LO] + T[L_KEEP_HI];
+    const uint32_t used = n_old + keep;
+    for (int side = 0; side < 2; side++) {                   // 0: to lo, 1: to hi
+        uint32_t* m = msg + 8 * side;
+        m[0] = T[3 * side]; m[1] = T[3 * side + 1]; m[2] = T[3 * side + 2];
+        m[3] = status; m[4] = xcap;
+        m[5] = cap > used ? (cap - used) / 2u : 0u;
+        m[6] = gcap > keep ? (gcap - keep) / 2u : 0u;
+        m[7] = 0u;
+    }
 }
 
-// order-preserving pack: list l, entry rank = (#members in earlier blocks) + (#members before me in this block)
+// order-preserving pack: list l, entry rank = (#members in earlier blocks) + (#members before me in this block).
+// A block covers kPackSpan rows as kPackIters slices of kPackThreads; one pass ballots every (slice, warp) into shared
+// memory, one warp per list turns them into running offsets, a second pass writes -- three barriers per block.
 __global__ void __launch_bounds__(kPackThreads)
 k_slab_pack(const uint8_t* __restrict__ cls, const float4* __restrict__ pos, const float4* __restrict__ vel,
-            const uint32_t* __restrict__ block_offsets, const uint8_t* __restrict__ block_any,
+            const uint32_t* __restrict__ block_counts, const uint32_t* __restrict__ block_offsets,
             float4* __restrict__ mig_lo, float4* __restrict__ mig_hi,
             float4* __restrict__ ghost_lo, float4* __restrict__ ghost_hi, float4* __restrict__ keep_lo,
             float4* __restrict__ keep_hi, const uint32_t rows, const uint32_t nblocks, const uint32_t xcap,
             const DevParams P, const float dt)
 {
-    if (!block_any[blockIdx.x]) return;              // interior blocks: nothing leaves, nothing is a ghost
-    __shared__ uint32_t wcnt[NLISTS][kPackThreads / 32];
-    __shared__ uint32_t run[NLISTS];
+    constexpr int kWarps = kPackThreads / 32, kCells = kPackIters * kWarps;     // (slice, warp) pairs in row order
+    __shared__ uint32_t off[NLISTS][kCells];
+    __shared__ uint32_t any_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < NLISTS) run[threadIdx.x] = block_offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    if (threadIdx.x == 0) {
+        uint32_t a = 0;
+        for (int l = 0; l < NLISTS; l++) a |= block_counts[(size_t)l * nblocks + blockIdx.x];
+        any_s = a;
+    }
     __syncthreads();
+    if (!any_s) return;                              // interior blocks: nothing leaves, nothing is a ghost
+    uint8_t k[kPackIters];
+    #pragma unroll
     for (int it = 0; it < kPackIters; it++) {
         const uint32_t s = blockIdx.x * kPackSpan + it * kPackThreads + threadIdx.x;
-        uint8_t k = 0;
-        bool keep = false;
+        k[it] = s < rows ? cls[s] : (uint8_t)0;
+    }
+    #pragma unroll
+    for (int it = 0; it < kPackIters; it++) {
+        #pragma unroll
+        for (int l = 0; l < NLISTS; l++) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, in_list(k[it], l));
+            if (lane == 0) off[l][it * kWarps + warp] = __popc(bal);
+        }
+    }
+    __syncthreads();
+    if (warp < NLISTS) {                             // warp l: counts of list l -> offsets, kCells / 32 consecutive cells per lane
+        constexpr int kPer = kCells / 32;
+        uint32_t v[kPer], sum = 0;
+        #pragma unroll
+        for (int j = 0; j < kPer; j++) { v[j] = off[warp][lane * kPer + j]; sum += v[j]; }
+        uint32_t inc = sum;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        uint32_t run = block_offsets[(size_t)warp * nblocks + blockIdx.x] + inc - sum;
+        #pragma unroll
+        for (int j = 0; j < kPer; j++) { off[warp][lane * kPer + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    #pragma unroll 1
+    for (int it = 0; it < kPackIters; it++) {
+        const uint8_t kk = k[it];
+        if (!__any_sync(0xffffffffu, kk != 0)) continue;
+        const uint32_t s = blockIdx.x * kPackSpan + it * kPackThreads + threadIdx.x;
         float4 p = make_float4(0, 0, 0, 0), v = p, pr = p;
-        if (s < rows) {
-            k = cls[s];
-            if (k) { p = pos[s]; v = vel[s]; keep = lands_adjacent(p, v, P, dt, &pr); }
-        }
-        uint32_t ball[NLISTS];
+        if (kk) { p = pos[s]; v = vel[s]; pr = ghost_pred_of(p, v, P, dt); }
         #pragma unroll
         for (int l = 0; l < NLISTS; l++) {
-            ball[l] = __ballot_sync(0xffffffffu, in_list(k, l, keep));
-            if (lane == 0) wcnt[l][warp] = __popc(ball[l]);
-        }
-        __syncthreads();
-        #pragma unroll
-        for (int l = 0; l < NLISTS; l++) {
-            if (!in_list(k, l, keep)) continue;
-            uint32_t off = run[l];
-            for (int w = 0; w < warp; w++) off += wcnt[l][w];
-            off += __popc(ball[l] & ((1u << lane) - 1u));
-            if (off >= xcap) continue;                       // overflow is detected on the host from the totals
+            const bool in = in_list(kk, l);
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (!in) continue;
+            const uint32_t o = off[l][it * kWarps + warp] + __popc(bal & ((1u << lane) - 1u));
+            if (o >= xcap) continue;                         // overflow is detected on the host from the totals
             switch (l) {
-            case L_MIG_LO: mig_lo[off] = p; mig_lo[xcap + off] = v; break;
-            case L_MIG_HI: mig_hi[off] = p; mig_hi[xcap + off] = v; break;
-            case L_GHOST_LO: ghost_lo[off] = pr; break;
-            case L_GHOST_HI: ghost_hi[off] = pr; break;
-            case L_KEEP_LO: keep_lo[off] = pr; break;
-            default: keep_hi[off] = pr; break;
+            case L_MIG_LO: mig_lo[o] = p; mig_lo[xcap + o] = v; break;
+            case L_MIG_HI: mig_hi[o] = p; mig_hi[xcap + o] = v; break;
+            case L_GHOST_LO: ghost_lo[o] = pr; break;
+            case L_GHOST_HI: ghost_hi[o] = pr; break;
+            case L_KEEP_LO: keep_lo[o] = pr; break;
+            default: keep_hi[o] = pr; break;
             }
         }
-        __syncthreads();
-        if (threadIdx.x < NLISTS) {
-            uint32_t t = 0;
-            for (int w = 0; w < kPackThreads / 32; w++) t += wcnt[threadIdx.x][w];
-            run[threadIdx.x] += t;
-        }
-        __syncthreads();
     }
-}
-
-// The count message of a side: (migrants, ghosts, kept migrants) towards that neighbour, then what the neighbour needs to
-// reach the same verdict about the link as this rank: status (0 = fine), rows an exchange buffer holds, free rows and free
-// ghost rows this rank can take FROM that side (half of what is left once its own kept migrants are in).
-__global__ void k_slab_msg(const uint32_t* __restrict__ totals, uint32_t* __restrict__ msg, const uint32_t status, const uint32_t xcap,
-                           const uint32_t cap, const uint32_t gcap, const uint32_t n_old)
-{
-    if (threadIdx.x >= 2) return;
-    const int side = threadIdx.x;                            // 0: to lo, 1: to hi
-    const uint32_t keep = totals[L_KEEP_LO] + totals[L_KEEP_HI];
-    const uint32_t used = n_old + keep;
-    uint32_t* m = msg + 8 * side;
-    m[0] = totals[3 * side]; m[1] = totals[3 * side + 1]; m[2] = totals[3 * side + 2];
-    m[3] = status; m[4] = xcap;
-    m[5] = cap > used ? (cap - used) / 2u : 0u;
-    m[6] = gcap > keep ? (gcap - keep) / 2u : 0u;
-    m[7] = 0u;
 }
 
 __global__ void k_slab_pick(const uint32_t* __restrict__ table, uint32_t* __restrict__ out, uint32_t i0, uint32_t i1,
@@ -369,7 +346,7 @@ void multi_teardown(SphContext* c)
         for (auto& e : s->pe) if (e) cudaEventDestroy(e);
     }
     void* ptrs[] = {s->cls, s->mig_send[0], s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0], s->keep[1],
-                    s->ghost_pred, s->block_counts, s->block_any, s->dev_small};
+                    s->ghost_pred, s->block_counts, s->dev_small};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->host_small) cudaFreeHost(s->host_small);
     if (s->hist_dev) cudaFree(s->hist_dev);
@@ -431,31 +408,31 @@ int multi_step(SphContext* c, float dt)
         if (!c->table_two_level) { SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, TL.total * sizeof(uint32_t), st)); c->table_two_level = true; }
         else launch_table_clear(st, c->tstart, TL, &c->launches);
     }
+    const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
+    SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
+    SPH_CUDA(c, cudaMemsetAsync(s->block_counts, 0, (size_t)NLISTS * nblocks * sizeof(uint32_t), st));
+    // ... which also counts, per pack block, the rows of each of the six lists (k_slab_scan / k_slab_pack below)
     launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, binned ? c->tstart : nullptr, c->perm_b,
-                       &c->launches);
+                       &c->launches, s->block_counts, nblocks);
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[1], st));
 
     #define SLAB_MARK(i) do { if (s->prof) cudaEventRecord(s->pe[i], st); } while (0)
     auto host_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     SLAB_MARK(0);
     // (2) order-preserving pack of the six lists
-    const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
-    uint32_t* totals = s->dev_small;            // [6]
+    uint32_t* totals = s->dev_small;            // [6] (word 7: k_slab_scan's finished-block counter)
     uint32_t* picks = s->dev_small + 16;        // [8]
     uint32_t* peer = s->dev_small + 24;         // [2] boundary lengths of the neighbours' layers
-    SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
     uint32_t* msg_out = s->dev_small + 32;
     uint32_t* msg_in = s->dev_small + 48;
-    if (n_old) {
-        k_slab_count<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, n_old, nblocks, P, dt);
-        k_slab_scan<<<NLISTS, kPackThreads, 0, st>>>(s->block_counts, totals, nblocks);
-        c->launches += 2;
-    }
-    // (3a) count messages to / from the neighbours (k_slab_msg).  They travel on the halo stream, with the copy of the
+    // (the per-block counts of the six lists were left by k_predict_key)
+    uint32_t* offsets = s->block_counts + (size_t)NLISTS * s->nblocks_cap;
+    k_slab_scan<<<NLISTS, kPackThreads, 0, st>>>(s->block_counts, offsets, totals, n_old ? nblocks : 0u, s->dev_small + 7, msg_out,
+                                                 s->failed ? 1u : 0u, s->xcap, c->cap, s->gcap, n_old);
+    ++c->launches;
+    // (3a) count messages to / from the neighbours (written by the last block of k_slab_scan).  They travel on the halo stream, with the copy of the
     // counts to the host behind them, WHILE the solver's stream packs the six lists: the host's round trip (the one
     // synchronisation of the step) is hidden behind the pack kernel instead of leaving the GPU idle.
-    k_slab_msg<<<1, 32, 0, st>>>(totals, msg_out, s->failed ? 1u : 0u, s->xcap, c->cap, s->gcap, n_old);
-    ++c->launches;
     cudaStream_t cs = s->halo_stream;
     SPH_CUDA(c, cudaEventRecord(s->ev_counts, st));
     SPH_CUDA(c, cudaStreamWaitEvent(cs, s->ev_counts, 0));
@@ -469,7 +446,7 @@ int multi_step(SphContext* c, float dt)
     SPH_CUDA(c, cudaEventRecord(s->ev_msg, cs));
     // (2) order-preserving pack of the six lists
     if (n_old) {
-        k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, s->block_any, s->mig_send[0],
+        k_slab_pack<<<nblocks, kPackThreads, 0, st>>>(s->cls, c->A_pos, c->A_vel, s->block_counts, offsets, s->mig_send[0],
                                                       s->mig_send[1], s->ghost_send[0], s->ghost_send[1], s->keep[0],
                                                       s->keep[1], n_old, nblocks, s->xcap, P, dt);
         ++c->launches;
@@ -745,7 +722,7 @@ int multi_step(SphContext* c, float dt)
 extern "C" {
 
 // Pure host function (no device, no communicator): may the link between two slab neighbours carry its payloads this
-// step?  `mine` is the 8-word count message this rank sent over the link, `theirs` the one it received (k_slab_msg:
+// step?  `mine` is the 8-word count message this rank sent over the link, `theirs` the one it received (k_slab_scan:
 // migrants, ghosts, kept migrants, status, exchange-buffer rows, free rows, free ghost rows, 0).  The expression is
 // symmetric -- sph_slab_link_ok(a, b) == sph_slab_link_ok(b, a) -- so both ends decide alike without another exchange.
 int sph_slab_link_ok(const uint32_t* mine, const uint32_t* theirs)
@@ -795,8 +772,7 @@ int sph_comm_init(SphContext* c, int rank, int nranks, const void* id, size_t id
         SPH_CUDA(c, cudaMalloc(&s->keep[d], (size_t)s->xcap * 16));
     }
     SPH_CUDA(c, cudaMalloc(&s->ghost_pred, (size_t)s->gcap * 16));
-    SPH_CUDA(c, cudaMalloc(&s->block_counts, (size_t)NLISTS * s->nblocks_cap * 4));
-    SPH_CUDA(c, cudaMalloc(&s->block_any, s->nblocks_cap));
+    SPH_CUDA(c, cudaMalloc(&s->block_counts, (size_t)2 * NLISTS * s->nblocks_cap * 4));   // counts, then offsets
     SPH_CUDA(c, cudaMalloc(&s->dev_small, 64 * sizeof(uint32_t)));
     SPH_CUDA(c, cudaMallocHost(&s->host_small, 64 * sizeof(uint32_t)));
     {   // highest priority: the halo's NCCL kernel must get SM slots ahead of the queued blocks of the interior pass
