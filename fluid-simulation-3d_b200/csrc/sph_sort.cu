@@ -328,6 +328,49 @@ k_scan_apply(uint4* __restrict__ data, const uint32_t* __restrict__ blocksums)
     }
 }
 constexpr uint32_t kFoldBlocks = 2048;
+
+// Small arrays (the segment counters of the reference's own scene sizes: a few thousand entries) in ONE launch of one
+// block: thread t scans its kSmallPer consecutive entries, the block scans the thread totals.  At 10 k particles every
+// launch of the step is latency, not work; this saves one.
+constexpr int kSmallThreads = 1024;
+constexpr uint32_t kSmallBlocks = 8;                          // up to 8 tiles = 32768 entries = 32 per thread
+__global__ void __launch_bounds__(kSmallThreads)
+k_scan_small(uint4* __restrict__ data, const uint32_t per4)   // per4: uint4 words per thread (entries / 4096)
+{
+    chain_prologue();
+    __shared__ uint32_t wsum[kSmallThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* p = data + (size_t)threadIdx.x * per4;
+    uint4 v[kSmallBlocks];
+    uint32_t s = 0;
+    #pragma unroll
+    for (uint32_t k = 0; k < kSmallBlocks; k++)
+        if (k < per4) { v[k] = p[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+    uint32_t inc = s;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];
+        uint32_t wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + inc - s;
+    #pragma unroll
+    for (uint32_t k = 0; k < kSmallBlocks; k++)
+        if (k < per4) {
+            uint4 o;
+            o.x = run; run += v[k].x;
+            o.y = run; run += v[k].y;
+            o.z = run; run += v[k].z;
+            o.w = run; run += v[k].w;
+            p[k] = o;
+        }
+}
 }  // namespace
 
 size_t scan_pad(size_t entries) { return (entries + kScanBlock - 1) / kScanBlock * kScanBlock; }
@@ -338,6 +381,11 @@ void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, 
     const uint32_t nb = (uint32_t)(padded_entries / kScanBlock);
     if (nb == 0) return;
     static const bool fold_ok = [] { const char* e = getenv("SPH_SCAN_FOLD"); return !(e && e[0] == '0'); }();
+    if (fold_ok && nb <= kSmallBlocks) {                       // entries = nb * 4096 = 1024 threads * (nb uint4 words)
+        launch_chained(k_scan_small, dim3(1), dim3(kSmallThreads), 0, st, (uint4*)data, nb);
+        if (launches) *launches += 1;
+        return;
+    }
     launch_chained(k_scan_reduce, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)data, blocksums);
     if (fold_ok && nb <= kFoldBlocks) {
         launch_chained(k_scan_apply<true>, dim3(nb), dim3(kScanThreads), 0, st, (uint4*)data, blocksums);
