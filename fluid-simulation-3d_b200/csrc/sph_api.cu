@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -200,10 +201,20 @@ int ensure_list(SphContext* c, NbrList* L)
         SPH_CUDA(c, cudaStreamSynchronize(c->st));
         if (c->nlist) cudaFree(c->nlist);
         c->nlist = nullptr; c->list_k_alloc = 0;
-        // rows [0, k) hold the neighbour indices, rows [k, 2k) the viscosity weights of the same entries
-        cudaError_t e = cudaMalloc(&c->nlist, 2 * (size_t)c->list_k * c->cap * sizeof(uint32_t));
+        // rows [0, k) hold the neighbour indices, rows [k, 2k) the viscosity weights of the same entries.  The allocation
+        // takes up to twice the rows asked for while that stays within a quarter of the free memory: the capacity can then
+        // grow (a splash, a pile-up in a corner) without another synchronise + free + allocate, a ~100 ms stall at 1 M rows
+        const size_t per_row = 2 * (size_t)c->cap * sizeof(uint32_t);
+        uint32_t k_alloc = c->list_k;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t roomy = std::min<size_t>(2 * (size_t)c->list_k, (free_b / 4) / per_row);
+            if (roomy > k_alloc) k_alloc = (uint32_t)roomy;
+        } else cudaGetLastError();
+        cudaError_t e = cudaMalloc(&c->nlist, (size_t)k_alloc * per_row);
+        if (e != cudaSuccess && k_alloc > c->list_k) { cudaGetLastError(); k_alloc = c->list_k; e = cudaMalloc(&c->nlist, (size_t)k_alloc * per_row); }
         if (e != cudaSuccess) { cudaGetLastError(); c->list_k = 0; }        // no room: fall back to walking every pass
-        else c->list_k_alloc = c->list_k;
+        else c->list_k_alloc = k_alloc;
     }
     L->idx = c->list_k ? c->nlist : nullptr;
     L->w = c->list_k ? reinterpret_cast<float*>(c->nlist + (size_t)c->list_k_alloc * c->cap) : nullptr;
