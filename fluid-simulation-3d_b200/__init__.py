@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sph_create", "sph_destroy", "sph_last_error", "sph_abi_version", "sph_default_params",
     "sph_set_params", "sph_get_params", "sph_set_table_mode", "sph_get_table_mode",
     "sph_set_stage_timing", "sph_set_neighbour_count_tap", "sph_set_neighbour_list_capacity", "sph_spawn_grid", "sph_spawn_block", "sph_upload_state",
-    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_set_graph_replay", "sph_noncanonical_cells", "sph_set_extras", "sph_get_extras", "sph_synchronize", "sph_refresh_densities",
+    "sph_num_particles", "sph_step", "sph_step_n", "sph_graph_replays", "sph_set_graph_replay", "sph_noncanonical_cells", "sph_density_stack_rows", "sph_set_extras", "sph_get_extras", "sph_synchronize", "sph_refresh_densities",
     "sph_download", "sph_download_table", "sph_get_particle", "sph_get_timings", "sph_launch_count", "sph_stream",
     "sph_get_grid", "sph_grid_x_subdivision", "sph_save_state", "sph_load_state", "sph_host_register", "sph_host_unregister",
     "sph_upload_state_begin", "sph_upload_state_commit", "sph_download_begin", "sph_download_wait",
@@ -139,6 +139,8 @@ def load_library():
     L.sph_set_graph_replay.argtypes = [vp, C.c_int]
     L.sph_noncanonical_cells.argtypes = [vp]
     L.sph_noncanonical_cells.restype = C.c_uint64
+    L.sph_density_stack_rows.argtypes = [vp]
+    L.sph_density_stack_rows.restype = C.c_int
     L.sph_stream.argtypes = [vp]
     L.sph_stream.restype = vp
     L.sph_get_grid.argtypes = [vp, vp, vp]
@@ -359,6 +361,9 @@ class FluidSimulation:
 
     def noncanonical_cells(self):
         return int(self.L.sph_noncanonical_cells(self.h))
+
+    def density_stack_rows(self):
+        return int(self.L.sph_density_stack_rows(self.h))
 
     def graph_replays(self):
         return int(self.L.sph_graph_replays(self.h))

@@ -454,6 +454,7 @@ uint64_t sph_noncanonical_cells(SphContext* c)
     return v;
 }
 void* sph_stream(const SphContext* c) { return c ? (void*)c->st : nullptr; }
+int sph_density_stack_rows(const SphContext* c) { return c ? (c->deep_stack ? 72 : 24) : 0; }
 
 int sph_grid_x_subdivision(const SphContext* c) { return c ? c->xsub : 0; }
 

@@ -733,7 +733,7 @@ k_density_pair2(const GatherArgs A, const DevParams P)
 #define SPH_PK_FENCE() do {} while (0)
 #endif
 constexpr int PKS = SPH_PKS;    // stack entries per thread: sparse scenes (one or two flushes per particle)
-constexpr int PKS_DENSE = 72;   // ... when the lists are long (list capacity above 128): fewer, fuller flushes
+constexpr int PKS_DENSE = 72;   // ... when the lists are long throughout (measured mean above 56 rows per warp, ensure_list): fewer, fuller flushes
 
 // ncu: bound by the L1 data pipe; candidates are read as a 16-byte (x0, x1, y0, y1) and an 8-byte (z0, z1) load per pair:
 // 24 bytes per pair instead of the former 32-byte record with its two dead w words (-26 % of the cull's wavefronts).

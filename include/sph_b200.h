@@ -184,6 +184,9 @@ int  sph_set_graph_replay(SphContext* ctx, int enabled);
  * the arrival order of their rows instead of the canonical ascending-index order: neighbour sets are unaffected, float sums lose
  * run-to-run reproducibility in the last bits.  Number of such cells over all steps so far (0 in any sane scene); synchronises. */
 uint64_t sph_noncanonical_cells(SphContext* ctx);
+/* Rows of the density pass's per-thread survivor stack in the last step: 24, or 72 once the neighbour lists the pass itself
+ * measures are long throughout (mean above 56 rows per warp; back to 24 below 40).  A tuning tap: results do not depend on it. */
+int  sph_density_stack_rows(const SphContext* ctx);
 int  sph_synchronize(SphContext* ctx);
 /* rebuild lookup + densities for the current positions without advancing (InitializeData's tail, .cc:144-145) */
 int  sph_refresh_densities(SphContext* ctx);

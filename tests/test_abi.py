@@ -150,6 +150,7 @@ def test_every_entry_point_survives_null_arguments(pkg):
         "sph_launch_count": (lambda: L.sph_launch_count(None), 0), "sph_stream": (lambda: L.sph_stream(None), None),
         "sph_grid_x_subdivision": (lambda: L.sph_grid_x_subdivision(None), 0),
         "sph_noncanonical_cells": (lambda: L.sph_noncanonical_cells(None), 0),
+        "sph_density_stack_rows": (lambda: L.sph_density_stack_rows(None), 0),
     }
     other = {"sph_default_params", "sph_last_error", "sph_abi_version", "sph_comm_id_bytes"}     # take no handle / checked elsewhere
     assert set(status) | set(benign) | other == set(pkg.ABI_SYMBOLS)

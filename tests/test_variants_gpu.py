@@ -58,21 +58,41 @@ def test_neighbour_list_overflow_and_disabled(pkg, cap):
 
 
 def test_long_lists_dense_stack(pkg):
-    """List capacity above 64 selects the deep survivor stack of the packed density kernel; the dense column has
-    ~90 neighbours per particle, so every warp goes through several partial flushes."""
+    """The packed density kernel picks its survivor-stack depth from the list lengths it measured in the steps before
+    (sph_density_stack_rows): the dense column has ~90 neighbours per particle, so the first step runs on the shallow
+    stack -- every warp goes through several partial flushes -- and the next one on the deep stack.  Both must match the
+    oracle, and each other bit for bit (the stack depth moves the flush points, not the order of the sums)."""
     from fluid_simulation_3d_b200 import scenes
     import helpers
-    orig = pkg.FluidSimulation.__init__
-
-    def patched(self, *a, **k):
-        orig(self, *a, **k)
-        self.set_neighbour_list_capacity(192)
-    pkg.FluidSimulation.__init__ = patched
+    sc = scenes.small_column(14, 40, 14)
+    out = helpers.check_step(pkg, sc, pkg.TABLE_GRID, scenes.DT)            # a fresh context: shallow stack
+    assert out["mean_neighbours"] > 50
+    sim = pkg.FluidSimulation(sc["n"], device=0, table_mode=pkg.TABLE_GRID, **sc["params"])
     try:
-        out = helpers.check_step(pkg, scenes.small_column(14, 40, 14), pkg.TABLE_GRID, scenes.DT)
-        assert out["mean_neighbours"] > 50
+        sim.set_neighbour_list_capacity(192)
+        sim.set_neighbour_count_tap(True)
+        fields = ("densities", "vel_after_pressure", "vel_after_viscosity", "positions", "velocities", "neighbour_count")
+        got = []
+        for _ in range(2):
+            sim.upload_state(sc["pos"], sc["vel"])
+            sim.step(scenes.DT)
+            got.append((sim.density_stack_rows(), [sim.download(f) for f in fields]))
+        assert got[0][0] == 24 and got[1][0] == 72, (got[0][0], got[1][0])
+        for f, a, b in zip(fields, got[0][1], got[1][1]):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f + ": deep and shallow stack differ"
+        ref, ps, vs = helpers.oracle_step(sc, scenes.DT)
+        helpers.assert_close("deep-stack density", got[1][1][0], ref.densities(), 0.0)
+        helpers.assert_close("deep-stack velocities", got[1][1][4], ref.velocities(), (ps + vs)[:, None])
+        assert np.array_equal(got[1][1][5], ref.neighbour_counts())
+        # a sparse state in the same context brings the shallow stack back (hysteresis: below 40 rows per warp)
+        sparse = scenes.small_dam_break(14)
+        sim.set_params(**sparse["params"])
+        for _ in range(3):
+            sim.upload_state(sparse["pos"], sparse["vel"])
+            sim.step(scenes.DT)
+        assert sim.density_stack_rows() == 24
     finally:
-        pkg.FluidSimulation.__init__ = orig
+        sim.close()
 
 
 @pytest.mark.parametrize("mode", ["grid", "reference_hash"])
