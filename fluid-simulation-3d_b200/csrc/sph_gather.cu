@@ -272,8 +272,10 @@ k_gather_list(const GatherArgs A, const DevParams P, const float dt)
 // band candidates were re-tested; padding entries and entries at d >= r carry weight 0).  The pass then needs no
 // positions at all: per entry one coalesced index, one coalesced weight and ONE 16-byte gather of v'_j.  The
 // particle's own entry contributes (v'_i - v'_i) * w = 0, exactly like the reference's `continue` (:450).
+// (12 blocks per SM = 40 registers, no spills: 61.5-63.5 us against 64.6 at the 42 registers ptxas picks unprompted; 16 blocks
+// spill and lose (71.7 us); the pressure pass gains nothing from 48 registers / 10 blocks)
 template <int MODE>
-__global__ void __launch_bounds__(kWalkThreads)
+__global__ void __launch_bounds__(kWalkThreads, 12)
 k_viscosity_w(const GatherArgs A, const DevParams P, const float dt)
 {
     chain_prologue();
