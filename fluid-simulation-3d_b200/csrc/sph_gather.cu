@@ -739,7 +739,16 @@ constexpr int PKS_DENSE = 72;   // ... when the lists are long throughout (measu
 
 // ncu: bound by the L1 data pipe; candidates are read as a 16-byte (x0, x1, y0, y1) and an 8-byte (z0, z1) load per pair:
 // 24 bytes per pair instead of the former 32-byte record with its two dead w words (-26 % of the cull's wavefronts).
+// (occupancy sweep at the end of round 2, profiles/r02_density_occupancy_sweep.txt: a 20- or 16-row stack, or 40 / 48 registers
+// by launch bounds, fill more warp slots and are no faster -- 135-152 us against 135-136 for 24 rows at 47 registers)
+#ifndef SPH_PK_BLOCKS
+#define SPH_PK_BLOCKS 1
+#endif
+#if SPH_PK_BLOCKS > 1
+__global__ void __launch_bounds__(kWalkThreads, SPH_PK_BLOCKS)
+#else
 __global__ void __launch_bounds__(kWalkThreads)
+#endif
 k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
 {
     chain_prologue();
