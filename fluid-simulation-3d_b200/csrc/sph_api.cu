@@ -173,6 +173,26 @@ int ensure_tables(SphContext* c, const DevParams& P)
     return SPH_OK;
 }
 
+// Depth of the density pass's survivor stack, from the list length the last steps actually produced (the running sums
+// of list rows and of the warps that wrote them, read back with the overflow word): the deep stack -- a quarter of the
+// occupancy -- pays only when lists are long THROUGHOUT (C5: ~110 rows per warp), not because one pile-up once pushed
+// the CAPACITY up (an evolved C2 run sat at 280 instead of 125 us per density pass that way).  Hysteresis 40 / 56 rows.
+// Called before every step, replayed ones too: a flipped decision changes the StepKey, so the step is launched plainly
+// and recorded again.
+static void update_stack_depth(SphContext* c)
+{
+    if (c->capturing || !c->h_overflow) return;
+    // (warps << 32 | rows) in one aligned 64-bit word: read whole, differences taken in 64 bits
+    const uint64_t now = *reinterpret_cast<const volatile uint64_t*>(c->h_overflow + 2);
+    const uint64_t d = now - c->rows_warps_seen;
+    const uint32_t rows = (uint32_t)d, warps = (uint32_t)(d >> 32);
+    if (!warps) return;
+    const double mean = (double)rows / (double)warps;
+    if (mean > 56.0) c->deep_stack = true;
+    else if (mean < 40.0) c->deep_stack = false;
+    c->rows_warps_seen = now;
+}
+
 int ensure_list(SphContext* c, NbrList* L)
 {
     if (!c->h_overflow) {
@@ -219,19 +239,7 @@ int ensure_list(SphContext* c, NbrList* L)
     L->idx = c->list_k ? c->nlist : nullptr;
     L->w = c->list_k ? reinterpret_cast<float*>(c->nlist + (size_t)c->list_k_alloc * c->cap) : nullptr;
     L->cnt = c->lcount;
-    // Depth of the density pass's survivor stack, from the list length the last steps actually produced (the running sums
-    // of list rows and of the warps that wrote them, read back with the overflow word): the deep stack -- a quarter of the
-    // occupancy -- pays only when lists are long THROUGHOUT (C5: ~110 rows per warp), not because one pile-up once pushed
-    // the CAPACITY up (an evolved C2 run sat at 280 instead of 125 us per density pass that way).  Hysteresis 40 / 56 rows.
-    if (!c->capturing) {
-        const uint32_t rows = c->h_overflow[2] - c->rows_seen, warps = c->h_overflow[3] - c->warps_seen;
-        if (warps) {
-            const double mean = (double)rows / (double)warps;
-            if (mean > 56.0) c->deep_stack = true;
-            else if (mean < 40.0) c->deep_stack = false;
-            c->rows_seen = c->h_overflow[2]; c->warps_seen = c->h_overflow[3];
-        }
-    }
+    update_stack_depth(c);
     L->deep = c->deep_stack;
     L->rows_sum = c->d_overflow + 2;
     L->overflow = c->d_overflow;
@@ -638,6 +646,7 @@ static int step_once(SphContext* c, float dt)
     if (c->nranks > 1) return multi_step(c, dt);
     const bool can = graphs_enabled() && !c->graph_disabled && !c->graph_user_off && c->n > 0;
     if (can) {
+        update_stack_depth(c);
         const bool grow = (c->list_auto && c->list_k && c->h_overflow && *c->h_overflow > c->list_k) ||
                           (c->h_tile_need && *c->h_tile_need > c->tile_capn);
         const SphContext::StepKey k = step_key(c, dt);

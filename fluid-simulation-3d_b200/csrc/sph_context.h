@@ -35,7 +35,7 @@ struct SphContext {
     bool list_auto = true;       // grow list_k when the density pass reports overflowing particles
     uint32_t* d_overflow = nullptr;  // device word written by the density kernel (longest list that did not fit)
     uint32_t* h_overflow = nullptr;  // pinned mirror (4 words, see ensure_list), refreshed asynchronously after every density pass
-    uint32_t rows_seen = 0, warps_seen = 0;   // running sums of list rows / warps already accounted for
+    uint64_t rows_warps_seen = 0;    // (warps << 32 | list rows) of the density passes already accounted for
     bool deep_stack = false;         // density pass: deep survivor stack (lists are long throughout)
     uint32_t* row_of = nullptr;           // id -> row of the device order, built on demand by sph_get_particle
     uint64_t row_of_stamp = ~0ull;        // c->launches when it was built: any kernel since then may have changed the order

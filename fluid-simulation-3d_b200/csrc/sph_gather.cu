@@ -915,7 +915,9 @@ k_density_pk(const GatherArgs A, const DevParams P, const uint32_t stack_rows)
         A.list_cnt[i] = kbase;
     }
     report_overflow(A, (valid && kbase > K) ? kbase : 0u);
-    if ((tid & 31) == 0 && A.rows_sum) { atomicAdd(&A.rows_sum[0], kbase); atomicAdd(&A.rows_sum[1], 1u); }   // kbase is warp-uniform
+    // list rows and warps so far, one 64-bit counter (warps << 32 | rows, the sums carry into each other consistently and the
+    // host takes 64-bit differences): kbase is warp-uniform
+    if ((tid & 31) == 0 && A.rows_sum) atomicAdd(reinterpret_cast<unsigned long long*>(A.rows_sum), (1ull << 32) | (unsigned long long)kbase);
 }
 
 template <int PASS>

@@ -76,4 +76,13 @@ def test_step_n_replay_with_growing_neighbour_lists(pkg):
     assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
     da, db = a.download("densities"), b.download("densities")
     assert np.all(np.abs(da - db) <= 1e-5 * np.maximum(np.abs(db), 1.0))
+    # the lists are long throughout, so by now both contexts have measured that and run the density pass on its deep
+    # survivor stack -- the replaying one too: the depth is re-evaluated before replayed steps as well, a flip makes
+    # the step run plainly and record again
+    a.step_n(scenes.DT, 4)
+    for _ in range(4):
+        b.step(scenes.DT)
+    assert a.density_stack_rows() == 72 and b.density_stack_rows() == 72
+    assert np.array_equal(a.download("neighbour_count"), b.download("neighbour_count"))
+    assert np.array_equal(_bits(a.download("positions")), _bits(b.download("positions")))
     a.close(); b.close()
