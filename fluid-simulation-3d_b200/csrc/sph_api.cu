@@ -82,6 +82,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P)
     P->row0 = 0; P->row1 = n; P->n_a = n;
     P->pair_cap = (c->cap + 8u) / 2u + kPairPad;
     P->seg_off = (uint32_t)table_layout(c->ncell).cells_pad;
+    P->cnt_off = P->seg_off + (uint32_t)table_layout(c->ncell).nseg_pad;
     P->noncanonical = c->d_noncanonical;
     P->extras = c->extras_on ? 1 : 0;
     for (int i = 0; i < 9; i++) P->rot[i] = c->rot[i];
@@ -267,6 +268,8 @@ static void free_all(SphContext* c)
     if (c->stage_out) cudaFree(c->stage_out);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {c->ev_h2d, c->ev_pack, c->ev_export, c->ev_d2h}) if (e) cudaEventDestroy(e);
+    if (c->st_fork) cudaStreamDestroy(c->st_fork);
+    for (cudaEvent_t e : {c->ev_fork, c->ev_join}) if (e) cudaEventDestroy(e);
     if (c->st_in) cudaStreamDestroy(c->st_in);
     if (c->st_out) cudaStreamDestroy(c->st_out);
     if (c->st) cudaStreamDestroy(c->st);
@@ -323,6 +326,10 @@ int sph_create(SphContext** out, int device, uint32_t capacity)
     } while (0)
     e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    // the fork of the recorded step (run_step); without it the step simply stays serial
+    if (cudaStreamCreateWithFlags(&c->st_fork, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); c->st_fork = nullptr; }
     ALLOC(c->A_pos, cap * 16); ALLOC(c->A_vel, cap * 16);
     ALLOC(c->S_pos, cap * 16); ALLOC(c->S_vel, cap * 16);
     ALLOC(c->pred, (cap + 8) * 16);   /* padded: the gather loads 4 rows at a time */  ALLOC(c->velp, cap * 16);
@@ -527,8 +534,21 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         } else launch_table_clear(st, c->tstart, T, &c->launches);
         launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, nullptr, P.n, false, P, dt, c->tstart, c->perm_b, &c->launches);
         if (timing) SPH_CUDA(c, stage_event(c, 1));
-        exclusive_scan_u32(st, c->tstart + T.cells_pad, T.nseg_pad, c->scan_tmp, &c->launches);
-        launch_inseg_scan(st, c->tstart, T, &c->launches);
+        // segment counts -> segment bases (out of place) and, independently of it, the in-segment prefixes of the occupied
+        // segments: in a recording the two run side by side (a fork through a second stream; plain launches stay serial,
+        // an event pair would cost what the overlap saves)
+        const uint32_t* seg_cnt = c->tstart + T.cells_pad + T.nseg_pad;
+        if (c->capturing && c->st_fork) {
+            SPH_CUDA(c, cudaEventRecord(c->ev_fork, st));
+            SPH_CUDA(c, cudaStreamWaitEvent(c->st_fork, c->ev_fork, 0));
+            exclusive_scan_u32(c->st_fork, seg_cnt, c->tstart + T.cells_pad, T.nseg_pad, c->scan_tmp, &c->launches);
+            SPH_CUDA(c, cudaEventRecord(c->ev_join, c->st_fork));
+            launch_inseg_scan(st, c->tstart, T, &c->launches);
+            SPH_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+        } else {
+            exclusive_scan_u32(st, seg_cnt, c->tstart + T.cells_pad, T.nseg_pad, c->scan_tmp, &c->launches);
+            launch_inseg_scan(st, c->tstart, T, &c->launches);
+        }
         launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, P.n, P, &c->launches);
         launch_reorder(st, c->perm_a, c->key_a, c->tstart, c->key_b, c->A_pos, c->A_vel, nullptr, c->S_pos, c->S_vel, c->pred,
                        c->predpk, P, dt, &c->launches);

@@ -59,6 +59,8 @@ struct SphContext {
 
     // pipelined transfers (sph_upload_state_begin / _commit, sph_download_begin / _wait): their own staging
     // buffers and copy streams, so a PCIe copy in either direction overlaps the step on `st`
+    cudaStream_t st_fork = nullptr;  // second branch of the recorded step (segment scan beside the in-segment scan)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t st_in = nullptr, st_out = nullptr;
     unsigned char* stage_in = nullptr;    // cap * 28 B: pos3 | vel3 | global ids (slab mode) of the pending upload
     unsigned char* stage_out = nullptr;   // cap * 20 B: the exported field (+ global ids, slab mode) of the pending download

@@ -42,6 +42,7 @@ struct DevParams {
     int      has_lo, has_hi;   // a neighbour rank exists below / above
     uint32_t n_a;              // reorder: perm values < n_a index the state arrays, the rest the ghost buffer
     uint32_t pair_cap;         // candidate pairs: float4 entries of the (x0,x1,y0,y1) array; the (z0,z1) array starts right behind it
+    uint32_t cnt_off;          // GRID table: word offset of the per-segment row COUNTS (count_segment; nonzero = the segment is occupied / dirty)
     uint32_t seg_off;          // GRID table: word offset of the per-segment base array behind the per-cell array (tbl(), sph_device.cuh)
     uint32_t* noncanonical;    // device counter: cells too crowded for the canonical-order ranking of the counting sort (sph_kernels.cu)
     // optional features (SphExtras): box rotation (rows of R: world = R * local) and wall stickiness
@@ -102,7 +103,7 @@ void launch_ghost_key(cudaStream_t st, const float4* ghost_pred, uint32_t* key, 
 void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, const uint32_t* table, uint32_t* slot_row,
                   uint32_t n, const DevParams& P, uint64_t* launches);
 // two-level GRID table (counting sort): clear what the last step touched, in-segment prefixes, flat copy for the taps
-struct TableLayout { size_t cells_pad, nseg, nseg_pad, total; };   // [cells][segment bases][dirty flags], in words
+struct TableLayout { size_t cells_pad, nseg, nseg_pad, total; };   // [cells][segment bases][segment row counts], in words
 TableLayout table_layout(uint32_t ncell);
 void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
 void launch_inseg_scan(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
@@ -110,7 +111,8 @@ void launch_table_flatten(cudaStream_t st, const uint32_t* table, const DevParam
 // sph_sort.cu: in-place exclusive scan of a zero-padded array (multiple of 4096 entries)
 size_t scan_pad(size_t entries);
 size_t scan_temp_entries(size_t entries);
-void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, uint32_t* blocksums, uint64_t* launches);
+// (src == dst: in place)
+void exclusive_scan_u32(cudaStream_t st, const uint32_t* src, uint32_t* dst, size_t padded_entries, uint32_t* blocksums, uint64_t* launches);
 void launch_build_table(cudaStream_t st, const uint32_t* key_sorted, uint32_t* table_start, uint32_t* table_end,
                         uint32_t* gap_list, const DevParams& P, uint64_t* launches);
 // key / table non-null: counting-sort path (perm = slot -> some row of the cell; canonical order restored here)

@@ -29,7 +29,7 @@ __device__ __forceinline__ void count_segment(uint32_t* __restrict__ count, cons
 {
     const uint32_t sg = k >> kSegShift;
     const uint32_t peers = __match_any_sync(__activemask(), sg);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[P.seg_off + sg], (uint32_t)__popc(peers));
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[P.cnt_off + sg], (uint32_t)__popc(peers));
     // (Keeping the sums of the scan's 4096-segment tiles here as well, to save the scan its reduce launch, was measured:
     // one more atomic per warp on a handful of addresses serialises -- k_predict_key 19 -> 46 us at 1 M rows, 0.11 -> 0.55 ms
     // at 8 M.  The reduce launch costs 3 us.)
@@ -127,20 +127,21 @@ k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, con
 }
 
 // ---- two-level GRID table (counting sort) -----------------------------------------------------------------------
-// Layout of the allocation: [cells: ncell + 3, padded][segment bases, padded for the scan][dirty flag per segment].
-// One warp per segment throughout.
+// Layout of the allocation: [cells: ncell + 3, padded][segment bases, padded for the scan][rows per segment, padded].
+// The counting kernels count into the third array; the scan turns it into the second (out of place), so the in-segment
+// scan -- which only needs to know WHICH segments hold rows -- does not depend on the segment scan and the two run side
+// by side in the recorded step (run_step).  A nonzero count also marks the segment as one the next step has to clear.
 __global__ void __launch_bounds__(256)
 k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg,
               const uint32_t nseg_pad)
-{   // zero the cell counters of the segments the LAST step touched, and every segment counter.  One THREAD looks at
+{   // zero the cell counters of the segments the LAST step touched (row count != 0), and their row counts.  One THREAD looks at
     // one segment's flag (coalesced); the warp then zeroes its dirty segments together, 64 cells at a time.
     chain_prologue();
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool in = sg < nseg;
     const bool dirty = in && table[dirty_off + sg] != 0u;
-    if (sg < nseg_pad) table[seg_off + sg] = 0u;          // the scan's padding too (it holds last step's totals)
-    if (dirty) table[dirty_off + sg] = 0u;
+    if (sg < nseg_pad && (dirty || !in)) table[dirty_off + sg] = 0u;      // (the bases are overwritten by the scan, padding included)
     uint32_t todo = __ballot_sync(0xffffffffu, dirty);
     const uint32_t sg0 = sg - lane;
     while (todo) {
@@ -157,8 +158,7 @@ k_inseg_scan(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_
     chain_prologue();
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    const bool occ = sg < nseg && table[seg_off + sg + 1] != table[seg_off + sg];   // empty: its cells are, and stay, zero
-    if (occ) table[dirty_off + sg] = 1u;
+    const bool occ = sg < nseg && table[dirty_off + sg] != 0u;                     // empty: its cells are, and stay, zero
     uint32_t todo = __ballot_sync(0xffffffffu, occ);
     const uint32_t sg0 = sg - lane;
     // four occupied segments per round: their loads are issued together (one round trip to the L2 for all four)

@@ -376,6 +376,7 @@ static int slab_params(SphContext* c, DevParams* P, uint32_t n_rows)
     P->ncell = (uint32_t)((uint64_t)P->gdim[0] * P->gdim[1] * P->gdim[2]);
     P->mode = SPH_TABLE_GRID;
     P->seg_off = (uint32_t)table_layout(P->ncell).cells_pad;      // the slab's own table, not the whole grid's
+    P->cnt_off = P->seg_off + (uint32_t)table_layout(P->ncell).nseg_pad;
     return SPH_OK;
 }
 
@@ -550,7 +551,7 @@ int multi_step(SphContext* c, float dt)
     launch_ghost_key(st, s->ghost_pred, c->key_a + n_a, n_ghost, P, binned ? c->tstart : nullptr, c->perm_b + n_a, &c->launches);
     if (binned) {
         // table over ncell + 1 "cells": the extra one collects the departed rows (key == ncell)
-        exclusive_scan_u32(st, c->tstart + TL.cells_pad, TL.nseg_pad, c->scan_tmp, &c->launches);
+        exclusive_scan_u32(st, c->tstart + TL.cells_pad + TL.nseg_pad, c->tstart + TL.cells_pad, TL.nseg_pad, c->scan_tmp, &c->launches);
         launch_inseg_scan(st, c->tstart, TL, &c->launches);
         launch_place(st, c->key_a, c->perm_b, c->tstart, c->perm_a, n_all, P, &c->launches);
         SLAB_MARK(4);

@@ -288,7 +288,7 @@ k_scan_top(uint32_t* __restrict__ blocksums, const uint32_t nb)
 // scenes); larger tables keep the three-kernel form.
 template <bool FOLD>
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_apply(uint4* __restrict__ data, const uint32_t* __restrict__ blocksums)
+k_scan_apply(const uint4* src, uint4* data, const uint32_t* __restrict__ blocksums)   // src == data: in place
 {
     chain_prologue();
     __shared__ uint32_t wsum[kScanThreads / 32];
@@ -303,11 +303,13 @@ k_scan_apply(uint4* __restrict__ data, const uint32_t* __restrict__ blocksums)
         if (lane == 0) fsum[warp] = a;
     }
     // thread t owns 16 CONSECUTIVE entries: uint4 words [4t, 4t+4) of the block
-    uint4* p = data + (size_t)blockIdx.x * (kScanBlock / 4) + (size_t)threadIdx.x * (kScanPer / 4);
+    const size_t at = (size_t)blockIdx.x * (kScanBlock / 4) + (size_t)threadIdx.x * (kScanPer / 4);
+    const uint4* q = src + at;
+    uint4* p = data + at;
     uint4 v[kScanPer / 4];
     uint32_t s = 0;
     #pragma unroll
-    for (int k = 0; k < kScanPer / 4; k++) { v[k] = p[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+    for (int k = 0; k < kScanPer / 4; k++) { v[k] = q[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
     uint32_t inc = s;
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -335,17 +337,18 @@ constexpr uint32_t kFoldBlocks = 2048;
 constexpr int kSmallThreads = 1024;
 constexpr uint32_t kSmallBlocks = 8;                          // up to 8 tiles = 32768 entries = 32 per thread
 __global__ void __launch_bounds__(kSmallThreads)
-k_scan_small(uint4* __restrict__ data, const uint32_t per4)   // per4: uint4 words per thread (entries / 4096)
+k_scan_small(const uint4* src, uint4* data, const uint32_t per4)   // per4: uint4 words per thread (entries / 4096)
 {
     chain_prologue();
     __shared__ uint32_t wsum[kSmallThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* q = src + (size_t)threadIdx.x * per4;
     uint4* p = data + (size_t)threadIdx.x * per4;
     uint4 v[kSmallBlocks];
     uint32_t s = 0;
     #pragma unroll
     for (uint32_t k = 0; k < kSmallBlocks; k++)
-        if (k < per4) { v[k] = p[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+        if (k < per4) { v[k] = q[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
     uint32_t inc = s;
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -376,24 +379,24 @@ k_scan_small(uint4* __restrict__ data, const uint32_t per4)   // per4: uint4 wor
 size_t scan_pad(size_t entries) { return (entries + kScanBlock - 1) / kScanBlock * kScanBlock; }
 size_t scan_temp_entries(size_t entries) { return scan_pad(entries) / kScanBlock + 1; }
 
-void exclusive_scan_u32(cudaStream_t st, uint32_t* data, size_t padded_entries, uint32_t* blocksums, uint64_t* launches)
+void exclusive_scan_u32(cudaStream_t st, const uint32_t* src, uint32_t* data, size_t padded_entries, uint32_t* blocksums, uint64_t* launches)
 {
     const uint32_t nb = (uint32_t)(padded_entries / kScanBlock);
     if (nb == 0) return;
     static const bool fold_ok = [] { const char* e = getenv("SPH_SCAN_FOLD"); return !(e && e[0] == '0'); }();
     if (fold_ok && nb <= kSmallBlocks) {                       // entries = nb * 4096 = 1024 threads * (nb uint4 words)
-        launch_chained(k_scan_small, dim3(1), dim3(kSmallThreads), 0, st, (uint4*)data, nb);
+        launch_chained(k_scan_small, dim3(1), dim3(kSmallThreads), 0, st, (const uint4*)src, (uint4*)data, nb);
         if (launches) *launches += 1;
         return;
     }
-    launch_chained(k_scan_reduce, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)data, blocksums);
+    launch_chained(k_scan_reduce, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)src, blocksums);
     if (fold_ok && nb <= kFoldBlocks) {
-        launch_chained(k_scan_apply<true>, dim3(nb), dim3(kScanThreads), 0, st, (uint4*)data, blocksums);
+        launch_chained(k_scan_apply<true>, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)src, (uint4*)data, blocksums);
         if (launches) *launches += 2;
         return;
     }
     launch_chained(k_scan_top, dim3(1), dim3(1024), 0, st, blocksums, nb);
-    launch_chained(k_scan_apply<false>, dim3(nb), dim3(kScanThreads), 0, st, (uint4*)data, blocksums);
+    launch_chained(k_scan_apply<false>, dim3(nb), dim3(kScanThreads), 0, st, (const uint4*)src, (uint4*)data, blocksums);
     if (launches) *launches += 3;
 }
 }  // namespace sphb200
