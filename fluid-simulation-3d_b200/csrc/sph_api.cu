@@ -194,6 +194,24 @@ static void update_stack_depth(SphContext* c)
     c->rows_warps_seen = now;
 }
 
+// List overflow / staging need / list-length sums of the density pass that `after` has just been given: one 16-byte copy to
+// the pinned mirror.  It leaves on a side stream: as a node of the solver's stream a device-to-host copy costs the step
+// ~9 us wherever it stands (C2 replayed: 0.2957 -> 0.2871 ms once it was off the chain).  The counters are monotonic and
+// read without synchronising, so nothing waits for the copy -- except a recording, which must join its branches
+// (run_step does, at the end of the step).
+int copy_list_words(SphContext* c, cudaStream_t after)
+{
+    if (!c->st_fork) {
+        SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, after));
+        return SPH_OK;
+    }
+    SPH_CUDA(c, cudaEventRecord(c->ev_fork, after));
+    SPH_CUDA(c, cudaStreamWaitEvent(c->st_fork, c->ev_fork, 0));
+    SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_fork));
+    if (c->capturing) SPH_CUDA(c, cudaEventRecord(c->ev_join, c->st_fork));
+    return SPH_OK;
+}
+
 int ensure_list(SphContext* c, NbrList* L)
 {
     if (!c->h_overflow) {
@@ -573,6 +591,9 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
     if (rc != SPH_OK) return rc;
     launch_density(st, c->pred, c->predpk, c->tstart, c->tend, c->dens, L, P, &c->launches);
     c->ncount_valid = true;
+    // (a recording forks the copy of the list words here, right behind the density pass; plain launches send it off at the end
+    // of the step, so that no event record stands between two kernels of the chain)
+    if (L.idx && c->capturing) { rc = copy_list_words(c, st); if (rc != SPH_OK) return rc; }
     if (timing) SPH_CUDA(c, stage_event(c, 3));
     if (advance) {
         launch_pressure(st, c->pred, c->dens, c->S_vel, c->tstart, c->tend, c->velp, L, P, dt, &c->launches);
@@ -588,9 +609,8 @@ static int run_step(SphContext* c, float dt, bool advance, bool allow_timing = t
         SPH_CUDA(c, cudaMemcpyAsync(c->A_pos, c->S_pos, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
         SPH_CUDA(c, cudaMemcpyAsync(c->A_vel, c->S_vel, (size_t)c->n * 16, cudaMemcpyDeviceToDevice, st));
     }
-    // list overflow / staging need / list-length sums of this step's density pass: one copy, at the END of the step (between
-    // the density and pressure passes it would cut the chain of dependent launches in two)
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx && c->capturing && c->st_fork) SPH_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));      // a recording must join its branches
+    else if (L.idx && !c->capturing) { rc = copy_list_words(c, st); if (rc != SPH_OK) return rc; }
     SPH_CUDA(c, cudaGetLastError());
     c->step_valid = true;
     return SPH_OK;

@@ -128,6 +128,7 @@ int make_dev_params(SphContext* c, uint32_t n, DevParams* P);
 int ensure_tables(SphContext* c, const DevParams& P);
 int export_field(SphContext* c, int field, void* dev_out, bool by_id, uint32_t n);
 int ensure_list(SphContext* c, NbrList* L);
+int copy_list_words(SphContext* c, cudaStream_t after);
 bool counting_sort_enabled();
 int ensure_pipeline(SphContext* c);      // copy streams + events of the pipelined transfers (sph_api.cu)
 

@@ -685,7 +685,7 @@ int multi_step(SphContext* c, float dt)
     interior(dens_rows);
     SPH_CUDA(c, cudaEventRecord(s->ev_i[0], st));
     SPH_CUDA(c, cudaStreamWaitEvent(st, s->ev_b[0], 0));            // the solver's stream has every owned density from here on
-    if (L.idx) SPH_CUDA(c, cudaMemcpyAsync(c->h_overflow, c->d_overflow, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (L.idx) { rc = copy_list_words(c, st); if (rc != SPH_OK) return rc; }        // on a side stream: nothing waits for it
     c->ncount_valid = true;
     if (timing) SPH_CUDA(c, cudaEventRecord(c->ev[3], st));
 
