@@ -105,7 +105,8 @@ void launch_place(cudaStream_t st, const uint32_t* key, const uint32_t* rank, co
 // two-level GRID table (counting sort): clear what the last step touched, in-segment prefixes, flat copy for the taps
 struct TableLayout { size_t cells_pad, nseg, nseg_pad, total; };   // [cells][segment bases][segment row counts], in words
 TableLayout table_layout(uint32_t ncell);
-void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
+void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches, uint32_t* extra_a = nullptr,
+                        uint32_t words_a = 0, uint32_t* extra_b = nullptr, uint32_t words_b = 0);   // extra_*: words to zero along the way
 void launch_inseg_scan(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches);
 void launch_table_flatten(cudaStream_t st, const uint32_t* table, const DevParams& P, uint32_t* flat, uint32_t entries, uint64_t* launches);
 // sph_sort.cu: in-place exclusive scan of a zero-padded array (multiple of 4096 entries)

@@ -133,13 +133,17 @@ k_place(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, con
 // by side in the recorded step (run_step).  A nonzero count also marks the segment as one the next step has to clear.
 __global__ void __launch_bounds__(256)
 k_table_clear(uint32_t* __restrict__ table, const uint32_t seg_off, const uint32_t dirty_off, const uint32_t nseg,
-              const uint32_t nseg_pad)
+              const uint32_t nseg_pad, uint32_t* __restrict__ extra_a, const uint32_t words_a, uint32_t* __restrict__ extra_b,
+              const uint32_t words_b)
 {   // zero the cell counters of the segments the LAST step touched (row count != 0), and their row counts.  One THREAD looks at
     // one segment's flag (coalesced); the warp then zeroes its dirty segments together, 64 cells at a time.
     chain_prologue();
     const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const bool in = sg < nseg;
+    // slab mode: the step's small counters ride along (two memset nodes less on the solver's stream)
+    for (uint32_t i = sg; i < words_a; i += gridDim.x * blockDim.x) extra_a[i] = 0u;
+    for (uint32_t i = sg; i < words_b; i += gridDim.x * blockDim.x) extra_b[i] = 0u;
     const bool dirty = in && table[dirty_off + sg] != 0u;
     if (sg < nseg_pad && (dirty || !in)) table[dirty_off + sg] = 0u;      // (the bases are overwritten by the scan, padding included)
     uint32_t todo = __ballot_sync(0xffffffffu, dirty);
@@ -638,10 +642,11 @@ TableLayout table_layout(const uint32_t ncell)
     return T;
 }
 
-void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches)
+void launch_table_clear(cudaStream_t st, uint32_t* table, const TableLayout& T, uint64_t* launches, uint32_t* extra_a, uint32_t words_a,
+                        uint32_t* extra_b, uint32_t words_b)
 {
     launch_chained(k_table_clear, dim3(blocks_for((uint32_t)T.nseg_pad, 256)), dim3(256), 0, st, table, (uint32_t)T.cells_pad, (uint32_t)(T.cells_pad + T.nseg_pad), (uint32_t)T.nseg,
-                   (uint32_t)T.nseg_pad);
+                   (uint32_t)T.nseg_pad, extra_a, words_a, extra_b, words_b);
     ++*launches;
 }
 

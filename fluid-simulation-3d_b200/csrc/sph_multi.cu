@@ -405,13 +405,16 @@ int multi_step(SphContext* c, float dt)
     const TableLayout TL = table_layout(P.ncell);
     if (c->table_ncell != P.ncell) { c->table_two_level = false; c->table_ncell = P.ncell; }   // the planes moved: another layout
     c->table_seg_off = P.seg_off;
+    const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
+    bool zeroed = false;                        // the step's small counters: dev_small and the per-pack-block list counts
     if (binned) {
         if (!c->table_two_level) { SPH_CUDA(c, cudaMemsetAsync(c->tstart, 0, TL.total * sizeof(uint32_t), st)); c->table_two_level = true; }
-        else launch_table_clear(st, c->tstart, TL, &c->launches);
+        else { launch_table_clear(st, c->tstart, TL, &c->launches, s->dev_small, 64u, s->block_counts, NLISTS * nblocks); zeroed = true; }
     }
-    const uint32_t nblocks = n_old ? (n_old + kPackSpan - 1) / kPackSpan : 1;
-    SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
-    SPH_CUDA(c, cudaMemsetAsync(s->block_counts, 0, (size_t)NLISTS * nblocks * sizeof(uint32_t), st));
+    if (!zeroed) {                              // (otherwise k_table_clear zeroed them on its way)
+        SPH_CUDA(c, cudaMemsetAsync(s->dev_small, 0, 64 * sizeof(uint32_t), st));
+        SPH_CUDA(c, cudaMemsetAsync(s->block_counts, 0, (size_t)NLISTS * nblocks * sizeof(uint32_t), st));
+    }
     // ... which also counts, per pack block, the rows of each of the six lists (k_slab_scan / k_slab_pack below)
     launch_predict_key(st, c->A_pos, c->A_vel, c->key_a, s->cls, n_old, true, P, dt, binned ? c->tstart : nullptr, c->perm_b,
                        &c->launches, s->block_counts, nblocks);
