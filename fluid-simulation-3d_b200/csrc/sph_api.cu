@@ -378,6 +378,7 @@ int sph_destroy(SphContext* c)
     if (!c) return SPH_OK;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st_fork) cudaStreamSynchronize(c->st_fork);      // the copy of the list words into the pinned mirror may still be on its way
     if (c->st_in) cudaStreamSynchronize(c->st_in);
     if (c->st_out) cudaStreamSynchronize(c->st_out);
     multi_teardown(c);
@@ -740,6 +741,7 @@ int sph_synchronize(SphContext* c)
     if (!c) return SPH_ERR_INVALID;
     SPH_CUDA(c, cudaSetDevice(c->device));
     SPH_CUDA(c, cudaStreamSynchronize(c->st));
+    if (c->st_fork) SPH_CUDA(c, cudaStreamSynchronize(c->st_fork));     // the list words of the last step have reached the host too
     return SPH_OK;
 }
 
