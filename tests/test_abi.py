@@ -215,3 +215,24 @@ def test_slab_link_verdict_is_symmetric_and_catches_every_overflow(pkg):
     assert ok(good, tight) == 0 and ok(tight, good) == 0
     tight = good.copy(); tight[6] = 6                                          # 7 ghosts > 6 free ghost rows
     assert ok(good, tight) == 0 and ok(tight, good) == 0
+
+
+def test_every_chained_launch_waits_in_kernel():
+    """launch_chained() (programmatic stream serialisation) lets a kernel start while its predecessor drains; the kernel
+    itself must order its memory accesses with chain_prologue() (griddepcontrol.wait) before it touches anything.  A kernel
+    launched that way without the wait would race silently, so the sources are checked: every kernel name handed to
+    launch_chained has chain_prologue() as the first statement of its body."""
+    import glob
+    import re
+    src = {}
+    for path in glob.glob(os.path.join(ROOT, "fluid-simulation-3d_b200", "csrc", "*.cu")):
+        src[path] = open(path).read()
+    text = "\n".join(src.values())
+    names = set(re.findall(r"launch_chained\(\s*(k_\w+)", text))
+    assert len(names) >= 10, names
+    for name in sorted(names):
+        m = re.search(r"__global__[^;{]*?\b" + name + r"\s*\([^{;]*?\)\s*(?://[^\n]*)?\s*\{(.*?)\n\}", text, re.S)
+        assert m, "no definition found for " + name
+        body = re.sub(r"//[^\n]*", "", m.group(1))               # drop comments
+        first = body.strip().split(";")[0].strip()
+        assert first == "chain_prologue()", "%s: first statement is %r" % (name, first)
